@@ -1,0 +1,179 @@
+/* momlevel_b200.h -- C ABI of libmomlevel_b200.so (sm_100a CUDA kernels for momlevel's
+ * steric sea-level path).
+ *
+ * The reference (jkrasting/momlevel) is pure Python and has no FFI of its own; its
+ * operator boundary is "numpy arrays in, numpy array out" (`eos.<name>.density(T,S,p)`,
+ * `spice.flament.spice(T,S)`) applied through `xr.apply_ufunc` (src/momlevel/derived.py:624-630).
+ * Each entry point below names the reference code it replaces.  INTEGRATION.md shows the
+ * ctypes stub a momlevel maintainer would add to call them.
+ *
+ * Conventions (all entry points)
+ *   - return 0 on success, <0 = ml_status argument error, >0 = cudaError_t;
+ *     `ml_last_error()` returns a thread-local message for the last non-zero return
+ *   - DEVICE entry points take device pointers owned by the caller (any allocator: torch,
+ *     cudaMalloc, DLPack imports), are asynchronous on `stream` (a cudaStream_t passed as
+ *     void*, NULL = legacy default stream) and use the calling thread's current device
+ *   - HOST entry points (`*_host`) take host pointers, do their own staging and
+ *     synchronise before returning
+ *   - field layout is MOM6 / C order [t][z][y][x], x fastest; (y,x) is passed flattened as
+ *     `ncol = ny*nx` water columns; NaN marks a missing (land) value
+ *   - `dtype` is the storage type of the 3-D/4-D input fields (ML_F32 or ML_F64); all
+ *     arithmetic and all outputs are fp64
+ *   - no exceptions cross the boundary; no global state besides __constant__ tables
+ */
+#ifndef MOMLEVEL_B200_H
+#define MOMLEVEL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ML_ABI_VERSION 1
+
+typedef enum ml_status {
+  ML_OK = 0,
+  ML_ERR_NULL = -1,      /* required pointer is NULL */
+  ML_ERR_SHAPE = -2,     /* non-positive or inconsistent extent */
+  ML_ERR_DTYPE = -3,     /* dtype is not ML_F32 / ML_F64 */
+  ML_ERR_EOS = -4,       /* unknown equation of state / function id */
+  ML_ERR_MODE = -5,      /* unknown pressure mode / flag combination */
+  ML_ERR_WORKSPACE = -6, /* workspace too small or NULL */
+  ML_ERR_ALIGN = -7,     /* pointer not aligned to its element size */
+  ML_ERR_DEVICE = -8     /* no CUDA device / not an sm_100 device */
+} ml_status;
+
+typedef enum ml_dtype { ML_F32 = 0, ML_F64 = 1 } ml_dtype;
+
+/* momlevel.eos.<name>: util.eos_func_from_str (src/momlevel/util.py:227-249) */
+typedef enum ml_eos { ML_EOS_WRIGHT = 0, ML_EOS_LINEAR = 1 } ml_eos;
+
+/* func_name argument of eos_func_from_str */
+typedef enum ml_eos_func {
+  ML_FUNC_DENSITY = 0,    /* wright.py:23-50,   linear.py:26-58   */
+  ML_FUNC_DRHO_DTEMP = 1, /* wright.py:53-85,   linear.py:61-85   */
+  ML_FUNC_DRHO_DSAL = 2,  /* wright.py:88-119,  linear.py:88-110  */
+  ML_FUNC_ALPHA = 3,      /* wright.py:122-142, linear.py:113-136 */
+  ML_FUNC_BETA = 4        /* wright.py:145-165, linear.py:139-162 */
+} ml_eos_func;
+
+/* how the pressure operand of ml_eos_eval broadcasts */
+typedef enum ml_pmode {
+  ML_P_SCALAR = 0,    /* one value (p[0]) for every point                   */
+  ML_P_PER_LEVEL = 1, /* p[nz], what steric.py:96 builds from z_l           */
+  ML_P_FULL = 2       /* p has the full [nouter][nz][ncol] shape            */
+} ml_pmode;
+
+/* which fused kernel family a launch used; see ml_last_path() */
+typedef enum ml_path { ML_PATH_NONE = 0, ML_PATH_DIRECT = 1, ML_PATH_TMA = 2 } ml_path;
+
+int ml_version(void);
+const char* ml_last_error(void);
+/* kernel family chosen by the most recent steric launch on this thread (ml_path) */
+int ml_last_path(void);
+/* number of kernels this library has launched from the calling thread (monotonic) */
+int64_t ml_launch_count(void);
+/* force ML_PATH_DIRECT (1) / allow ML_PATH_TMA (0) for this thread; returns previous */
+int ml_set_force_direct(int on);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_eos_eval -- elementwise equation of state, fp64 out.
+ * Replaces eos.wright.* / eos.linear.* as applied by derived.calc_rho
+ * (src/momlevel/derived.py:597-639) and calc_alpha/calc_beta (:74-159).
+ *   T, S      [nouter][nz][ncol] of `dtype`; if t_bcast / s_bcast is non-zero that operand
+ *             is [nz][ncol] and is broadcast over nouter (thermosteric / halosteric,
+ *             steric.py:115-121)
+ *   p         fp64, shape per `pmode`
+ *   out       [nouter][nz][ncol] fp64
+ * ------------------------------------------------------------------------------------- */
+int ml_eos_eval(int eos, int func, int dtype, const void* T, const void* S, int t_bcast,
+                int s_bcast, const double* p, int pmode, int64_t nouter, int64_t nz,
+                int64_t ncol, double* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_flament_spice -- Flament (2002) spiciness, elementwise, fp64 out.
+ * Replaces spice.flament.spice (src/momlevel/spice/flament.py:43-95) as applied by
+ * derived.calc_spice (src/momlevel/derived.py:669-711).
+ * ------------------------------------------------------------------------------------- */
+int ml_flament_spice(int dtype, const void* T, const void* S, int64_t n, double* out,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_calc_dz -- partial-bottom-cell thickness, out[nz][ncol] fp64.
+ * Replaces derived.calc_dz (src/momlevel/derived.py:249-325); the sign asserts
+ * (:284-292) stay on the host.  `has_bottom` = 0 means bottom=None.
+ * ------------------------------------------------------------------------------------- */
+int ml_calc_dz(const double* z_i, const double* deptho, double top, double bottom,
+               int has_bottom, int fraction, int64_t nz, int64_t ncol, double* out,
+               void* stream);
+
+/* bytes of device scratch the reducing entry points need (block partials) */
+size_t ml_workspace_bytes(int64_t nt, int64_t nz, int64_t ncol);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_reference_state -- rho_ref = EOS(T0,S0,p) plus the two global sums, one pass.
+ * Replaces reference.setup_reference_state (src/momlevel/reference.py:71-80) =
+ * calc_rho + calc_volo (derived.py:787-789) + calc_masso (derived.py:435-438).
+ *   T0,S0,V0  [nz][ncol] of `dtype` (the time_index slab)
+ *   p_level   [nz] fp64
+ *   rho_ref   [nz][ncol] fp64 out
+ *   sums      device fp64[2] out: {volo = nansum(V0), masso = nansum(rho_ref*V0)}
+ * ------------------------------------------------------------------------------------- */
+int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const void* V0,
+                       const double* p_level, int64_t nz, int64_t ncol, double* rho_ref,
+                       double* sums, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_steric_local -- fused EOS -> delta_rho -> clipped dz -> column integral.
+ * Replaces the local branch of steric.steric (src/momlevel/steric.py:128,150-166) and the
+ * inline use of derived.calc_dz (derived.py:295-318, top=0, bottom=None).
+ *   T, S        [nt][nz][ncol] of `dtype` (or [nz][ncol] when *_bcast, see ml_eos_eval)
+ *   rho_ref     [nz][ncol] fp64           reference["rho"]
+ *   v_ref       [nz][ncol] of `vref_dtype` reference["volcello"]; NaN = dry cell
+ *   z_i         [nz+1] fp64, deptho [ncol] fp64 (NaN = land -> 0, derived.py:295)
+ *   p_level     [nz] fp64
+ *   neg_inv_rhozero = -1.0/rhozero (steric.py:163)
+ *   eta         [nt][ncol] fp64 out; NaN where v_ref[0][col] is NaN (steric.py:166)
+ *   delta_rho   [nt][nz][ncol] fp64 out, or NULL to skip the 4-D field
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                    const double* rho_ref, const void* v_ref, int vref_dtype, const double* z_i,
+                    const double* deptho, const double* p_level, double neg_inv_rhozero,
+                    int64_t nt, int64_t nz, int64_t ncol, double* eta, double* delta_rho,
+                    void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_steric_global -- fused EOS -> sum_{z,col} rho * v_ref per time step.
+ * Replaces calc_masso(rho, reference["volcello"]) in the global branch
+ * (src/momlevel/steric.py:135, derived.py:435-438); the ln() formula (steric.py:136-142)
+ * is host arithmetic on nt doubles.
+ *   masso       device fp64[nt] out
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                     const void* v_ref, int vref_dtype, const double* p_level, int64_t nt,
+                     int64_t nz, int64_t ncol, double* masso, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_steric_local_host -- the same computation as reference_state + steric_local for
+ * variant="steric" on HOST buffers: time steps are staged to the device through two
+ * pinned/registered windows so the copy of step k+1 overlaps the kernels of step k.
+ * This is the end-to-end call bench.py times as `e2e`.
+ *   T, S        host [nt][nz][ncol] of `dtype`;  v0 host [nz][ncol] of `dtype`
+ *               (volcello at time_index 0); reference state = time step 0 (reference.py:60-68)
+ *   eta         host [nt][ncol] fp64 out
+ *   rho_ref_out host [nz][ncol] fp64 out or NULL; sums_out host fp64[2] {volo, masso}
+ *   steps_per_window  time steps per staging window (>=1)
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
+                         const double* z_i, const double* deptho, const double* p_level,
+                         double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                         int steps_per_window, double* eta, double* rho_ref_out,
+                         double* sums_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOMLEVEL_B200_H */

@@ -1,0 +1,291 @@
+"""Array-level API: torch CUDA tensors (or numpy / DLPack objects) in, fp64 CUDA tensors out.
+
+Thin marshalling over the C ABI (``_lib``): torch is the allocator and the stream owner,
+every number is computed by libmomlevel_b200's kernels.  Field layout is MOM6 order
+``[t][z][y][x]``; trailing horizontal dims are flattened into ``ncol`` for the library.
+
+Each function names the reference code it stands in for; see include/momlevel_b200.h.
+"""
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = [
+    "to_device",
+    "eos_eval",
+    "flament_spice",
+    "calc_dz",
+    "reference_state",
+    "steric_local",
+    "steric_global",
+    "steric_local_host",
+    "last_path",
+    "launch_count",
+    "force_direct",
+]
+
+
+def _device():
+    if not torch.cuda.is_available():
+        raise _lib.MLError(-8, "no CUDA device: momlevel_b200 has no CPU path")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(x, dtype=None):
+    """numpy / DLPack / torch -> contiguous CUDA tensor (fp32 and fp64 kept, others -> fp64)."""
+    dev = _device()
+    if isinstance(x, torch.Tensor):
+        t = x
+    elif isinstance(x, np.ndarray):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    elif hasattr(x, "__dlpack__"):
+        t = torch.from_dlpack(x)
+    else:
+        t = torch.as_tensor(np.asarray(x, dtype=np.float64))
+    if dtype is None:
+        dtype = t.dtype if t.dtype in (torch.float32, torch.float64) else torch.float64
+    return t.to(device=dev, dtype=dtype, non_blocking=True).contiguous()
+
+
+def _field_dtype(*ts):
+    """Common storage dtype of the 3-D/4-D operands (fp32 only if all are fp32)."""
+    return torch.float32 if all(t.dtype == torch.float32 for t in ts) else torch.float64
+
+
+def _dt_id(t):
+    return _lib.F32 if t.dtype == torch.float32 else _lib.F64
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _eos_id(eos):
+    # util.py:243-249
+    assert isinstance(eos, str), "Expecting string for equation of state"
+    key = eos.lower()
+    if key not in _lib.EOS_IDS:
+        raise ValueError(f"Unknown equation of state: {key}")
+    return _lib.EOS_IDS[key]
+
+
+def _f64(x):
+    return to_device(x, torch.float64)
+
+
+def last_path():
+    return _lib.lib().ml_last_path()
+
+
+def launch_count():
+    return int(_lib.lib().ml_launch_count())
+
+
+def force_direct(on):
+    return _lib.lib().ml_set_force_direct(1 if on else 0)
+
+
+# --------------------------------------------------------------------------- elementwise
+
+
+def eos_eval(eos, func, T, S, p=None, z_axis=None, t_bcast=False, s_bcast=False):
+    """``momlevel.eos.<eos>.<func>(T, S, p)`` elementwise, fp64 out, shape of the full operand.
+
+    ``p`` may be a scalar, an array of the full shape, or -- with ``z_axis`` naming the
+    level axis of the fields -- a per-level vector ``[nz]`` (what steric.py:96 builds).
+    With ``t_bcast`` / ``s_bcast`` that operand lacks the leading (time) axis of the other
+    and is broadcast over it (steric.py:115-121); the level axis is then axis 1.
+    """
+    L = _lib.lib()
+    if func not in _lib.FUNC_IDS:
+        raise ValueError(f"Unknown equation of state function: {func}")
+    eos_id = _eos_id(eos)
+    T, S = to_device(T), to_device(S)
+    dt = _field_dtype(T, S)
+    T, S = T.to(dt), S.to(dt)
+    full = S if t_bcast else T
+    if t_bcast or s_bcast:
+        small = T if t_bcast else S
+        if full.dim() < 2 or tuple(small.shape) != tuple(full.shape[1:]):
+            raise ValueError("broadcast operand must match the trailing dims of the other")
+        z_axis = 1
+    elif T.shape != S.shape:
+        raise ValueError("T and S must have the same shape")
+    if z_axis is not None:
+        z_axis = z_axis % full.dim()
+        nouter = int(np.prod(full.shape[:z_axis], dtype=np.int64))
+        nz = int(full.shape[z_axis])
+        ncol = int(np.prod(full.shape[z_axis + 1:], dtype=np.int64))
+    else:
+        nouter, nz, ncol = 1, 1, full.numel()
+    pt, pmode = None, _lib.P_SCALAR
+    if p is not None:
+        pt = _f64(p)
+        if pt.numel() == 1:
+            pmode = _lib.P_SCALAR
+        elif z_axis is not None and pt.dim() <= 1 and pt.numel() == nz:
+            pmode = _lib.P_PER_LEVEL
+        elif pt.numel() == full.numel():
+            pmode = _lib.P_FULL
+        else:
+            raise ValueError("pressure must be a scalar, a per-level vector (with z_axis) or full-shape")
+    elif eos_id == 0:
+        raise ValueError("the Wright equation of state needs a pressure")
+    out = torch.empty(full.shape, dtype=torch.float64, device=full.device)
+    _lib.check(
+        L.ml_eos_eval(eos_id, _lib.FUNC_IDS[func], _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                      pt.data_ptr() if pt is not None else None, pmode, nouter, nz, ncol, out.data_ptr(), _stream())
+    )
+    return out
+
+
+def flament_spice(T, S):
+    """``momlevel.spice.flament.spice`` (flament.py:43-95)."""
+    L = _lib.lib()
+    T, S = to_device(T), to_device(S)
+    assert T.shape == S.shape, "thetao and so must have the same shape"  # flament.py:75
+    dt = _field_dtype(T, S)
+    T, S = T.to(dt), S.to(dt)
+    out = torch.empty(T.shape, dtype=torch.float64, device=T.device)
+    _lib.check(L.ml_flament_spice(_dt_id(T), T.data_ptr(), S.data_ptr(), T.numel(), out.data_ptr(), _stream()))
+    return out
+
+
+def calc_dz(z_i, deptho, top=0.0, bottom=None, fraction=False):
+    """``derived.calc_dz`` (derived.py:295-323) -> ``[nz] + deptho.shape`` fp64."""
+    L = _lib.lib()
+    z_i, depth = _f64(z_i), _f64(deptho)
+    nz = z_i.numel() - 1
+    out = torch.empty((nz,) + tuple(depth.shape), dtype=torch.float64, device=depth.device)
+    _lib.check(
+        L.ml_calc_dz(z_i.data_ptr(), depth.data_ptr(), float(top), float(bottom) if bottom is not None else 0.0,
+                     int(bottom is not None), int(bool(fraction)), nz, depth.numel(), out.data_ptr(), _stream())
+    )
+    return out
+
+
+# ------------------------------------------------------------------------------ reducing
+
+
+def _workspace(nt, nz, ncol, device):
+    n = _lib.lib().ml_workspace_bytes(nt, nz, ncol)
+    return torch.empty((n + 7) // 8, dtype=torch.float64, device=device), n
+
+
+def reference_state(T0, S0, V0, p_level, eos="Wright"):
+    """``reference.setup_reference_state`` arithmetic (reference.py:71-80).
+
+    Returns ``(rho_ref [nz,...] fp64, sums fp64[2] = {volo, masso})`` on the device.
+    """
+    L = _lib.lib()
+    T0, S0, V0 = to_device(T0), to_device(S0), to_device(V0)
+    dt = _field_dtype(T0, S0, V0)
+    T0, S0, V0 = T0.to(dt), S0.to(dt), V0.to(dt)
+    assert T0.shape == S0.shape == V0.shape
+    nz = T0.shape[0]
+    ncol = T0.numel() // nz
+    p = _f64(p_level)
+    rho = torch.empty(T0.shape, dtype=torch.float64, device=T0.device)
+    sums = torch.empty(2, dtype=torch.float64, device=T0.device)
+    ws, nbytes = _workspace(2, nz, ncol, T0.device)
+    _lib.check(
+        L.ml_reference_state(_eos_id(eos), _dt_id(T0), T0.data_ptr(), S0.data_ptr(), V0.data_ptr(), p.data_ptr(), nz,
+                             ncol, rho.data_ptr(), sums.data_ptr(), ws.data_ptr(), nbytes, _stream())
+    )
+    return rho, sums
+
+
+def _steric_operands(T, S, t_bcast, s_bcast):
+    T, S = to_device(T), to_device(S)
+    dt = _field_dtype(T, S)
+    T, S = T.to(dt), S.to(dt)
+    full = S if t_bcast else T
+    nt, nz = full.shape[0], full.shape[1]
+    hshape = tuple(full.shape[2:])
+    ncol = int(np.prod(hshape, dtype=np.int64))
+    if t_bcast or s_bcast:
+        small = T if t_bcast else S
+        if tuple(small.shape) != tuple(full.shape[1:]):
+            raise ValueError("broadcast operand must be [nz][...]")
+    elif T.shape != S.shape:
+        raise ValueError("T and S must have the same shape")
+    return T, S, nt, nz, ncol, hshape
+
+
+def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False,
+                 s_bcast=False, want_delta_rho=False):
+    """Local branch of ``steric.steric`` (steric.py:128,150-166).
+
+    Returns ``(eta [nt,...], delta_rho [nt,nz,...] or None)`` fp64 on the device.
+    """
+    L = _lib.lib()
+    T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
+    rho_ref = _f64(rho_ref)
+    v_ref = to_device(v_ref)
+    z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
+    assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and depth.numel() == ncol
+    assert z_i.numel() == nz + 1 and p.numel() == nz
+    eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
+    drho = torch.empty((nt, nz) + hshape, dtype=torch.float64, device=T.device) if want_delta_rho else None
+    _lib.check(
+        L.ml_steric_local(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                          rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(),
+                          p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(),
+                          drho.data_ptr() if drho is not None else None, _stream())
+    )
+    return eta, drho
+
+
+def steric_global(T, S, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):
+    """``calc_masso(rho, reference.volcello)`` of the global branch (steric.py:135) -> ``masso[nt]``."""
+    L = _lib.lib()
+    T, S, nt, nz, ncol, _ = _steric_operands(T, S, t_bcast, s_bcast)
+    v_ref = to_device(v_ref)
+    p = _f64(p_level)
+    assert v_ref.numel() == nz * ncol and p.numel() == nz
+    masso = torch.empty(nt, dtype=torch.float64, device=T.device)
+    ws, nbytes = _workspace(nt, nz, ncol, T.device)
+    _lib.check(
+        L.ml_steric_global(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                           v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol, masso.data_ptr(),
+                           ws.data_ptr(), nbytes, _stream())
+    )
+    return masso
+
+
+def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", steps_per_window=1,
+                      want_rho_ref=False, eta_out=None):
+    """End-to-end host call: HOST arrays in (numpy or CPU torch, pinned for speed), numpy out.
+
+    ``reference_state`` + ``steric_local`` for variant="steric" with the reference taken
+    from time step 0; copies are pipelined against the kernels inside the library.
+    Returns ``(eta [nt,...], rho_ref or None, (volo, masso))``.
+    """
+    L = _lib.lib()
+    _device()
+
+    def host(x):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        assert t.device.type == "cpu"
+        return t.contiguous()
+
+    T, S, V0 = host(T), host(S), host(V0)
+    dt = _field_dtype(T, S, V0)
+    T, S, V0 = T.to(dt), S.to(dt), V0.to(dt)
+    nt, nz = T.shape[0], T.shape[1]
+    hshape = tuple(T.shape[2:])
+    ncol = int(np.prod(hshape, dtype=np.int64))
+    z_i = host(np.asarray(z_i, dtype=np.float64))
+    depth = host(np.asarray(deptho, dtype=np.float64))
+    p = host(np.asarray(p_level, dtype=np.float64))
+    eta = eta_out if eta_out is not None else torch.empty((nt,) + hshape, dtype=torch.float64)
+    rho = torch.empty((nz,) + hshape, dtype=torch.float64) if want_rho_ref else None
+    sums = torch.empty(2, dtype=torch.float64)
+    _lib.check(
+        L.ml_steric_local_host(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), V0.data_ptr(), z_i.data_ptr(),
+                               depth.data_ptr(), p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, int(steps_per_window),
+                               eta.data_ptr(), rho.data_ptr() if rho is not None else None, sums.data_ptr())
+    )
+    return eta, rho, (float(sums[0]), float(sums[1]))

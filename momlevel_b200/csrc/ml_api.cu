@@ -1,0 +1,486 @@
+// ml_api.cu -- C ABI entry points of libmomlevel_b200 and the "direct" kernel family.
+//
+// The direct kernels read global memory straight into registers with coalesced loads, one
+// water column per thread, and accept any extent and alignment.  They are the path for
+// small or ragged grids (the reference's 5x5x5 test dataset) and the correctness baseline
+// for the TMA-staged kernels in ml_tma.cu, which the entry points prefer when the grid
+// meets TMA's 16-byte stride rule.
+//
+// Loop order (both families): a thread owns one column; z is the outer serial loop and a
+// chunk of TC time steps the inner one, so rho_ref / v_ref / dz are fetched once per
+// (level, column) and reused for TC steps, and the column sum never leaves registers.
+#include "ml_common.cuh"
+#include "ml_host.cuh"
+#include "ml_tma.cuh"
+
+namespace ml {
+
+ThreadState& tls() {
+  static thread_local ThreadState s = {{0}, ML_PATH_NONE, 0, 0};
+  return s;
+}
+
+constexpr int kBlock = 256;
+constexpr int kWarps = kBlock / 32;
+constexpr int kTC = 12;  // time steps per register chunk of the direct kernels
+constexpr int kPNone = 3;  // internal pressure mode: operand absent
+
+__device__ __forceinline__ bool vref_wet(const void* v, int v_f32, i64 i) {
+  return v_f32 ? !isnan(__ldg(reinterpret_cast<const float*>(v) + i))
+               : !isnan(__ldg(reinterpret_cast<const double*>(v) + i));
+}
+__device__ __forceinline__ double vref_val(const void* v, int v_f32, i64 i) {
+  return v_f32 ? (double)__ldg(reinterpret_cast<const float*>(v) + i)
+               : __ldg(reinterpret_cast<const double*>(v) + i);
+}
+
+// ------------------------------------------------------------------ K1: elementwise EOS
+template <typename TIn, int EOS, int FUNC>
+__global__ void __launch_bounds__(kBlock) k_eos_eval(const TIn* __restrict__ T, const TIn* __restrict__ S,
+                                                     i64 t_stride, i64 s_stride, const double* __restrict__ p,
+                                                     int pmode, i64 nrows, int nz, i64 ncol,
+                                                     double* __restrict__ out) {
+  const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
+  if (c >= ncol) return;
+  for (i64 row = blockIdx.y; row < nrows; row += gridDim.y) {
+    const i64 t = row / nz;
+    const int z = (int)(row - t * nz);
+    const i64 o = row * ncol + c;
+    double pv = 0.0;  // kPNone: the linear EOS takes no pressure (linear.py:26)
+    if (pmode == ML_P_SCALAR) pv = __ldg(p);
+    else if (pmode == ML_P_PER_LEVEL) pv = __ldg(p + z);
+    else if (pmode == ML_P_FULL) pv = __ldg(p + o);
+    const double Tv = ldf(T + t * t_stride + (i64)z * ncol + c);
+    const double Sv = ldf(S + t * s_stride + (i64)z * ncol + c);
+    out[o] = eos_func<EOS, FUNC>(Tv, Sv, pv);
+  }
+}
+
+// ---------------------------------------------------------------------------- K5: spice
+template <typename TIn>
+__global__ void __launch_bounds__(kBlock) k_spice(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 n,
+                                                  double* __restrict__ out) {
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+    out[i] = flament_spice(ldf(T + i), ldf(S + i));
+}
+
+// ------------------------------------------------------------------------------- K6: dz
+__global__ void __launch_bounds__(kBlock) k_calc_dz(const double* __restrict__ z_i, const double* __restrict__ deptho,
+                                                    double top, double bottom, int has_bottom, int fraction,
+                                                    int nz, i64 ncol, double* __restrict__ out) {
+  const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
+  if (c >= ncol) return;
+  double depth = __ldg(deptho + c);
+  if (isnan(depth)) depth = 0.0;                  // derived.py:295
+  if (has_bottom) depth = fmin(depth, bottom);    // derived.py:298
+  for (int z = blockIdx.y; z < nz; z += gridDim.y) {
+    const double ztop = __ldg(z_i + z), zbot = __ldg(z_i + z + 1);
+    const double full = zbot - ztop;
+    double r = fmin(fmax(depth - ztop, 0.0), full);  // derived.py:308-313
+    r = fmin(fmax(zbot - top, 0.0), r);              // derived.py:316-318
+    if (fraction) {                                  // derived.py:320-323
+      const double num = r == 0.0 ? nan("") : r;
+      const double den = full == 0.0 ? nan("") : full;
+      r = num / den;
+    }
+    out[(i64)z * ncol + c] = r;
+  }
+}
+
+// ------------------------------------------------------- fixed-order second reduce stage
+// out[row] = sum_b partials[row][b]; one block per row, each thread a strided serial sum.
+__global__ void __launch_bounds__(kBlock) k_reduce_rows(const double* __restrict__ partials, i64 nblk,
+                                                        double* __restrict__ out) {
+  __shared__ double sm[kWarps];
+  const double* row = partials + (i64)blockIdx.x * nblk;
+  double a = 0.0;
+  for (i64 b = threadIdx.x; b < nblk; b += kBlock) a += row[b];
+  a = block_sum<kWarps>(a, sm);
+  if (threadIdx.x == 0) out[blockIdx.x] = a;
+}
+
+// ------------------------------------------------------------------ K2: reference state
+template <typename TIn, int EOS>
+__global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restrict__ T0, const TIn* __restrict__ S0,
+                                                            const TIn* __restrict__ V0, const double* __restrict__ p_level,
+                                                            int nz, i64 ncol, double* __restrict__ rho_ref,
+                                                            double* __restrict__ partials /* [2][gridDim.x] */) {
+  __shared__ double sm[kWarps];
+  const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
+  double vol = 0.0, mass = 0.0;
+  Eos<EOS> eos;
+  if (c < ncol) {
+    for (int z = 0; z < nz; ++z) {
+      const i64 i = (i64)z * ncol + c;
+      eos.set_level(__ldg(p_level + z));
+      const double rho = eos.rho(ldf(T0 + i), ldf(S0 + i));
+      const double v = ldf(V0 + i);
+      rho_ref[i] = rho;
+      if (!isnan(v)) {  // nansum (derived.py:787-789, :435-438)
+        vol += v;
+        const double m = rho * v;
+        if (!is_nan_q(m)) mass += m;
+      }
+    }
+  }
+  vol = block_sum<kWarps>(vol, sm);
+  mass = block_sum<kWarps>(mass, sm);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = vol;
+    partials[(i64)gridDim.x + blockIdx.x] = mass;
+  }
+}
+
+// ------------------------------------------------------------- K3 direct: local steric
+template <typename TIn, int EOS, bool WRITE_DRHO>
+__global__ void __launch_bounds__(kBlock)
+    k_steric_local_direct(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 t_stride, i64 s_stride,
+                          const double* __restrict__ rho_ref, const void* __restrict__ v_ref, int v_f32,
+                          const double* __restrict__ z_i, const double* __restrict__ deptho,
+                          const double* __restrict__ p_level, double coef, int nt, int nz, i64 ncol,
+                          double* __restrict__ eta, double* __restrict__ drho) {
+  const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
+  if (c >= ncol) return;
+  const int t0 = blockIdx.y * kTC;
+  const i64 lvl = ncol;  // elements per level
+
+  double depth = __ldg(deptho + c);
+  if (isnan(depth)) depth = 0.0;  // derived.py:295
+  const bool surface_wet = vref_wet(v_ref, v_f32, c);  // steric.py:166
+
+  double acc[kTC];
+#pragma unroll
+  for (int k = 0; k < kTC; ++k) acc[k] = 0.0;
+  Eos<EOS> eos;
+
+  for (int z = 0; z < nz; ++z) {
+    const i64 i = (i64)z * lvl + c;
+    const double dz = clipped_dz(depth, __ldg(z_i + z), __ldg(z_i + z + 1));
+    // steric.py:151-153: delta_rho is NaN wherever the reference volume is missing
+    const double rref = vref_wet(v_ref, v_f32, i) ? __ldg(rho_ref + i) : nan("");
+    eos.set_level(__ldg(p_level + z));
+    // all loads of the chunk first (time index clamped: a short last chunk re-reads the
+    // final step instead of branching), then the arithmetic
+    TIn tv[kTC], sv[kTC];
+#pragma unroll
+    for (int k = 0; k < kTC; ++k) {
+      const i64 t = min(t0 + k, nt - 1);
+      tv[k] = __ldg(T + t * t_stride + i);
+      sv[k] = __ldg(S + t * s_stride + i);
+    }
+#pragma unroll
+    for (int k = 0; k < kTC; ++k) {
+      const double d = eos.rho((double)tv[k], (double)sv[k]) - rref;
+      if (WRITE_DRHO) {
+        if (t0 + k < nt) drho[((i64)(t0 + k) * nz + z) * lvl + c] = d;
+      }
+      if (!is_nan_q(d)) acc[k] = fma(dz, d, acc[k]);  // skipna sum, steric.py:163
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kTC; ++k) {
+    const int t = t0 + k;
+    if (t < nt) eta[(i64)t * ncol + c] = surface_wet ? coef * acc[k] : nan("");
+  }
+}
+
+// ------------------------------------------------------------ K4 direct: global steric
+template <typename TIn, int EOS>
+__global__ void __launch_bounds__(kBlock)
+    k_steric_global_direct(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 t_stride, i64 s_stride,
+                           const void* __restrict__ v_ref, int v_f32, const double* __restrict__ p_level, int nt,
+                           int nz, i64 ncol, double* __restrict__ partials /* [nt][gridDim.x] */) {
+  __shared__ double sm[kWarps];
+  const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
+  const int t0 = blockIdx.y * kTC;
+  double acc[kTC];
+#pragma unroll
+  for (int k = 0; k < kTC; ++k) acc[k] = 0.0;
+  Eos<EOS> eos;
+  if (c < ncol) {
+    for (int z = 0; z < nz; ++z) {
+      const i64 i = (i64)z * ncol + c;
+      const double v = vref_val(v_ref, v_f32, i);
+      if (isnan(v)) continue;  // rho*NaN is dropped by the skipna sum (derived.py:435-438)
+      eos.set_level(__ldg(p_level + z));
+      TIn tv[kTC], sv[kTC];
+#pragma unroll
+      for (int k = 0; k < kTC; ++k) {
+        const i64 t = min(t0 + k, nt - 1);
+        tv[k] = __ldg(T + t * t_stride + i);
+        sv[k] = __ldg(S + t * s_stride + i);
+      }
+#pragma unroll
+      for (int k = 0; k < kTC; ++k) {
+        const double rho = eos.rho((double)tv[k], (double)sv[k]);
+        if (!is_nan_q(rho)) acc[k] = fma(rho, v, acc[k]);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < kTC; ++k) {
+    const int t = t0 + k;
+    if (t < nt) {  // uniform across the block
+      const double s = block_sum<kWarps>(acc[k], sm);
+      if (threadIdx.x == 0) partials[(i64)t * gridDim.x + blockIdx.x] = s;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------- dispatch
+inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
+
+inline int check_common(int eos, int dtype) {
+  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  return ML_OK;
+}
+
+inline int check_bcast(int t_bcast, int s_bcast) {
+  if (t_bcast && s_bcast) return fail(ML_ERR_MODE, "T and S cannot both be broadcast over time");
+  return ML_OK;
+}
+
+template <int EOS, int FUNC>
+int launch_eos(int dtype, const void* T, const void* S, i64 ts, i64 ss, const double* p, int pmode, i64 nrows, int nz,
+               i64 ncol, double* out, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)(nrows < 65535 ? nrows : 65535));
+  if (dtype == ML_F32)
+    k_eos_eval<float, EOS, FUNC><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, ts, ss, p, pmode, nrows, nz, ncol, out);
+  else
+    k_eos_eval<double, EOS, FUNC><<<grid, kBlock, 0, st>>>((const double*)T, (const double*)S, ts, ss, p, pmode, nrows, nz, ncol, out);
+  return launched("k_eos_eval");
+}
+
+template <int EOS>
+int launch_eos_func(int func, int dtype, const void* T, const void* S, i64 ts, i64 ss, const double* p, int pmode,
+                    i64 nrows, int nz, i64 ncol, double* out, cudaStream_t st) {
+  switch (func) {
+    case ML_FUNC_DENSITY: return launch_eos<EOS, 0>(dtype, T, S, ts, ss, p, pmode, nrows, nz, ncol, out, st);
+    case ML_FUNC_DRHO_DTEMP: return launch_eos<EOS, 1>(dtype, T, S, ts, ss, p, pmode, nrows, nz, ncol, out, st);
+    case ML_FUNC_DRHO_DSAL: return launch_eos<EOS, 2>(dtype, T, S, ts, ss, p, pmode, nrows, nz, ncol, out, st);
+    case ML_FUNC_ALPHA: return launch_eos<EOS, 3>(dtype, T, S, ts, ss, p, pmode, nrows, nz, ncol, out, st);
+    case ML_FUNC_BETA: return launch_eos<EOS, 4>(dtype, T, S, ts, ss, p, pmode, nrows, nz, ncol, out, st);
+  }
+  return fail(ML_ERR_EOS, "unknown eos function id %d", func);
+}
+
+template <typename TIn, int EOS>
+int launch_local_direct(const void* T, const void* S, i64 ts, i64 ss, const double* rho_ref, const void* v_ref,
+                        int v_f32, const double* z_i, const double* deptho, const double* p_level, double coef, int nt,
+                        int nz, i64 ncol, double* eta, double* drho, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)cdiv(nt, kTC));
+  if (drho)
+    k_steric_local_direct<TIn, EOS, true><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, coef, nt, nz, ncol, eta, drho);
+  else
+    k_steric_local_direct<TIn, EOS, false><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, coef, nt, nz, ncol, eta, drho);
+  return launched("k_steric_local_direct");
+}
+
+template <typename TIn, int EOS>
+int launch_global_direct(const void* T, const void* S, i64 ts, i64 ss, const void* v_ref, int v_f32,
+                         const double* p_level, int nt, int nz, i64 ncol, double* masso, double* partials,
+                         cudaStream_t st) {
+  const i64 nblk = cdiv(ncol, kBlock);
+  dim3 grid((unsigned)nblk, (unsigned)cdiv(nt, kTC));
+  k_steric_global_direct<TIn, EOS><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, v_ref, v_f32, p_level, nt, nz, ncol, partials);
+  int rc = launched("k_steric_global_direct");
+  if (rc) return rc;
+  k_reduce_rows<<<nt, kBlock, 0, st>>>(partials, nblk, masso);
+  return launched("k_reduce_rows");
+}
+
+}  // namespace ml
+
+using namespace ml;
+
+extern "C" {
+
+int ml_version(void) { return ML_ABI_VERSION; }
+const char* ml_last_error(void) { return tls().err; }
+int ml_last_path(void) { return tls().last_path; }
+int64_t ml_launch_count(void) { return tls().launches; }
+int ml_set_force_direct(int on) {
+  const int prev = tls().force_direct;
+  tls().force_direct = on ? 1 : 0;
+  return prev;
+}
+
+size_t ml_workspace_bytes(int64_t nt, int64_t nz, int64_t ncol) {
+  (void)nz;
+  if (nt < 2) nt = 2;  // reference_state needs two rows
+  // direct family: ceil(ncol/256) block partials per row; the TMA family uses fewer.
+  const int64_t nblk = cdiv(ncol > 0 ? ncol : 1, 128);
+  return (size_t)(nt * nblk) * sizeof(double) + 256;
+}
+
+int ml_eos_eval(int eos, int func, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* p,
+                int pmode, int64_t nouter, int64_t nz, int64_t ncol, double* out, void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(out);
+  if (pmode != ML_P_SCALAR && pmode != ML_P_PER_LEVEL && pmode != ML_P_FULL)
+    return fail(ML_ERR_MODE, "unknown pressure mode %d", pmode);
+  if (eos == ML_EOS_WRIGHT) ML_REQUIRE_PTR(p);
+  if (nouter < 0 || nz <= 0 || ncol < 0 || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nouter=%lld nz=%lld ncol=%lld", (long long)nouter, (long long)nz, (long long)ncol);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(out, 8);
+  if (nouter == 0 || ncol == 0) return ML_OK;  // empty input, nothing to launch
+  const i64 lvl = nz * ncol;
+  const i64 ts = t_bcast ? 0 : lvl, ss = s_bcast ? 0 : lvl;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p == nullptr) pmode = kPNone;  // linear EOS ignores pressure (linear.py:26)
+  if (eos == ML_EOS_WRIGHT) return launch_eos_func<0>(func, dtype, T, S, ts, ss, p, pmode, nouter * nz, (int)nz, ncol, out, st);
+  return launch_eos_func<1>(func, dtype, T, S, ts, ss, p, pmode, nouter * nz, (int)nz, ncol, out, st);
+}
+
+int ml_flament_spice(int dtype, const void* T, const void* S, int64_t n, double* out, void* stream) {
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  if (n < 0) return fail(ML_ERR_SHAPE, "n=%lld", (long long)n);
+  if (n == 0) return ML_OK;
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(out);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(out, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (tma::spice_eligible(dtype, T, S, n, out)) return tma::launch_spice(dtype, T, S, n, out, st);
+  const unsigned grid = (unsigned)(cdiv(n, kBlock) < 148 * 16 ? cdiv(n, kBlock) : 148 * 16);
+  if (dtype == ML_F32)
+    k_spice<float><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, n, out);
+  else
+    k_spice<double><<<grid, kBlock, 0, st>>>((const double*)T, (const double*)S, n, out);
+  return launched("k_spice");
+}
+
+int ml_calc_dz(const double* z_i, const double* deptho, double top, double bottom, int has_bottom, int fraction,
+               int64_t nz, int64_t ncol, double* out, void* stream) {
+  ML_REQUIRE_PTR(z_i);
+  ML_REQUIRE_PTR(deptho);
+  ML_REQUIRE_PTR(out);
+  if (nz <= 0 || ncol < 0 || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nz=%lld ncol=%lld", (long long)nz, (long long)ncol);
+  if (ncol == 0) return ML_OK;
+  dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)(nz < 65535 ? nz : 65535));
+  k_calc_dz<<<grid, kBlock, 0, (cudaStream_t)stream>>>(z_i, deptho, top, bottom, has_bottom, fraction, (int)nz, ncol, out);
+  return launched("k_calc_dz");
+}
+
+int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const void* V0, const double* p_level,
+                       int64_t nz, int64_t ncol, double* rho_ref, double* sums, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  ML_REQUIRE_PTR(T0);
+  ML_REQUIRE_PTR(S0);
+  ML_REQUIRE_PTR(V0);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(rho_ref);
+  ML_REQUIRE_PTR(sums);
+  if (nz <= 0 || ncol <= 0 || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nz=%lld ncol=%lld", (long long)nz, (long long)ncol);
+  if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
+    return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
+  ML_REQUIRE_ALIGNED(workspace, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partials = (double*)workspace;
+  const i64 nblk = cdiv(ncol, kBlock);
+#define ML_LAUNCH_REF(TIN, E) \
+  k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, (const TIN*)V0, p_level, (int)nz, ncol, rho_ref, partials)
+  if (dtype == ML_F32) {
+    if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REF(float, 0); else ML_LAUNCH_REF(float, 1);
+  } else {
+    if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REF(double, 0); else ML_LAUNCH_REF(double, 1);
+  }
+#undef ML_LAUNCH_REF
+  if ((rc = launched("k_reference_state"))) return rc;
+  k_reduce_rows<<<2, kBlock, 0, st>>>(partials, nblk, sums);
+  return launched("k_reduce_rows");
+}
+
+int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                    const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
+                    double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol, double* eta, double* delta_rho,
+                    void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(rho_ref);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(z_i);
+  ML_REQUIRE_PTR(deptho);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(eta);
+  if (nt < 0 || nz <= 0 || ncol < 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
+  if (nt == 0 || ncol == 0) return ML_OK;
+  const i64 lvl = nz * ncol;
+  const i64 ts = t_bcast ? 0 : lvl, ss = s_bcast ? 0 : lvl;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int v_f32 = vref_dtype == ML_F32;
+
+  if (!tls().force_direct &&
+      tma::local_eligible(dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, nt, nz, ncol, eta, delta_rho)) {
+    tls().last_path = ML_PATH_TMA;
+    return tma::launch_local(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
+                             neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+  }
+  tls().last_path = ML_PATH_DIRECT;
+  if (dtype == ML_F32) {
+    if (eos == ML_EOS_WRIGHT) return launch_local_direct<float, 0>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+    return launch_local_direct<float, 1>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+  }
+  if (eos == ML_EOS_WRIGHT) return launch_local_direct<double, 0>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+  return launch_local_direct<double, 1>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+}
+
+int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
+                     int vref_dtype, const double* p_level, int64_t nt, int64_t nz, int64_t ncol, double* masso,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(masso);
+  if (nt < 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (nt == 0) return ML_OK;
+  if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(nt, nz, ncol))
+    return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(nt, nz, ncol), workspace_bytes);
+  ML_REQUIRE_ALIGNED(workspace, 8);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
+  const i64 lvl = nz * ncol;
+  const i64 ts = t_bcast ? 0 : lvl, ss = s_bcast ? 0 : lvl;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int v_f32 = vref_dtype == ML_F32;
+  double* partials = (double*)workspace;
+
+  if (!tls().force_direct && tma::global_eligible(dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, nt, nz, ncol)) {
+    tls().last_path = ML_PATH_TMA;
+    return tma::launch_global(eos, dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, p_level, (int)nt, (int)nz, ncol,
+                              masso, partials, st);
+  }
+  tls().last_path = ML_PATH_DIRECT;
+  if (dtype == ML_F32) {
+    if (eos == ML_EOS_WRIGHT) return launch_global_direct<float, 0>(T, S, ts, ss, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, masso, partials, st);
+    return launch_global_direct<float, 1>(T, S, ts, ss, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, masso, partials, st);
+  }
+  if (eos == ML_EOS_WRIGHT) return launch_global_direct<double, 0>(T, S, ts, ss, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, masso, partials, st);
+  return launch_global_direct<double, 1>(T, S, ts, ss, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, masso, partials, st);
+}
+
+}  // extern "C"

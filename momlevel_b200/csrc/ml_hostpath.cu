@@ -1,0 +1,118 @@
+// ml_hostpath.cu -- ml_steric_local_host: the steric path on HOST buffers.
+//
+// What momlevel.steric(dset) does for variant="steric", domain="local" when the Dataset
+// lives in host memory (src/momlevel/steric.py:84-184 with the reference state taken from
+// time step 0, src/momlevel/reference.py:60-80): time steps are streamed through two device
+// windows, the host->device copy of window k+1 running on a copy stream while the kernels of
+// window k run on the compute stream.  Pinned (page-locked) host buffers make the copies
+// truly asynchronous; pageable buffers work but serialise inside the driver.
+#include <vector>
+
+#include "ml_host.cuh"
+
+namespace {
+
+struct Resources {
+  std::vector<void*> dev;
+  cudaStream_t copy = nullptr, comp = nullptr;
+  cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  ~Resources() {
+    for (void* p : dev) cudaFree(p);
+    for (int i = 0; i < 2; ++i) {
+      if (copied[i]) cudaEventDestroy(copied[i]);
+      if (freed[i]) cudaEventDestroy(freed[i]);
+    }
+    if (copy) cudaStreamDestroy(copy);
+    if (comp) cudaStreamDestroy(comp);
+  }
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) dev.push_back(*p);
+    return e;
+  }
+};
+
+}  // namespace
+
+extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
+                                    const double* z_i, const double* deptho, const double* p_level,
+                                    double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                                    int steps_per_window, double* eta, double* rho_ref_out, double* sums_out) {
+  using namespace ml;
+  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(v0);
+  ML_REQUIRE_PTR(z_i);
+  ML_REQUIRE_PTR(deptho);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(eta);
+  if (nt <= 0 || nz <= 0 || ncol <= 0 || steps_per_window < 1)
+    return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld window=%d", (long long)nt, (long long)nz,
+                (long long)ncol, steps_per_window);
+
+  const size_t es = (size_t)elem_size(dtype);
+  const size_t lvl = (size_t)nz * (size_t)ncol;
+  const int64_t spw = steps_per_window < nt ? steps_per_window : nt;
+  const size_t win_bytes = (size_t)spw * lvl * es;
+  const size_t ws_bytes = ml_workspace_bytes(2, nz, ncol);
+
+  Resources r;
+  void *dT[2], *dS[2], *dV, *dRho, *dEta, *dZi, *dDepth, *dP, *dSums, *dWs;
+  for (int b = 0; b < 2; ++b) {
+    ML_CUDA(r.alloc(&dT[b], win_bytes));
+    ML_CUDA(r.alloc(&dS[b], win_bytes));
+  }
+  ML_CUDA(r.alloc(&dV, lvl * es));
+  ML_CUDA(r.alloc(&dRho, lvl * sizeof(double)));
+  ML_CUDA(r.alloc(&dEta, (size_t)nt * ncol * sizeof(double)));
+  ML_CUDA(r.alloc(&dZi, (size_t)(nz + 1) * sizeof(double)));
+  ML_CUDA(r.alloc(&dDepth, (size_t)ncol * sizeof(double)));
+  ML_CUDA(r.alloc(&dP, (size_t)nz * sizeof(double)));
+  ML_CUDA(r.alloc(&dSums, 2 * sizeof(double)));
+  ML_CUDA(r.alloc(&dWs, ws_bytes));
+  ML_CUDA(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
+  ML_CUDA(cudaStreamCreateWithFlags(&r.comp, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; ++b) {
+    ML_CUDA(cudaEventCreateWithFlags(&r.copied[b], cudaEventDisableTiming));
+    ML_CUDA(cudaEventCreateWithFlags(&r.freed[b], cudaEventDisableTiming));
+  }
+
+  ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(dV, v0, lvl * es, cudaMemcpyHostToDevice, r.copy));
+
+  const int64_t nwin = (nt + spw - 1) / spw;
+  for (int64_t w = 0; w < nwin; ++w) {
+    const int b = (int)(w & 1);
+    const int64_t t_first = w * spw;
+    const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
+    const size_t off = (size_t)t_first * lvl * es;
+    const size_t bytes = (size_t)nt_w * lvl * es;
+    if (w >= 2) ML_CUDA(cudaStreamWaitEvent(r.copy, r.freed[b], 0));
+    ML_CUDA(cudaMemcpyAsync(dT[b], (const char*)T + off, bytes, cudaMemcpyHostToDevice, r.copy));
+    ML_CUDA(cudaMemcpyAsync(dS[b], (const char*)S + off, bytes, cudaMemcpyHostToDevice, r.copy));
+    ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
+
+    ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
+    int rc;
+    if (w == 0) {  // reference state from time step 0 (reference.py:60-80)
+      rc = ml_reference_state(eos, dtype, dT[0], dS[0], dV, (const double*)dP, nz, ncol, (double*)dRho,
+                              (double*)dSums, dWs, ws_bytes, r.comp);
+      if (rc) return rc;
+    }
+    rc = ml_steric_local(eos, dtype, dT[b], dS[b], 0, 0, (const double*)dRho, dV, dtype, (const double*)dZi,
+                         (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
+                         (double*)dEta + (size_t)t_first * ncol, nullptr, r.comp);
+    if (rc) return rc;
+    ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
+  }
+  ML_CUDA(cudaMemcpyAsync(eta, dEta, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  ML_CUDA(cudaStreamSynchronize(r.comp));
+  ML_CUDA(cudaStreamSynchronize(r.copy));
+  return ML_OK;
+}

@@ -1,0 +1,26 @@
+// ml_tma.cuh -- interface of the TMA-staged kernel family (ml_tma.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ml {
+namespace tma {
+
+bool local_eligible(int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                    const void* v_ref, int vref_dtype, int64_t nt, int64_t nz, int64_t ncol, const double* eta,
+                    const double* delta_rho);
+int launch_local(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                 const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
+                 double coef, int nt, int nz, int64_t ncol, double* eta, double* delta_rho, cudaStream_t st);
+
+bool global_eligible(int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
+                     int vref_dtype, int64_t nt, int64_t nz, int64_t ncol);
+int launch_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
+                  int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
+                  cudaStream_t st);
+
+bool spice_eligible(int dtype, const void* T, const void* S, int64_t n, const double* out);
+int launch_spice(int dtype, const void* T, const void* S, int64_t n, double* out, cudaStream_t st);
+
+}  // namespace tma
+}  // namespace ml

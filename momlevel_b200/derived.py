@@ -1,0 +1,149 @@
+"""derived.py -- the ``momlevel.derived`` functions on the steric path, labelled arrays in/out.
+
+Mirrors ``src/momlevel/derived.py``: ``calc_rho`` (:597-639), ``calc_dz`` (:249-325),
+``calc_masso`` (:414-444), ``calc_volo`` (:769-795), ``calc_rhoga`` (:642-666),
+``calc_spice`` (:669-711), plus ``calc_alpha`` / ``calc_beta`` (:74-159) and ``calc_pdens``
+(:447-486) which reuse the same elementwise kernel.  Field arithmetic runs in
+libmomlevel_b200; attributes are the reference's CF metadata.
+"""
+
+import numpy as np
+
+from . import core, util
+from .labeled import DataArray
+
+__all__ = ["calc_alpha", "calc_beta", "calc_dz", "calc_masso", "calc_pdens", "calc_rho", "calc_rhoga", "calc_spice",
+           "calc_volo"]
+
+
+def _as_labeled(x):
+    return x if isinstance(x, DataArray) else DataArray(x)
+
+
+def _eos_apply(func_name, thetao, so, pres, eos):
+    """``xr.apply_ufunc(eos_func, thetao, so, pres)`` for the operand layouts of the path."""
+    util.eos_func_from_str(eos, func_name=func_name)  # ValueError / AssertionError as util.py:243-249
+    thetao, so = _as_labeled(thetao), _as_labeled(so)
+    t_bcast = so.ndim == thetao.ndim + 1 and so.dims[1:] == thetao.dims
+    s_bcast = thetao.ndim == so.ndim + 1 and thetao.dims[1:] == so.dims
+    full = so if t_bcast else thetao
+    if not (t_bcast or s_bcast) and thetao.dims != so.dims:
+        raise ValueError(f"cannot broadcast thetao{thetao.dims} against so{so.dims}")
+    z_axis, p = None, pres
+    if isinstance(pres, DataArray):
+        if pres.ndim == 0:
+            p = float(pres)
+        elif pres.ndim == 1 and pres.dims[0] in full.dims:
+            z_axis, p = full.dims.index(pres.dims[0]), pres.data
+        elif pres.dims == full.dims:
+            p = pres.data
+        else:
+            raise ValueError(f"cannot broadcast pres{pres.dims} against {full.dims}")
+    if (t_bcast or s_bcast) and z_axis not in (None, 1):
+        raise ValueError("with a time-invariant operand the pressure must vary along the level axis")
+    out = core.eos_eval(eos, func_name, thetao.data, so.data, p, z_axis=z_axis, t_bcast=t_bcast, s_bcast=s_bcast)
+    return DataArray(out, full.dims, coords=full.coords)
+
+
+def calc_rho(thetao, so, pres, eos="Wright"):
+    """In situ density (derived.py:597-639)."""
+    rho = _eos_apply("density", thetao, so, pres, eos)
+    rho.attrs = {
+        "standard_name": "sea_water_density",
+        "long_name": "In situ sea water density",
+        "comment": f"calculated with the {eos} equation of state",
+        "units": "kg m-3",
+    }
+    return rho
+
+
+def calc_alpha(thetao, so, pres, eos="Wright"):
+    """Thermal expansion coefficient (derived.py:74-115)."""
+    alpha = _eos_apply("alpha", thetao, so, pres, eos)
+    alpha.attrs = {
+        "long_name": "Thermal expansion coefficient",
+        "comment": f"calculated with the {eos} equation of state",
+        "units": "degC-1",
+    }
+    return alpha
+
+
+def calc_beta(thetao, so, pres, eos="Wright"):
+    """Haline contraction coefficient (derived.py:118-159)."""
+    beta = _eos_apply("beta", thetao, so, pres, eos)
+    beta.attrs = {
+        "long_name": "Haline contraction coefficient",
+        "comment": f"calculated with the {eos} equation of state",
+        "units": "PSU-1",
+    }
+    return beta
+
+
+def calc_pdens(thetao, so, level=0.0, patm=101325, eos="Wright"):
+    """Potential density referenced to ``level`` dbar (derived.py:447-486)."""
+    pres = (level * 1.0e4) + patm
+    rhopot = _eos_apply("density", thetao, so, float(pres), eos)
+    rhopot.attrs = {
+        "long_name": f"Potential density referenced to {level} dbar",
+        "comment": f"calculated with the {eos} equation of state",
+        "units": "kg m-3",
+    }
+    return rhopot
+
+
+def calc_spice(thetao, so):
+    """Seawater spiciness, Flament 2002 (derived.py:669-711)."""
+    thetao, so = _as_labeled(thetao), _as_labeled(so)
+    pi = DataArray(core.flament_spice(thetao.data, so.data), thetao.dims, coords=thetao.coords)
+    pi.attrs = {
+        "long_name": "Sea water spiciness",
+        "comment": "calculated based on Flament 2002 methodology",
+        "units": "1",
+    }
+    return pi
+
+
+def calc_dz(levels, interfaces, depth, top=0.0, bottom=None, fraction=False):
+    """dz with partial bottom cells (derived.py:249-325); dims ``(y, x, z)`` as the reference."""
+    levels, interfaces, depth = _as_labeled(levels), _as_labeled(interfaces), _as_labeled(depth)
+    # derived.py:284-292
+    assert bool(np.all(np.nan_to_num(depth.values, nan=0.0) >= 0)), "Depth values must all be positive-definite"
+    assert bool(np.all(levels.values >= 0)), "Vertical coordinate levels must all be positive-definite"
+    assert bool(np.all(interfaces.values >= 0)), "Vertical coordinate interfaces must all be positive-definite"
+    dz = core.calc_dz(interfaces.data, depth.data, top=top, bottom=bottom, fraction=fraction)  # [z][y][x]
+    out = DataArray(dz, levels.dims + depth.dims)
+    return out.transpose(*(depth.dims + levels.dims))
+
+
+def calc_volo(volcello):
+    """Total ocean volume (derived.py:769-795)."""
+    volcello = _as_labeled(volcello)
+    assert len(volcello.dims) == 3, "Expecting only 3 dimensions for volcello"
+    volo = volcello.sum()
+    volo.attrs = {"standard_name": "sea_water_volume", "long_name": "Sea Water Volume", "units": "m3"}
+    return volo
+
+
+def calc_masso(rho, volcello, tcoord="time"):
+    """Total ocean mass per time step (derived.py:414-444): skipna sum of ``rho * volcello``."""
+    rho, volcello = _as_labeled(rho), _as_labeled(volcello)
+    import torch
+
+    r, v = core.to_device(rho.data, torch.float64), core.to_device(volcello.data, torch.float64)
+    if tcoord in rho.dims and tcoord not in volcello.dims:
+        v = v.unsqueeze(rho.dims.index(tcoord))
+    prod = r * v
+    if tcoord in rho.dims:
+        axes = tuple(i for i, d in enumerate(rho.dims) if d != tcoord)
+        masso = DataArray(torch.nansum(prod, dim=axes), (tcoord,))
+    else:
+        masso = DataArray(torch.nansum(prod), ())
+    masso.attrs = {"standard_name": "sea_water_mass", "long_name": "Sea Water Mass", "units": "kg"}
+    return masso
+
+
+def calc_rhoga(masso, volo):
+    """Global average density (derived.py:642-666)."""
+    rhoga = _as_labeled(masso) / _as_labeled(volo)
+    rhoga.attrs = {"long_name": "Global Average Sea Water Density", "units": "kg m-3"}
+    return rhoga

@@ -1,0 +1,54 @@
+"""reference.py -- sea level reference state (mirrors ``src/momlevel/reference.py:15-85``).
+
+One fused kernel (``ml_reference_state``) evaluates the reference density and both global
+sums in a single pass over the ``time_index`` slab.
+"""
+
+import numpy as np
+
+from . import core, util
+from .labeled import DataArray, Dataset
+
+__all__ = ["setup_reference_state"]
+
+
+def _pressure(dset, zcoord, patm):
+    """steric.py:96 / reference.py:54: 1 m ~ 1 dbar = 1e4 Pa, plus the surface pressure."""
+    if not isinstance(patm, (int, float, np.floating, np.integer)):
+        if getattr(patm, "ndim", np.ndim(patm)) != 0:
+            raise NotImplementedError("momlevel_b200 supports a scalar `patm` only")
+        patm = float(patm)
+    return (np.asarray(dset[zcoord].values, dtype=np.float64) * 1.0e4) + float(patm)
+
+
+def setup_reference_state(dset, patm=101325.0, eos="Wright", coord_names=None, time_index=0):
+    """Generate the reference dataset (reference.py:15-85).
+
+    Returns a Dataset with ``thetao``, ``so``, ``volcello``, ``rho`` (3-D), ``volo``,
+    ``masso``, ``rhoga`` (scalars) and ``areacello``.
+    """
+    tcoord, zcoord, _ = util.default_coords(coord_names)
+    util.eos_func_from_str(eos)
+    pres = _pressure(dset, zcoord, patm)
+
+    reference = Dataset()
+    for name in ("thetao", "so", "volcello"):
+        reference[name] = dset[name].isel({tcoord: time_index}).squeeze().reset_coords(drop=True)
+
+    rho, sums = core.reference_state(reference["thetao"].data, reference["so"].data, reference["volcello"].data,
+                                     pres, eos=eos)
+    volo, masso = (float(x) for x in sums.cpu())
+    reference["rho"] = DataArray(rho, reference["thetao"].dims, attrs={
+        "standard_name": "sea_water_density",
+        "long_name": "In situ sea water density",
+        "comment": f"calculated with the {eos} equation of state",
+        "units": "kg m-3",
+    })
+    reference["volo"] = DataArray(np.float64(volo), (), attrs={
+        "standard_name": "sea_water_volume", "long_name": "Sea Water Volume", "units": "m3"})
+    reference["masso"] = DataArray(np.float64(masso), (), attrs={
+        "standard_name": "sea_water_mass", "long_name": "Sea Water Mass", "units": "kg"})
+    reference["rhoga"] = DataArray(np.float64(masso) / np.float64(volo), (), attrs={
+        "long_name": "Global Average Sea Water Density", "units": "kg m-3"})
+    reference["areacello"] = dset["areacello"]
+    return reference

@@ -1,0 +1,147 @@
+"""steric.py -- local and global steric sea level (mirrors ``src/momlevel/steric.py:17-196``).
+
+Same signature, same result/reference Datasets, same errors.  The hot loop -- equation of
+state, density anomaly, bathymetry-clipped column integral, or the volume-weighted global
+sum -- is one fused CUDA kernel per call (``ml_steric_local`` / ``ml_steric_global``); the
+4-D ``delta_rho`` field is produced on first access so a call that only needs the height
+writes only the 2-D field.
+"""
+
+import numpy as np
+
+from . import core
+from .labeled import DataArray, Dataset
+from .reference import _pressure, setup_reference_state
+from .util import annual_average, default_coords, validate_dataset
+
+__all__ = ["halosteric", "steric", "thermosteric"]
+
+
+def steric(
+    dset,
+    reference=None,
+    coord_names=None,
+    varname_map=None,
+    rhozero=1035.0,
+    patm=101325.0,
+    equation_of_state="Wright",
+    variant="steric",
+    domain="local",
+    dtype="float32",
+    strict=True,
+    annual=False,
+    verbose=False,
+    days_in_month=None,
+):
+    """Steric, thermosteric or halosteric sea level change relative to a reference state.
+
+    Arguments as ``momlevel.steric`` (steric.py:17-82).  ``days_in_month`` is the one
+    addition: the annual-mean weights when ``annual=True`` and the time axis carries no
+    calendar (the reference reads them from cftime).
+
+    Returns ``(result, reference)``.
+    """
+    xarray_in = type(dset).__module__.startswith("xarray")
+    if xarray_in:
+        from . import xarray_io
+
+        dset_x = dset
+        dset = xarray_io.from_xarray(dset)
+        if reference is not None:
+            assert type(reference).__module__.startswith("xarray"), "`reference` must be an xarray Dataset"
+            reference = xarray_io.from_xarray(reference)
+
+    # steric.py:84-91
+    dset = dset.rename(varname_map)
+    tcoord, zcoord, zbounds = default_coords(coord_names)
+    additional_vars = None if domain == "global" else [zbounds, "deptho"]
+    validate_dataset(dset, strict=strict, additional_vars=additional_vars)
+
+    # steric.py:96
+    pres = _pressure(dset, zcoord, patm)
+
+    # steric.py:98-112
+    if reference is not None:
+        assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
+        if verbose:
+            print("Using supplied reference state")
+    else:
+        reference = setup_reference_state(dset, patm=patm, eos=equation_of_state, coord_names=coord_names)
+        if verbose:
+            print("Generating reference state from first timestep")
+    validate_dataset(reference, reference=True, strict=strict)
+
+    # steric.py:115-125: which field, if any, is held at its reference value
+    if variant == "thermosteric":
+        thetao, so, t_bcast, s_bcast = dset["thetao"], reference["so"], False, True
+    elif variant == "halosteric":
+        thetao, so, t_bcast, s_bcast = reference["thetao"], dset["so"], True, False
+    elif variant == "steric":
+        thetao, so, t_bcast, s_bcast = dset["thetao"], dset["so"], False, False
+    else:
+        raise ValueError(f"Unknown variant '{variant}' passed to `steric`")
+
+    full = dset["so"] if t_bcast else dset["thetao"]
+    if full.dims[0] != tcoord or full.dims[1] != zcoord:
+        raise ValueError(f"expecting fields laid out ({tcoord}, {zcoord}, y, x), got {full.dims}")
+    hdims = full.dims[2:]
+    result = Dataset()
+
+    if domain == "global":
+        # steric.py:134-147
+        masso = core.steric_global(thetao.data, so.data, reference["volcello"].data, pres, eos=equation_of_state,
+                                   t_bcast=t_bcast, s_bcast=s_bcast).cpu().numpy()
+        volo, rhoga = float(reference["volo"]), float(reference["rhoga"])
+        expansion_coeff = np.log(rhoga / (masso / volo))
+        reference_height = volo / float(reference["areacello"].sum())
+        sealevel = reference_height * expansion_coeff
+        result["reference_height"] = DataArray(np.float64(reference_height), (), attrs={
+            "long_name": "Reference column height", "units": "m"})
+        result["reference_height"].encoding["dtype"] = dtype
+        result[variant] = DataArray(sealevel, (tcoord,))
+    else:
+        # steric.py:150-166
+        args = (thetao.data, so.data, reference["rho"].data, reference["volcello"].data, dset[zbounds].data,
+                dset["deptho"].data, pres)
+        kw = dict(rhozero=rhozero, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
+        # derived.py:284-292 (calc_dz's sign checks, on metadata-sized arrays)
+        assert bool(np.all(np.nan_to_num(dset["deptho"].values, nan=0.0) >= 0)), "Depth values must all be positive-definite"
+        assert bool(np.all(dset[zcoord].values >= 0)), "Vertical coordinate levels must all be positive-definite"
+        assert bool(np.all(dset[zbounds].values >= 0)), "Vertical coordinate interfaces must all be positive-definite"
+        eta, _ = core.steric_local(*args, want_delta_rho=False, **kw)
+
+        def _delta_rho():
+            return core.steric_local(*args, want_delta_rho=True, **kw)[1]
+
+        result["delta_rho"] = DataArray.lazy(_delta_rho, full.shape, full.dims, attrs={
+            "long_name": "change in in situ density from reference state", "units": "kg m-3"})
+        result["delta_rho"].encoding["dtype"] = dtype
+        result[variant] = DataArray(eta, (tcoord,) + hdims)
+
+    # steric.py:169-179
+    result[variant].attrs = {"long_name": f"{variant.capitalize()} height adjustment", "units": "m"}
+    result[variant].encoding["dtype"] = dtype
+    for var in set(result.dims):
+        if var in dset.variables:
+            coord = dset[var].copy(deep=False)
+            coord.attrs = dict(dset[var].attrs)
+            result[var] = coord
+
+    if annual:
+        result = annual_average(result, tcoord=tcoord, days_in_month=days_in_month)
+
+    if xarray_in:
+        return xarray_io.to_xarray(result, like=dset_x), xarray_io.to_xarray(reference, like=dset_x)
+    return (result, reference)
+
+
+def halosteric(*args, **kwargs):
+    """Wrapper for halosteric calculation (steric.py:187-190)."""
+    result, reference = steric(*args, **kwargs, variant="halosteric")
+    return (result, reference)
+
+
+def thermosteric(*args, **kwargs):
+    """Wrapper for thermosteric calculation (steric.py:193-196)."""
+    result, reference = steric(*args, **kwargs, variant="thermosteric")
+    return (result, reference)

@@ -1,0 +1,161 @@
+"""Host-side helpers of the steric path: coordinate names, EOS dispatch, dataset validation.
+
+Same names, arguments and error behaviour as the reference functions they mirror
+(``src/momlevel/util.py``): ``default_coords`` (:199-224), ``eos_func_from_str``
+(:227-249), ``validate_areacello`` (:669-694), ``validate_dataset`` (:697-814).
+Validation works on metadata (names, ranks, one area sum) and stays on the host so that
+messages, warnings and exception types are drop-in.
+"""
+
+import warnings
+
+import numpy as np
+
+__all__ = ["default_coords", "eos_func_from_str", "validate_areacello", "validate_dataset", "annual_average"]
+
+
+def default_coords(coord_names=None):
+    """util.py:199-224 -> ``(tcoord, zcoord, zbounds)``."""
+    coord_names = {} if coord_names is None else coord_names
+    assert isinstance(coord_names, dict), "Coordinate mapping must be a dictionary."
+    zcoord = coord_names["z"] if "z" in coord_names.keys() else "z_l"
+    zbounds = coord_names["zbounds"] if "zbounds" in coord_names.keys() else "z_i"
+    tcoord = coord_names["t"] if "t" in coord_names.keys() else "time"
+    return (tcoord, zcoord, zbounds)
+
+
+def eos_func_from_str(eos_str, func_name="density"):
+    """util.py:227-249: resolve ``momlevel_b200.eos.<eos_str>.<func_name>``."""
+    from . import eos
+
+    assert isinstance(eos_str, str), "Expecting string for equation of state"
+    eos_str = eos_str.lower()
+    avail_eos = [k for k, v in eos.__dict__.items() if not k.startswith("_")]
+    if eos_str not in avail_eos:
+        raise ValueError(f"Unknown equation of state: {eos_str}")
+    return eos.__dict__[eos_str].__dict__[func_name]
+
+
+def _total(arr):
+    """``DataArray.sum()`` as a python float, for xarray, labelled or plain arrays."""
+    s = arr.sum()
+    return float(s.values) if hasattr(s, "values") else float(s)
+
+
+def validate_areacello(areacello, reference=3.6111092e14, tolerance=0.02):
+    """util.py:669-694: ocean area within ``tolerance`` of the real-world total."""
+    error = (_total(areacello) - reference) / reference
+    return bool(np.abs(error) < tolerance)
+
+
+def validate_dataset(dset, reference=False, strict=True, additional_vars=None):
+    """util.py:697-814: presence and rank of the required variables.
+
+    All problems are collected, printed, and reported as one ``ValueError``; a bad
+    ``areacello`` is only a warning when ``strict`` is False.
+    """
+    dset_varlist = list(dset.variables)
+    exceptions = []
+
+    # util.py:726-734 -- the reference compares bound methods (`x.lower` without the call),
+    # so this check can never fire there; kept inert for drop-in behaviour.
+
+    expected_varlist = ["thetao", "so", "volcello", "areacello"]
+    if additional_vars is not None:
+        additional_vars = [additional_vars] if not isinstance(additional_vars, list) else additional_vars
+    else:
+        additional_vars = []
+    expected_varlist = expected_varlist + additional_vars
+    reference_varlist = ["rho", "volo", "masso", "rhoga"]
+    expected_varlist = expected_varlist + reference_varlist if reference else expected_varlist
+
+    missing = list(set(expected_varlist) - set(dset_varlist))
+
+    def _collect(cond, message):
+        if not cond:
+            exceptions.append(AssertionError(message))
+
+    _collect(len(missing) == 0, f"Reference dataset is missing variables: {missing}")
+
+    ranks = (3, "(z,y,x)") if reference else (4, ("t,z,y,x"))
+    for var in ["thetao", "so", "volcello"]:
+        if var in dset_varlist:
+            _collect(len(dset[var].dims) == ranks[0], f"Variable {var} must have exactly {ranks[0]} dimensions {ranks[1]}")
+
+    for var in ["areacello", "deptho"]:
+        if var in dset_varlist:
+            _collect(len(dset[var].dims) == 2, f"Variable {var} must have exactly 2 dimensions (y,x)")
+
+    if "areacello" in dset_varlist:
+        if not validate_areacello(dset["areacello"]):
+            message = "Variable `areacello` field is out of range. It may not be masked."
+            if not strict:
+                warnings.warn(message)
+            else:
+                exceptions.append(AssertionError(message))
+
+    if reference:
+        if "rho" not in missing:
+            _collect(len(dset["rho"].dims) == 3, "Variable areacello must have exactly 3 dimensions (z,y,x)")
+        for var in ["masso", "volo", "rhoga"]:
+            if var not in missing:
+                _collect(len(dset[var].dims) == 0, f"Variable {var} must be a scalar")
+
+    if len(exceptions) > 0:
+        for e in exceptions:
+            print(e)
+        raise ValueError("Errors found in dataset.")
+
+
+def annual_average(xobj, tcoord="time", days_in_month=None):
+    """Days-in-month weighted annual means (util.py:49-119), for labelled Datasets.
+
+    The reference derives the weights from a cftime calendar; cftime is not a dependency
+    here, so ``days_in_month`` (length nt, a multiple of 12) must be supplied -- or, for a
+    real ``xarray`` object with a cftime axis, they are read from ``time.dt.days_in_month``.
+    """
+    from .labeled import DataArray, Dataset
+
+    if days_in_month is None:
+        t = xobj[tcoord]
+        if hasattr(t, "dt"):
+            days_in_month = np.asarray(t.dt.days_in_month)
+        else:
+            raise ValueError("annual_average needs `days_in_month` when the time axis is not a cftime index")
+    w = np.asarray(days_in_month, dtype=np.float64)
+    assert w.size % 12 == 0, "annual averaging needs whole years of monthly data"
+    nyears = w.size // 12
+    w = w.reshape(nyears, 12)
+
+    def _one(da):
+        if tcoord not in da.dims:
+            return da
+        import torch
+
+        d = da.data
+        ax = da.dims.index(tcoord)
+        lib = torch if isinstance(d, torch.Tensor) else np
+        d = lib.movedim(d, ax, 0) if ax else d
+        d = d.reshape((nyears, 12) + tuple(d.shape[1:]))
+        ww = w.reshape((nyears, 12) + (1,) * (d.ndim - 2))
+        if lib is torch:
+            ww = torch.as_tensor(ww, device=d.device)
+        # xarray's weighted mean: NaNs are skipped and the weights renormalised per cell
+        valid = ~lib.isnan(d)
+        num = lib.where(valid, d, lib.zeros_like(d) if lib is torch else 0.0) * ww
+        den = valid * ww
+        out = num.sum(1) / den.sum(1)
+        dims = (tcoord,) + tuple(x for x in da.dims if x != tcoord)
+        res = DataArray(out, dims, attrs=da.attrs)
+        res.encoding = dict(da.encoding)
+        return res
+
+    if isinstance(xobj, DataArray):
+        return _one(xobj)
+    out = Dataset(attrs=xobj.attrs)
+    for k, v in xobj.data_vars.items():
+        out[k] = _one(v)
+    for k, v in xobj.coords.items():
+        if k != tcoord:
+            out[k] = v
+    return out
