@@ -1,0 +1,410 @@
+"""bench.py -- steric grid-points/s on the OM4p25-shaped workload (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch: what ``momlevel.steric(dset)`` computes
+for variant="steric", domain="local", Wright EOS on a 12-month 1440x1080x75 dataset --
+the reference-state kernel (rho_ref + volo + masso) followed by the fused
+EOS -> delta_rho -> clipped-dz -> column-integral kernel, fp32 T/S resident in HBM, eta out.
+Inputs (11.2 GB) are far larger than L2 (126 MB), so no flush is needed between steps.
+
+Prints ONE JSON line (rank 0).  ``value`` = points of all ranks / max-over-ranks device time;
+``e2e`` = the same metric through the host-buffer C-ABI entry (``ml_steric_local_host``:
+pinned host -> device copies and the eta read-back inside the timed region);
+``roofline`` is for the dominant kernel, timed with CUDA events on its stream;
+``cpu_baseline`` = the numpy oracle (a port of the reference's path) on a bounded sample.
+``--impl reference`` times only that CPU path, threaded over all host cores.
+"""
+
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "steric grid-points/s (EOS+column integral)"
+UNIT = "grid-points/s"
+WORKLOADS = {
+    # name -> (nt, nz, ny, nx)
+    "om4p25": (12, 75, 1080, 1440),
+    "spear1deg": (120, 75, 320, 360),
+    "small": (12, 75, 120, 160),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("ML_BENCH_WORKLOAD", "om4p25"), choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--force-direct", action="store_true", help="use the direct kernel family (A/B against TMA)")
+    return ap.parse_args()
+
+
+def config_of(args):
+    nt, nz, ny, nx = WORKLOADS[args.workload]
+    return {
+        "workload": f"{args.workload}: {nx}x{ny}x{nz} z*, {nt} monthly steps, Wright EOS, variant=steric, domain=local"
+                    " (reference state + fused column integral per step)",
+        "grid": [nt, nz, ny, nx],
+        "input_dtype": "f32",
+        "l2_policy": "inputs (T+S per step batch) larger than L2; no flush",
+        "sharding": "one independent 12-step batch (ensemble member) per GPU, no collective on the data path",
+    }
+
+
+# ------------------------------------------------------------------------------ clocks
+
+
+class ClockSampler:
+    """`nvidia-smi` clocks and throttle reasons sampled during the timed region."""
+
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons, power = [], [], set(), []
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------- CPU baseline
+
+
+def _oracle_slab(args_tuple):
+    """One y-slab of the whole path on the host: reference state + local steric (numpy oracle)."""
+    from oracle import steric as osteric
+
+    T, S, V, area, depth, z_l, z_i = args_tuple
+    T, S, V = (np.asarray(x, dtype=np.float64) for x in (T, S, V))  # the parity definition: fp64 upcast
+    ref = osteric.reference_state(T, S, V[None], area, z_l)
+    eta, _ = osteric.steric_local(T, S, z_l, z_i, depth, ref)
+    return eta
+
+
+def cpu_path(fields, rows_per_slab, nslabs, workers, row0=0):
+    """Run the oracle over ``nslabs`` y-slabs on ``workers`` threads; returns (seconds, points, etas)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    T, S, V, area, depth, z_l, z_i = fields
+    jobs = []
+    for k in range(nslabs):
+        ys = slice(row0 + k * rows_per_slab, row0 + (k + 1) * rows_per_slab)
+        jobs.append((T[:, :, ys], S[:, :, ys], V[:, ys], area[ys], depth[ys], z_l, z_i))
+    t0 = time.perf_counter()
+    if workers == 1:
+        etas = [_oracle_slab(j) for j in jobs]
+    else:
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            etas = list(ex.map(_oracle_slab, jobs))
+    dt = time.perf_counter() - t0
+    points = sum(j[0].size for j in jobs)
+    return dt, points, etas
+
+
+def run_reference(args):
+    """`--impl reference`: the reference's CPU path (numpy port) on all host cores, bounded sample."""
+    import torch
+
+    from momlevel_b200 import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nt, nz, ny, nx = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    workers = min(cores, 64)
+    rows = 4
+    nslabs = min(max(workers, 1) * 2, ny // rows)
+    # generate only the rows of the sample (the generator is seeded per step, not per row, so
+    # the sample is a same-statistics slab rather than a bit-identical crop)
+    grid = synth.make_grid(nz, rows * nslabs, nx, seed=123, device="cpu")
+    T, S, V = synth.make_fields(grid, nt, seed=123, dtype=torch.float32)
+    fields = (T.numpy(), S.numpy(), V.numpy(), grid["areacello"].numpy(), grid["deptho"].numpy(),
+              grid["z_l"].numpy(), grid["z_i"].numpy())
+    times = []
+    points = 0
+    for it in range(args.warmup + args.steps):
+        dt, points, _ = cpu_path(fields, rows, nslabs, workers)
+        if it >= args.warmup:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    value = points / sec
+    sample = f"{nslabs} slabs of {rows}x{nx} columns x {nz} levels x {nt} steps = {points} points per step"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
+                         "host_cpu_count": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "numpy port of momlevel's steric path (oracle/), y-slabs on a thread pool; xarray is not installable here",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ our arm
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import momlevel_b200 as ml
+    from momlevel_b200 import core, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.force_direct:
+        core.force_direct(True)
+
+    nt, nz, ny, nx = WORKLOADS[args.workload]
+    ncol = ny * nx
+    points = nt * nz * ncol
+    grid = synth.make_grid(nz, ny, nx, seed=123, device=dev)
+    T, S, V = synth.make_fields(grid, nt, seed=123 + rank, dtype=torch.float32)
+    pres = (grid["z_l"] * 1.0e4 + 101325.0).contiguous()
+    z_i, depth = grid["z_i"].contiguous(), grid["deptho"].contiguous()
+    torch.cuda.synchronize()
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    k3_pairs = []
+
+    def step(record=False):
+        rho_ref, sums = core.reference_state(T[0], S[0], V, pres)
+        if record:
+            a, b = ev(), ev()
+            a.record()
+        eta, _ = core.steric_local(T, S, rho_ref, V, z_i, depth, pres)
+        if record:
+            b.record()
+            k3_pairs.append((a, b))
+        return eta, rho_ref, sums
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = core.launch_count()
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = ev(), ev()
+        e0.record()
+        for _ in range(args.steps):
+            eta, rho_ref, sums = step(record=True)
+        e1.record()
+        barrier()
+    launches = core.launch_count() - launches0
+    ms_total = e0.elapsed_time(e1)
+    k3_ms = [a.elapsed_time(b) for a, b in k3_pairs]
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t[0]) / args.steps
+    value = world * points / (ms_step * 1e-3)
+    path = {1: "direct", 2: "tma"}.get(core.last_path(), "none")
+
+    # roofline of the dominant kernel (ml_steric_local): algorithmic bytes per launch, DESIGN.md
+    N = nz * ncol
+    alg_bytes = nt * N * 8 + N * (8 + 4) + ncol * 8 * (nt + 1)
+    k3_avg_ms = sum(k3_ms) / len(k3_ms)
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except (OSError, ValueError):
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes / (k3_avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": f"ml_steric_local ({path} family)", "kernel_ms": k3_avg_ms,
+                "kernel_share_of_step": k3_avg_ms / (ms_total / args.steps),
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(args), "roofline": roofline, "clocks": clk.summary(),
+        "gpu_launches": launches * world, "kernel_family": path,
+    }
+
+    # ---- extras: the other variants / domains of the same dataset, a few steps each
+    if not args.no_extras:
+        def timed(fn, n=3):
+            fn()
+            torch.cuda.synchronize()
+            a, b = ev(), ev()
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        extras = {}
+        ms = timed(lambda: core.steric_local(T, S[0], rho_ref, V, z_i, depth, pres, s_bcast=True))
+        extras["thermosteric_local_gpts"] = points / ms / 1e6
+        ms = timed(lambda: core.steric_local(T[0], S, rho_ref, V, z_i, depth, pres, t_bcast=True))
+        extras["halosteric_local_gpts"] = points / ms / 1e6
+        ms = timed(lambda: core.steric_global(T, S, V, pres))
+        extras["steric_global_gpts"] = points / ms / 1e6
+        ms = timed(lambda: core.reference_state(T[0], S[0], V, pres))
+        extras["reference_state_gpts"] = N / ms / 1e6
+        ms = timed(lambda: core.steric_local(T, S, rho_ref, V, z_i, depth, pres, eos="linear"))
+        extras["linear_local_gpts"] = points / ms / 1e6
+        half = nt // 2  # spice writes an fp64 field as large as both inputs; half the steps keeps HBM use bounded
+        ms = timed(lambda: core.flament_spice(T[:half], S[:half]))
+        extras["flament_spice_gpts"] = half * N / ms / 1e6
+        extras["steric_local_kernel_only_gpts"] = points / k3_avg_ms / 1e6
+        line["extras_Gpts_per_s"] = extras
+        torch.cuda.empty_cache()
+
+    # ---- e2e: host buffers through ml_steric_local_host, copies inside the timed region
+    if not args.no_e2e:
+        Th = torch.empty(T.shape, dtype=T.dtype, pin_memory=True)
+        Sh = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+        Vh = torch.empty(V.shape, dtype=V.dtype, pin_memory=True)
+        eta_h = torch.empty((nt, ny, nx), dtype=torch.float64, pin_memory=True)
+        Th.copy_(T)
+        Sh.copy_(S)
+        Vh.copy_(V)
+        z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
+        del T, S
+        torch.cuda.empty_cache()
+        n_e2e = max(1, min(args.steps, 3))
+
+        def e2e_step():
+            return core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, eta_out=eta_h)
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        h2d = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
+        d2h = eta_h.numel() * 8 + 16
+        line["e2e"] = {"value": world * points / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                       "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
+                       "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)"}
+        # the device-resident and the host-streamed paths must agree
+        err = (eta_h.to(dev) - eta).abs()
+        line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
+        host_fields = (Th.numpy(), Sh.numpy(), Vh.numpy(), grid["areacello"].cpu().numpy(), d_h,
+                       grid["z_l"].cpu().numpy(), z_h)
+    else:
+        host_fields = None
+
+    # ---- cpu_baseline: the oracle on a bounded sample of the same workload (rank 0, N=1 only)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        if host_fields is None:
+            host_fields = (T.cpu().numpy(), S.cpu().numpy(), V.cpu().numpy(), grid["areacello"].cpu().numpy(),
+                           depth.cpu().numpy(), grid["z_l"].cpu().numpy(), z_i.cpu().numpy())
+        rows, nslabs = 8, 3
+        row0 = max(0, ny // 2 - rows * nslabs // 2)
+        cpu_path(host_fields, rows, 1, 1, row0)  # warm-up
+        sec, pts, etas = cpu_path(host_fields, rows, nslabs, 1, row0)
+        got = eta[:, row0: row0 + rows * nslabs].cpu().numpy()
+        want = np.concatenate(etas, axis=1)
+        same_nan = bool(np.array_equal(np.isnan(got), np.isnan(want)))
+        m = ~np.isnan(want)
+        m[0, 0, 0] = m.any() or True  # never reduce over an empty set
+        got, want = np.nan_to_num(got), np.nan_to_num(want)
+        line["cpu_baseline"] = {
+            "value": pts / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"rows {row0}..{row0 + rows * nslabs} of {ny}: {rows * nslabs}x{nx} columns x {nz} levels x {nt} steps"
+                      f" = {pts} points, numpy oracle on fp64-upcast inputs, single thread",
+            "seconds": sec, "host_cpu_count": os.cpu_count(),
+            "parity_max_abs_err_m": float(np.max(np.abs(got[m] - want[m]))), "parity_nan_pattern_equal": same_nan,
+        }
+
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -325,6 +325,14 @@ class Dataset:
             out[name_dict.get(k, k)] = nv
         return out
 
+    def drop_vars(self, names):
+        names = [names] if isinstance(names, str) else list(names)
+        out = Dataset(attrs=self.attrs)
+        for k, v in self._vars.items():
+            if k not in names:
+                out[k] = v
+        return out
+
     def copy(self, deep=False):
         out = Dataset(attrs=self.attrs)
         for k, v in self._vars.items():

@@ -158,4 +158,9 @@ def annual_average(xobj, tcoord="time", days_in_month=None):
     for k, v in xobj.coords.items():
         if k != tcoord:
             out[k] = v
+    # the reference labels each mean with the mid-point of its year (util.py:96-107); without a
+    # calendar the label is the mean of the twelve original time values
+    if tcoord in xobj.variables and np.issubdtype(np.asarray(xobj[tcoord].values).dtype, np.number):
+        tv = np.asarray(xobj[tcoord].values, dtype=np.float64).reshape(nyears, 12).mean(1)
+        out[tcoord] = DataArray(tv, (tcoord,), attrs=xobj[tcoord].attrs)
     return out

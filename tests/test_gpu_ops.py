@@ -1,0 +1,224 @@
+"""GPU parity of the elementwise operators against the oracle and the reference's goldens.
+
+Tolerances (BASELINE.json north_star): density within 1e-10 relative of the reference's
+numpy path on the same fp64-upcast inputs.  Everything goes through the C ABI.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import eos as oeos
+from oracle import spice as ospice
+from oracle import steric as osteric
+from oracle import testdata
+
+pytestmark = pytest.mark.gpu
+
+RHO_RTOL = 1e-10  # north_star: 1e-10 relative on density
+
+
+@pytest.fixture(scope="module")
+def ml():
+    import momlevel_b200
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device: there is no CPU path"
+    return momlevel_b200
+
+
+def _relerr(a, b):
+    m = ~np.isnan(b)
+    assert np.array_equal(np.isnan(a), np.isnan(b)), "NaN pattern differs"
+    return np.max(np.abs(a[m] - b[m]) / np.abs(b[m])) if m.any() else 0.0
+
+
+# ------------------------------------------------------------------------------ Wright
+
+
+def test_wright_scalar_kats(ml):
+    # tests/test_wright.py:12,31,51,71,121
+    w = ml.eos.wright
+    assert w.density(18.0, 35.0, 200000.0) == pytest.approx(1025.359957453976, rel=RHO_RTOL)
+    assert w.drho_dtemp(18.0, 35.0, 200000.0) == pytest.approx(-0.24680005918175105, rel=1e-12)
+    assert w.drho_dsal(18.0, 35.0, 200000.0) == pytest.approx(0.7652676800174607, rel=1e-12)
+    assert w.alpha(18.0, 35.0, 200000.0) == pytest.approx(0.0002406960183958898, rel=1e-12)
+    assert w.beta(18.0, 35.0, 200000.0) == pytest.approx(0.0007463405162784603, rel=1e-12)
+
+
+def test_wright_array_kat(ml):
+    # tests/test_wright.py:4-27
+    rng = np.random.default_rng(123)
+    T, S, p = rng.normal(15.0, 5.0, (5, 5)), rng.normal(35.0, 1.5, (5, 5)), rng.normal(2000.0, 500.0, (5, 5))
+    rho = ml.eos.wright.density(T, S, p)
+    assert rho.shape == (5, 5) and rho.dtype == np.float64
+    assert np.allclose(rho[0], [1026.77225958, 1027.8498461, 1025.60122596, 1026.20882763, 1024.87391971],
+                       rtol=0, atol=6e-9)
+    assert _relerr(rho, oeos.wright_density(T, S, p)) < RHO_RTOL
+
+
+@pytest.mark.parametrize("func", ["density", "drho_dtemp", "drho_dsal", "alpha", "beta"])
+def test_wright_golden(ml, golden, func):
+    g = golden("eos_wright.npz")
+    got = getattr(ml.eos.wright, func)(g["T"], g["S"], g["p"])
+    assert _relerr(got, g[func]) < (RHO_RTOL if func == "density" else 1e-11)
+
+
+def test_wright_fp32_storage_equals_fp64_upcast(ml, golden):
+    """fp32 T/S are widened exactly on load: same result as handing in the fp64 upcast."""
+    g = golden("eos_wright.npz")
+    T32, S32 = g["T"].astype(np.float32), g["S"].astype(np.float32)
+    a = ml.eos.wright.density(T32, S32, g["p"])
+    b = ml.eos.wright.density(T32.astype(np.float64), S32.astype(np.float64), g["p"])
+    np.testing.assert_array_equal(a, b)
+    assert _relerr(a, oeos.wright_density(T32.astype(np.float64), S32.astype(np.float64), g["p"])) < RHO_RTOL
+
+
+def test_wright_wide_range_and_broadcast(ml):
+    rng = np.random.default_rng(7)
+    T = rng.uniform(-2, 40, (3, 7, 11)).astype(np.float32).astype(np.float64)
+    S = rng.uniform(0, 42, (3, 7, 11)).astype(np.float32).astype(np.float64)
+    p = rng.uniform(1e5, 7e7, (7, 1))  # numpy broadcasting against (3,7,11)
+    assert _relerr(ml.eos.wright.density(T, S, p), oeos.wright_density(T, S, p)) < RHO_RTOL
+    # scalar T against array S
+    assert _relerr(ml.eos.wright.density(10.0, S, 2e5), oeos.wright_density(10.0, S, 2e5)) < RHO_RTOL
+
+
+def test_wright_degenerate_denominator_matches_ieee(ml):
+    """Far outside the ocean range the lean reciprocal hands over to IEEE division."""
+    # T = 1e78 puts the denominator at ~7e307, where 1/d is subnormal
+    T = np.array([1e78, 9e77, 1e120, 18.0])
+    S = np.array([35.0, 35.0, 35.0, 35.0])
+    with np.errstate(all="ignore"):
+        want = oeos.wright_density(T, S, 2e5)
+    got = ml.eos.wright.density(T, S, 2e5)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    m = np.isfinite(want)
+    assert m[:2].all() and np.all(want[:2] > 0)
+    assert np.allclose(got[m], want[m], rtol=1e-10, atol=0)
+
+
+def test_empty_input(ml):
+    out = ml.eos.wright.density(np.zeros((0, 4)), np.zeros((0, 4)), 1e5)
+    assert out.shape == (0, 4)
+    assert ml.spice.flament.spice(np.zeros(0), np.zeros(0)).shape == (0,)
+
+
+def test_device_tensors_stay_on_device(ml):
+    T = torch.full((4, 6), 18.0, device="cuda", dtype=torch.float32)
+    S = torch.full((4, 6), 35.0, device="cuda", dtype=torch.float32)
+    rho = ml.eos.wright.density(T, S, 200000.0)
+    assert rho.is_cuda and rho.dtype == torch.float64
+    assert float(rho[0, 0]) == pytest.approx(1025.359957453976, rel=RHO_RTOL)
+
+
+# ------------------------------------------------------------------------------ linear
+
+
+def test_linear_kats_and_golden(ml, golden):
+    # tests/test_linear.py:12
+    lin = ml.eos.linear
+    assert lin.density(18.0, 35.0, 200000.0) == pytest.approx(1024.4, rel=1e-15)
+    assert lin.drho_dtemp() == -0.2 and lin.drho_dsal() == 0.8
+    g = golden("eos_linear.npz")
+    assert _relerr(lin.density(g["T"], g["S"], g["p"]), g["density"]) < 1e-14
+    assert _relerr(lin.alpha(g["T"], g["S"], g["p"]), g["alpha"]) < 1e-14
+    assert _relerr(lin.beta(g["T"], g["S"], g["p"]), g["beta"]) < 1e-14
+    m = ~np.isnan(g["density_rho_ref"])
+    assert np.max(np.abs(lin.density(g["T"], g["S"], None, rho_ref=1035.0)[m] - g["density_rho_ref"][m])) < 1e-12
+
+
+# ------------------------------------------------------------------------------- spice
+
+
+def test_flament_kat(ml):
+    # tests/test_flament.py:4-13
+    S = np.arange(33.0, 37.1, 0.1)
+    T = np.arange(0.0, 31.0, 1.0)
+    SS = np.tile(S[None, :], (len(T), 1))
+    TT = np.tile(T[:, None], (1, len(S)))
+    pi = ml.spice.flament.spice(TT, SS)
+    assert pi.shape == TT.shape
+    assert pi.sum() == pytest.approx(3283.680384169385, rel=1e-13)
+
+
+def test_flament_golden_and_scalar(ml, golden):
+    g = golden("spice.npz")
+    got = ml.spice.flament.spice(g["T"], g["S"])
+    assert np.array_equal(np.isnan(got), np.isnan(g["spice"]))
+    m = ~np.isnan(g["spice"])
+    assert np.max(np.abs(got[m] - g["spice"][m])) < 1e-13
+    assert ml.spice.flament.spice(10.0, 35.0).shape == (1,)
+    with pytest.raises(AssertionError):
+        ml.spice.flament.spice(np.zeros(3), np.zeros(4))
+
+
+def test_calc_spice_kat(ml):
+    # tests/test_derived.py:135-137
+    d = ml.test_data.generate_test_data()
+    pi = ml.derived.calc_spice(d["thetao"], d["so"])
+    assert pi.dims == d["thetao"].dims and pi.attrs["long_name"] == "Sea water spiciness"
+    assert float(pi.sum()) == pytest.approx(1412.03593361, abs=5e-9)
+
+
+def test_spice_large_fp32(ml):
+    rng = np.random.default_rng(5)
+    T = rng.uniform(-2, 32, 1_000_003).astype(np.float32)
+    S = rng.uniform(30, 40, 1_000_003).astype(np.float32)
+    T[17] = np.nan
+    got = ml.spice.flament.spice(T, S)
+    want = ospice.flament_spice(T.astype(np.float64), S.astype(np.float64))
+    assert np.isnan(got[17])
+    m = ~np.isnan(want)
+    assert np.max(np.abs(got[m] - want[m])) < 1e-12
+
+
+# ---------------------------------------------------------------------------------- dz
+
+
+def test_calc_dz_kats(ml):
+    # tests/test_derived.py:26-45
+    d = ml.test_data.generate_test_data_dz()
+    dz = ml.derived.calc_dz(d.z_l, d.z_i, d.deptho)
+    assert dz.dims == ("yh", "xh", "z_l")
+    assert float(dz.sum()) == pytest.approx(1130.67307641, abs=5e-9)
+    assert float(ml.derived.calc_dz(d.z_l, d.z_i, d.deptho, fraction=True).sum()) == pytest.approx(85.53726628, abs=5e-9)
+    assert float(ml.derived.calc_dz(d.z_l, d.z_i, d.deptho, top=12.0, bottom=33.0).sum()) == pytest.approx(
+        363.71725794, abs=5e-9)
+    o = testdata.generate_test_data_dz()
+    want = osteric.calc_dz(o["z_l"], o["z_i"], o["deptho"])
+    np.testing.assert_array_equal(dz.transpose("z_l", "yh", "xh").values, want)
+    bad = d.deptho.copy()
+    bad[4, 4] = -200.0
+    with pytest.raises(AssertionError):
+        ml.derived.calc_dz(d.z_l, d.z_i, bad)
+
+
+# ------------------------------------------------------------------ derived.calc_rho etc
+
+
+def test_calc_rho_and_friends(ml):
+    d = ml.test_data.generate_test_data()
+    o = testdata.generate_test_data()
+    pres = d["z_l"] * 1.0e4
+    rho = ml.derived.calc_rho(d["thetao"], d["so"], pres, eos="Wright")
+    want = oeos.wright_density(o["thetao"], o["so"], (o["z_l"] * 1e4)[None, :, None, None])
+    assert rho.dims == d["thetao"].dims and rho.attrs["units"] == "kg m-3"
+    assert _relerr(rho.values, want) < RHO_RTOL
+    # tests/test_derived.py:48-51 holds a stale constant (643872.597, rel 4.7e-6 from the code);
+    # the reference's own tolerance still accepts the code's value
+    assert np.allclose(float(rho.sum()), 643872.59725673)
+    # tests/test_derived.py:73-81
+    assert float(ml.derived.calc_alpha(d["thetao"], d["so"], pres).sum()) == pytest.approx(0.14302587, abs=5e-9)
+    assert float(ml.derived.calc_beta(d["thetao"], d["so"], pres).sum()) == pytest.approx(0.4639801, abs=5e-8)
+    # tests/test_derived.py:84-103
+    masso = ml.derived.calc_masso(rho, d["volcello"])
+    assert masso.dims == ("time",)
+    assert float(masso.sum()) == pytest.approx(6.45215577e08, rel=2e-9)
+    assert float(ml.derived.calc_volo(d["volcello"].isel(time=0))) == pytest.approx(125921.15458782, abs=5e-9)
+    with pytest.raises(AssertionError):
+        ml.derived.calc_volo(d["volcello"])
+    with pytest.raises(ValueError):
+        ml.derived.calc_rho(d["thetao"], d["so"], pres, eos="nope")
+    # potential density = density at a fixed pressure (derived.py:477)
+    pd = ml.derived.calc_pdens(d["thetao"], d["so"], level=2000.0)
+    assert _relerr(pd.values, oeos.wright_density(o["thetao"], o["so"], 2000.0 * 1e4 + 101325)) < RHO_RTOL

@@ -1,0 +1,146 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels involved).
+
+Cases follow the reference's own tests: tests/test_util.py:48-122 (coords, area and dataset
+validation) and the error paths of src/momlevel/steric.py that fire before any compute.
+"""
+
+import numpy as np
+import pytest
+
+import momlevel_b200 as momlevel
+from momlevel_b200 import util
+from momlevel_b200.labeled import DataArray, Dataset
+from momlevel_b200.test_data import generate_test_data, generate_test_data_dz
+
+dset = generate_test_data()
+
+
+def test_default_coords_1():
+    assert util.default_coords() == ("time", "z_l", "z_i")
+
+
+def test_default_coords_2():
+    assert util.default_coords(coord_names={"z": "lev", "t": "TIME"}) == ("TIME", "lev", "z_i")
+    with pytest.raises(AssertionError):
+        util.default_coords(coord_names=["z"])
+
+
+def test_validate_areacello():
+    assert util.validate_areacello(dset.areacello)
+    assert not util.validate_areacello(dset.areacello * 1.3)
+
+
+def test_validate_dataset_ok():
+    util.validate_dataset(dset)
+    util.validate_dataset(dset, additional_vars=["z_i", "deptho"])
+
+
+def test_validate_dataset_missing_variable(capsys):
+    with pytest.raises(ValueError, match="Errors found in dataset."):
+        util.validate_dataset(dset.drop_vars(["thetao"]))
+    assert "missing variables" in capsys.readouterr().out
+
+
+def test_validate_dataset_bad_area_strict_and_lenient():
+    bad = dset.copy()
+    bad["areacello"] = bad["areacello"] * 1.3
+    with pytest.raises(ValueError):
+        util.validate_dataset(bad)
+    with pytest.warns(UserWarning):
+        util.validate_dataset(bad, strict=False)
+
+
+def test_validate_dataset_reference_rank():
+    # a 4-D dataset is not a reference state (tests/test_util.py:96-100)
+    with pytest.raises(ValueError):
+        util.validate_dataset(dset.copy(), reference=True)
+
+
+def test_validate_dataset_reference_fields():
+    ref = Dataset()
+    for k in ("thetao", "so", "volcello"):
+        ref[k] = dset[k].isel(time=0)
+    ref["rho"] = dset["thetao"].isel(time=0)
+    for k in ("volo", "masso", "rhoga"):
+        ref[k] = DataArray(np.float64(1.0), ())
+    ref["areacello"] = dset["areacello"]
+    util.validate_dataset(ref, reference=True)
+    with pytest.raises(ValueError):
+        util.validate_dataset(ref.drop_vars(["rhoga"]), reference=True)
+    ref["volo"] = DataArray(np.ones(3), ("x",))
+    with pytest.raises(ValueError):
+        util.validate_dataset(ref, reference=True)
+
+
+def test_validate_dataset_additional_vars():
+    with pytest.raises(ValueError):
+        util.validate_dataset(dset.copy(), additional_vars=["foo", "bar"])
+
+
+def test_eos_func_from_str():
+    from momlevel_b200.eos import linear, wright
+
+    assert util.eos_func_from_str("Wright") is wright.density
+    assert util.eos_func_from_str("LINEAR", func_name="alpha") is linear.alpha
+    with pytest.raises(ValueError, match="Unknown equation of state"):
+        util.eos_func_from_str("teos10")
+    with pytest.raises(AssertionError):
+        util.eos_func_from_str(10)
+
+
+def test_steric_rejects_bad_area_before_compute():
+    # tests/test_steric.py:25-29
+    bad = dset.copy()
+    bad["areacello"] = bad["areacello"] * 1.3
+    with pytest.raises(Exception):
+        momlevel.steric(bad)
+
+
+def test_wrapper_duplicate_variant_kwarg():
+    # steric.py:187-196: the wrappers pass variant= themselves
+    with pytest.raises(TypeError):
+        momlevel.thermosteric(dset, variant="steric")
+
+
+def test_labeled_basics():
+    t = dset["thetao"]
+    assert t.dims == ("time", "z_l", "yh", "xh") and t.shape == (5, 5, 5, 5)
+    assert t.isel(time=0).dims == ("z_l", "yh", "xh")
+    assert float(t[0, 1, 2, 3]) == t.values[0, 1, 2, 3]
+    assert t.transpose("z_l", ...).dims == ("z_l", "time", "yh", "xh")
+    a = DataArray(np.array([1.0, np.nan, 3.0]), ("x",))
+    assert float(a.sum()) == 4.0 and a.notnull().values.tolist() == [True, False, True]
+    ds = dset.rename({"thetao": "temp"})
+    assert "temp" in ds and "thetao" not in ds
+    assert dset.rename(None)["so"].dims == dset["so"].dims
+    assert set(dset.coords) == {"time", "xh", "yh", "z_i", "z_l"}
+    s = dset.sum()
+    assert float(s["thetao"]) == pytest.approx(dset["thetao"].values.sum())
+    lazy = DataArray.lazy(lambda: np.ones((2, 2)), (2, 2), ("a", "b"))
+    assert lazy.is_lazy and lazy.shape == (2, 2)
+    assert float(lazy.sum()) == 4.0 and not lazy.is_lazy
+
+
+def test_test_data_matches_reference_draws():
+    # reference sums of the t=0 slab, tests/test_steric.py:32-36
+    assert dset["thetao"].values[0].sum() == pytest.approx(1921.05772939, abs=5e-9)
+    assert dset["so"].values[0].sum() == pytest.approx(4388.81731882, abs=5e-9)
+    assert dset["volcello"].values[0].sum() == pytest.approx(125921.15458782, abs=5e-9)
+    assert float(dset["areacello"].sum()) == pytest.approx(3.6111092e14, rel=1e-12)
+    dz = generate_test_data_dz()
+    assert np.isnan(dz["deptho"].values[2, 2]) and dz["z_l"].values.tolist() == [2.5, 7.5, 15.0, 35.0, 75.0]
+    d3 = generate_test_data(start_year=1983, nyears=2, calendar="julian")
+    assert d3["thetao"].shape == (24, 5, 5, 5)
+    assert d3["days_in_month"].values[[1, 13]].tolist() == [28.0, 29.0]  # 1984 is a julian leap year
+
+
+def test_annual_average_weights():
+    d = Dataset()
+    vals = np.arange(24, dtype=np.float64)
+    d["time"] = DataArray(np.arange(24.0), ("time",))
+    d["x"] = DataArray(vals.reshape(24, 1) * np.ones((1, 3)), ("time", "p"))
+    w = np.tile([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], 2).astype(float)
+    out = util.annual_average(d, days_in_month=w)
+    expect = [(vals[:12] * w[:12]).sum() / w[:12].sum(), (vals[12:] * w[12:]).sum() / w[12:].sum()]
+    assert out["x"].shape == (2, 3)
+    assert np.allclose(out["x"].values[:, 0], expect, rtol=1e-15)
