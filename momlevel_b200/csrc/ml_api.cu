@@ -291,6 +291,13 @@ int launch_global_direct(const void* T, const void* S, i64 ts, i64 ss, const voi
   return launched("k_reduce_rows");
 }
 
+namespace tma {
+int reduce_rows(const double* partials, int64_t nblk, double* out, int nrows, cudaStream_t st) {
+  k_reduce_rows<<<nrows, kBlock, 0, st>>>(partials, nblk, out);
+  return launched("k_reduce_rows");
+}
+}  // namespace tma
+
 }  // namespace ml
 
 using namespace ml;

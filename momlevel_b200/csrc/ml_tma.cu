@@ -1,19 +1,374 @@
-// ml_tma.cu -- TMA-staged kernel family (under construction: eligibility is off, so every
-// launch takes the direct family in ml_api.cu).
+// ml_tma.cu -- TMA-staged kernel family for the fused steric kernels (sm_100a).
+//
+// Layout of the work: fields are [t][z][col] fp32 (col = flattened y,x).  A CTA owns a tile
+// of kTile = 256 adjacent columns and a chunk of TC time steps.  One producer warp walks the
+// levels and, for each level, issues ONE 3-D TMA box per field ({256 cols, 1 level, TC steps}
+// = TC KB) into a ring of shared-memory stages guarded by full/empty mbarriers.  Eight
+// consumer warps (one column per thread) read T,S from shared memory, evaluate the EOS in
+// fp64 registers and keep the TC running column sums in registers, so
+//   - every byte of T and S crosses HBM exactly once, in 1 KB contiguous rows,
+//   - rho_ref / v_ref (3-D, time-invariant) are fetched once per (level, column, chunk)
+//     with ordinary loads, prefetched one level ahead, and reused for TC steps,
+//   - loads cost no registers and no issue slots in the compute warps; the depth of the
+//     ring (not occupancy) hides HBM latency,
+//   - out-of-range columns / time steps of edge tiles are zero-filled by the TMA unit.
+// Levels at which no lane of a warp has any water (dz = 0: land, below the sea floor) are
+// skipped by that warp: their terms are multiplied by dz = 0 in steric.py:163 and vanish.
+//
+// Eligibility: fp32 fields, 16-byte aligned bases, ncol % 4 == 0 (TMA global strides are
+// multiples of 16 bytes), ncol >= kTile, no delta_rho output.  Everything else takes the
+// direct family in ml_api.cu.
+#include <cuda.h>
+
+#include "ml_common.cuh"
+#include "ml_host.cuh"
 #include "ml_tma.cuh"
 
 namespace ml {
 namespace tma {
 
-bool local_eligible(int, const void*, const void*, int, int, const double*, const void*, int, int64_t, int64_t, int64_t,
-                    const double*, const double*) { return false; }
-int launch_local(int, int, const void*, const void*, int, int, const double*, const void*, int, const double*,
-                 const double*, const double*, double, int, int, int64_t, double*, double*, cudaStream_t) { return -100; }
-bool global_eligible(int, const void*, const void*, int, int, const void*, int, int64_t, int64_t, int64_t) { return false; }
-int launch_global(int, int, const void*, const void*, int, int, const void*, int, const double*, int, int, int64_t,
-                  double*, double*, cudaStream_t) { return -100; }
+constexpr int kTile = 256;                    // columns per CTA = consumer threads
+constexpr int kConsumerWarps = kTile / 32;    // 8
+constexpr int kThreads = kTile + 32;          // + 1 producer warp
+constexpr int kStages = 4;
+
+// ------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// acc += w * d unless d is NaN (xarray's skipna sum).  d comes out of fp64 arithmetic, so a
+// NaN is quiet and the test is one integer compare on the high word.
+__device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
+  asm("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
+      "mov.b64 {lo, hi}, %1;\n\t"
+      "add.u32 hi, hi, hi;\n\t"
+      "setp.le.u32 p, hi, 0xffe00000;\n\t"
+      "@p fma.rn.f64 %0, %2, %1, %0;\n\t}"
+      : "+d"(acc)
+      : "d"(d), "d"(w));
+}
+
+__device__ __forceinline__ double ld_vref(const void* v, int v_f32, i64 i) {
+  return v_f32 ? (double)__ldg(reinterpret_cast<const float*>(v) + i) : __ldg(reinterpret_cast<const double*>(v) + i);
+}
+
+struct Params {
+  const double* rho_ref;  // local only
+  const void* v_ref;
+  int v_f32;
+  const double* z_i;      // local only
+  const double* deptho;   // local only
+  const double* p_level;
+  double coef;
+  int nt, nz;
+  i64 ncol;
+  double* eta;            // local: [nt][ncol]
+  double* partials;       // global: [nt][gridDim.x]
+};
+
+// BC: 0 = T and S both [t][z][col]; 1 = T is [z][col] (halosteric); 2 = S is [z][col] (thermosteric)
+template <int EOS, int TC, int BC, bool GLOBAL>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
+  constexpr int kRowsT = (BC == 1) ? 1 : TC;
+  constexpr int kRowsS = (BC == 2) ? 1 : TC;
+  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(float);
+
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
+  uint64_t* empty = full + kStages;
+  double* red = reinterpret_cast<double*>(empty + kStages);  // GLOBAL: [kConsumerWarps][TC]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c0 = blockIdx.x * kTile;
+  const int t0 = blockIdx.y * TC;
+  const int nz = P.nz;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full + s, 1);
+      mbar_init(empty + s, kConsumerWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  double acc[TC];
+#pragma unroll
+  for (int k = 0; k < TC; ++k) acc[k] = 0.0;
+
+  if (warp == kConsumerWarps) {
+    // ------------------------------------------------------------------ producer warp
+    if (lane == 0) {
+      for (int z = 0; z < nz; ++z) {
+        const int s = z % kStages;
+        const uint32_t round = (uint32_t)(z / kStages);
+        if (round > 0) mbar_wait(empty + s, (round - 1) & 1u);
+        float* dT = stage_base + (size_t)s * (kStageBytes / sizeof(float));
+        float* dS = dT + kRowsT * kTile;
+        mbar_expect_tx(full + s, kStageBytes);
+        if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
+        if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
+      }
+    }
+  } else {
+    // ----------------------------------------------------------------- consumer warps
+    const i64 c = (i64)c0 + tid;
+    const bool in = c < P.ncol;
+    const i64 cc = in ? c : (P.ncol - 1);  // clamp: edge lanes read a valid column, never store
+    Eos<EOS> eos;
+    double depth = 0.0;
+    if (!GLOBAL) {
+      depth = __ldg(P.deptho + cc);
+      if (isnan(depth)) depth = 0.0;  // derived.py:295
+    }
+    // per-level operands, fetched one level ahead
+    double rref_n = 0.0, v_n = 0.0;
+    {
+      v_n = ld_vref(P.v_ref, P.v_f32, cc);
+      if (!GLOBAL) rref_n = __ldg(P.rho_ref + cc);
+    }
+    const bool surface_wet = !isnan(v_n);  // steric.py:166
+    for (int z = 0; z < nz; ++z) {
+      const int s = z % kStages;
+      const double rref_z = rref_n, v_z = v_n;
+      if (z + 1 < nz) {
+        const i64 j = (i64)(z + 1) * P.ncol + cc;
+        v_n = ld_vref(P.v_ref, P.v_f32, j);
+        if (!GLOBAL) rref_n = __ldg(P.rho_ref + j);
+      }
+      // weight of this cell in the sum and the value subtracted from rho
+      double w, sub;
+      if (GLOBAL) {
+        w = isnan(v_z) ? 0.0 : v_z;  // rho * NaN is dropped by the skipna sum (derived.py:435-438)
+        sub = 0.0;
+      } else {
+        w = clipped_dz(depth, __ldg(P.z_i + z), __ldg(P.z_i + z + 1));
+        // steric.py:151-153: delta_rho is NaN (and skipped) wherever the reference volume is missing
+        sub = isnan(v_z) ? nan("") : rref_z;
+        if (is_nan_q(sub + 0.0)) w = 0.0;
+      }
+      eos.set_level(__ldg(P.p_level + z));
+      mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
+      if (__any_sync(0xffffffffu, w != 0.0)) {
+        const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
+        const float* sS = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + kRowsT * kTile + tid;
+#pragma unroll
+        for (int k = 0; k < TC; ++k) {
+          const double Tv = (double)sT[(BC == 1 ? 0 : k) * kTile];
+          const double Sv = (double)sS[(BC == 2 ? 0 : k) * kTile];
+          const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
+          fma_skipnan(acc[k], w, d);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty + s);
+    }
+    if (!GLOBAL) {
+      if (in) {
+#pragma unroll
+        for (int k = 0; k < TC; ++k)
+          if (t0 + k < P.nt) P.eta[(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[k] : nan("");
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TC; ++k) {
+        const double sacc = warp_sum(in ? acc[k] : 0.0);
+        if (lane == 0) red[warp * TC + k] = sacc;
+      }
+    }
+  }
+  if (GLOBAL) {
+    __syncthreads();
+    if (tid < TC && t0 + tid < P.nt) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * TC + tid];
+      P.partials[(i64)(t0 + tid) * gridDim.x + blockIdx.x] = sacc;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// fp32 field [nt][nz][ncol] (rank 3) or [nz][ncol] (rank 2); box = {kTile, 1, tc}
+static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)ncol, (cuuint64_t)nz, (cuuint64_t)nt};
+  cuuint64_t strides[2] = {(cuuint64_t)ncol * 4, (cuuint64_t)ncol * (cuuint64_t)nz * 4};
+  cuuint32_t box[3] = {(cuuint32_t)kTile, 1, (cuuint32_t)tc};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool common_eligible(int dtype, const void* T, const void* S, int64_t nt, int64_t nz, int64_t ncol) {
+  if (dtype != ML_F32) return false;
+  if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
+  if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
+  if (nt < 1 || nz < 1) return false;
+  // TMA global strides must stay below 2^40 bytes
+  if ((double)ncol * (double)nz * 4.0 >= 1099511627776.0) return false;
+  return encode_fn() != nullptr;
+}
+
+bool local_eligible(int dtype, const void* T, const void* S, int, int, const double*, const void*, int, int64_t nt,
+                    int64_t nz, int64_t ncol, const double*, const double* delta_rho) {
+  return delta_rho == nullptr && common_eligible(dtype, T, S, nt, nz, ncol);
+}
+
+bool global_eligible(int dtype, const void* T, const void* S, int, int, const void*, int, int64_t nt, int64_t nz,
+                     int64_t ncol) {
+  return common_eligible(dtype, T, S, nt, nz, ncol);
+}
+
+template <int TC>
+constexpr size_t smem_bytes(int bc) {
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
+         (size_t)kConsumerWarps * TC * sizeof(double) + 128;
+}
+
+template <int EOS, int TC, int BC, bool GLOBAL>
+static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
+                      cudaStream_t st) {
+  auto kern = k_steric_tma<EOS, TC, BC, GLOBAL>;
+  const size_t smem = smem_bytes<TC>(BC);
+  static bool configured = false;  // per instantiation
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma)");
+    configured = true;
+  }
+  kern<<<dim3(tiles, chunks), kThreads, smem, st>>>(mT, mS, P);
+  return launched("k_steric_tma");
+}
+
+template <int EOS, int TC, bool GLOBAL>
+static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles,
+                     unsigned chunks, cudaStream_t st) {
+  if (bc == 0) return launch_one<EOS, TC, 0, GLOBAL>(mT, mS, P, tiles, chunks, st);
+  if (bc == 1) return launch_one<EOS, TC, 1, GLOBAL>(mT, mS, P, tiles, chunks, st);
+  return launch_one<EOS, TC, 2, GLOBAL>(mT, mS, P, tiles, chunks, st);
+}
+
+template <bool GLOBAL>
+static int launch_any(int eos, const void* T, const void* S, int t_bcast, int s_bcast, Params P, cudaStream_t st) {
+  const int bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
+  const int tc = P.nt >= 12 ? 12 : (P.nt >= 8 ? 8 : 4);
+  CUtensorMap mT, mS;
+  const bool okT = t_bcast ? make_map(&mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&mT, T, 3, P.ncol, P.nz, P.nt, tc);
+  const bool okS = s_bcast ? make_map(&mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&mS, S, 3, P.ncol, P.nz, P.nt, tc);
+  if (!okT || !okS) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
+  const unsigned tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
+  const unsigned chunks = (unsigned)((P.nt + tc - 1) / tc);
+#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, GLOBAL>(bc, mT, mS, P, tiles, chunks, st)
+  if (eos == ML_EOS_WRIGHT) {
+    if (tc == 12) ML_TMA_GO(0, 12);
+    if (tc == 8) ML_TMA_GO(0, 8);
+    ML_TMA_GO(0, 4);
+  }
+  if (tc == 12) ML_TMA_GO(1, 12);
+  if (tc == 8) ML_TMA_GO(1, 8);
+  ML_TMA_GO(1, 4);
+#undef ML_TMA_GO
+}
+
+int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                 const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
+                 double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st) {
+  Params P;
+  P.rho_ref = rho_ref;
+  P.v_ref = v_ref;
+  P.v_f32 = vref_dtype == ML_F32;
+  P.z_i = z_i;
+  P.deptho = deptho;
+  P.p_level = p_level;
+  P.coef = coef;
+  P.nt = nt;
+  P.nz = nz;
+  P.ncol = ncol;
+  P.eta = eta;
+  P.partials = nullptr;
+  return launch_any<false>(eos, T, S, t_bcast, s_bcast, P, st);
+}
+
+int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
+                  int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
+                  cudaStream_t st) {
+  Params P;
+  P.rho_ref = nullptr;
+  P.v_ref = v_ref;
+  P.v_f32 = vref_dtype == ML_F32;
+  P.z_i = nullptr;
+  P.deptho = nullptr;
+  P.p_level = p_level;
+  P.coef = 0.0;
+  P.nt = nt;
+  P.nz = nz;
+  P.ncol = ncol;
+  P.eta = nullptr;
+  P.partials = partials;
+  int rc = launch_any<true>(eos, T, S, t_bcast, s_bcast, P, st);
+  if (rc) return rc;
+  return reduce_rows(partials, (ncol + kTile - 1) / kTile, masso, nt, st);
+}
+
 bool spice_eligible(int, const void*, const void*, int64_t, const double*) { return false; }
-int launch_spice(int, const void*, const void*, int64_t, double*, cudaStream_t) { return -100; }
+int launch_spice(int, const void*, const void*, int64_t, double*, cudaStream_t) { return ML_ERR_MODE; }
 
 }  // namespace tma
 }  // namespace ml

@@ -46,7 +46,10 @@ def make_grid(nz, ny, nx, seed=123, device="cpu", land_fraction=0.3):
     coarse = torch.rand((by, bx), generator=g)
     land = coarse < land_fraction
     ry, rx = -(-ny // by), -(-nx // bx)
-    land = land.repeat_interleave(ry, 0).repeat_interleave(rx, 1)[:ny, :nx]
+    land = land.repeat_interleave(ry, 0).repeat_interleave(rx, 1)[:ny, :nx].clone()
+    if by * bx < 8:  # tiny grids: scattered land points instead of blocks, never all land
+        land = torch.rand((ny, nx), generator=g) < land_fraction
+        land[ny // 2, nx // 2] = False
     depth = torch.rand((ny, nx), generator=g, dtype=torch.float64) * (z_i[-1] - 10.0) + 10.0
     depth = torch.where(land, torch.full_like(depth, float("nan")), depth)
     area = 0.5 + torch.rand((ny, nx), generator=g, dtype=torch.float64)
