@@ -80,8 +80,17 @@ __device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
       : "d"(d), "d"(w));
 }
 
-__device__ __forceinline__ double ld_vref(const void* v, int v_f32, i64 i) {
-  return v_f32 ? (double)__ldg(reinterpret_cast<const float*>(v) + i) : __ldg(reinterpret_cast<const double*>(v) + i);
+// v_ref is prefetched one level ahead as a raw bit pattern: converting (or testing) the value
+// at load time would make the warp wait for the load it is trying to hide.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 ld_vraw(const void* v, int v_f32, i64 i) {
+  return v_f32 ? (u64)__ldg(reinterpret_cast<const unsigned*>(v) + i) : __ldg(reinterpret_cast<const u64*>(v) + i);
+}
+__device__ __forceinline__ bool vraw_isnan(u64 raw, int v_f32) {
+  return v_f32 ? (((unsigned)raw & 0x7fffffffu) > 0x7f800000u) : ((raw & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
+}
+__device__ __forceinline__ double vraw_value(u64 raw, int v_f32) {
+  return v_f32 ? (double)__uint_as_float((unsigned)raw) : __longlong_as_double((long long)raw);
 }
 
 struct Params {
@@ -111,6 +120,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
   uint64_t* empty = full + kStages;
   double* red = reinterpret_cast<double*>(empty + kStages);  // GLOBAL: [kConsumerWarps][TC]
+  double* s_p = red + kConsumerWarps * TC;                   // [nz]   pressure per level
+  double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local only)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = blockIdx.x * kTile;
@@ -126,6 +137,9 @@ __global__ void __launch_bounds__(kThreads, 2)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < P.nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
+  if (!GLOBAL)
+    for (int i = threadIdx.x; i <= P.nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
   __syncthreads();
 
   double acc[TC];
@@ -157,33 +171,33 @@ __global__ void __launch_bounds__(kThreads, 2)
       depth = __ldg(P.deptho + cc);
       if (isnan(depth)) depth = 0.0;  // derived.py:295
     }
-    // per-level operands, fetched one level ahead
-    double rref_n = 0.0, v_n = 0.0;
-    {
-      v_n = ld_vref(P.v_ref, P.v_f32, cc);
-      if (!GLOBAL) rref_n = __ldg(P.rho_ref + cc);
-    }
-    const bool surface_wet = !isnan(v_n);  // steric.py:166
+    // per-level operands, fetched one level ahead (raw bits, see ld_vraw)
+    double rref_n = 0.0;
+    u64 v_n = ld_vraw(P.v_ref, P.v_f32, cc);
+    if (!GLOBAL) rref_n = __ldg(P.rho_ref + cc);
+    const bool surface_wet = !vraw_isnan(v_n, P.v_f32);  // steric.py:166
     for (int z = 0; z < nz; ++z) {
       const int s = z % kStages;
-      const double rref_z = rref_n, v_z = v_n;
+      const double rref_z = rref_n;
+      const u64 v_z = v_n;
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
-        v_n = ld_vref(P.v_ref, P.v_f32, j);
+        v_n = ld_vraw(P.v_ref, P.v_f32, j);
         if (!GLOBAL) rref_n = __ldg(P.rho_ref + j);
       }
       // weight of this cell in the sum and the value subtracted from rho
+      const bool dry = vraw_isnan(v_z, P.v_f32);
       double w, sub;
       if (GLOBAL) {
-        w = isnan(v_z) ? 0.0 : v_z;  // rho * NaN is dropped by the skipna sum (derived.py:435-438)
+        w = dry ? 0.0 : vraw_value(v_z, P.v_f32);  // rho * NaN is dropped by the skipna sum (derived.py:435-438)
         sub = 0.0;
       } else {
-        w = clipped_dz(depth, __ldg(P.z_i + z), __ldg(P.z_i + z + 1));
+        w = clipped_dz(depth, s_zi[z], s_zi[z + 1]);
         // steric.py:151-153: delta_rho is NaN (and skipped) wherever the reference volume is missing
-        sub = isnan(v_z) ? nan("") : rref_z;
-        if (is_nan_q(sub + 0.0)) w = 0.0;
+        sub = rref_z;
+        if (dry || isnan(rref_z)) w = 0.0;
       }
-      eos.set_level(__ldg(P.p_level + z));
+      eos.set_level(s_p[z]);
       mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
       if (__any_sync(0xffffffffu, w != 0.0)) {
         const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
@@ -260,7 +274,7 @@ static bool common_eligible(int dtype, const void* T, const void* S, int64_t nt,
   if (dtype != ML_F32) return false;
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
   if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
-  if (nt < 1 || nz < 1) return false;
+  if (nt < 1 || nz < 1 || nz > 512) return false;
   // TMA global strides must stay below 2^40 bytes
   if ((double)ncol * (double)nz * 4.0 >= 1099511627776.0) return false;
   return encode_fn() != nullptr;
@@ -277,21 +291,21 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
 }
 
 template <int TC>
-constexpr size_t smem_bytes(int bc) {
+inline size_t smem_bytes(int bc, int nz) {
   return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
-         (size_t)kConsumerWarps * TC * sizeof(double) + 128;
+         (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 128;
 }
 
 template <int EOS, int TC, int BC, bool GLOBAL>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
   auto kern = k_steric_tma<EOS, TC, BC, GLOBAL>;
-  const size_t smem = smem_bytes<TC>(BC);
-  static bool configured = false;  // per instantiation
-  if (!configured) {
+  const size_t smem = smem_bytes<TC>(BC, P.nz);
+  static size_t configured = 0;  // per instantiation: largest size opted in so far
+  if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma)");
-    configured = true;
+    configured = smem;
   }
   kern<<<dim3(tiles, chunks), kThreads, smem, st>>>(mT, mS, P);
   return launched("k_steric_tma");

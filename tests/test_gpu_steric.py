@@ -277,13 +277,19 @@ def big(ml):
 
 
 def test_property_reference_step_is_zero(ml, big):
-    """Step 0 is the reference state: eta(t=0) == 0 exactly wherever the column is wet."""
+    """Step 0 is the reference state: eta(t=0) vanishes wherever the column is wet.
+
+    The reference gets exact zeros (it evaluates the same numpy expression twice).  Here
+    rho_ref is rounded to fp64 when the reference-state kernel stores it, while the fused
+    kernel subtracts it from the unrounded product inside one FMA, so eta(0) is the rounding
+    residue of rho_ref integrated over the column: ~1e-14 m, five orders below tolerance.
+    """
     result, reference = ml.steric(big)
     eta0 = result["steric"].data[0]
     wet = ~torch.isnan(reference["volcello"].data[0])
-    assert torch.all(eta0[wet] == 0.0) and torch.all(torch.isnan(eta0[~wet]))
+    assert float(eta0[wet].abs().max()) < 1e-12 and torch.all(torch.isnan(eta0[~wet]))
     g, _ = ml.steric(big, domain="global", reference=reference)
-    assert float(g["steric"].values[0]) == 0.0
+    assert abs(float(g["steric"].values[0])) < 1e-11
 
 
 def test_property_linear_eos_is_additive(ml, big):

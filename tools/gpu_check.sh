@@ -32,7 +32,7 @@ for s in $STAGES; do
       echo "[nculist] exit $?"; tail -3 gpurun_out/ncu_list.log ;;
     ncufull)
       timeout 600 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_plain2.log 2>&1 &&
-      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_steric_local -s 1 -c 2 \
+      timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_steric -s 1 -c 1 \
           -o gpurun_out/prof_local python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu --no-extras > gpurun_out/ncu_full.log 2>&1
       echo "[ncufull] exit $?"; tail -3 gpurun_out/ncu_full.log ;;
   esac
