@@ -145,6 +145,23 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ml_steric_local_selfref -- ml_reference_state + ml_steric_local in one pass when the
+ * reference state is the first time step of the dataset itself, which is what
+ * steric.steric does when no `reference` is supplied (src/momlevel/steric.py:105-107 ->
+ * reference.py:60-80 with time_index = 0).  rho_ref is evaluated from the step-0 rows that
+ * the column integral reads anyway, stored for the caller and reduced into volo / masso,
+ * so T and S cross HBM once for the whole call.
+ *   T, S        as ml_steric_local; a broadcast operand IS the reference slab of that field
+ *   v_ref       [nz][ncol] volcello at step 0
+ *   rho_ref     [nz][ncol] fp64 out;  sums device fp64[2] out {volo, masso}
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, int t_bcast,
+                            int s_bcast, const void* v_ref, int vref_dtype, const double* z_i,
+                            const double* deptho, const double* p_level, double neg_inv_rhozero,
+                            int64_t nt, int64_t nz, int64_t ncol, double* eta, double* rho_ref,
+                            double* sums, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * ml_steric_global -- fused EOS -> sum_{z,col} rho * v_ref per time step.
  * Replaces calc_masso(rho, reference["volcello"]) in the global branch
  * (src/momlevel/steric.py:135, derived.py:435-438); the ln() formula (steric.py:136-142)

@@ -19,6 +19,7 @@ __all__ = [
     "calc_dz",
     "reference_state",
     "steric_local",
+    "steric_local_selfref",
     "steric_global",
     "steric_local_host",
     "last_path",
@@ -236,6 +237,30 @@ def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos
                           drho.data_ptr() if drho is not None else None, _stream())
     )
     return eta, drho
+
+
+def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False, s_bcast=False):
+    """``setup_reference_state`` + the local branch in one pass; reference = step 0 (steric.py:105-107).
+
+    A broadcast operand is the step-0 slab of that field.  Returns
+    ``(eta [nt,...], rho_ref [nz,...], sums fp64[2] = {volo, masso})`` on the device.
+    """
+    L = _lib.lib()
+    T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
+    v_ref = to_device(v_ref)
+    z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
+    assert v_ref.numel() == nz * ncol and depth.numel() == ncol and z_i.numel() == nz + 1 and p.numel() == nz
+    eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
+    rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+    sums = torch.empty(2, dtype=torch.float64, device=T.device)
+    ws, nbytes = _workspace(2, nz, ncol, T.device)
+    _lib.check(
+        L.ml_steric_local_selfref(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                                  v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(), p.data_ptr(),
+                                  -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(), rho.data_ptr(), sums.data_ptr(),
+                                  ws.data_ptr(), nbytes, _stream())
+    )
+    return eta, rho, sums
 
 
 def steric_global(T, S, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):

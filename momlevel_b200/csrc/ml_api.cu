@@ -103,7 +103,8 @@ __global__ void __launch_bounds__(kBlock) k_reduce_rows(const double* __restrict
 // ------------------------------------------------------------------ K2: reference state
 template <typename TIn, int EOS>
 __global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restrict__ T0, const TIn* __restrict__ S0,
-                                                            const TIn* __restrict__ V0, const double* __restrict__ p_level,
+                                                            const void* __restrict__ V0, int v_f32,
+                                                            const double* __restrict__ p_level,
                                                             int nz, i64 ncol, double* __restrict__ rho_ref,
                                                             double* __restrict__ partials /* [2][gridDim.x] */) {
   __shared__ double sm[kWarps];
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restric
       const i64 i = (i64)z * ncol + c;
       eos.set_level(__ldg(p_level + z));
       const double rho = eos.rho(ldf(T0 + i), ldf(S0 + i));
-      const double v = ldf(V0 + i);
+      const double v = vref_val(V0, v_f32, i);
       rho_ref[i] = rho;
       if (!isnan(v)) {  // nansum (derived.py:787-789, :435-438)
         vol += v;
@@ -378,11 +379,12 @@ int ml_calc_dz(const double* z_i, const double* deptho, double top, double botto
   return launched("k_calc_dz");
 }
 
-int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const void* V0, const double* p_level,
-                       int64_t nz, int64_t ncol, double* rho_ref, double* sums, void* workspace, size_t workspace_bytes,
-                       void* stream) {
+static int reference_state_impl(int eos, int dtype, const void* T0, const void* S0, const void* V0, int v_dtype,
+                                const double* p_level, int64_t nz, int64_t ncol, double* rho_ref, double* sums,
+                                void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_common(eos, dtype);
   if (rc) return rc;
+  if (v_dtype != ML_F32 && v_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown volcello dtype id %d", v_dtype);
   ML_REQUIRE_PTR(T0);
   ML_REQUIRE_PTR(S0);
   ML_REQUIRE_PTR(V0);
@@ -396,8 +398,9 @@ int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)workspace;
   const i64 nblk = cdiv(ncol, kBlock);
+  const int v_f32 = v_dtype == ML_F32;
 #define ML_LAUNCH_REF(TIN, E) \
-  k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, (const TIN*)V0, p_level, (int)nz, ncol, rho_ref, partials)
+  k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, V0, v_f32, p_level, (int)nz, ncol, rho_ref, partials)
   if (dtype == ML_F32) {
     if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REF(float, 0); else ML_LAUNCH_REF(float, 1);
   } else {
@@ -407,6 +410,54 @@ int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const
   if ((rc = launched("k_reference_state"))) return rc;
   k_reduce_rows<<<2, kBlock, 0, st>>>(partials, nblk, sums);
   return launched("k_reduce_rows");
+}
+
+int ml_reference_state(int eos, int dtype, const void* T0, const void* S0, const void* V0, const double* p_level,
+                       int64_t nz, int64_t ncol, double* rho_ref, double* sums, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+  return reference_state_impl(eos, dtype, T0, S0, V0, dtype, p_level, nz, ncol, rho_ref, sums, workspace,
+                              workspace_bytes, stream);
+}
+
+int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                            const void* v_ref, int vref_dtype, const double* z_i, const double* deptho,
+                            const double* p_level, double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                            double* eta, double* rho_ref, double* sums, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(z_i);
+  ML_REQUIRE_PTR(deptho);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(eta);
+  ML_REQUIRE_PTR(rho_ref);
+  ML_REQUIRE_PTR(sums);
+  if (nt <= 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
+    return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
+  ML_REQUIRE_ALIGNED(workspace, 8);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!tls().force_direct &&
+      tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref, vref_dtype, nt, nz, ncol, eta, nullptr)) {
+    tls().last_path = ML_PATH_TMA;
+    return tma::launch_selfref(eos, T, S, t_bcast, s_bcast, v_ref, vref_dtype, z_i, deptho, p_level, neg_inv_rhozero,
+                               (int)nt, (int)nz, ncol, eta, rho_ref, sums, (double*)workspace, st);
+  }
+  // direct family: the reference-state pass, then the column integral against its rho_ref.
+  // The reference T, S are the first step of whichever operand carries the time axis.
+  rc = reference_state_impl(eos, dtype, T, S, v_ref, vref_dtype, p_level, nz, ncol, rho_ref, sums, workspace,
+                            workspace_bytes, stream);
+  if (rc) return rc;
+  return ml_steric_local(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
+                         neg_inv_rhozero, nt, nz, ncol, eta, nullptr, stream);
 }
 
 int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,

@@ -98,14 +98,14 @@ extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const voi
 
     ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
     int rc;
-    if (w == 0) {  // reference state from time step 0 (reference.py:60-80)
-      rc = ml_reference_state(eos, dtype, dT[0], dS[0], dV, (const double*)dP, nz, ncol, (double*)dRho,
-                              (double*)dSums, dWs, ws_bytes, r.comp);
-      if (rc) return rc;
-    }
-    rc = ml_steric_local(eos, dtype, dT[b], dS[b], 0, 0, (const double*)dRho, dV, dtype, (const double*)dZi,
-                         (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
-                         (double*)dEta + (size_t)t_first * ncol, nullptr, r.comp);
+    if (w == 0)  // the window that starts at the reference step (reference.py:60-80): fused pass
+      rc = ml_steric_local_selfref(eos, dtype, dT[0], dS[0], 0, 0, dV, dtype, (const double*)dZi,
+                                   (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
+                                   (double*)dEta, (double*)dRho, (double*)dSums, dWs, ws_bytes, r.comp);
+    else
+      rc = ml_steric_local(eos, dtype, dT[b], dS[b], 0, 0, (const double*)dRho, dV, dtype, (const double*)dZi,
+                           (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
+                           (double*)dEta + (size_t)t_first * ncol, nullptr, r.comp);
     if (rc) return rc;
     ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
   }

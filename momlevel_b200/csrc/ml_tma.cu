@@ -94,38 +94,52 @@ __device__ __forceinline__ double vraw_value(u64 raw, int v_f32) {
 }
 
 struct Params {
-  const double* rho_ref;  // local only
+  const double* rho_ref;  // kLocal: read
+  double* rho_ref_out;    // kSelfRef: written (may be NULL)
   const void* v_ref;
   int v_f32;
-  const double* z_i;      // local only
-  const double* deptho;   // local only
+  const double* z_i;      // local modes
+  const double* deptho;   // local modes
   const double* p_level;
   double coef;
   int nt, nz;
+  int chunk0;             // first time chunk covered by this launch
   i64 ncol;
-  double* eta;            // local: [nt][ncol]
-  double* partials;       // global: [nt][gridDim.x]
+  double* eta;            // local modes: [nt][ncol]
+  double* partials;       // kGlobal: [nt][gridDim.x];  kSelfRef: [2][gridDim.x] = {volo, masso}
 };
 
+// What a launch computes.
+//   kLocal   eta from rho - rho_ref with rho_ref read from memory          (steric.py:150-166)
+//   kGlobal  per-step sums of rho * v_ref                                    (steric.py:135)
+//   kSelfRef kLocal for the chunk that starts at the reference step itself: rho_ref is the
+//            density of row 0 of every stage, evaluated here, stored for the caller and
+//            reduced into volo / masso on the way -- the reference-state pass
+//            (reference.py:71-80) costs no extra read of T, S.
+enum Mode { kLocal = 0, kGlobal = 1, kSelfRef = 2 };
+
 // BC: 0 = T and S both [t][z][col]; 1 = T is [z][col] (halosteric); 2 = S is [z][col] (thermosteric)
-template <int EOS, int TC, int BC, bool GLOBAL>
+template <int EOS, int TC, int BC, int MODE>
 __global__ void __launch_bounds__(kThreads, 2)
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
+  constexpr bool GLOBAL = MODE == kGlobal;
+  constexpr bool SELFREF = MODE == kSelfRef;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
   constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(float);
+  constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
   uint64_t* empty = full + kStages;
-  double* red = reinterpret_cast<double*>(empty + kStages);  // GLOBAL: [kConsumerWarps][TC]
+  double* red = reinterpret_cast<double*>(empty + kStages);  // [kConsumerWarps][TC]
   double* s_p = red + kConsumerWarps * TC;                   // [nz]   pressure per level
-  double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local only)
+  double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local modes)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = blockIdx.x * kTile;
-  const int t0 = blockIdx.y * TC;
+  const int t0 = (P.chunk0 + (int)blockIdx.y) * TC;
   const int nz = P.nz;
 
   if (tid == 0) {
@@ -141,10 +155,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   if (!GLOBAL)
     for (int i = threadIdx.x; i <= P.nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
   __syncthreads();
-
-  double acc[TC];
-#pragma unroll
-  for (int k = 0; k < TC; ++k) acc[k] = 0.0;
 
   if (warp == kConsumerWarps) {
     // ------------------------------------------------------------------ producer warp
@@ -166,6 +176,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     const bool in = c < P.ncol;
     const i64 cc = in ? c : (P.ncol - 1);  // clamp: edge lanes read a valid column, never store
     Eos<EOS> eos;
+    double acc[TC];
+#pragma unroll
+    for (int k = 0; k < TC; ++k) acc[k] = 0.0;
+    double vol = 0.0, mass = 0.0;  // kSelfRef
     double depth = 0.0;
     if (!GLOBAL) {
       depth = __ldg(P.deptho + cc);
@@ -174,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     // per-level operands, fetched one level ahead (raw bits, see ld_vraw)
     double rref_n = 0.0;
     u64 v_n = ld_vraw(P.v_ref, P.v_f32, cc);
-    if (!GLOBAL) rref_n = __ldg(P.rho_ref + cc);
+    if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
     const bool surface_wet = !vraw_isnan(v_n, P.v_f32);  // steric.py:166
     for (int z = 0; z < nz; ++z) {
       const int s = z % kStages;
@@ -183,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
         v_n = ld_vraw(P.v_ref, P.v_f32, j);
-        if (!GLOBAL) rref_n = __ldg(P.rho_ref + j);
+        if (MODE == kLocal) rref_n = __ldg(P.rho_ref + j);
       }
       // weight of this cell in the sum and the value subtracted from rho
       const bool dry = vraw_isnan(v_z, P.v_f32);
@@ -195,15 +209,26 @@ __global__ void __launch_bounds__(kThreads, 2)
         w = clipped_dz(depth, s_zi[z], s_zi[z + 1]);
         // steric.py:151-153: delta_rho is NaN (and skipped) wherever the reference volume is missing
         sub = rref_z;
-        if (dry || isnan(rref_z)) w = 0.0;
+        if (dry || (MODE == kLocal && isnan(rref_z))) w = 0.0;
       }
       eos.set_level(s_p[z]);
+      const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
+      const float* sS = sT + kRowsT * kTile;
       mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
+      if (SELFREF) {
+        // reference density of this cell = density of the chunk's first step (reference.py:60-71)
+        sub = eos.rho((double)sT[0], (double)sS[0]);
+        if (in && P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = sub;
+        if (!dry && in) {  // derived.py:787-789 / :435-438, skipna sums
+          const double v = vraw_value(v_z, P.v_f32);
+          vol += v;
+          const double m = sub * v;
+          if (!is_nan_q(m)) mass += m;
+        }
+      }
       if (__any_sync(0xffffffffu, w != 0.0)) {
-        const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
-        const float* sS = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + kRowsT * kTile + tid;
 #pragma unroll
-        for (int k = 0; k < TC; ++k) {
+        for (int k = SELFREF ? 1 : 0; k < TC; ++k) {  // kSelfRef: step 0 is the reference, its anomaly is 0
           const double Tv = (double)sT[(BC == 1 ? 0 : k) * kTile];
           const double Sv = (double)sS[(BC == 2 ? 0 : k) * kTile];
           const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
@@ -219,21 +244,30 @@ __global__ void __launch_bounds__(kThreads, 2)
         for (int k = 0; k < TC; ++k)
           if (t0 + k < P.nt) P.eta[(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[k] : nan("");
       }
-    } else {
+    }
+    if (GLOBAL) {
 #pragma unroll
       for (int k = 0; k < TC; ++k) {
         const double sacc = warp_sum(in ? acc[k] : 0.0);
         if (lane == 0) red[warp * TC + k] = sacc;
       }
+    } else if (SELFREF) {
+      vol = warp_sum(vol);
+      mass = warp_sum(mass);
+      if (lane == 0) {
+        red[warp * TC + 0] = vol;
+        red[warp * TC + 1] = mass;
+      }
     }
   }
-  if (GLOBAL) {
+  if (GLOBAL || SELFREF) {
     __syncthreads();
-    if (tid < TC && t0 + tid < P.nt) {
+    if (tid < kRed && (SELFREF || t0 + tid < P.nt)) {
       double sacc = 0.0;
 #pragma unroll
       for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * TC + tid];
-      P.partials[(i64)(t0 + tid) * gridDim.x + blockIdx.x] = sacc;
+      const i64 row = SELFREF ? tid : (t0 + tid);
+      P.partials[row * gridDim.x + blockIdx.x] = sacc;
     }
   }
 }
@@ -296,10 +330,10 @@ inline size_t smem_bytes(int bc, int nz) {
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 128;
 }
 
-template <int EOS, int TC, int BC, bool GLOBAL>
+template <int EOS, int TC, int BC, int MODE>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
-  auto kern = k_steric_tma<EOS, TC, BC, GLOBAL>;
+  auto kern = k_steric_tma<EOS, TC, BC, MODE>;
   const size_t smem = smem_bytes<TC>(BC, P.nz);
   static size_t configured = 0;  // per instantiation: largest size opted in so far
   if (smem > configured) {
@@ -311,60 +345,52 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
   return launched("k_steric_tma");
 }
 
-template <int EOS, int TC, bool GLOBAL>
+template <int EOS, int TC, int MODE>
 static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles,
                      unsigned chunks, cudaStream_t st) {
-  if (bc == 0) return launch_one<EOS, TC, 0, GLOBAL>(mT, mS, P, tiles, chunks, st);
-  if (bc == 1) return launch_one<EOS, TC, 1, GLOBAL>(mT, mS, P, tiles, chunks, st);
-  return launch_one<EOS, TC, 2, GLOBAL>(mT, mS, P, tiles, chunks, st);
+  if (bc == 0) return launch_one<EOS, TC, 0, MODE>(mT, mS, P, tiles, chunks, st);
+  if (bc == 1) return launch_one<EOS, TC, 1, MODE>(mT, mS, P, tiles, chunks, st);
+  return launch_one<EOS, TC, 2, MODE>(mT, mS, P, tiles, chunks, st);
 }
 
-template <bool GLOBAL>
-static int launch_any(int eos, const void* T, const void* S, int t_bcast, int s_bcast, Params P, cudaStream_t st) {
-  const int bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
-  const int tc = P.nt >= 12 ? 12 : (P.nt >= 8 ? 8 : 4);
+// time steps per register chunk: the largest of {12, 8, 4} that nt fills at least once
+static int plan_tc(int nt) { return nt >= 12 ? 12 : (nt >= 8 ? 8 : 4); }
+
+struct Plan {
   CUtensorMap mT, mS;
-  const bool okT = t_bcast ? make_map(&mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&mT, T, 3, P.ncol, P.nz, P.nt, tc);
-  const bool okS = s_bcast ? make_map(&mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&mS, S, 3, P.ncol, P.nz, P.nt, tc);
+  int bc, tc;
+  unsigned tiles, chunks;
+};
+
+static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P) {
+  pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
+  pl->tc = plan_tc(P.nt);
+  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc);
+  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc);
   if (!okT || !okS) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
-  const unsigned tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
-  const unsigned chunks = (unsigned)((P.nt + tc - 1) / tc);
-#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, GLOBAL>(bc, mT, mS, P, tiles, chunks, st)
+  pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
+  pl->chunks = (unsigned)((P.nt + pl->tc - 1) / pl->tc);
+  return ML_OK;
+}
+
+template <int MODE>
+static int launch_mode(int eos, const Plan& pl, const Params& P, unsigned chunks, cudaStream_t st) {
+#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, MODE>(pl.bc, pl.mT, pl.mS, P, pl.tiles, chunks, st)
   if (eos == ML_EOS_WRIGHT) {
-    if (tc == 12) ML_TMA_GO(0, 12);
-    if (tc == 8) ML_TMA_GO(0, 8);
+    if (pl.tc == 12) ML_TMA_GO(0, 12);
+    if (pl.tc == 8) ML_TMA_GO(0, 8);
     ML_TMA_GO(0, 4);
   }
-  if (tc == 12) ML_TMA_GO(1, 12);
-  if (tc == 8) ML_TMA_GO(1, 8);
+  if (pl.tc == 12) ML_TMA_GO(1, 12);
+  if (pl.tc == 8) ML_TMA_GO(1, 8);
   ML_TMA_GO(1, 4);
 #undef ML_TMA_GO
 }
 
-int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
-                 const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
-                 double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st) {
-  Params P;
-  P.rho_ref = rho_ref;
-  P.v_ref = v_ref;
-  P.v_f32 = vref_dtype == ML_F32;
-  P.z_i = z_i;
-  P.deptho = deptho;
-  P.p_level = p_level;
-  P.coef = coef;
-  P.nt = nt;
-  P.nz = nz;
-  P.ncol = ncol;
-  P.eta = eta;
-  P.partials = nullptr;
-  return launch_any<false>(eos, T, S, t_bcast, s_bcast, P, st);
-}
-
-int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
-                  int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
-                  cudaStream_t st) {
+static Params base_params(const void* v_ref, int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol) {
   Params P;
   P.rho_ref = nullptr;
+  P.rho_ref_out = nullptr;
   P.v_ref = v_ref;
   P.v_f32 = vref_dtype == ML_F32;
   P.z_i = nullptr;
@@ -373,12 +399,63 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   P.coef = 0.0;
   P.nt = nt;
   P.nz = nz;
+  P.chunk0 = 0;
   P.ncol = ncol;
   P.eta = nullptr;
-  P.partials = partials;
-  int rc = launch_any<true>(eos, T, S, t_bcast, s_bcast, P, st);
+  P.partials = nullptr;
+  return P;
+}
+
+int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                 const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
+                 double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st) {
+  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  P.rho_ref = rho_ref;
+  P.z_i = z_i;
+  P.deptho = deptho;
+  P.coef = coef;
+  P.eta = eta;
+  Plan pl;
+  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
   if (rc) return rc;
-  return reduce_rows(partials, (ncol + kTile - 1) / kTile, masso, nt, st);
+  return launch_mode<kLocal>(eos, pl, P, pl.chunks, st);
+}
+
+int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref, int vref_dtype,
+                   const double* z_i, const double* deptho, const double* p_level, double coef, int nt, int nz,
+                   int64_t ncol, double* eta, double* rho_ref, double* sums, double* partials, cudaStream_t st) {
+  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  P.rho_ref_out = rho_ref;
+  P.z_i = z_i;
+  P.deptho = deptho;
+  P.coef = coef;
+  P.eta = eta;
+  P.partials = partials;
+  Plan pl;
+  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
+  if (rc) return rc;
+  // the chunk that starts at the reference step: rho_ref, volo, masso and eta in one pass
+  if ((rc = launch_mode<kSelfRef>(eos, pl, P, 1, st))) return rc;
+  if ((rc = reduce_rows(partials, pl.tiles, sums, 2, st))) return rc;
+  if (pl.chunks > 1) {  // later chunks read the rho_ref just written (same stream: ordered)
+    P.rho_ref = rho_ref;
+    P.rho_ref_out = nullptr;
+    P.chunk0 = 1;
+    rc = launch_mode<kLocal>(eos, pl, P, pl.chunks - 1, st);
+  }
+  return rc;
+}
+
+int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
+                  int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
+                  cudaStream_t st) {
+  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  P.partials = partials;
+  Plan pl;
+  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
+  if (rc) return rc;
+  if ((rc = launch_mode<kGlobal>(eos, pl, P, pl.chunks, st))) return rc;
+  return reduce_rows(partials, pl.tiles, masso, nt, st);
 }
 
 bool spice_eligible(int, const void*, const void*, int64_t, const double*) { return false; }

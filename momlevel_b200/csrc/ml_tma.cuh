@@ -13,6 +13,11 @@ int launch_local(int eos, int dtype, const void* T, const void* S, int t_bcast, 
                  const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
                  double coef, int nt, int nz, int64_t ncol, double* eta, double* delta_rho, cudaStream_t st);
 
+// kSelfRef: reference state (rho_ref, volo, masso) and eta from one pass; reference = step 0
+int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref, int vref_dtype,
+                   const double* z_i, const double* deptho, const double* p_level, double coef, int nt, int nz,
+                   int64_t ncol, double* eta, double* rho_ref, double* sums, double* partials, cudaStream_t st);
+
 bool global_eligible(int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
                      int vref_dtype, int64_t nt, int64_t nz, int64_t ncol);
 int launch_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,

@@ -61,12 +61,17 @@ def steric(
     pres = _pressure(dset, zcoord, patm)
 
     # steric.py:98-112
+    fused_eta = None
     if reference is not None:
         assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
         if verbose:
             print("Using supplied reference state")
     else:
-        reference = setup_reference_state(dset, patm=patm, eos=equation_of_state, coord_names=coord_names)
+        if domain != "global" and variant in ("steric", "thermosteric", "halosteric"):
+            # reference state and column integral in one pass over T, S (ml_steric_local_selfref)
+            reference, fused_eta = _selfref(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord, zbounds)
+        else:
+            reference = setup_reference_state(dset, patm=patm, eos=equation_of_state, coord_names=coord_names)
         if verbose:
             print("Generating reference state from first timestep")
     validate_dataset(reference, reference=True, strict=strict)
@@ -104,11 +109,8 @@ def steric(
         args = (thetao.data, so.data, reference["rho"].data, reference["volcello"].data, dset[zbounds].data,
                 dset["deptho"].data, pres)
         kw = dict(rhozero=rhozero, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
-        # derived.py:284-292 (calc_dz's sign checks, on metadata-sized arrays)
-        assert bool(np.all(np.nan_to_num(dset["deptho"].values, nan=0.0) >= 0)), "Depth values must all be positive-definite"
-        assert bool(np.all(dset[zcoord].values >= 0)), "Vertical coordinate levels must all be positive-definite"
-        assert bool(np.all(dset[zbounds].values >= 0)), "Vertical coordinate interfaces must all be positive-definite"
-        eta, _ = core.steric_local(*args, want_delta_rho=False, **kw)
+        _check_depths(dset, zcoord, zbounds)
+        eta = fused_eta if fused_eta is not None else core.steric_local(*args, want_delta_rho=False, **kw)[0]
 
         def _delta_rho():
             return core.steric_local(*args, want_delta_rho=True, **kw)[1]
@@ -133,6 +135,41 @@ def steric(
     if xarray_in:
         return xarray_io.to_xarray(result, like=dset_x), xarray_io.to_xarray(reference, like=dset_x)
     return (result, reference)
+
+
+def _check_depths(dset, zcoord, zbounds):
+    """derived.py:284-292: calc_dz's sign checks, on metadata-sized arrays."""
+    assert bool(np.all(np.nan_to_num(dset["deptho"].values, nan=0.0) >= 0)), "Depth values must all be positive-definite"
+    assert bool(np.all(dset[zcoord].values >= 0)), "Vertical coordinate levels must all be positive-definite"
+    assert bool(np.all(dset[zbounds].values >= 0)), "Vertical coordinate interfaces must all be positive-definite"
+
+
+def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
+    """``setup_reference_state(dset)`` (reference.py:57-83) with the local column integral fused in."""
+    from .util import eos_func_from_str
+
+    eos_func_from_str(eos)
+    _check_depths(dset, zcoord, zbounds)
+    reference = Dataset()
+    for name in ("thetao", "so", "volcello"):
+        reference[name] = dset[name].isel({tcoord: 0}).squeeze().reset_coords(drop=True)
+    T = reference["thetao"].data if variant == "halosteric" else dset["thetao"].data
+    S = reference["so"].data if variant == "thermosteric" else dset["so"].data
+    eta, rho, sums = core.steric_local_selfref(
+        T, S, reference["volcello"].data, dset[zbounds].data, dset["deptho"].data, pres, rhozero=rhozero, eos=eos,
+        t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric")
+    volo, masso = (float(x) for x in sums.cpu())
+    reference["rho"] = DataArray(rho, reference["thetao"].dims, attrs={
+        "standard_name": "sea_water_density", "long_name": "In situ sea water density",
+        "comment": f"calculated with the {eos} equation of state", "units": "kg m-3"})
+    reference["volo"] = DataArray(np.float64(volo), (), attrs={
+        "standard_name": "sea_water_volume", "long_name": "Sea Water Volume", "units": "m3"})
+    reference["masso"] = DataArray(np.float64(masso), (), attrs={
+        "standard_name": "sea_water_mass", "long_name": "Sea Water Mass", "units": "kg"})
+    reference["rhoga"] = DataArray(np.float64(masso) / np.float64(volo), (), attrs={
+        "long_name": "Global Average Sea Water Density", "units": "kg m-3"})
+    reference["areacello"] = dset["areacello"]
+    return reference, eta
 
 
 def halosteric(*args, **kwargs):

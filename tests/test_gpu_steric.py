@@ -279,17 +279,50 @@ def big(ml):
 def test_property_reference_step_is_zero(ml, big):
     """Step 0 is the reference state: eta(t=0) vanishes wherever the column is wet.
 
-    The reference gets exact zeros (it evaluates the same numpy expression twice).  Here
-    rho_ref is rounded to fp64 when the reference-state kernel stores it, while the fused
-    kernel subtracts it from the unrounded product inside one FMA, so eta(0) is the rounding
-    residue of rho_ref integrated over the column: ~1e-14 m, five orders below tolerance.
+    With the reference built from the dataset itself (the fused self-reference pass) the zero
+    is exact, as in the reference.  With a *supplied* reference, rho_ref arrives rounded to
+    fp64 while the kernel subtracts it from the unrounded product inside one FMA, so eta(0) is
+    the rounding residue of rho_ref integrated over the column: ~1e-14 m.
     """
     result, reference = ml.steric(big)
     eta0 = result["steric"].data[0]
     wet = ~torch.isnan(reference["volcello"].data[0])
+    assert torch.all(eta0[wet] == 0.0) and torch.all(torch.isnan(eta0[~wet]))
+    again, _ = ml.steric(big, reference=reference)
+    eta0 = again["steric"].data[0]
     assert float(eta0[wet].abs().max()) < 1e-12 and torch.all(torch.isnan(eta0[~wet]))
+    a, b = result["steric"].data, again["steric"].data
+    assert float(torch.nan_to_num(a - b).abs().max()) < 1e-12
     g, _ = ml.steric(big, domain="global", reference=reference)
     assert abs(float(g["steric"].values[0])) < 1e-11
+
+
+@pytest.mark.parametrize("shape", [(14, 9, 16, 64), (3, 10, 37, 53), (5, 75, 8, 96)])
+@pytest.mark.parametrize("bcast", ["none", "t", "s"])
+@pytest.mark.parametrize("eos", ["Wright", "linear"])
+def test_selfref_equals_two_pass(ml, shape, bcast, eos):
+    """ml_steric_local_selfref == ml_reference_state followed by ml_steric_local, both families."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(*shape, seed=21, device="cuda", dtype=torch.float32)
+    T, S, V = ds["thetao"].data, ds["so"].data, ds["volcello"].data[0]
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    Tin = T[0].contiguous() if bcast == "t" else T
+    Sin = S[0].contiguous() if bcast == "s" else S
+    kw = dict(eos=eos, t_bcast=bcast == "t", s_bcast=bcast == "s")
+    rho2, sums2 = core.reference_state(T[0], S[0], V, pres, eos=eos)
+    eta2, _ = core.steric_local(Tin, Sin, rho2, V, ds["z_i"].data, ds["deptho"].data, pres, **kw)
+    for direct in (False, True):
+        prev = core.force_direct(direct)
+        try:
+            eta1, rho1, sums1 = core.steric_local_selfref(Tin, Sin, V, ds["z_i"].data, ds["deptho"].data, pres, **kw)
+        finally:
+            core.force_direct(prev)
+        assert torch.equal(torch.isnan(rho1), torch.isnan(rho2))
+        assert torch.equal(torch.nan_to_num(rho1), torch.nan_to_num(rho2))  # bit-identical reference density
+        assert torch.allclose(sums1, sums2, rtol=1e-13, atol=0)
+        assert torch.equal(torch.isnan(eta1), torch.isnan(eta2))
+        assert float(torch.nan_to_num(eta1 - eta2).abs().max()) < 1e-12
 
 
 def test_property_linear_eos_is_additive(ml, big):
