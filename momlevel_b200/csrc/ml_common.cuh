@@ -81,20 +81,26 @@ struct Eos<0> {
   double b0p;
   __device__ __forceinline__ Eos() : K(kWrightC), b0p(0.0) {}
   __device__ __forceinline__ void set_level(double p) { b0p = K.b0 + p; }
-  __device__ __forceinline__ void terms(double T, double S, double& pp, double& den) const {
+  __device__ __forceinline__ void terms(double T, double S, double b0p_, double& pp, double& den) const {
     const double al0 = fma(K.a2, S, fma(K.a1, T, K.a0));
-    pp = fma(T, fma(K.b5, S, fma(T, fma(K.b3, T, K.b2), K.b1)), fma(K.b4, S, b0p));
+    pp = fma(T, fma(K.b5, S, fma(T, fma(K.b3, T, K.b2), K.b1)), fma(K.b4, S, b0p_));
     const double lam = fma(T, fma(K.c5, S, fma(T, fma(K.c3, T, K.c2), K.c1)), fma(K.c4, S, K.c0));
     den = fma(al0, pp, lam);
   }
   __device__ __forceinline__ double rho(double T, double S) const {
     double pp, den;
-    terms(T, S, pp, den);
+    terms(T, S, b0p, pp, den);
+    return div_lean(pp, den);
+  }
+  // density at another level's pressure without disturbing the current level
+  __device__ __forceinline__ double rho_at(double T, double S, double p) const {
+    double pp, den;
+    terms(T, S, K.b0 + p, pp, den);
     return div_lean(pp, den);
   }
   __device__ __forceinline__ double rho_checked(double T, double S) const {
     double pp, den;
-    terms(T, S, pp, den);
+    terms(T, S, b0p, pp, den);
     return div_checked(pp, den);
   }
 };
@@ -108,6 +114,7 @@ struct Eos<1> {
   __device__ __forceinline__ Eos() {}
   __device__ __forceinline__ void set_level(double) {}
   __device__ __forceinline__ double rho(double T, double S) const { return linear_rho(T, S); }
+  __device__ __forceinline__ double rho_at(double T, double S, double) const { return linear_rho(T, S); }
   __device__ __forceinline__ double rho_checked(double T, double S) const { return linear_rho(T, S); }
 };
 

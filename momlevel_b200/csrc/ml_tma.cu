@@ -190,9 +190,20 @@ __global__ void __launch_bounds__(kThreads, 2)
     u64 v_n = ld_vraw(P.v_ref, P.v_f32, cc);
     if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
     const bool surface_wet = !vraw_isnan(v_n, P.v_f32);  // steric.py:166
+    // kSelfRef: the reference density of level z is evaluated while level z-1 is integrated
+    // (from row 0 of the next stage), so no point of a level ever waits for it.
+    double sub_n = 0.0;
+    auto reference_cell = [&](int z) -> double {
+      const float* row = stage_base + (size_t)(z % kStages) * (kStageBytes / sizeof(float)) + tid;
+      mbar_wait(full + (z % kStages), (uint32_t)(z / kStages) & 1u);
+      const double r = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[z]);  // reference.py:60-71
+      if (in && P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = r;
+      return r;
+    };
+    if (SELFREF) sub_n = reference_cell(0);
     for (int z = 0; z < nz; ++z) {
       const int s = z % kStages;
-      const double rref_z = rref_n;
+      const double rref_z = SELFREF ? sub_n : rref_n;
       const u64 v_z = v_n;
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
@@ -210,22 +221,18 @@ __global__ void __launch_bounds__(kThreads, 2)
         // steric.py:151-153: delta_rho is NaN (and skipped) wherever the reference volume is missing
         sub = rref_z;
         if (dry || (MODE == kLocal && isnan(rref_z))) w = 0.0;
+        if (SELFREF && in && !dry) {  // volo, masso: skipna sums (derived.py:787-789, :435-438)
+          const double v = vraw_value(v_z, P.v_f32);
+          vol += v;
+          const double m = rref_z * v;
+          if (!is_nan_q(m)) mass += m;
+        }
       }
       eos.set_level(s_p[z]);
       const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
       const float* sS = sT + kRowsT * kTile;
       mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
-      if (SELFREF) {
-        // reference density of this cell = density of the chunk's first step (reference.py:60-71)
-        sub = eos.rho((double)sT[0], (double)sS[0]);
-        if (in && P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = sub;
-        if (!dry && in) {  // derived.py:787-789 / :435-438, skipna sums
-          const double v = vraw_value(v_z, P.v_f32);
-          vol += v;
-          const double m = sub * v;
-          if (!is_nan_q(m)) mass += m;
-        }
-      }
+      if (SELFREF && z + 1 < nz) sub_n = reference_cell(z + 1);
       if (__any_sync(0xffffffffu, w != 0.0)) {
 #pragma unroll
         for (int k = SELFREF ? 1 : 0; k < TC; ++k) {  // kSelfRef: step 0 is the reference, its anomaly is 0

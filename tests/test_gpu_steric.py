@@ -337,7 +337,10 @@ def test_property_linear_eos_is_additive(ml, big):
 
 
 def test_property_kernel_families_agree_and_are_deterministic(ml, big):
-    r1, ref = ml.steric(big)
+    r0, ref = ml.steric(big)
+    r0b, _ = ml.steric(big)
+    assert torch.equal(torch.nan_to_num(r0["steric"].data), torch.nan_to_num(r0b["steric"].data))
+    r1, _ = ml.steric(big, reference=ref)
     r2, _ = ml.steric(big, reference=ref)
     assert torch.equal(torch.nan_to_num(r1["steric"].data), torch.nan_to_num(r2["steric"].data))
     g1, _ = ml.steric(big, domain="global", reference=ref)
