@@ -287,8 +287,15 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes / (k3_avg_ms * 1e-3) / 1e9
+    traffic = None  # dram__bytes_read + dram__bytes_write of one launch, from the committed ncu capture
+    try:
+        tr = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(args.workload)
+        if tr and path == "tma":
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": f"ml_steric_local_selfref ({path} family)", "kernel_ms": k3_avg_ms,
+                "traffic": traffic, "kernel": f"ml_steric_local_selfref ({path} family)", "kernel_ms": k3_avg_ms,
                 "kernel_share_of_step": k3_avg_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}

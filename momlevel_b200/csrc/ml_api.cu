@@ -65,6 +65,38 @@ __global__ void __launch_bounds__(kBlock) k_spice(const TIn* __restrict__ T, con
     out[i] = flament_spice(ldf(T + i), ldf(S + i));
 }
 
+// Vectorised variant: four consecutive points per thread, 128-bit loads and stores, streaming
+// cache hints (every byte is touched once).  Needs 16-byte aligned pointers; the host falls
+// back to k_spice for the ragged tail.
+__device__ __forceinline__ void ld4(const float* p, double v[4]) {
+  float4 f;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p));
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double v[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
+}
+__device__ __forceinline__ void st4(double* p, const double v[4]) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(kBlock) k_spice_vec(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 n4,
+                                                      double* __restrict__ out) {
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 q = (i64)blockIdx.x * kBlock + threadIdx.x; q < n4; q += stride) {
+    double t[4], s[4], r[4];
+    ld4(T + 4 * q, t);
+    ld4(S + 4 * q, s);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = flament_spice(t[j], s[j]);
+    st4(out + 4 * q, r);
+  }
+}
+
 // ------------------------------------------------------------------------------- K6: dz
 __global__ void __launch_bounds__(kBlock) k_calc_dz(const double* __restrict__ z_i, const double* __restrict__ deptho,
                                                     double top, double bottom, int has_bottom, int fraction,
@@ -358,12 +390,29 @@ int ml_flament_spice(int dtype, const void* T, const void* S, int64_t n, double*
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(out, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (tma::spice_eligible(dtype, T, S, n, out)) return tma::launch_spice(dtype, T, S, n, out, st);
-  const unsigned grid = (unsigned)(cdiv(n, kBlock) < 148 * 16 ? cdiv(n, kBlock) : 148 * 16);
+  const int es = elem_size(dtype);
+  i64 done = 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (aligned && n >= 4) {
+    const i64 n4 = n / 4;
+    const unsigned grid = (unsigned)(cdiv(n4, kBlock) < 148 * 8 ? cdiv(n4, kBlock) : 148 * 8);
+    if (dtype == ML_F32)
+      k_spice_vec<float><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, n4, out);
+    else
+      k_spice_vec<double><<<grid, kBlock, 0, st>>>((const double*)T, (const double*)S, n4, out);
+    int rc = launched("k_spice_vec");
+    if (rc) return rc;
+    done = 4 * n4;
+    if (done == n) return ML_OK;
+  }
+  const i64 rest = n - done;
+  const unsigned grid = (unsigned)(cdiv(rest, kBlock) < 148 * 16 ? cdiv(rest, kBlock) : 148 * 16);
+  const char* Tt = (const char*)T + done * es;
+  const char* St = (const char*)S + done * es;
   if (dtype == ML_F32)
-    k_spice<float><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, n, out);
+    k_spice<float><<<grid, kBlock, 0, st>>>((const float*)Tt, (const float*)St, rest, out + done);
   else
-    k_spice<double><<<grid, kBlock, 0, st>>>((const double*)T, (const double*)S, n, out);
+    k_spice<double><<<grid, kBlock, 0, st>>>((const double*)Tt, (const double*)St, rest, out + done);
   return launched("k_spice");
 }
 

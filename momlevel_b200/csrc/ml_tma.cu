@@ -465,8 +465,5 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   return reduce_rows(partials, pl.tiles, masso, nt, st);
 }
 
-bool spice_eligible(int, const void*, const void*, int64_t, const double*) { return false; }
-int launch_spice(int, const void*, const void*, int64_t, double*, cudaStream_t) { return ML_ERR_MODE; }
-
 }  // namespace tma
 }  // namespace ml

@@ -27,8 +27,6 @@ int launch_global(int eos, int dtype, const void* T, const void* S, int t_bcast,
 // fixed-order second reduction stage (defined in ml_api.cu): out[r] = sum_b partials[r][b]
 int reduce_rows(const double* partials, int64_t nblk, double* out, int nrows, cudaStream_t st);
 
-bool spice_eligible(int dtype, const void* T, const void* S, int64_t n, const double* out);
-int launch_spice(int dtype, const void* T, const void* S, int64_t n, double* out, cudaStream_t st);
 
 }  // namespace tma
 }  // namespace ml

@@ -1,0 +1,79 @@
+"""Sharding the steric path over the GPUs of one box (one process per GPU).
+
+Every water column and every time step is independent given the reference state
+(src/momlevel/steric.py:150-166 has no horizontal coupling), so the time axis -- or the
+member axis of an ensemble -- is cut into contiguous blocks, one per rank, with no halo and no
+collective on the data path.  The only exchange is the gather of the per-step global mass
+series ``M(t)`` (<= a few hundred doubles) before the ``ln`` formula of steric.py:136-142.
+
+``torch.distributed`` is the plumbing: NCCL over NVLink on GPUs, gloo in the CPU tests.
+"""
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+__all__ = ["shard_range", "shard_sizes", "assign_members", "gather_series", "global_sea_level",
+           "steric_global_sharded"]
+
+
+def shard_sizes(n, world):
+    """Sizes of ``world`` contiguous blocks covering ``n`` items; the first ``n % world`` get one more."""
+    base, extra = divmod(int(n), int(world))
+    return [base + (1 if r < extra else 0) for r in range(world)]
+
+
+def shard_range(n, world, rank):
+    """``(start, stop)`` of this rank's block, e.g. 365 steps on 8 ranks -> 46,46,46,46,46,45,45,45."""
+    sizes = shard_sizes(n, world)
+    start = sum(sizes[:rank])
+    return start, start + sizes[rank]
+
+
+def assign_members(n_members, world, rank):
+    """Ensemble members owned by ``rank`` (contiguous blocks; 30 members on 8 ranks -> 4,4,4,4,4,4,3,3)."""
+    start, stop = shard_range(n_members, world, rank)
+    return list(range(start, stop))
+
+
+def gather_series(local, n_total, group=None):
+    """All-gather the ranks' contiguous shards of a 1-D series into the full series on every rank.
+
+    ``local`` is this rank's block (length ``shard_sizes(n_total, world)[rank]``), a tensor on
+    the device the process group communicates with.  Blocks are padded to a common length so
+    a single ``all_gather_into_tensor`` moves them.
+    """
+    if not dist.is_available() or not dist.is_initialized():
+        assert local.numel() == n_total
+        return local.clone()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = shard_sizes(n_total, world)
+    assert local.numel() == sizes[rank], f"rank {rank} holds {local.numel()} values, expected {sizes[rank]}"
+    width = max(sizes)
+    send = torch.zeros(width, dtype=local.dtype, device=local.device)
+    send[: local.numel()] = local
+    recv = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, width)
+    return torch.cat([recv[r, : sizes[r]] for r in range(world)])
+
+
+def global_sea_level(masso, volo, rhoga, area_sum):
+    """steric.py:136-142: ``(volo / sum(areacello)) * ln(rhoga / (masso / volo))`` on the host."""
+    masso = np.asarray(masso, dtype=np.float64)
+    reference_height = np.float64(volo) / np.float64(area_sum)
+    return reference_height * np.log(np.float64(rhoga) / (masso / np.float64(volo))), reference_height
+
+
+def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_sum, n_total, eos="Wright", group=None):
+    """Global steric series with the time axis sharded over ranks.
+
+    Each rank passes its own contiguous block of time steps ``T_local, S_local`` (resident on
+    its GPU) plus the shared reference volume; returns ``(eta[n_total], reference_height)`` on
+    every rank.
+    """
+    from . import core
+
+    masso_local = core.steric_global(T_local, S_local, v_ref, p_level, eos=eos)
+    masso = gather_series(masso_local, n_total, group=group)
+    return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
