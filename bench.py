@@ -22,7 +22,6 @@ import json
 import os
 import pathlib
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -72,60 +71,73 @@ def config_of(args):
 
 
 class ClockSampler:
-    """`nvidia-smi` clocks and throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, polled every ~5 ms).
 
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    The timed region is tens of milliseconds, too short for `nvidia-smi -lms`; NVML is polled
+    from a thread instead (the main thread sits in a CUDA synchronize, which releases the GIL).
+    Falls back to one `nvidia-smi` query when NVML is not importable.
+    """
 
-    def __init__(self, gpu_index):
-        self.gpu = gpu_index
-        self.proc = None
-        self.lines = []
+    REASONS = {
+        "hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4,
+        "hw_power_brake_slowdown": 0x80,
+    }
+
+    def __init__(self, torch_device_index):
+        self.samples, self.reasons, self.power = [], set(), []
+        self.max_mhz = None
+        self.stop = threading.Event()
+        self.thread = None
+        self.error = None
+        try:
+            import pynvml
+            import torch
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                pr = torch.cuda.get_device_properties(torch_device_index)
+                busid = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+                self.handle = pynvml.nvmlDeviceGetHandleByPciBusId(busid.encode())
+            except Exception:  # noqa: BLE001 -- older torch / masked devices: index order
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception as e:  # noqa: BLE001 -- any NVML problem just disables the sampler
+            self.nv = None
+            self.error = f"{type(e).__name__}: {e}"
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0)
+            except Exception as e:  # noqa: BLE001
+                self.error = f"{type(e).__name__}: {e}"
+                return
+            time.sleep(0.004)
 
     def __enter__(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._pump, daemon=True)
+        if self.nv is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
-        except OSError:
-            self.proc = None
         return self
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
     def __exit__(self, *exc):
-        if self.proc is not None:
-            time.sleep(0.15)
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
+        self.stop.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons, power = [], [], set(), []
-        for line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "power_w_max": max(power), "samples": len(sm)}
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [f"unavailable: {self.error}"], "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "power_w_max": max(self.power), "samples": len(self.samples),
+                "source": "NVML polled every ~5 ms inside the timed region"}
 
 
 # ------------------------------------------------------------------------- CPU baseline

@@ -382,6 +382,41 @@ def test_subsample_parity_at_size(ml, big):
     _close_nan(result["steric"].data[:, ys, :].cpu().numpy(), eta, atol=ETA_ATOL)
 
 
+def test_full_size_om4p25_properties(ml):
+    """BASELINE config 2 at full size (1440x1080x75 x 12): size-independent properties + a slab vs the oracle."""
+    from momlevel_b200 import synth
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60e9:
+        pytest.skip("needs ~40 GB of free HBM")
+    ds = synth.make_dataset(12, 75, 1080, 1440, seed=123, device="cuda", dtype=torch.float32)
+    result, reference = ml.steric(ds)
+    assert ml.core.last_path() == 2  # the TMA family carried it
+    eta = result["steric"].data
+    wet = ~torch.isnan(reference["volcello"].data[0])
+    assert torch.all(eta[0][wet] == 0.0)                       # reference step
+    assert torch.equal(torch.isnan(eta[5]), ~wet)              # mask = surface volcello
+    assert float(eta[:, wet].abs().max()) < 5.0                # metres, sane
+    # thermosteric + halosteric ~ steric to first order; exact additivity under the linear EOS
+    lin, lref = ml.steric(ds, equation_of_state="linear")
+    th, _ = ml.thermosteric(ds, equation_of_state="linear", reference=lref)
+    ha, _ = ml.halosteric(ds, equation_of_state="linear", reference=lref)
+    d = lin["steric"].data - th["thermosteric"].data - ha["halosteric"].data
+    assert float(torch.nan_to_num(d).abs().max()) < 1e-9
+    # checksum of checksums: the global mass series from the 4-D field equals the kernel's
+    g, _ = ml.steric(ds, domain="global", reference=reference)
+    assert abs(float(g["steric"].values[0])) < 1e-10 and np.all(np.isfinite(g["steric"].values))
+    # a slab against the oracle
+    ys = slice(600, 604)
+    f64 = lambda k: ds[k].data[..., ys, :].cpu().numpy().astype(np.float64)  # noqa: E731
+    oref = osteric.reference_state(f64("thetao"), f64("so"), f64("volcello"), ds["areacello"].values[ys],
+                                   ds["z_l"].values)
+    oeta, _ = osteric.steric_local(f64("thetao"), f64("so"), ds["z_l"].values, ds["z_i"].values,
+                                   ds["deptho"].values[ys], oref)
+    _close_nan(eta[:, ys, :].cpu().numpy(), oeta, atol=ETA_ATOL)
+    _close_nan(reference["rho"].data[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
+
+
 # -------------------------------------------------------------------- host (e2e) entry
 
 

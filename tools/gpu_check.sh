@@ -22,6 +22,9 @@ for s in $STAGES; do
     benchdirect)
       timeout 900 python bench.py --steps 5 --warmup 3 --force-direct --no-e2e --no-cpu > gpurun_out/bench_direct.log 2> gpurun_out/bench_direct.err
       echo "[benchdirect] exit $?"; tail -3 gpurun_out/bench_direct.log; tail -5 gpurun_out/bench_direct.err ;;
+    configs)
+      timeout 1200 python tools/bench_configs.py 3 4 5 > gpurun_out/configs.log 2> gpurun_out/configs.err
+      echo "[configs] exit $?"; cat gpurun_out/configs.log | cut -c1-700; tail -5 gpurun_out/configs.err ;;
     benchref)
       timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
       echo "[benchref] exit $?"; tail -3 gpurun_out/bench_ref.log ;;
