@@ -27,9 +27,9 @@
 namespace ml {
 namespace tma {
 
-constexpr int kTile = 256;                    // columns per CTA = consumer threads
+constexpr int kTile = 256;                    // columns per CTA = threads per CTA
 constexpr int kConsumerWarps = kTile / 32;    // 8
-constexpr int kThreads = kTile + 32;          // + 1 producer warp
+constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
 constexpr int kStages = 4;
 
 // ------------------------------------------------------------------------- PTX wrappers
@@ -80,17 +80,29 @@ __device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
       : "d"(d), "d"(w));
 }
 
-// v_ref is prefetched one level ahead as a raw bit pattern: converting (or testing) the value
-// at load time would make the warp wait for the load it is trying to hide.
+// v_ref is prefetched one level ahead as a raw bit pattern: converting, testing or even
+// MOVing the value at load time makes the warp wait for the very load it is trying to hide
+// (25-30 % of all stall samples in two profiles).  The fp32 and the fp64 case therefore load
+// into separate registers -- a common destination would need a zero-extending move right
+// behind the load -- and the choice between them is made when the value is used.
 typedef unsigned long long u64;
-__device__ __forceinline__ u64 ld_vraw(const void* v, int v_f32, i64 i) {
-  return v_f32 ? (u64)__ldg(reinterpret_cast<const unsigned*>(v) + i) : __ldg(reinterpret_cast<const u64*>(v) + i);
+struct VRaw {
+  unsigned w32;
+  u64 w64;
+};
+__device__ __forceinline__ VRaw ld_vraw(const void* v, int v_f32, i64 i) {
+  VRaw r;
+  r.w32 = 0u;
+  r.w64 = 0ull;
+  if (v_f32) r.w32 = __ldg(reinterpret_cast<const unsigned*>(v) + i);
+  else r.w64 = __ldg(reinterpret_cast<const u64*>(v) + i);
+  return r;
 }
-__device__ __forceinline__ bool vraw_isnan(u64 raw, int v_f32) {
-  return v_f32 ? (((unsigned)raw & 0x7fffffffu) > 0x7f800000u) : ((raw & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
+__device__ __forceinline__ bool vraw_isnan(const VRaw& r, int v_f32) {
+  return v_f32 ? ((r.w32 & 0x7fffffffu) > 0x7f800000u) : ((r.w64 & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
 }
-__device__ __forceinline__ double vraw_value(u64 raw, int v_f32) {
-  return v_f32 ? (double)__uint_as_float((unsigned)raw) : __longlong_as_double((long long)raw);
+__device__ __forceinline__ double vraw_value(const VRaw& r, int v_f32) {
+  return v_f32 ? (double)__uint_as_float(r.w32) : __longlong_as_double((long long)r.w64);
 }
 
 struct Params {
@@ -119,8 +131,14 @@ struct Params {
 enum Mode { kLocal = 0, kGlobal = 1, kSelfRef = 2 };
 
 // BC: 0 = T and S both [t][z][col]; 1 = T is [z][col] (halosteric); 2 = S is [z][col] (thermosteric)
+#ifdef ML_TMA_MAXNREG  // experiment builds: explicit register cap instead of the occupancy hint
+#define ML_TMA_KERNEL_ATTR __maxnreg__(ML_TMA_MAXNREG)
+#else
+#define ML_TMA_KERNEL_ATTR __launch_bounds__(kThreads, 2)
+#endif
+
 template <int EOS, int TC, int BC, int MODE>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
@@ -132,8 +150,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
-  uint64_t* empty = full + kStages;
-  double* red = reinterpret_cast<double*>(empty + kStages);  // [kConsumerWarps][TC]
+  int* released = reinterpret_cast<int*>(full + kStages);     // [kStages] warps that are done with the stage
+  double* red = reinterpret_cast<double*>(full + 2 * kStages);  // [kConsumerWarps][TC]
   double* s_p = red + kConsumerWarps * TC;                   // [nz]   pressure per level
   double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local modes)
 
@@ -142,35 +160,35 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int t0 = (P.chunk0 + (int)blockIdx.y) * TC;
   const int nz = P.nz;
 
+  // Loads one level of this CTA's tile into a stage.  Called by thread 0 for the first kStages
+  // levels and afterwards by whichever warp is the LAST to finish with a stage (a shared-memory
+  // counter tells): the refill is issued the moment the slot is free, without a producer warp
+  // spinning on "empty" barriers and taking registers and issue slots from the math warps.
+  auto refill_stage = [&](int z) {
+    const int s = z % kStages;
+    float* dT = stage_base + (size_t)s * (kStageBytes / sizeof(float));
+    float* dS = dT + kRowsT * kTile;
+    mbar_expect_tx(full + s, kStageBytes);
+    if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
+    if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
+  };
+
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full + s, 1);
-      mbar_init(empty + s, kConsumerWarps);
+      released[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int z = 0; z < kStages && z < nz; ++z) refill_stage(z);
   }
   for (int i = threadIdx.x; i < P.nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
   if (!GLOBAL)
     for (int i = threadIdx.x; i <= P.nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
   __syncthreads();
 
-  if (warp == kConsumerWarps) {
-    // ------------------------------------------------------------------ producer warp
-    if (lane == 0) {
-      for (int z = 0; z < nz; ++z) {
-        const int s = z % kStages;
-        const uint32_t round = (uint32_t)(z / kStages);
-        if (round > 0) mbar_wait(empty + s, (round - 1) & 1u);
-        float* dT = stage_base + (size_t)s * (kStageBytes / sizeof(float));
-        float* dS = dT + kRowsT * kTile;
-        mbar_expect_tx(full + s, kStageBytes);
-        if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
-        if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
-      }
-    }
-  } else {
+  {
     // ----------------------------------------------------------------- consumer warps
     const i64 c = (i64)c0 + tid;
     const bool in = c < P.ncol;
@@ -187,7 +205,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     // per-level operands, fetched one level ahead (raw bits, see ld_vraw)
     double rref_n = 0.0;
-    u64 v_n = ld_vraw(P.v_ref, P.v_f32, cc);
+    VRaw v_n = ld_vraw(P.v_ref, P.v_f32, cc);
     if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
     const bool surface_wet = !vraw_isnan(v_n, P.v_f32);  // steric.py:166
     // kSelfRef: the reference density of level z is evaluated while level z-1 is integrated
@@ -204,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     for (int z = 0; z < nz; ++z) {
       const int s = z % kStages;
       const double rref_z = SELFREF ? sub_n : rref_n;
-      const u64 v_z = v_n;
+      const VRaw v_z = v_n;
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
         v_n = ld_vraw(P.v_ref, P.v_f32, j);
@@ -243,7 +261,11 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(empty + s);
+      if (lane == 0) {
+        // the 8th warp to leave the stage refills it with level z + kStages
+        const int before = atomicAdd(released + s, 1);
+        if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz) refill_stage(z + kStages);
+      }
     }
     if (!GLOBAL) {
       if (in) {
@@ -355,9 +377,14 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
 template <int EOS, int TC, int MODE>
 static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles,
                      unsigned chunks, cudaStream_t st) {
+#ifdef ML_TMA_FAST_BUILD  // experiment builds: only the Wright / 12-step / no-broadcast kernels
+  if (EOS != 0 || TC != 12 || bc != 0) return fail(ML_ERR_MODE, "kernel not instantiated in a fast build");
+  return launch_one<0, 12, 0, MODE>(mT, mS, P, tiles, chunks, st);
+#else
   if (bc == 0) return launch_one<EOS, TC, 0, MODE>(mT, mS, P, tiles, chunks, st);
   if (bc == 1) return launch_one<EOS, TC, 1, MODE>(mT, mS, P, tiles, chunks, st);
   return launch_one<EOS, TC, 2, MODE>(mT, mS, P, tiles, chunks, st);
+#endif
 }
 
 // time steps per register chunk: the largest of {12, 8, 4} that nt fills at least once

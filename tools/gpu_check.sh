@@ -25,6 +25,14 @@ for s in $STAGES; do
     configs)
       timeout 1200 python tools/bench_configs.py 3 4 5 > gpurun_out/configs.log 2> gpurun_out/configs.err
       echo "[configs] exit $?"; cat gpurun_out/configs.log | cut -c1-700; tail -5 gpurun_out/configs.err ;;
+    ncuk3)
+      # full captures of one kLocal and one kGlobal launch of the A/B harness (launch order: see k3_bench.py)
+      timeout 300 python tools/k3_bench.py plain > gpurun_out/k3_plain.log 2>&1 &&
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_steric_tma -s 8 -c 1 \
+          -o gpurun_out/prof_klocal python tools/k3_bench.py ncu > gpurun_out/ncu_k3a.log 2>&1 &&
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_steric_tma -s 14 -c 1 \
+          -o gpurun_out/prof_kglobal python tools/k3_bench.py ncu > gpurun_out/ncu_k3b.log 2>&1
+      echo "[ncuk3] exit $?"; cat gpurun_out/k3_plain.log | tail -1 ;;
     benchref)
       timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
       echo "[benchref] exit $?"; tail -3 gpurun_out/bench_ref.log ;;
