@@ -30,7 +30,11 @@ namespace tma {
 constexpr int kTile = 256;                    // columns per CTA = threads per CTA
 constexpr int kConsumerWarps = kTile / 32;    // 8
 constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
-constexpr int kStages = 4;
+#ifndef ML_TMA_NSUB
+#define ML_TMA_NSUB 1
+#endif
+constexpr int kSub = ML_TMA_NSUB;             // a level's chunk of TC steps is staged in kSub pieces
+constexpr int kStages = 4 * kSub;             // ring depth (the ring's bytes do not depend on kSub)
 
 // ------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,36 +84,28 @@ __device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
       : "d"(d), "d"(w));
 }
 
-// v_ref is prefetched one level ahead as a raw bit pattern: converting, testing or even
-// MOVing the value at load time makes the warp wait for the very load it is trying to hide
-// (25-30 % of all stall samples in two profiles).  The fp32 and the fp64 case therefore load
-// into separate registers -- a common destination would need a zero-extending move right
-// behind the load -- and the choice between them is made when the value is used.
-typedef unsigned long long u64;
-struct VRaw {
-  unsigned w32;
-  u64 w64;
-};
-__device__ __forceinline__ VRaw ld_vraw(const void* v, int v_f32, i64 i) {
-  VRaw r;
-  r.w32 = 0u;
-  r.w64 = 0ull;
-  if (v_f32) r.w32 = __ldg(reinterpret_cast<const unsigned*>(v) + i);
-  else r.w64 = __ldg(reinterpret_cast<const u64*>(v) + i);
-  return r;
+// v_ref (fp32 in this family) is prefetched one level ahead as a raw bit pattern: converting,
+// testing or even MOVing the value at load time makes the warp wait for the very load it is
+// trying to hide (25-30 % of all stall samples in two profiles).
+__device__ __forceinline__ unsigned ld_vraw(const float* v, i64 i) { return __ldg(reinterpret_cast<const unsigned*>(v) + i); }
+__device__ __forceinline__ bool vraw_isnan(unsigned w) { return (w & 0x7fffffffu) > 0x7f800000u; }
+__device__ __forceinline__ double vraw_value(unsigned w) { return (double)__uint_as_float(w); }
+
+// partial-cell thickness, derived.py:308-318 for top = 0 / bottom = None, written with plain
+// compares: depth and z_i are never NaN here (deptho is NaN-filled with 0 on entry, derived.py:295)
+__device__ __forceinline__ double level_dz(double depth, double ztop, double zbot) {
+  const double part = depth - ztop, full = zbot - ztop;
+  const double p0 = part < 0.0 ? 0.0 : part;
+  return p0 < full ? p0 : full;
 }
-__device__ __forceinline__ bool vraw_isnan(const VRaw& r, int v_f32) {
-  return v_f32 ? ((r.w32 & 0x7fffffffu) > 0x7f800000u) : ((r.w64 & 0x7fffffffffffffffull) > 0x7ff0000000000000ull);
-}
-__device__ __forceinline__ double vraw_value(const VRaw& r, int v_f32) {
-  return v_f32 ? (double)__uint_as_float(r.w32) : __longlong_as_double((long long)r.w64);
+__device__ __forceinline__ bool nonzero(double x) {  // x != 0 without touching the fp64 pipe
+  return ((((unsigned)__double2hiint(x)) << 1) | (unsigned)__double2loint(x)) != 0u;
 }
 
 struct Params {
   const double* rho_ref;  // kLocal: read
   double* rho_ref_out;    // kSelfRef: written (may be NULL)
-  const void* v_ref;
-  int v_f32;
+  const float* v_ref;     // fp32 volcello of the reference state
   const double* z_i;      // local modes
   const double* deptho;   // local modes
   const double* p_level;
@@ -142,8 +138,9 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
-  constexpr int kRowsT = (BC == 1) ? 1 : TC;
-  constexpr int kRowsS = (BC == 2) ? 1 : TC;
+  constexpr int TS = TC / kSub;  // time steps per stage
+  constexpr int kRowsT = (BC == 1) ? 1 : TS;
+  constexpr int kRowsS = (BC == 2) ? 1 : TS;
   constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(float);
   constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
@@ -164,13 +161,13 @@ __global__ void ML_TMA_KERNEL_ATTR
   // levels and afterwards by whichever warp is the LAST to finish with a stage (a shared-memory
   // counter tells): the refill is issued the moment the slot is free, without a producer warp
   // spinning on "empty" barriers and taking registers and issue slots from the math warps.
-  auto refill_stage = [&](int z) {
-    const int s = z % kStages;
+  auto refill_stage = [&](int q) {  // q = level * kSub + piece
+    const int s = q % kStages, z = q / kSub, tq = t0 + (q % kSub) * TS;
     float* dT = stage_base + (size_t)s * (kStageBytes / sizeof(float));
     float* dS = dT + kRowsT * kTile;
     mbar_expect_tx(full + s, kStageBytes);
-    if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
-    if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
+    if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, tq);
+    if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, tq);
   };
 
   if (tid == 0) {
@@ -181,7 +178,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int z = 0; z < kStages && z < nz; ++z) refill_stage(z);
+    for (int q = 0; q < kStages && q < nz * kSub; ++q) refill_stage(q);
   }
   for (int i = threadIdx.x; i < P.nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
   if (!GLOBAL)
@@ -205,66 +202,80 @@ __global__ void ML_TMA_KERNEL_ATTR
     }
     // per-level operands, fetched one level ahead (raw bits, see ld_vraw)
     double rref_n = 0.0;
-    VRaw v_n = ld_vraw(P.v_ref, P.v_f32, cc);
+    unsigned v_n = ld_vraw(P.v_ref, cc);
     if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
-    const bool surface_wet = !vraw_isnan(v_n, P.v_f32);  // steric.py:166
-    // kSelfRef: the reference density of level z is evaluated while level z-1 is integrated
-    // (from row 0 of the next stage), so no point of a level ever waits for it.
+    const bool surface_wet = !vraw_isnan(v_n);  // steric.py:166
+    // kSelfRef: the reference density of level z+1 is evaluated together with the points of
+    // level z (from row 0 of the next stage, inside the same unrolled block so the scheduler
+    // interleaves it), stored for the caller and used one iteration later.
     double sub_n = 0.0;
-    auto reference_cell = [&](int z) -> double {
-      const float* row = stage_base + (size_t)(z % kStages) * (kStageBytes / sizeof(float)) + tid;
-      mbar_wait(full + (z % kStages), (uint32_t)(z / kStages) & 1u);
-      const double r = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[z]);  // reference.py:60-71
-      if (in && P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = r;
-      return r;
-    };
-    if (SELFREF) sub_n = reference_cell(0);
+    if (SELFREF) {
+      mbar_wait(full + 0, 0u);
+      const float* row = stage_base + tid;
+      sub_n = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[0]);  // reference.py:60-71
+      if (in && P.rho_ref_out) P.rho_ref_out[c] = sub_n;
+    }
     for (int z = 0; z < nz; ++z) {
-      const int s = z % kStages;
       const double rref_z = SELFREF ? sub_n : rref_n;
-      const VRaw v_z = v_n;
+      const unsigned v_z = v_n;
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
-        v_n = ld_vraw(P.v_ref, P.v_f32, j);
+        v_n = ld_vraw(P.v_ref, j);
         if (MODE == kLocal) rref_n = __ldg(P.rho_ref + j);
       }
       // weight of this cell in the sum and the value subtracted from rho
-      const bool dry = vraw_isnan(v_z, P.v_f32);
+      const bool dry = vraw_isnan(v_z);
       double w, sub;
       if (GLOBAL) {
-        w = dry ? 0.0 : vraw_value(v_z, P.v_f32);  // rho * NaN is dropped by the skipna sum (derived.py:435-438)
+        w = dry ? 0.0 : vraw_value(v_z);  // rho * NaN is dropped by the skipna sum (derived.py:435-438)
         sub = 0.0;
       } else {
-        w = clipped_dz(depth, s_zi[z], s_zi[z + 1]);
+        w = level_dz(depth, s_zi[z], s_zi[z + 1]);
         // steric.py:151-153: delta_rho is NaN (and skipped) wherever the reference volume is missing
         sub = rref_z;
         if (dry || (MODE == kLocal && isnan(rref_z))) w = 0.0;
         if (SELFREF && in && !dry) {  // volo, masso: skipna sums (derived.py:787-789, :435-438)
-          const double v = vraw_value(v_z, P.v_f32);
+          const double v = vraw_value(v_z);
           vol += v;
           const double m = rref_z * v;
           if (!is_nan_q(m)) mass += m;
         }
       }
       eos.set_level(s_p[z]);
-      const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
-      const float* sS = sT + kRowsT * kTile;
-      mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
-      if (SELFREF && z + 1 < nz) sub_n = reference_cell(z + 1);
-      if (__any_sync(0xffffffffu, w != 0.0)) {
+      const bool any_water = __any_sync(0xffffffffu, nonzero(w));
+      // kSelfRef: row 0 of the NEXT level's first piece (clamped at the bottom level, where the
+      // value is recomputed and discarded) -- wait for it up front so that the reference point
+      // and the TC points below form one straight-line block
+      const int zn = (z + 1 < nz) ? z + 1 : z;
+      const int qn = zn * kSub;
+      const float* rowN = stage_base + (size_t)(qn % kStages) * (kStageBytes / sizeof(float)) + tid;
+      const double p_next = s_p[zn];
+      if (SELFREF) mbar_wait(full + (qn % kStages), (uint32_t)(qn / kStages) & 1u);
 #pragma unroll
-        for (int k = SELFREF ? 1 : 0; k < TC; ++k) {  // kSelfRef: step 0 is the reference, its anomaly is 0
-          const double Tv = (double)sT[(BC == 1 ? 0 : k) * kTile];
-          const double Sv = (double)sS[(BC == 2 ? 0 : k) * kTile];
-          const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
-          fma_skipnan(acc[k], w, d);
+      for (int h = 0; h < kSub; ++h) {
+        const int q = z * kSub + h, s = q % kStages;
+        const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
+        const float* sS = sT + kRowsT * kTile;
+        mbar_wait(full + s, (uint32_t)(q / kStages) & 1u);
+        if (any_water) {
+          if (SELFREF && h == 0) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
+#pragma unroll
+          for (int kk = (SELFREF && h == 0) ? 1 : 0; kk < TS; ++kk) {  // kSelfRef: step 0 is the reference itself
+            const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
+            const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
+            const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
+            fma_skipnan(acc[h * TS + kk], w, d);
+          }
+        } else if (SELFREF && h == 0) {
+          sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
         }
-      }
-      __syncwarp();
-      if (lane == 0) {
-        // the 8th warp to leave the stage refills it with level z + kStages
-        const int before = atomicAdd(released + s, 1);
-        if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz) refill_stage(z + kStages);
+        if (SELFREF && h == 0 && in && z + 1 < nz && P.rho_ref_out) P.rho_ref_out[(i64)(z + 1) * P.ncol + c] = sub_n;
+        __syncwarp();
+        if (lane == 0) {
+          // the 8th warp to leave the stage refills it with the piece kStages further on
+          const int before = atomicAdd(released + s, 1);
+          if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && q + kStages < nz * kSub) refill_stage(q + kStages);
+        }
       }
     }
     if (!GLOBAL) {
@@ -333,8 +344,9 @@ static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static bool common_eligible(int dtype, const void* T, const void* S, int64_t nt, int64_t nz, int64_t ncol) {
-  if (dtype != ML_F32) return false;
+static bool common_eligible(int dtype, int vref_dtype, const void* T, const void* S, int64_t nt, int64_t nz,
+                            int64_t ncol) {
+  if (dtype != ML_F32 || vref_dtype != ML_F32) return false;
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
   if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
   if (nt < 1 || nz < 1 || nz > 512) return false;
@@ -343,19 +355,19 @@ static bool common_eligible(int dtype, const void* T, const void* S, int64_t nt,
   return encode_fn() != nullptr;
 }
 
-bool local_eligible(int dtype, const void* T, const void* S, int, int, const double*, const void*, int, int64_t nt,
-                    int64_t nz, int64_t ncol, const double*, const double* delta_rho) {
-  return delta_rho == nullptr && common_eligible(dtype, T, S, nt, nz, ncol);
+bool local_eligible(int dtype, const void* T, const void* S, int, int, const double*, const void*, int vref_dtype,
+                    int64_t nt, int64_t nz, int64_t ncol, const double*, const double* delta_rho) {
+  return delta_rho == nullptr && common_eligible(dtype, vref_dtype, T, S, nt, nz, ncol);
 }
 
-bool global_eligible(int dtype, const void* T, const void* S, int, int, const void*, int, int64_t nt, int64_t nz,
-                     int64_t ncol) {
-  return common_eligible(dtype, T, S, nt, nz, ncol);
+bool global_eligible(int dtype, const void* T, const void* S, int, int, const void*, int vref_dtype, int64_t nt,
+                     int64_t nz, int64_t ncol) {
+  return common_eligible(dtype, vref_dtype, T, S, nt, nz, ncol);
 }
 
 template <int TC>
 inline size_t smem_bytes(int bc, int nz) {
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * (TC / kSub) : TC / kSub + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 128;
 }
 
@@ -399,8 +411,8 @@ struct Plan {
 static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P) {
   pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
   pl->tc = plan_tc(P.nt);
-  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc);
-  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc);
+  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc / kSub);
+  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc / kSub);
   if (!okT || !okS) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
   pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
   pl->chunks = (unsigned)((P.nt + pl->tc - 1) / pl->tc);
@@ -425,8 +437,8 @@ static Params base_params(const void* v_ref, int vref_dtype, const double* p_lev
   Params P;
   P.rho_ref = nullptr;
   P.rho_ref_out = nullptr;
-  P.v_ref = v_ref;
-  P.v_f32 = vref_dtype == ML_F32;
+  P.v_ref = static_cast<const float*>(v_ref);
+  (void)vref_dtype;  // eligibility guarantees fp32
   P.z_i = nullptr;
   P.deptho = nullptr;
   P.p_level = p_level;
