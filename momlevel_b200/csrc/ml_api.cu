@@ -34,6 +34,22 @@ __device__ __forceinline__ double vref_val(const void* v, int v_f32, i64 i) {
                : __ldg(reinterpret_cast<const double*>(v) + i);
 }
 
+// 128-bit streaming loads / stores of four consecutive values (every byte is touched once).
+__device__ __forceinline__ void ld4(const float* p, double v[4]) {
+  float4 f;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p));
+  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+__device__ __forceinline__ void ld4(const double* p, double v[4]) {
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
+}
+__device__ __forceinline__ void st4(double* p, const double v[4]) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(v[2]), "d"(v[3]) : "memory");
+}
+
 // ------------------------------------------------------------------ K1: elementwise EOS
 template <typename TIn, int EOS, int FUNC>
 __global__ void __launch_bounds__(kBlock) k_eos_eval(const TIn* __restrict__ T, const TIn* __restrict__ S,
@@ -56,6 +72,34 @@ __global__ void __launch_bounds__(kBlock) k_eos_eval(const TIn* __restrict__ T, 
   }
 }
 
+// Vectorised K1: a thread owns four adjacent columns and walks the rows assigned to its block.
+// Needs ncol % 4 == 0 and 16-byte aligned bases (rows then stay aligned).
+template <typename TIn, int EOS, int FUNC>
+__global__ void __launch_bounds__(kBlock) k_eos_eval_vec(const TIn* __restrict__ T, const TIn* __restrict__ S,
+                                                         i64 t_stride, i64 s_stride, const double* __restrict__ p,
+                                                         int pmode, i64 nrows, int nz, i64 ncol,
+                                                         double* __restrict__ out) {
+  const i64 c = 4 * ((i64)blockIdx.x * kBlock + threadIdx.x);
+  if (c >= ncol) return;
+  for (i64 row = blockIdx.y; row < nrows; row += gridDim.y) {
+    const i64 t = row / nz;
+    const int z = (int)(row - t * nz);
+    const i64 o = row * ncol + c;
+    double tv[4], sv[4], pv[4], r[4];
+    ld4(T + t * t_stride + (i64)z * ncol + c, tv);
+    ld4(S + t * s_stride + (i64)z * ncol + c, sv);
+    if (pmode == ML_P_FULL) {
+      ld4(p + o, pv);
+    } else {
+      const double p1 = pmode == ML_P_SCALAR ? __ldg(p) : (pmode == ML_P_PER_LEVEL ? __ldg(p + z) : 0.0);
+      pv[0] = pv[1] = pv[2] = pv[3] = p1;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r[j] = eos_func<EOS, FUNC>(tv[j], sv[j], pv[j]);
+    st4(out + o, r);
+  }
+}
+
 // ---------------------------------------------------------------------------- K5: spice
 template <typename TIn>
 __global__ void __launch_bounds__(kBlock) k_spice(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 n,
@@ -65,24 +109,7 @@ __global__ void __launch_bounds__(kBlock) k_spice(const TIn* __restrict__ T, con
     out[i] = flament_spice(ldf(T + i), ldf(S + i));
 }
 
-// Vectorised variant: four consecutive points per thread, 128-bit loads and stores, streaming
-// cache hints (every byte is touched once).  Needs 16-byte aligned pointers; the host falls
-// back to k_spice for the ragged tail.
-__device__ __forceinline__ void ld4(const float* p, double v[4]) {
-  float4 f;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-               : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "l"(p));
-  v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
-}
-__device__ __forceinline__ void ld4(const double* p, double v[4]) {
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
-  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[2]), "=d"(v[3]) : "l"(p + 2));
-}
-__device__ __forceinline__ void st4(double* p, const double v[4]) {
-  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(v[0]), "d"(v[1]) : "memory");
-  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p + 2), "d"(v[2]), "d"(v[3]) : "memory");
-}
-
+// Vectorised variant (helpers ld4 / st4 above): four consecutive points per thread.
 template <typename TIn>
 __global__ void __launch_bounds__(kBlock) k_spice_vec(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 n4,
                                                       double* __restrict__ out) {
@@ -162,6 +189,59 @@ __global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restric
   if (threadIdx.x == 0) {
     partials[blockIdx.x] = vol;
     partials[(i64)gridDim.x + blockIdx.x] = mass;
+  }
+}
+
+// Vectorised K2: one level per blockIdx.y, four adjacent columns per thread, 128-bit accesses.
+// Block partials are laid out [2][gridDim.y * gridDim.x] for k_reduce_rows.
+template <typename TIn, int EOS>
+__global__ void __launch_bounds__(kBlock) k_reference_state_vec(const TIn* __restrict__ T0, const TIn* __restrict__ S0,
+                                                                const TIn* __restrict__ V0,
+                                                                const double* __restrict__ p_level, i64 ncol,
+                                                                double* __restrict__ rho_ref,
+                                                                double* __restrict__ partials) {
+  __shared__ double sm[kWarps];
+  const int z = blockIdx.y;
+  const i64 nq = ncol / 4, base = (i64)z * ncol;
+  Eos<EOS> eos;
+  eos.set_level(__ldg(p_level + z));
+  double vol = 0.0, mass = 0.0;
+  const i64 stride = (i64)gridDim.x * kBlock;
+  for (i64 q0 = (i64)blockIdx.x * kBlock + threadIdx.x; q0 < nq; q0 += 2 * stride) {
+    // two quads per trip: all six loads are issued before any arithmetic
+    const bool two = q0 + stride < nq;
+    const i64 q1 = two ? q0 + stride : q0;
+    double ta[4], sa[4], va[4], ra[4], tb[4], sb[4], vb[4], rb[4];
+    ld4(T0 + base + 4 * q0, ta);
+    ld4(S0 + base + 4 * q0, sa);
+    ld4(V0 + base + 4 * q0, va);
+    ld4(T0 + base + 4 * q1, tb);
+    ld4(S0 + base + 4 * q1, sb);
+    ld4(V0 + base + 4 * q1, vb);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ra[j] = eos.rho(ta[j], sa[j]);
+      rb[j] = eos.rho(tb[j], sb[j]);
+      if (!isnan(va[j])) {  // nansum (derived.py:787-789, :435-438)
+        vol += va[j];
+        const double m = ra[j] * va[j];
+        if (!is_nan_q(m)) mass += m;
+      }
+      if (two && !isnan(vb[j])) {
+        vol += vb[j];
+        const double m = rb[j] * vb[j];
+        if (!is_nan_q(m)) mass += m;
+      }
+    }
+    st4(rho_ref + base + 4 * q0, ra);
+    if (two) st4(rho_ref + base + 4 * q1, rb);
+  }
+  vol = block_sum<kWarps>(vol, sm);
+  mass = block_sum<kWarps>(mass, sm);
+  if (threadIdx.x == 0) {
+    const i64 nblk = (i64)gridDim.x * gridDim.y, b = (i64)blockIdx.y * gridDim.x + blockIdx.x;
+    partials[b] = vol;
+    partials[nblk + b] = mass;
   }
 }
 
@@ -278,6 +358,20 @@ inline int check_bcast(int t_bcast, int s_bcast) {
 template <int EOS, int FUNC>
 int launch_eos(int dtype, const void* T, const void* S, i64 ts, i64 ss, const double* p, int pmode, i64 nrows, int nz,
                i64 ncol, double* out, cudaStream_t st) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(out) |
+                         (pmode == ML_P_FULL ? reinterpret_cast<uintptr_t>(p) : 0);
+  if (ncol % 4 == 0 && (bits & 15u) == 0) {
+    // ~16 resident blocks per SM; each block walks its share of the rows
+    const i64 gx = cdiv(ncol / 4, kBlock);
+    i64 gy = cdiv(148 * 16, gx);
+    gy = gy < 1 ? 1 : (gy > nrows ? nrows : gy);
+    dim3 grid((unsigned)gx, (unsigned)(gy < 65535 ? gy : 65535));
+    if (dtype == ML_F32)
+      k_eos_eval_vec<float, EOS, FUNC><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, ts, ss, p, pmode, nrows, nz, ncol, out);
+    else
+      k_eos_eval_vec<double, EOS, FUNC><<<grid, kBlock, 0, st>>>((const double*)T, (const double*)S, ts, ss, p, pmode, nrows, nz, ncol, out);
+    return launched("k_eos_eval_vec");
+  }
   dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)(nrows < 65535 ? nrows : 65535));
   if (dtype == ML_F32)
     k_eos_eval<float, EOS, FUNC><<<grid, kBlock, 0, st>>>((const float*)T, (const float*)S, ts, ss, p, pmode, nrows, nz, ncol, out);
@@ -348,11 +442,13 @@ int ml_set_force_direct(int on) {
 }
 
 size_t ml_workspace_bytes(int64_t nt, int64_t nz, int64_t ncol) {
-  (void)nz;
   if (nt < 2) nt = 2;  // reference_state needs two rows
-  // direct family: ceil(ncol/256) block partials per row; the TMA family uses fewer.
+  if (nz < 1) nz = 1;
+  // per-row block partials: ceil(ncol/256) (direct family) or fewer (TMA family); the vectorised
+  // reference-state kernel keeps up to 512 blocks per level for each of its two sums
   const int64_t nblk = cdiv(ncol > 0 ? ncol : 1, 128);
-  return (size_t)(nt * nblk) * sizeof(double) + 256;
+  const int64_t ref = 2 * nz * 512;
+  return (size_t)(nt * nblk > ref ? nt * nblk : ref) * sizeof(double) + 256;
 }
 
 int ml_eos_eval(int eos, int func, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* p,
@@ -446,8 +542,33 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
   ML_REQUIRE_ALIGNED(workspace, 8);
   cudaStream_t st = (cudaStream_t)stream;
   double* partials = (double*)workspace;
-  const i64 nblk = cdiv(ncol, kBlock);
   const int v_f32 = v_dtype == ML_F32;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(T0) | reinterpret_cast<uintptr_t>(S0) |
+                         reinterpret_cast<uintptr_t>(V0) | reinterpret_cast<uintptr_t>(rho_ref);
+  if (v_dtype == dtype && ncol % 4 == 0 && (bits & 15u) == 0 && nz <= 65535) {
+    // ~12 resident blocks per SM over all levels; each thread walks its level in 2-quad trips
+    i64 gx = cdiv(148 * 12, nz);
+    const i64 need = cdiv(cdiv(ncol / 4, kBlock), 2);
+    if (gx > need) gx = need;
+    i64 cap = (i64)(workspace_bytes / sizeof(double) / 2 / nz);  // partials must fit the workspace
+    if (cap > 512) cap = 512;
+    if (gx > cap) gx = cap;
+    if (gx >= 1) {
+      dim3 grid((unsigned)gx, (unsigned)nz);
+#define ML_LAUNCH_REFV(TIN, E) \
+  k_reference_state_vec<TIN, E><<<grid, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, (const TIN*)V0, p_level, ncol, rho_ref, partials)
+      if (dtype == ML_F32) {
+        if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REFV(float, 0); else ML_LAUNCH_REFV(float, 1);
+      } else {
+        if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REFV(double, 0); else ML_LAUNCH_REFV(double, 1);
+      }
+#undef ML_LAUNCH_REFV
+      if ((rc = launched("k_reference_state_vec"))) return rc;
+      k_reduce_rows<<<2, kBlock, 0, st>>>(partials, gx * nz, sums);
+      return launched("k_reduce_rows");
+    }
+  }
+  const i64 nblk = cdiv(ncol, kBlock);
 #define ML_LAUNCH_REF(TIN, E) \
   k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, V0, v_f32, p_level, (int)nz, ncol, rho_ref, partials)
   if (dtype == ML_F32) {
