@@ -190,6 +190,10 @@ int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const
                          int steps_per_window, double* eta, double* rho_ref_out,
                          double* sums_out);
 
+/* Frees the device staging buffers, streams and events that ml_steric_local_host keeps per
+ * host thread between calls. */
+int ml_host_release(void);
+
 #ifdef __cplusplus
 }
 #endif

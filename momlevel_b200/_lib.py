@@ -37,6 +37,7 @@ EXPORTS = {
     "ml_steric_local_selfref": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _d, _i64, _i64, _i64, _vp, _vp, _vp,
                                      _vp, _sz, _vp]),
     "ml_steric_global": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "ml_host_release": (_i, []),
     "ml_steric_local_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i64, _i64, _i64, _i, _vp, _vp, _vp]),
 }
 

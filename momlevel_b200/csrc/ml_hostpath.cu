@@ -12,27 +12,75 @@
 
 namespace {
 
+// Device staging buffers, streams and events are kept per host thread between calls (a year of
+// OM4p25 needs ~5 GB of windows; allocating and freeing them costs tens of milliseconds per call)
+// and released by ml_host_release() or at thread exit.
 struct Resources {
-  std::vector<void*> dev;
+  static constexpr int kSlots = 12;
+  void* buf[kSlots] = {nullptr};
+  size_t cap[kSlots] = {0};
+  int device = -1;
   cudaStream_t copy = nullptr, comp = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-  ~Resources() {
-    for (void* p : dev) cudaFree(p);
+  void release() {
+    for (int i = 0; i < kSlots; ++i) {
+      if (buf[i]) cudaFree(buf[i]);
+      buf[i] = nullptr;
+      cap[i] = 0;
+    }
     for (int i = 0; i < 2; ++i) {
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (freed[i]) cudaEventDestroy(freed[i]);
+      copied[i] = freed[i] = nullptr;
     }
     if (copy) cudaStreamDestroy(copy);
     if (comp) cudaStreamDestroy(comp);
+    copy = comp = nullptr;
+    device = -1;
   }
-  cudaError_t alloc(void** p, size_t bytes) {
-    cudaError_t e = cudaMalloc(p, bytes);
-    if (e == cudaSuccess) dev.push_back(*p);
-    return e;
+  ~Resources() { release(); }
+  cudaError_t prepare() {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev != device) {
+      release();
+      device = dev;
+    }
+    if (!copy && (e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if (!comp && (e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    for (int b = 0; b < 2; ++b) {
+      if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  }
+  // slot i grows to at least `bytes`
+  cudaError_t alloc(int i, void** p, size_t bytes) {
+    if (cap[i] < bytes) {
+      if (buf[i]) cudaFree(buf[i]);
+      buf[i] = nullptr;
+      cap[i] = 0;
+      cudaError_t e = cudaMalloc(&buf[i], bytes);
+      if (e != cudaSuccess) return e;
+      cap[i] = bytes;
+    }
+    *p = buf[i];
+    return cudaSuccess;
   }
 };
 
+Resources& resources() {
+  static thread_local Resources r;
+  return r;
+}
+
 }  // namespace
+
+extern "C" int ml_host_release(void) {
+  resources().release();
+  return ML_OK;
+}
 
 extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
                                     const double* z_i, const double* deptho, const double* p_level,
@@ -58,26 +106,21 @@ extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const voi
   const size_t win_bytes = (size_t)spw * lvl * es;
   const size_t ws_bytes = ml_workspace_bytes(2, nz, ncol);
 
-  Resources r;
+  Resources& r = resources();
+  ML_CUDA(r.prepare());
   void *dT[2], *dS[2], *dV, *dRho, *dEta, *dZi, *dDepth, *dP, *dSums, *dWs;
   for (int b = 0; b < 2; ++b) {
-    ML_CUDA(r.alloc(&dT[b], win_bytes));
-    ML_CUDA(r.alloc(&dS[b], win_bytes));
+    ML_CUDA(r.alloc(2 * b, &dT[b], win_bytes));
+    ML_CUDA(r.alloc(2 * b + 1, &dS[b], win_bytes));
   }
-  ML_CUDA(r.alloc(&dV, lvl * es));
-  ML_CUDA(r.alloc(&dRho, lvl * sizeof(double)));
-  ML_CUDA(r.alloc(&dEta, (size_t)nt * ncol * sizeof(double)));
-  ML_CUDA(r.alloc(&dZi, (size_t)(nz + 1) * sizeof(double)));
-  ML_CUDA(r.alloc(&dDepth, (size_t)ncol * sizeof(double)));
-  ML_CUDA(r.alloc(&dP, (size_t)nz * sizeof(double)));
-  ML_CUDA(r.alloc(&dSums, 2 * sizeof(double)));
-  ML_CUDA(r.alloc(&dWs, ws_bytes));
-  ML_CUDA(cudaStreamCreateWithFlags(&r.copy, cudaStreamNonBlocking));
-  ML_CUDA(cudaStreamCreateWithFlags(&r.comp, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; ++b) {
-    ML_CUDA(cudaEventCreateWithFlags(&r.copied[b], cudaEventDisableTiming));
-    ML_CUDA(cudaEventCreateWithFlags(&r.freed[b], cudaEventDisableTiming));
-  }
+  ML_CUDA(r.alloc(4, &dV, lvl * es));
+  ML_CUDA(r.alloc(5, &dRho, lvl * sizeof(double)));
+  ML_CUDA(r.alloc(6, &dEta, (size_t)nt * ncol * sizeof(double)));
+  ML_CUDA(r.alloc(7, &dZi, (size_t)(nz + 1) * sizeof(double)));
+  ML_CUDA(r.alloc(8, &dDepth, (size_t)ncol * sizeof(double)));
+  ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
+  ML_CUDA(r.alloc(10, &dSums, 2 * sizeof(double)));
+  ML_CUDA(r.alloc(11, &dWs, ws_bytes));
 
   ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));

@@ -222,3 +222,11 @@ def test_calc_rho_and_friends(ml):
     # potential density = density at a fixed pressure (derived.py:477)
     pd = ml.derived.calc_pdens(d["thetao"], d["so"], level=2000.0)
     assert _relerr(pd.values, oeos.wright_density(o["thetao"], o["so"], 2000.0 * 1e4 + 101325)) < RHO_RTOL
+
+
+def test_inverse_barometer_kat(ml):
+    # tests/test_dynamic.py:6-11
+    d = ml.test_data.generate_test_data().isel(z_l=0)
+    result = ml.inverse_barometer(d["thetao"], d["so"], 101325.0)
+    assert result.attrs == {"long_name": "Inverse Barometer Height", "units": "m"}
+    assert float(result.sum()) == pytest.approx(-1259.79345168, abs=5e-9)
