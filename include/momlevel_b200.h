@@ -145,6 +145,17 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
                     void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ml_delta_rho -- the 4-D density anomaly on its own:
+ *   delta_rho = where(v_ref notnull, rho(T,S,p) - rho_ref, NaN)   (src/momlevel/steric.py:151-158)
+ * The reference always materialises this field; here the fused kernels integrate it without
+ * storing it and this entry point produces it when a caller reads result["delta_rho"].
+ *   delta_rho   [nt][nz][ncol] fp64 out; other arguments as ml_steric_local
+ * ------------------------------------------------------------------------------------- */
+int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                 const double* rho_ref, const void* v_ref, int vref_dtype, const double* p_level,
+                 int64_t nt, int64_t nz, int64_t ncol, double* delta_rho, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * ml_steric_local_selfref -- ml_reference_state + ml_steric_local in one pass when the
  * reference state is the first time step of the dataset itself, which is what
  * steric.steric does when no `reference` is supplied (src/momlevel/steric.py:105-107 ->

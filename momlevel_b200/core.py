@@ -20,6 +20,7 @@ __all__ = [
     "reference_state",
     "steric_local",
     "steric_local_selfref",
+    "delta_rho",
     "steric_global",
     "steric_local_host",
     "last_path",
@@ -237,6 +238,21 @@ def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos
                           drho.data_ptr() if drho is not None else None, _stream())
     )
     return eta, drho
+
+
+def delta_rho(T, S, rho_ref, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):
+    """``where(v_ref.notnull(), rho - rho_ref, nan)`` time-first (steric.py:151-158), fp64 on the device."""
+    L = _lib.lib()
+    T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
+    rho_ref, v_ref, p = _f64(rho_ref), to_device(v_ref), _f64(p_level)
+    assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and p.numel() == nz
+    out = torch.empty((nt, nz) + hshape, dtype=torch.float64, device=T.device)
+    _lib.check(
+        L.ml_delta_rho(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                       rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol,
+                       out.data_ptr(), _stream())
+    )
+    return out
 
 
 def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False, s_bcast=False):

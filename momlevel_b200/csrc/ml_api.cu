@@ -100,6 +100,53 @@ __global__ void __launch_bounds__(kBlock) k_eos_eval_vec(const TIn* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ K1b: density anomaly
+// delta_rho[t][z][col] = V_ref notnull ? rho(T,S,p_z) - rho_ref : NaN   (steric.py:151-153).
+// One level per trip of blockIdx.y; rho_ref / v_ref are read once per (level, column) and reused
+// for every time step.  VEC = 4 adjacent columns per thread with 128-bit accesses, or 1.
+template <typename TIn, int EOS, int VEC>
+__global__ void __launch_bounds__(kBlock) k_delta_rho(const TIn* __restrict__ T, const TIn* __restrict__ S,
+                                                      i64 t_stride, i64 s_stride,
+                                                      const double* __restrict__ rho_ref,
+                                                      const void* __restrict__ v_ref, int v_f32,
+                                                      const double* __restrict__ p_level, int nt, int nz, i64 ncol,
+                                                      double* __restrict__ out) {
+  const i64 c = VEC * ((i64)blockIdx.x * kBlock + threadIdx.x);
+  if (c >= ncol) return;
+  Eos<EOS> eos;
+  for (int z = blockIdx.y; z < nz; z += gridDim.y) {
+    const i64 i = (i64)z * ncol + c;
+    eos.set_level(__ldg(p_level + z));
+    double ref[VEC];
+    if (VEC == 4) {
+      ld4(rho_ref + i, ref);
+    } else {
+      ref[0] = __ldg(rho_ref + i);
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+      if (!vref_wet(v_ref, v_f32, i + j)) ref[j] = nan("");
+    for (int t = 0; t < nt; ++t) {
+      double tv[VEC], sv[VEC], r[VEC];
+      if (VEC == 4) {
+        ld4(T + t * t_stride + i, tv);
+        ld4(S + t * s_stride + i, sv);
+      } else {
+        tv[0] = ldf(T + t * t_stride + i);
+        sv[0] = ldf(S + t * s_stride + i);
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) r[j] = eos.rho(tv[j], sv[j]) - ref[j];
+      double* o = out + ((i64)t * nz + z) * ncol + c;
+      if (VEC == 4) {
+        st4(o, r);
+      } else {
+        o[0] = r[0];
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------- K5: spice
 template <typename TIn>
 __global__ void __launch_bounds__(kBlock) k_spice(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 n,
@@ -669,6 +716,49 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
   }
   if (eos == ML_EOS_WRIGHT) return launch_local_direct<double, 0>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
   return launch_local_direct<double, 1>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
+}
+
+int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                 const void* v_ref, int vref_dtype, const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
+                 double* delta_rho, void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(rho_ref);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(delta_rho);
+  if (nt < 0 || nz <= 0 || ncol < 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
+  ML_REQUIRE_ALIGNED(delta_rho, 8);
+  if (nt == 0 || ncol == 0) return ML_OK;
+  const i64 lvl = nz * ncol;
+  const i64 ts = t_bcast ? 0 : lvl, ss = s_bcast ? 0 : lvl;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int v_f32 = vref_dtype == ML_F32;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) |
+                         reinterpret_cast<uintptr_t>(rho_ref) | reinterpret_cast<uintptr_t>(delta_rho);
+  const bool vec = ncol % 4 == 0 && (bits & 15u) == 0;
+  const i64 gx = cdiv(vec ? ncol / 4 : ncol, kBlock);
+  i64 gy = cdiv(148 * 16, gx);
+  gy = gy < 1 ? 1 : (gy > nz ? nz : gy);
+  dim3 grid((unsigned)gx, (unsigned)gy);
+#define ML_LAUNCH_DRHO(TIN, E, V) \
+  k_delta_rho<TIN, E, V><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, delta_rho)
+  if (dtype == ML_F32) {
+    if (eos == ML_EOS_WRIGHT) { if (vec) ML_LAUNCH_DRHO(float, 0, 4); else ML_LAUNCH_DRHO(float, 0, 1); }
+    else { if (vec) ML_LAUNCH_DRHO(float, 1, 4); else ML_LAUNCH_DRHO(float, 1, 1); }
+  } else {
+    if (eos == ML_EOS_WRIGHT) { if (vec) ML_LAUNCH_DRHO(double, 0, 4); else ML_LAUNCH_DRHO(double, 0, 1); }
+    else { if (vec) ML_LAUNCH_DRHO(double, 1, 4); else ML_LAUNCH_DRHO(double, 1, 1); }
+  }
+#undef ML_LAUNCH_DRHO
+  return launched("k_delta_rho");
 }
 
 int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,

@@ -113,7 +113,8 @@ def steric(
         eta = fused_eta if fused_eta is not None else core.steric_local(*args, want_delta_rho=False, **kw)[0]
 
         def _delta_rho():
-            return core.steric_local(*args, want_delta_rho=True, **kw)[1]
+            return core.delta_rho(thetao.data, so.data, reference["rho"].data, reference["volcello"].data, pres,
+                                  eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
 
         result["delta_rho"] = DataArray.lazy(_delta_rho, full.shape, full.dims, attrs={
             "long_name": "change in in situ density from reference state", "units": "kg m-3"})

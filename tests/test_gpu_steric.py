@@ -417,6 +417,25 @@ def test_full_size_om4p25_properties(ml):
     _close_nan(reference["rho"].data[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
 
 
+@pytest.mark.parametrize("shape", [(3, 10, 37, 53), (5, 9, 16, 64)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_delta_rho_entry_equals_fused_output(ml, shape, dtype):
+    """ml_delta_rho (vectorised and scalar paths) == the delta_rho the direct column kernel writes."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(*shape, seed=4, device="cuda", dtype=dtype)
+    T, S, V = ds["thetao"].data, ds["so"].data, ds["volcello"].data[0]
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    rho_ref, _ = core.reference_state(T[0], S[0], V, pres)
+    for kw in ({}, {"s_bcast": True}, {"t_bcast": True}):
+        Tin = T[0].contiguous() if kw.get("t_bcast") else T
+        Sin = S[0].contiguous() if kw.get("s_bcast") else S
+        a = core.delta_rho(Tin, Sin, rho_ref, V, pres, **kw)
+        _, b = core.steric_local(Tin, Sin, rho_ref, V, ds["z_i"].data, ds["deptho"].data, pres, want_delta_rho=True, **kw)
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        assert torch.equal(torch.nan_to_num(a), torch.nan_to_num(b))
+
+
 # -------------------------------------------------------------------- host (e2e) entry
 
 

@@ -29,6 +29,7 @@ ms = timed(lambda: core.reference_state(T[0], S[0], V, pres)); res["reference_st
 ms = timed(lambda: core.calc_dz(grid["z_i"], grid["deptho"])); res["calc_dz"] = (N / ms / 1e6, N * 8 / ms / 1e6)
 rho_ref, _ = core.reference_state(T[0], S[0], V, pres)
 ms = timed(lambda: core.steric_local(T, S, rho_ref, V, grid["z_i"], grid["deptho"], pres, want_delta_rho=True)); res["local_with_delta_rho(direct)"] = (pts / ms / 1e6, pts * 16 / ms / 1e6)
+ms = timed(lambda: core.delta_rho(T, S, rho_ref, V, pres)); res["delta_rho_entry"] = (pts / ms / 1e6, pts * 16.2 / ms / 1e6)
 core.force_direct(True)
 ms = timed(lambda: core.steric_local(T, S, rho_ref, V, grid["z_i"], grid["deptho"], pres)); res["local_direct_wright"] = (pts / ms / 1e6, pts * 8.2 / ms / 1e6)
 ms = timed(lambda: core.steric_local(T, S, rho_ref, V, grid["z_i"], grid["deptho"], pres, eos="linear")); res["local_direct_linear"] = (pts / ms / 1e6, pts * 8.2 / ms / 1e6)
