@@ -216,6 +216,52 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, depth, pres, eta, nt, ny, nx, points):
+    """`e2e`: the same metric through ml_steric_local_host -- pinned host buffers in, host eta out."""
+    import torch
+
+    ok = 1
+    try:
+        Th = torch.empty(T.shape, dtype=T.dtype, pin_memory=True)
+        Sh = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
+        Vh = torch.empty(V.shape, dtype=V.dtype, pin_memory=True)
+        eta_h = torch.empty((nt, ny, nx), dtype=torch.float64, pin_memory=True)
+    except (RuntimeError, MemoryError):
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+    if world > 1:  # all ranks take the same decision, or the timing collective below would hang
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag[0]) == 0:
+        raise RuntimeError("could not pin the host buffers of the e2e leg on every rank")
+    Th.copy_(T)
+    Sh.copy_(S)
+    Vh.copy_(V)
+    z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
+    n_e2e = max(1, min(args.steps, 3))
+
+    def e2e_step():
+        return core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, eta_out=eta_h)
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        e2e_step()
+    torch.cuda.synchronize()
+    dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    h2d = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
+    d2h = eta_h.numel() * 8 + 16
+    line["e2e"] = {"value": world * points / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                   "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
+                   "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)"}
+    # the device-resident and the host-streamed paths must agree
+    err = (eta_h.to(dev) - eta).abs()
+    line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
+    return (Th.numpy(), Sh.numpy(), Vh.numpy(), grid["areacello"].cpu().numpy(), d_h, grid["z_l"].cpu().numpy(), z_h)
+
+
 # ------------------------------------------------------------------------------ our arm
 
 
@@ -359,43 +405,16 @@ def run_ours(args):
         torch.cuda.empty_cache()
 
     # ---- e2e: host buffers through ml_steric_local_host, copies inside the timed region
+    host_fields = None
     if not args.no_e2e:
-        Th = torch.empty(T.shape, dtype=T.dtype, pin_memory=True)
-        Sh = torch.empty(S.shape, dtype=S.dtype, pin_memory=True)
-        Vh = torch.empty(V.shape, dtype=V.dtype, pin_memory=True)
-        eta_h = torch.empty((nt, ny, nx), dtype=torch.float64, pin_memory=True)
-        Th.copy_(T)
-        Sh.copy_(S)
-        Vh.copy_(V)
-        z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
-        del T, S
-        torch.cuda.empty_cache()
-        n_e2e = max(1, min(args.steps, 3))
-
-        def e2e_step():
-            return core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, eta_out=eta_h)
-
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            e2e_step()
-        torch.cuda.synchronize()
-        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        h2d = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
-        d2h = eta_h.numel() * 8 + 16
-        line["e2e"] = {"value": world * points / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                       "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
-                       "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)"}
-        # the device-resident and the host-streamed paths must agree
-        err = (eta_h.to(dev) - eta).abs()
-        line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
-        host_fields = (Th.numpy(), Sh.numpy(), Vh.numpy(), grid["areacello"].cpu().numpy(), d_h,
-                       grid["z_l"].cpu().numpy(), z_h)
-    else:
-        host_fields = None
+        try:
+            host_fields = run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, depth, pres, eta,
+                                  nt, ny, nx, points)
+        except (RuntimeError, MemoryError) as exc:  # e.g. not enough pinnable host memory for 8 ranks
+            line["e2e"] = {"value": None, "unit": UNIT, "error": f"{type(exc).__name__}: {exc}"[:300]}
+        if host_fields is not None:
+            del T, S
+            torch.cuda.empty_cache()
 
     # ---- cpu_baseline: the oracle on a bounded sample of the same workload (rank 0, N=1 only)
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -349,7 +349,7 @@ static bool common_eligible(int dtype, int vref_dtype, const void* T, const void
   if (dtype != ML_F32 || vref_dtype != ML_F32) return false;
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
   if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
-  if (nt < 1 || nz < 1 || nz > 512) return false;
+  if (nt < 1 || nz < 1 || nz > 512 || nt > 4 * 65535) return false;  // grid.y = time chunks
   // TMA global strides must stay below 2^40 bytes
   if ((double)ncol * (double)nz * 4.0 >= 1099511627776.0) return false;
   return encode_fn() != nullptr;
@@ -376,12 +376,10 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
                       cudaStream_t st) {
   auto kern = k_steric_tma<EOS, TC, BC, MODE>;
   const size_t smem = smem_bytes<TC>(BC, P.nz);
-  static size_t configured = 0;  // per instantiation: largest size opted in so far
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma)");
-    configured = smem;
-  }
+  // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
+  // is set on every launch (a host-side table lookup) rather than cached in a static
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma)");
   kern<<<dim3(tiles, chunks), kThreads, smem, st>>>(mT, mS, P);
   return launched("k_steric_tma");
 }
