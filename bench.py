@@ -362,6 +362,11 @@ def run_ours(args):
                 "traffic": traffic, "kernel": f"ml_steric_local_selfref ({path} family)", "kernel_ms": k3_avg_ms,
                 "kernel_share_of_step": k3_avg_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_launch": alg_bytes,
+                # the other side of the ridge: 18 fp64 instructions per point (SASS count)
+                # against the DFMA rate measured on this pool by tools/microbench.cu (18.1e12/s)
+                "fp64": {"dfma_per_point": 18, "achieved_tdfma_s": 18 * points / (k3_avg_ms * 1e-3) / 1e12,
+                         "peak_tdfma_s": 18.1, "frac": 18 * points / (k3_avg_ms * 1e-3) / 18.1e12,
+                         "peak_source": "profiles/r01_microbench_b200.txt (measured)"},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
     line = {

@@ -12,6 +12,7 @@ What it restates (reference = jkrasting/momlevel, paths relative to its root):
 * ``oracle.steric``   -- ``src/momlevel/steric.py:84-184``, ``src/momlevel/reference.py:48-85``,
   ``src/momlevel/derived.py:249-325,414-444,642-666,769-795`` with xarray's
   name-based broadcasting / ``skipna`` sums written out in plain numpy
+* ``oracle.stratification`` -- ``src/momlevel/derived.py:30-71, 328-411`` (cell-centre N2, "next" row)
 * ``oracle.testdata`` -- ``src/momlevel/test_data/__init__.py:16-140``,
   ``test_data/tripolar/horizontal.py:110-115``, ``test_data/tripolar/vertical.py:37-68``
 
@@ -26,4 +27,4 @@ nothing; for those the oracle follows the reference code a
 the golden file records what that code evaluates to.
 """
 
-from . import eos, spice, steric, testdata  # noqa: F401
+from . import eos, spice, steric, stratification, testdata  # noqa: F401

@@ -8,7 +8,7 @@ the reference prints allow, and bit-exact where the reference prints all 16.
 import numpy as np
 import pytest
 
-from oracle import eos, spice, steric, testdata
+from oracle import eos, spice, steric, stratification, testdata
 
 
 # --------------------------------------------------------------------------- EOS
@@ -227,3 +227,19 @@ def test_nan_semantics():
     assert np.all(eta[0][np.isfinite(eta[0])] == 0.0)
     g, href, masso = steric.steric_global(T, S, d["z_l"], ref)
     assert np.all(np.isfinite(g)) and g[0] == 0.0
+
+
+# ---------------------------------------------------------------- stratification (next row)
+
+
+def test_calc_n2_kats():
+    # tests/test_derived.py:54-61 and :14-18
+    d = testdata.generate_test_data()
+    n2 = stratification.calc_n2(d["thetao"], d["so"], d["z_l"])
+    assert n2.shape == (5, 5, 5, 5)
+    assert n2.sum() == pytest.approx(0.00338354, abs=5e-9)
+    adj = stratification.calc_n2(d["thetao"], d["so"], d["z_l"], adjust_negative=True)
+    assert np.nansum(adj) == pytest.approx(0.12093286, abs=5e-9)
+    assert np.array_equal(adj, stratification.adjust_negative_n2(n2), equal_nan=True)
+    # time 0 is filled everywhere (the reference's `adjusted[0]` is the first axis), later steps only forward-filled
+    assert np.all(adj[0] > 0) and np.all(adj[np.isfinite(adj)] > 0)
