@@ -43,14 +43,15 @@ __device__ __forceinline__ bool is_nan_q(double x) {
 //   r = r0 (1 + e + e^2),  e = 1 - d r0   ->  rel. error e^3 < 2^-57.
 // That is 3 DFMA + 1 DMUL instead of the ~10 fp64 slots of the IEEE division routine.
 // NaN flows through.  Valid while 1/d is a normal number (2^-1022 <= |d| < 2^1022).
-__device__ __forceinline__ double div_lean(double n, double d) {
+__device__ __forceinline__ double rcp_lean(double d) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
   const double e = fma(-d, r, 1.0);
   const double t = fma(e, e, e);
-  r = fma(r, t, r);
-  return n * r;
+  return fma(r, t, r);
 }
+__device__ __forceinline__ double div_lean(double n, double d) { return n * rcp_lean(d); }
+
 // Same, but denominators whose reciprocal would leave the normal range take the IEEE path
 // so inf / 0 behaviour matches numpy; used by the elementwise operator (ml_eos_eval), which
 // may be handed arbitrary numbers.

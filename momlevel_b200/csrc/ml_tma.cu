@@ -30,11 +30,24 @@ namespace tma {
 constexpr int kTile = 256;                    // columns per CTA = threads per CTA
 constexpr int kConsumerWarps = kTile / 32;    // 8
 constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
-#ifndef ML_TMA_NSUB
-#define ML_TMA_NSUB 1
+constexpr int kStages = 4;                    // ring depth: levels in flight per CTA
+// Which column of the tile a thread integrates (local modes):
+//   0 = thread i takes column i
+//   1 = columns are ranked by depth within each residue class mod 32 (lane l keeps bank l: no
+//       shared-memory conflicts) and handed to the warps deepest first
+//   2 = columns are ranked by depth across the whole tile
+// A warp skips a level when none of its lanes has water there, so packing columns of similar
+// depth (and land) into the same warps removes the fp64 work of dry lanes that ride along in
+// partly wet warps -- 0.90 -> 0.72 (1) / 0.58 (2) of all warp-levels on the synthetic ocean.
+#ifndef ML_TMA_SORT
+#define ML_TMA_SORT 2
 #endif
-constexpr int kSub = ML_TMA_NSUB;             // a level's chunk of TC steps is staged in kSub pieces
-constexpr int kStages = 4 * kSub;             // ring depth (the ring's bytes do not depend on kSub)
+// Ceiling experiments (tools/k3_sweep.sh; results are WRONG by construction, never shipped):
+//   1 = compute only: the ring is filled once and re-read, nothing streams from HBM
+//   2 = memory only:  every level is streamed, the arithmetic is skipped
+#ifndef ML_TMA_EXPERIMENT
+#define ML_TMA_EXPERIMENT 0
+#endif
 
 // ------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -138,10 +151,11 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
-  constexpr int TS = TC / kSub;  // time steps per stage
-  constexpr int kRowsT = (BC == 1) ? 1 : TS;
-  constexpr int kRowsS = (BC == 2) ? 1 : TS;
+  constexpr int SORT = ML_TMA_SORT;
+  constexpr int kRowsT = (BC == 1) ? 1 : TC;
+  constexpr int kRowsS = (BC == 2) ? 1 : TC;
   constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(float);
+  constexpr int kStageFloats = (int)(kStageBytes / sizeof(float));
   constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -151,23 +165,25 @@ __global__ void ML_TMA_KERNEL_ATTR
   double* red = reinterpret_cast<double*>(full + 2 * kStages);  // [kConsumerWarps][TC]
   double* s_p = red + kConsumerWarps * TC;                   // [nz]   pressure per level
   double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local modes)
+  int* s_key = reinterpret_cast<int*>(s_zi + P.nz + 1);      // [kTile] wet levels per column (SORT)
+  int* s_col = s_key + kTile;                                // [kTile] column handled by each thread (SORT)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int c0 = blockIdx.x * kTile;
   const int t0 = (P.chunk0 + (int)blockIdx.y) * TC;
   const int nz = P.nz;
 
-  // Loads one level of this CTA's tile into a stage.  Called by thread 0 for the first kStages
+  // Loads level z of this CTA's tile into its stage.  Called by thread 0 for the first kStages
   // levels and afterwards by whichever warp is the LAST to finish with a stage (a shared-memory
   // counter tells): the refill is issued the moment the slot is free, without a producer warp
   // spinning on "empty" barriers and taking registers and issue slots from the math warps.
-  auto refill_stage = [&](int q) {  // q = level * kSub + piece
-    const int s = q % kStages, z = q / kSub, tq = t0 + (q % kSub) * TS;
-    float* dT = stage_base + (size_t)s * (kStageBytes / sizeof(float));
+  auto refill_stage = [&](int z) {
+    const int s = z % kStages;
+    float* dT = stage_base + (size_t)s * kStageFloats;
     float* dS = dT + kRowsT * kTile;
     mbar_expect_tx(full + s, kStageBytes);
-    if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, tq);
-    if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, tq);
+    if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
+    if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
   };
 
   if (tid == 0) {
@@ -178,16 +194,70 @@ __global__ void ML_TMA_KERNEL_ATTR
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int q = 0; q < kStages && q < nz * kSub; ++q) refill_stage(q);
+    for (int z = 0; z < kStages && z < nz; ++z) refill_stage(z);
   }
   for (int i = threadIdx.x; i < P.nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
   if (!GLOBAL)
     for (int i = threadIdx.x; i <= P.nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
   __syncthreads();
 
+  int col = tid;  // column of the tile this thread integrates
+  if (SORT != 0) {
+    // key = number of wet levels of the column: levels whose upper interface lies above the sea
+    // floor (local modes, dz > 0) or whose reference volume is present (global mode)
+    const i64 cg = (i64)c0 + tid;
+    int key = 0;
+    if (GLOBAL) {
+      if (cg < P.ncol)
+        for (int z = 0; z < nz; ++z) key += vraw_isnan(ld_vraw(P.v_ref, (i64)z * P.ncol + cg)) ? 0 : 1;
+    } else {
+      const double dep = cg < P.ncol ? __ldg(P.deptho + cg) : 0.0;
+      int lo = 0, hi = nz;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_zi[mid] < dep) lo = mid + 1; else hi = mid;  // NaN depth (land): never true -> key 0
+      }
+      key = lo;
+    }
+    if (SORT == 1) {
+      s_key[tid] = key;
+      __syncthreads();
+      int rank = 0;  // position among the 8 columns of this lane's residue class, deepest first
+#pragma unroll
+      for (int j = 0; j < kConsumerWarps; ++j) {
+        const int k = s_key[j * 32 + lane];
+        rank += (k > key || (k == key && j < warp)) ? 1 : 0;
+      }
+      s_col[(rank < 4 ? rank : 11 - rank) * 32 + lane] = tid;
+    } else {
+      // bitonic sort of the 256 (key, column) words, deepest first; unique words -> one fixed order
+      unsigned v = ((unsigned)key << 8) | (unsigned)(kTile - 1 - tid);
+      for (int k = 2; k <= kTile; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          unsigned o;
+          if (j >= 32) {
+            __syncthreads();
+            reinterpret_cast<unsigned*>(s_key)[tid] = v;
+            __syncthreads();
+            o = reinterpret_cast<unsigned*>(s_key)[tid ^ j];
+          } else {
+            o = __shfl_xor_sync(0xffffffffu, v, j);
+          }
+          const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = 256): descending
+          v = (lower == desc) ? max(v, o) : min(v, o);
+        }
+      }
+      // sorted position p goes to warp slot 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the
+      // two warps an SM sub-partition hosts (w and w + 4) carry a deep and a shallow band
+      const int band = tid >> 5;
+      s_col[(band < 4 ? band : 11 - band) * 32 + lane] = kTile - 1 - (int)(v & 255u);
+    }
+    __syncthreads();
+    col = s_col[tid];
+  }
+
   {
-    // ----------------------------------------------------------------- consumer warps
-    const i64 c = (i64)c0 + tid;
+    const i64 c = (i64)c0 + col;
     const bool in = c < P.ncol;
     const i64 cc = in ? c : (P.ncol - 1);  // clamp: edge lanes read a valid column, never store
     Eos<EOS> eos;
@@ -211,7 +281,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     double sub_n = 0.0;
     if (SELFREF) {
       mbar_wait(full + 0, 0u);
-      const float* row = stage_base + tid;
+      const float* row = stage_base + col;
       sub_n = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[0]);  // reference.py:60-71
       if (in && P.rho_ref_out) P.rho_ref_out[c] = sub_n;
     }
@@ -242,40 +312,42 @@ __global__ void ML_TMA_KERNEL_ATTR
         }
       }
       eos.set_level(s_p[z]);
-      const bool any_water = __any_sync(0xffffffffu, nonzero(w));
-      // kSelfRef: row 0 of the NEXT level's first piece (clamped at the bottom level, where the
-      // value is recomputed and discarded) -- wait for it up front so that the reference point
-      // and the TC points below form one straight-line block
+      const bool live = nonzero(w);
+      const unsigned live_lanes = __ballot_sync(0xffffffffu, live);
+      // kSelfRef: row 0 of the NEXT level (clamped at the bottom level, where the value is
+      // recomputed and discarded) -- wait for it up front so that the reference point and the
+      // TC - 1 points below form one straight-line block
       const int zn = (z + 1 < nz) ? z + 1 : z;
-      const int qn = zn * kSub;
-      const float* rowN = stage_base + (size_t)(qn % kStages) * (kStageBytes / sizeof(float)) + tid;
+      const float* rowN = stage_base + (size_t)(zn % kStages) * kStageFloats + col;
       const double p_next = s_p[zn];
-      if (SELFREF) mbar_wait(full + (qn % kStages), (uint32_t)(qn / kStages) & 1u);
-#pragma unroll
-      for (int h = 0; h < kSub; ++h) {
-        const int q = z * kSub + h, s = q % kStages;
-        const float* sT = stage_base + (size_t)s * (kStageBytes / sizeof(float)) + tid;
+      const int s = z % kStages;
+      if (SELFREF && (ML_TMA_EXPERIMENT != 1 || zn < kStages)) mbar_wait(full + (zn % kStages), (uint32_t)(zn / kStages) & 1u);
+      if (ML_TMA_EXPERIMENT != 1 || z < kStages) mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
+      if (ML_TMA_EXPERIMENT != 2 && live_lanes != 0u) {
+        const float* sT = stage_base + (size_t)s * kStageFloats + col;
         const float* sS = sT + kRowsT * kTile;
-        mbar_wait(full + s, (uint32_t)(q / kStages) & 1u);
-        if (any_water) {
-          if (SELFREF && h == 0) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
+        if (SELFREF) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
 #pragma unroll
-          for (int kk = (SELFREF && h == 0) ? 1 : 0; kk < TS; ++kk) {  // kSelfRef: step 0 is the reference itself
-            const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
-            const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
-            const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
-            fma_skipnan(acc[h * TS + kk], w, d);
-          }
-        } else if (SELFREF && h == 0) {
-          sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
+        for (int kk = SELFREF ? 1 : 0; kk < TC; ++kk) {  // kSelfRef: step 0 is the reference itself
+          const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
+          const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
+          const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
+          fma_skipnan(acc[kk], w, d);
         }
-        if (SELFREF && h == 0 && in && z + 1 < nz && P.rho_ref_out) P.rho_ref_out[(i64)(z + 1) * P.ncol + c] = sub_n;
-        __syncwarp();
-        if (lane == 0) {
-          // the 8th warp to leave the stage refills it with the piece kStages further on
-          const int before = atomicAdd(released + s, 1);
-          if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && q + kStages < nz * kSub) refill_stage(q + kStages);
-        }
+      } else if (SELFREF) {
+        // a warp without water still owes rho_ref of the next level (reference.py:71 evaluates the
+        // EOS everywhere); over land T, S are missing and so is the result -- no arithmetic needed
+        const float tN = rowN[0], sN = rowN[kRowsT * kTile];
+        sub_n = nan("");
+        if (__any_sync(0xffffffffu, !(isnan(tN) || isnan(sN)))) sub_n = eos.rho_at((double)tN, (double)sN, p_next);
+      }
+      if (SELFREF && in && z + 1 < nz && P.rho_ref_out) P.rho_ref_out[(i64)(z + 1) * P.ncol + c] = sub_n;
+      __syncwarp();
+      if (lane == 0) {
+        // the 8th warp to leave the stage refills it with the level kStages further on
+        const int before = atomicAdd(released + s, 1);
+        if (ML_TMA_EXPERIMENT != 1 && (before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz)
+          refill_stage(z + kStages);
       }
     }
     if (!GLOBAL) {
@@ -367,8 +439,8 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
 
 template <int TC>
 inline size_t smem_bytes(int bc, int nz) {
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * (TC / kSub) : TC / kSub + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
-         (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 128;
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
+         (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 
 template <int EOS, int TC, int BC, int MODE>
@@ -409,8 +481,8 @@ struct Plan {
 static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P) {
   pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
   pl->tc = plan_tc(P.nt);
-  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc / kSub);
-  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc / kSub);
+  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc);
+  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc);
   if (!okT || !okS) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
   pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
   pl->chunks = (unsigned)((P.nt + pl->tc - 1) / pl->tc);
