@@ -344,6 +344,10 @@ def run_ours(args):
     N = nz * ncol
     alg_bytes = nt * N * 8 + N * 4 + N * 8 + ncol * 8 * (nt + 1)
     k3_avg_ms = sum(k3_ms) / len(k3_ms)
+    # share of the grid that carries water (upper interface above the sea floor and a reference volume)
+    wet = (z_i[:-1].view(nz, 1, 1) < torch.nan_to_num(depth, nan=0.0).unsqueeze(0)) & ~torch.isnan(V)
+    wet_fraction = float(wet.sum()) / float(N)
+    del wet
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -362,10 +366,12 @@ def run_ours(args):
                 "traffic": traffic, "kernel": f"ml_steric_local_selfref ({path} family)", "kernel_ms": k3_avg_ms,
                 "kernel_share_of_step": k3_avg_ms / (ms_total / args.steps),
                 "algorithmic_bytes_per_launch": alg_bytes,
-                # the other side of the ridge: 18 fp64 instructions per point (SASS count)
+                # the other side of the ridge: 18 fp64 instructions per WET point (SASS count, DESIGN.md section 4;
+                # cells with dz = 0 or no reference volume are skipped warp-wise once the tile is depth-sorted)
                 # against the DFMA rate measured on this pool by tools/microbench.cu (18.1e12/s)
-                "fp64": {"dfma_per_point": 18, "achieved_tdfma_s": 18 * points / (k3_avg_ms * 1e-3) / 1e12,
-                         "peak_tdfma_s": 18.1, "frac": 18 * points / (k3_avg_ms * 1e-3) / 18.1e12,
+                "fp64": {"dfma_per_wet_point": 18, "wet_fraction": wet_fraction,
+                         "achieved_tdfma_s": 18 * wet_fraction * points / (k3_avg_ms * 1e-3) / 1e12,
+                         "peak_tdfma_s": 18.1, "frac": 18 * wet_fraction * points / (k3_avg_ms * 1e-3) / 18.1e12,
                          "peak_source": "profiles/r01_microbench_b200.txt (measured)"},
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"}
 
