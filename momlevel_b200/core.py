@@ -255,20 +255,32 @@ def delta_rho(T, S, rho_ref, v_ref, p_level, eos="Wright", t_bcast=False, s_bcas
     return out
 
 
-def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False, s_bcast=False):
+def selfref_outputs(T, S, t_bcast=False, s_bcast=False):
+    """Empty ``(eta, rho_ref, sums)`` for :func:`steric_local_selfref`, allocated on the current stream."""
+    full = S if t_bcast else T
+    nt, nz, hshape = full.shape[0], full.shape[1], tuple(full.shape[2:])
+    dev = full.device
+    return (torch.empty((nt,) + hshape, dtype=torch.float64, device=dev),
+            torch.empty((nz,) + hshape, dtype=torch.float64, device=dev),
+            torch.empty(2, dtype=torch.float64, device=dev))
+
+
+def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False, s_bcast=False,
+                         out=None):
     """``setup_reference_state`` + the local branch in one pass; reference = step 0 (steric.py:105-107).
 
     A broadcast operand is the step-0 slab of that field.  Returns
-    ``(eta [nt,...], rho_ref [nz,...], sums fp64[2] = {volo, masso})`` on the device.
+    ``(eta [nt,...], rho_ref [nz,...], sums fp64[2] = {volo, masso})`` on the device; ``out`` may
+    hand in those three tensors (see :func:`selfref_outputs`) when the caller manages streams.
     """
     L = _lib.lib()
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     v_ref = to_device(v_ref)
     z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
     assert v_ref.numel() == nz * ncol and depth.numel() == ncol and z_i.numel() == nz + 1 and p.numel() == nz
-    eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
-    rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
-    sums = torch.empty(2, dtype=torch.float64, device=T.device)
+    eta, rho, sums = out if out is not None else selfref_outputs(T, S, t_bcast, s_bcast)
+    assert eta.dtype == rho.dtype == sums.dtype == torch.float64 and eta.is_contiguous() and rho.is_contiguous()
+    assert eta.numel() == nt * ncol and rho.numel() == nz * ncol and sums.numel() == 2
     ws, nbytes = _workspace(2, nz, ncol, T.device)
     _lib.check(
         L.ml_steric_local_selfref(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),

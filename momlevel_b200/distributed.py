@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_sizes", "assign_members", "gather_series", "global_sea_level",
-           "steric_global_sharded"]
+           "steric_global_sharded", "steric_local_members"]
 
 
 def shard_sizes(n, world):
@@ -77,3 +77,48 @@ def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_su
     masso_local = core.steric_global(T_local, S_local, v_ref, p_level, eos=eos)
     masso = gather_series(masso_local, n_total, group=group)
     return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
+
+
+_STREAMS = {}  # device index -> side streams, kept so that the allocator's per-stream pools stay warm
+
+
+def _member_streams(dev, n):
+    pool = _STREAMS.setdefault(dev.index if dev.index is not None else torch.cuda.current_device(), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
+def steric_local_members(members, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", n_streams=4):
+    """Local steric height of this rank's ensemble members, one ``steric()`` problem each.
+
+    The reference API is strictly 4-D (``util.py:762-770``), so an ensemble is a loop over members;
+    every member carries its own reference state (its step 0).  ``members`` is a sequence of
+    ``(T, S, v_ref)`` device tensors.  Members are issued round-robin on ``n_streams`` CUDA streams:
+    a member of a 1-degree grid is only a few waves of CTAs per launch, and with several streams the
+    tail of one member's launch is filled by the head of the next member's.  Results are ordered
+    after the calling stream.  Returns a list of ``(eta, rho_ref, sums)``.
+    """
+    from . import core
+
+    members = list(members)
+    if not members:
+        return []
+    dev = members[0][0].device
+    caller = torch.cuda.current_stream(dev)
+    streams = _member_streams(dev, max(1, min(int(n_streams), len(members))))
+    # outputs live on the caller's stream: allocated before the fork, used after the join
+    outs = [core.selfref_outputs(T, S) for T, S, _ in members]
+    fork = torch.cuda.Event()
+    fork.record(caller)
+    for i, (T, S, V) in enumerate(members):
+        st = streams[i % len(streams)]
+        if i < len(streams):
+            st.wait_event(fork)
+        with torch.cuda.stream(st):  # the reduction scratch is allocated (and recycled) on this stream
+            core.steric_local_selfref(T, S, V, z_i, deptho, p_level, rhozero=rhozero, eos=eos, out=outs[i])
+    for st in streams:
+        join = torch.cuda.Event()
+        join.record(st)
+        caller.wait_event(join)
+    return outs

@@ -91,3 +91,23 @@ def test_sharded_global_matches_unsharded_on_gpu():
                                      float(reference["areacello"].sum()))
     assert np.allclose(eta, res["steric"].values, rtol=0, atol=1e-12)
     assert href == pytest.approx(float(res["reference_height"]), rel=1e-15)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_streams", [1, 2, 3])
+def test_members_on_streams_equal_sequential_calls(n_streams):
+    """Config 3's member loop: issuing members on several CUDA streams changes nothing but the timing."""
+    from momlevel_b200 import core, synth
+
+    shape = (25, 10, 16, 64)  # three 12-step chunks (one short) per member: self-reference + local launches
+    grid = synth.make_grid(*shape[1:], seed=4, device="cuda")
+    pres = grid["z_l"] * 1.0e4 + 101325.0
+    fields = [synth.make_fields(grid, shape[0], seed=100 + m, dtype=torch.float32) for m in range(5)]
+    want = [core.steric_local_selfref(T, S, V, grid["z_i"], grid["deptho"], pres) for T, S, V in fields]
+    torch.cuda.synchronize()
+    for _ in range(3):  # repeated: a missing stream dependency would show as a flaky mismatch
+        got = mld.steric_local_members(fields, grid["z_i"], grid["deptho"], pres, n_streams=n_streams)
+        for (e1, r1, s1), (e2, r2, s2) in zip(got, want):
+            assert torch.equal(torch.nan_to_num(e1, nan=-1.0), torch.nan_to_num(e2, nan=-1.0))
+            assert torch.equal(torch.nan_to_num(r1, nan=-1.0), torch.nan_to_num(r2, nan=-1.0))
+            assert torch.equal(s1, s2)

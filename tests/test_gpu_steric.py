@@ -264,6 +264,55 @@ def test_nan_semantics(ml):
     assert np.all(np.isnan(eta[:, 0, 0])) and np.all(np.isnan(eta[:, 4, 4])) and np.all(np.isfinite(eta[:, 1, 1]))
 
 
+def test_nan_semantics_tma_family(ml):
+    """The same literal reading of steric.py:151-166 on a grid the TMA family takes, with masks that
+    disagree with the bathymetry, so the depth-sorted tile cannot rely on either being consistent."""
+    from momlevel_b200 import core, synth
+
+    shape = (13, 12, 16, 64)  # ncol = 1024: four tiles; 13 steps: a 12-step chunk and a 1-step tail
+    ds = synth.make_dataset(*shape, seed=5, device="cpu", dtype=torch.float32)
+    T, S = ds["thetao"].data.clone(), ds["so"].data.clone()
+    V = ds["volcello"].data[0].clone()
+    depth = ds["deptho"].data.clone()
+    g = torch.Generator().manual_seed(7)
+    ny, nx = shape[2], shape[3]
+    for _ in range(40):  # holes in T or S at single cells and steps (wet or not)
+        t, z, y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in shape)
+        (T if _ % 2 else S)[t, z, y, x] = float("nan")
+    for _ in range(20):  # reference volume missing where there is water, present where there is none
+        z, y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in shape[1:])
+        V[z, y, x] = float("nan") if torch.isfinite(V[z, y, x]) else 1.0e9
+    for _ in range(12):  # bathymetry that disagrees with the masks: land with data, deep water over missing data
+        y, x = int(torch.randint(0, ny, (1,), generator=g)), int(torch.randint(0, nx, (1,), generator=g))
+        depth[y, x] = float("nan") if torch.isfinite(depth[y, x]) else 3000.0
+    V[0, 3, 7] = float("nan")  # surface volume missing: eta is masked (steric.py:166)
+    d = ml.Dataset()
+    for k in ("time", "z_l", "z_i", "yh", "xh", "areacello"):
+        d[k] = ds[k]
+    dims = ("time", "z_l", "yh", "xh")
+    d["thetao"], d["so"] = ml.DataArray(T.cuda(), dims), ml.DataArray(S.cuda(), dims)
+    d["volcello"] = ml.DataArray(V.cuda().unsqueeze(0).expand(shape[0], -1, -1, -1), dims)
+    d["deptho"] = ml.DataArray(depth.cuda(), ("yh", "xh"))
+    T64, S64, V64 = T.double().numpy(), S.double().numpy(), V.double().numpy()
+    V4 = np.broadcast_to(V64, T64.shape)
+    z_l, z_i = ds["z_l"].values, ds["z_i"].values
+    oref = osteric.reference_state(T64, S64, V4, ds["areacello"].values, z_l)
+    for variant in ("steric", "thermosteric", "halosteric"):
+        eta, drho = osteric.steric_local(T64, S64, z_l, z_i, depth.numpy(), oref, variant=variant)
+        gser, href, masso = osteric.steric_global(T64, S64, z_l, oref, variant=variant)
+        result, reference = ml.steric(d, variant=variant)
+        assert core.last_path() == 2, "expected the TMA family"
+        _close_nan(reference["rho"].values, oref["rho"], rtol=RHO_RTOL)
+        assert float(reference["masso"]) == pytest.approx(oref["masso"], rel=1e-12)
+        _close_nan(result[variant].values, eta, atol=ETA_ATOL)
+        again, _ = ml.steric(d, variant=variant, reference=reference)
+        assert core.last_path() == 2
+        _close_nan(again[variant].values, eta, atol=ETA_ATOL)
+        gres, _ = ml.steric(d, variant=variant, domain="global", reference=reference)
+        assert core.last_path() == 2
+        assert np.allclose(gres[variant].values, gser, rtol=0, atol=ETA_ATOL)
+
+
 # ------------------------------------------------------- size-independent properties
 
 

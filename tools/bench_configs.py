@@ -56,22 +56,28 @@ def config3(rank, world, dev):
         members = members[:4]  # what rank 0 of an 8-GPU run owns
     grid = synth.make_grid(nz, ny, nx, seed=7, device=dev)
     pres = grid["z_l"] * 1.0e4 + 101325.0
-    pairs = []
-    for m in members:
-        T, S, V = synth.make_fields(grid, nt, seed=1000 + m, dtype=torch.float32)
-        core.steric_local_selfref(T, S, V, grid["z_i"], grid["deptho"], pres)  # warm-up
+    z_i, depth = grid["z_i"].contiguous(), grid["deptho"].contiguous()
+    # all members of the rank are resident (4 x 8.3 GB) -- generating them is not timed
+    fields = [synth.make_fields(grid, nt, seed=1000 + m, dtype=torch.float32) for m in members]
+    n_streams = int(os.environ.get("ML_MEMBER_STREAMS", "4"))
+    mld.steric_local_members(fields, z_i, depth, pres, n_streams=n_streams)  # warm-up
+    torch.cuda.synchronize()
+    best = float("inf")
+    for _ in range(3):
+        a, b = ev(), ev()
+        a.record()
+        res = mld.steric_local_members(fields, z_i, depth, pres, n_streams=n_streams)
+        b.record()
         torch.cuda.synchronize()
-        _, p = timed(lambda: core.steric_local_selfref(T, S, V, grid["z_i"], grid["deptho"], pres))
-        pairs.append(p)
-        torch.cuda.synchronize()
-        del T, S, V
-    ms = sum(a.elapsed_time(b) for a, b in pairs)
-    ms = max_over_ranks(ms, dev, world)
+        best = min(best, a.elapsed_time(b))
+        del res
+    del fields
+    ms = max_over_ranks(best, dev, world)
     n_members = 30 if world > 1 else len(members)
     pts = n_members * nt * nz * ny * nx
     per_member_bytes = nt * nz * ny * nx * 8 + nz * ny * nx * (4 + 8) + ny * nx * 8 * (nt + 1) + (nt // 12 - 1) * nz * ny * nx * 12
     return {"config": 3, "workload": f"SPEAR 1deg {nx}x{ny}x{nz}, {n_members} members x {nt} months, local steric, Wright",
-            "n_gpus": world, "members_per_rank_max": len(members), "kernel_ms_max_rank": ms,
+            "n_gpus": world, "members_per_rank_max": len(members), "member_streams": n_streams, "kernel_ms_max_rank": ms,
             "value": pts / (ms * 1e-3), "unit": "grid-points/s",
             "hbm_frac": per_member_bytes * len(members) / (ms * 1e-3) / 1e9 / PEAK}
 
