@@ -411,6 +411,11 @@ def run_ours(args):
         half = nt // 2  # spice writes an fp64 field as large as both inputs; half the steps keeps HBM use bounded
         ms = timed(lambda: core.flament_spice(T[:half], S[:half]))
         extras["flament_spice_gpts"] = half * N / ms / 1e6
+        z_l = grid["z_l"].contiguous()  # the column diagnostics of SURVEY 8f: 8 B in + 8 B out per point, like spice
+        ms = timed(lambda: core.calc_n2(T[:half], S[:half], z_l))
+        extras["calc_n2_gpts"] = half * N / ms / 1e6
+        ms = timed(lambda: core.calc_n2(T[:half], S[:half], z_l, adjust_negative=True))
+        extras["calc_n2_adjusted_gpts"] = half * N / ms / 1e6
         extras["steric_local_selfref_call_gpts"] = points / k3_avg_ms / 1e6
         line["extras_Gpts_per_s"] = extras
         torch.cuda.empty_cache()

@@ -205,6 +205,44 @@ int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const
  * host thread between calls. */
 int ml_host_release(void);
 
+/* =======================================================================================
+ * Stratification diagnostics that share the vertical sweep of the steric path (csrc/ml_strat.cu).
+ * T, S are [nouter][nz][ncol] of `dtype`, z_l is [nz] fp64 (3 <= nz <= 1024: the vertical
+ * derivative is numpy.gradient(f, z_l, edge_order=2), what DataArray.differentiate evaluates).
+ * `fill_mode` selects which cells adjust_negative_n2's `adjusted[0] = adjusted[0].fillna(1e-8)`
+ * (src/momlevel/derived.py:63) touches: index 0 of the array's FIRST axis, i.e.
+ *   0 = the surface level of every slab   (a 3-D field [z][y][x], passed with nouter = 1)
+ *   1 = every level of outer slab 0       (a 4-D field [t][z][y][x]: its first time step)
+ * ===================================================================================== */
+
+/* ml_calc_n2 -- squared buoyancy frequency at cell centres, g * (alpha dT/dz - beta dS/dz) with
+ * locally referenced pressure p = z_l * 1e4 + patm.
+ * Replaces derived.calc_n2 without `interfaces` (src/momlevel/derived.py:391-411), including
+ * adjust_negative=True (:409 -> :30-71).  out is [nouter][nz][ncol] fp64. */
+int ml_calc_n2(int eos, int dtype, const void* T, const void* S, const double* z_l, double gravity,
+               double patm, int adjust_negative, int fill_mode, int64_t nouter, int64_t nz,
+               int64_t ncol, double* out, void* stream);
+
+/* ml_adjust_negative_n2 -- Chelton et al. (1998) adjustment of an existing N2 field:
+ * non-positive values are replaced by the last positive value above them in the column.
+ * Replaces derived.adjust_negative_n2 (src/momlevel/derived.py:30-71). */
+int ml_adjust_negative_n2(const double* n2, int fill_mode, int64_t nouter, int64_t nz, int64_t ncol,
+                          double* out, void* stream);
+
+/* ml_stability_angle -- Turner angle degrees(arctan((1 + R) / (1 - R))), R = beta dS/dz / (alpha dT/dz).
+ * Replaces derived.calc_stability_angle (src/momlevel/derived.py:714-766); p_level is the
+ * caller's pressure per level, [nz] fp64. */
+int ml_stability_angle(int eos, int dtype, const void* T, const void* S, const double* p_level,
+                       const double* z_l, int64_t nouter, int64_t nz, int64_t ncol, double* out,
+                       void* stream);
+
+/* ml_wave_speed -- first-baroclinic-mode gravity wave speed, sum_z sqrt(adjusted N2) dz / pi (skipna).
+ * Replaces the arithmetic of derived.calc_wave_speed (src/momlevel/derived.py:821); the mask of
+ * :822 is array bookkeeping done by the host.  n2 [nouter][nz][ncol], dz [nz][ncol],
+ * out [nouter][ncol], all fp64. */
+int ml_wave_speed(const double* n2, const double* dz, int fill_mode, int64_t nouter, int64_t nz,
+                  int64_t ncol, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -168,6 +168,82 @@ def calc_dz(z_i, deptho, top=0.0, bottom=None, fraction=False):
     return out
 
 
+# ------------------------------------------------------------------------- stratification
+
+
+def _column_view(x, z_axis):
+    """``(nouter, nz, ncol)`` of a C-contiguous field whose level axis is ``z_axis``."""
+    z_axis = z_axis % x.dim()
+    return (int(np.prod(x.shape[:z_axis], dtype=np.int64)), int(x.shape[z_axis]),
+            int(np.prod(x.shape[z_axis + 1:], dtype=np.int64)))
+
+
+def _fill_mode(ndim, z_axis):
+    # adjust_negative_n2's ``adjusted[0]`` is index 0 of the FIRST axis (derived.py:63): the surface level
+    # when the level axis leads, the first outer (time) slab otherwise
+    return 0 if z_axis % ndim == 0 else 1
+
+
+def calc_n2(T, S, z_l, eos="Wright", gravity=-9.8, patm=101325.0, z_axis=1, adjust_negative=False):
+    """``derived.calc_n2`` at cell centres (derived.py:391-411), fp64 out, same shape as ``T``."""
+    L = _lib.lib()
+    T, S = to_device(T), to_device(S)
+    assert T.shape == S.shape, "thetao and so must have the same shape"
+    dt = _field_dtype(T, S)
+    T, S = T.to(dt), S.to(dt)
+    nouter, nz, ncol = _column_view(T, z_axis)
+    z = _f64(z_l)
+    assert z.numel() == nz, "one level coordinate per level"
+    out = torch.empty(T.shape, dtype=torch.float64, device=T.device)
+    _lib.check(
+        L.ml_calc_n2(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), z.data_ptr(), float(gravity), float(patm),
+                     int(bool(adjust_negative)), _fill_mode(T.dim(), z_axis), nouter, nz, ncol, out.data_ptr(), _stream())
+    )
+    return out
+
+
+def adjust_negative_n2(n2, z_axis=1):
+    """``derived.adjust_negative_n2`` (derived.py:30-71) on an existing field."""
+    L = _lib.lib()
+    n2 = _f64(n2)
+    nouter, nz, ncol = _column_view(n2, z_axis)
+    out = torch.empty_like(n2)
+    _lib.check(L.ml_adjust_negative_n2(n2.data_ptr(), _fill_mode(n2.dim(), z_axis), nouter, nz, ncol, out.data_ptr(),
+                                       _stream()))
+    return out
+
+
+def stability_angle(T, S, p_level, z_l, eos="Wright", z_axis=1):
+    """``derived.calc_stability_angle`` (derived.py:714-766) with a per-level pressure."""
+    L = _lib.lib()
+    T, S = to_device(T), to_device(S)
+    assert T.shape == S.shape, "thetao and so must have the same shape"
+    dt = _field_dtype(T, S)
+    T, S = T.to(dt), S.to(dt)
+    nouter, nz, ncol = _column_view(T, z_axis)
+    z, p = _f64(z_l), _f64(p_level)
+    assert z.numel() == nz and p.numel() == nz
+    out = torch.empty(T.shape, dtype=torch.float64, device=T.device)
+    _lib.check(
+        L.ml_stability_angle(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), p.data_ptr(), z.data_ptr(), nouter,
+                             nz, ncol, out.data_ptr(), _stream())
+    )
+    return out
+
+
+def wave_speed(n2, dz, z_axis=1):
+    """``(sqrt(adjust_negative_n2(n2)) * dz).sum(z) / pi`` (derived.py:821); ``dz`` is ``[nz][...]``."""
+    L = _lib.lib()
+    n2, dz = _f64(n2), _f64(dz)
+    nouter, nz, ncol = _column_view(n2, z_axis)
+    assert dz.numel() == nz * ncol, "dz must be [nz][columns]"
+    z_axis = z_axis % n2.dim()
+    out = torch.empty(tuple(n2.shape[:z_axis]) + tuple(n2.shape[z_axis + 1:]), dtype=torch.float64, device=n2.device)
+    _lib.check(L.ml_wave_speed(n2.data_ptr(), dz.data_ptr(), _fill_mode(n2.dim(), z_axis), nouter, nz, ncol,
+                               out.data_ptr(), _stream()))
+    return out
+
+
 # ------------------------------------------------------------------------------ reducing
 
 

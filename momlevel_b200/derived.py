@@ -3,7 +3,9 @@
 Mirrors ``src/momlevel/derived.py``: ``calc_rho`` (:597-639), ``calc_dz`` (:249-325),
 ``calc_masso`` (:414-444), ``calc_volo`` (:769-795), ``calc_rhoga`` (:642-666),
 ``calc_spice`` (:669-711), plus ``calc_alpha`` / ``calc_beta`` (:74-159) and ``calc_pdens``
-(:447-486) which reuse the same elementwise kernel.  Field arithmetic runs in
+(:447-486) which reuse the same elementwise kernel, and the column diagnostics that share the
+vertical sweep: ``calc_n2`` at cell centres (:328-411), ``adjust_negative_n2`` (:30-71),
+``calc_stability_angle`` (:714-766), ``calc_wave_speed`` (:798-828).  Field arithmetic runs in
 libmomlevel_b200; attributes are the reference's CF metadata.
 """
 
@@ -12,8 +14,8 @@ import numpy as np
 from . import core, util
 from .labeled import DataArray
 
-__all__ = ["calc_alpha", "calc_beta", "calc_dz", "calc_masso", "calc_pdens", "calc_rho", "calc_rhoga", "calc_spice",
-           "calc_volo"]
+__all__ = ["adjust_negative_n2", "calc_alpha", "calc_beta", "calc_dz", "calc_masso", "calc_n2", "calc_pdens", "calc_rho",
+           "calc_rhoga", "calc_spice", "calc_stability_angle", "calc_volo", "calc_wave_speed"]
 
 
 def _as_labeled(x):
@@ -147,3 +149,93 @@ def calc_rhoga(masso, volo):
     rhoga = _as_labeled(masso) / _as_labeled(volo)
     rhoga.attrs = {"long_name": "Global Average Sea Water Density", "units": "kg m-3"}
     return rhoga
+
+
+# ------------------------------------------------------------------ column diagnostics
+
+
+def _levels(da, zcoord):
+    """Values of the level coordinate ``da[zcoord]`` (what ``differentiate(zcoord)`` uses)."""
+    if zcoord not in da.dims:
+        raise KeyError(zcoord)
+    z = da.coords.get(zcoord)
+    if z is None:
+        raise KeyError(f"{zcoord!r} is a dimension without coordinate values; take the variable out of its Dataset "
+                       "or pass coords={...}")
+    return z.data if isinstance(z, DataArray) else z
+
+
+def adjust_negative_n2(n2, zcoord="z_l"):
+    """Chelton et al. (1998) adjustment of negative N2 (derived.py:30-71)."""
+    n2 = _as_labeled(n2)
+    out = DataArray(core.adjust_negative_n2(n2.data, z_axis=n2.dims.index(zcoord)), n2.dims, coords=n2.coords)
+    out.attrs = {**n2.attrs, "comment": "adjustment applied for negative values"}
+    return out
+
+
+def calc_n2(thetao, so, eos="Wright", gravity=-9.8, patm=101325.0, zcoord="z_l", interfaces=None, adjust_negative=False):
+    """Squared buoyancy frequency at cell centres (derived.py:328-411)."""
+    if interfaces is not None:
+        raise NotImplementedError("calc_n2 on cell interfaces needs xgcm's vertical transform (derived.py:391-395)")
+    util.eos_func_from_str(eos, func_name="alpha")
+    thetao, so = _as_labeled(thetao), _as_labeled(so)
+    if thetao.dims != so.dims:
+        raise ValueError(f"cannot broadcast thetao{thetao.dims} against so{so.dims}")
+    if not np.ndim(patm) == 0:
+        raise NotImplementedError("a non-scalar patm is not supported")
+    out = core.calc_n2(thetao.data, so.data, _levels(thetao, zcoord), eos=eos, gravity=gravity, patm=float(patm),
+                       z_axis=thetao.dims.index(zcoord), adjust_negative=adjust_negative)
+    n2 = DataArray(out, thetao.dims, coords=thetao.coords)
+    n2.attrs = {
+        "standard_name": "square_of_brunt_vaisala_frequency_in_sea_water",
+        "long_name": "Square of seawater buoyancy frequency",
+        "units": "s-2",
+    }
+    if adjust_negative:
+        n2.attrs["comment"] = "adjustment applied for negative values"
+    return n2
+
+
+def calc_stability_angle(thetao, so, pres, eos="Wright", zcoord="z_l"):
+    """Stability (Turner) angle in degrees (derived.py:714-766)."""
+    util.eos_func_from_str(eos, func_name="alpha")
+    thetao, so, pres = _as_labeled(thetao), _as_labeled(so), _as_labeled(pres)
+    if thetao.dims != so.dims:
+        raise ValueError(f"cannot broadcast thetao{thetao.dims} against so{so.dims}")
+    if pres.dims != (zcoord,):
+        raise NotImplementedError("calc_stability_angle takes a pressure that varies along the level axis only")
+    out = core.stability_angle(thetao.data, so.data, pres.data, _levels(thetao, zcoord), eos=eos,
+                               z_axis=thetao.dims.index(zcoord))
+    result = DataArray(out, thetao.dims, coords=thetao.coords, name="tu_angle")
+    result.attrs = {"long_name": "Stability angle", "units": "degrees"}
+    return result
+
+
+def calc_wave_speed(n2, dz, zcoord="z_l"):
+    """Gravity wave speed of the first baroclinic mode (derived.py:798-828).
+
+    As in the reference, the mask ``xr.where(n2[0].isnull(), nan, result)`` pairs index 0 of n2's
+    FIRST axis with the column sums, so for a 4-D ``n2`` the result carries the dims
+    ``(z, y, x, time)``: the column sums repeated over the levels where the first time step is present.
+    """
+    import torch
+
+    n2, dz = _as_labeled(n2), _as_labeled(dz)
+    zax = n2.dims.index(zcoord)
+    hdims = n2.dims[zax + 1:]
+    dzt = dz.transpose(zcoord, *hdims)  # the reference's dz is (y, x, z)
+    dz_data = core.to_device(dzt.data, torch.float64).contiguous()
+    c1 = core.wave_speed(n2.data, dz_data, z_axis=zax)  # dims: n2.dims without zcoord
+    sdims = n2.dims[:zax] + hdims
+    first = n2[0]
+    null = torch.isnan(core.to_device(first.data, torch.float64))
+    # xr.where broadcasts by dimension name: the dims of n2[0] first, then the remaining dims of the sums
+    rdims = first.dims + tuple(d for d in sdims if d not in first.dims)
+    size = dict(zip(n2.dims, n2.shape))
+    sums = c1.permute(*[sdims.index(d) for d in rdims if d in sdims])
+    sums = sums.reshape([size[d] if d in sdims else 1 for d in rdims])
+    null = null.reshape([size[d] if d in first.dims else 1 for d in rdims])
+    out = torch.where(null, torch.full((), float("nan"), dtype=torch.float64, device=c1.device), sums)
+    result = DataArray(out, rdims)
+    result.attrs = {"long name": "Ocean gravity wave speed of the first baroclinic mode", "units": "m s-1"}
+    return result

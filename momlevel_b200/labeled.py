@@ -272,7 +272,15 @@ class Dataset:
         self._vars[name] = value
 
     def __getitem__(self, name):
-        return self._vars[name]
+        var = self._vars[name]
+        # like xarray, a variable taken out of a Dataset carries the index coordinates of its dims
+        # (derived.calc_n2 reads thetao[zcoord], derived.py:396)
+        if not var.is_lazy:
+            for d in var.dims:
+                idx = self._vars.get(d)
+                if d != name and d not in var.coords and idx is not None and idx.dims == (d,):
+                    var.coords[d] = idx
+        return var
 
     def __getattr__(self, name):
         try:

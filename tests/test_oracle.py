@@ -243,3 +243,18 @@ def test_calc_n2_kats():
     assert np.array_equal(adj, stratification.adjust_negative_n2(n2), equal_nan=True)
     # time 0 is filled everywhere (the reference's `adjusted[0]` is the first axis), later steps only forward-filled
     assert np.all(adj[0] > 0) and np.all(adj[np.isfinite(adj)] > 0)
+
+
+def test_stability_angle_and_wave_speed_kats():
+    # tests/test_derived.py:140-151
+    d = testdata.generate_test_data()
+    tu = stratification.calc_stability_angle(d["thetao"], d["so"], d["z_l"] * 1.0e4, d["z_l"])
+    assert tu.shape == (5, 5, 5, 5)
+    assert tu.sum() == pytest.approx(5838.68533435, abs=5e-8)
+    n2 = stratification.calc_n2(d["thetao"], d["so"], d["z_l"])
+    dz = steric.calc_dz(d["z_l"], d["z_i"], d["deptho"])
+    c1, broadcast = stratification.calc_wave_speed(n2, dz)
+    assert c1.shape == (5, 5, 5) and broadcast.shape == (5, 5, 5, 5)  # (t,y,x) and the reference's (z,y,x,t)
+    assert broadcast.sum() == pytest.approx(524.30956095, abs=5e-8)
+    # no missing values here: the broadcast repeats the column sums over the five levels
+    assert np.array_equal(broadcast[2], np.moveaxis(c1, 0, -1))
