@@ -207,7 +207,7 @@ int ml_host_release(void);
 
 /* =======================================================================================
  * Stratification diagnostics that share the vertical sweep of the steric path (csrc/ml_strat.cu).
- * T, S are [nouter][nz][ncol] of `dtype`, z_l is [nz] fp64 (3 <= nz <= 1024: the vertical
+ * T, S are [nouter][nz][ncol] of `dtype`, z_l is [nz] fp64 (3 <= nz <= 512: the vertical
  * derivative is numpy.gradient(f, z_l, edge_order=2), what DataArray.differentiate evaluates).
  * `fill_mode` selects which cells adjust_negative_n2's `adjusted[0] = adjusted[0].fillna(1e-8)`
  * (src/momlevel/derived.py:63) touches: index 0 of the array's FIRST axis, i.e.

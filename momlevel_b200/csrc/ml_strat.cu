@@ -9,7 +9,8 @@
 //   derived.calc_wave_speed      src/momlevel/derived.py:798-828
 //
 // One thread owns one water column of one outer (time) slab and walks it top to bottom with a
-// three-level window in registers, so T and S cross HBM once (8 B per point in, 8 B out) and the
+// three-level window in registers (fed through a cp.async ring in shared memory, see k_strat), so
+// T and S cross HBM once (8 B per point in, 8 B out) and the
 // vertical derivative -- numpy.gradient(..., edge_order=2) on the uneven z grid, which is what
 // DataArray.differentiate evaluates -- never materialises dT/dz, dS/dz, alpha or beta.  Threads
 // are adjacent along x, so every load and store of a warp is one contiguous row segment.
@@ -20,7 +21,7 @@ namespace ml {
 namespace {
 
 constexpr int kBlock = 128;
-constexpr int kMaxLevels = 1024;  // gradient coefficients of every level live in shared memory
+constexpr int kMaxLevels = 512;  // gradient coefficients of every level live in shared memory (<= 48 KB with the ring)
 
 // numpy.gradient's second-order coefficients for an uneven grid (numpy/lib/function_base.py,
 // `gradient`: interior a,b,c from dx1 = x[i]-x[i-1], dx2 = x[i+1]-x[i]; one-sided three-point
@@ -56,18 +57,27 @@ __device__ void gradient_coefficients(const double* __restrict__ z, int nz, doub
 
 // alpha = -(drho/dT)/rho and beta = (drho/dS)/rho (wright.py:122-165) from ONE division:
 // rho = pp/den and drho/dX = N_X/den^2 give alpha = -N_T/(den pp), beta = N_S/(den pp).
+// Coefficients are DFMA operands straight from the constant bank (as literals each would be
+// rebuilt from two 32-bit moves in front of its instruction, cf. ml_common.cuh).
+struct WrightD {
+  double b2x2, b3x3, c2x2, c3x3;  // coefficients of the T-derivatives of p0 and lambda (wright.py:75-78)
+};
+__constant__ WrightD kWrightD = {2.0 * wr::b2, 3.0 * wr::b3, 2.0 * wr::c2, 3.0 * wr::c3};
+
 template <int EOS>
 __device__ __forceinline__ void alpha_beta(double T, double S, double p, double& alpha, double& beta) {
   if (EOS == 0) {
-    double al0, p0, lam;
-    wright_terms(T, S, al0, p0, lam);
-    const double pp = p + p0;
+    const WrightC K = kWrightC;  // warp-uniform copies: the compiler keeps them in uniform registers
+    const WrightD D = kWrightD;
+    const double al0 = fma(K.a2, S, fma(K.a1, T, K.a0));
+    const double pp = fma(T, fma(K.b5, S, fma(T, fma(K.b3, T, K.b2), K.b1)), fma(K.b4, S, K.b0 + p));
+    const double lam = fma(T, fma(K.c5, S, fma(T, fma(K.c3, T, K.c2), K.c1)), fma(K.c4, S, K.c0));
     const double den = fma(al0, pp, lam);
-    const double dp0_t = fma(wr::b5, S, fma(T, fma(3.0 * wr::b3, T, 2.0 * wr::b2), wr::b1));
-    const double dlam_t = fma(wr::c5, S, fma(T, fma(3.0 * wr::c3, T, 2.0 * wr::c2), wr::c1));
-    const double n_t = fma(lam, dp0_t, -(pp * fma(pp, wr::a1, dlam_t)));
-    const double n_s = fma(lam, fma(wr::b5, T, wr::b4), -(pp * fma(pp, wr::a2, fma(wr::c5, T, wr::c4))));
-    const double r = 1.0 / (den * pp);
+    const double dp0_t = fma(K.b5, S, fma(T, fma(D.b3x3, T, D.b2x2), K.b1));
+    const double dlam_t = fma(K.c5, S, fma(T, fma(D.c3x3, T, D.c2x2), K.c1));
+    const double n_t = fma(lam, dp0_t, -(pp * fma(pp, K.a1, dlam_t)));
+    const double n_s = fma(lam, fma(K.b5, T, K.b4), -(pp * fma(pp, K.a2, fma(K.c5, T, K.c4))));
+    const double r = div_checked(1.0, den * pp);
     alpha = -(n_t * r);
     beta = n_s * r;
   } else {
@@ -91,13 +101,34 @@ __device__ __forceinline__ double adjust_step(double n2, bool fill, double& carr
   return missing ? nan("") : adj;
 }
 
+// Each thread streams its own column through a private slot of a shared-memory ring with
+// cp.async: kRing - 3 levels of T and S are in flight per thread at no register cost (the
+// three-level window itself lives in registers), and because a thread only ever reads what it
+// copied itself, cp.async.wait_group is the only synchronisation.  With plain loads the sweep had
+// two loads in flight per thread and ran latency-bound at a third of the HBM bandwidth.
+constexpr int kRing = 16;
+
+template <typename TIn>
+__device__ __forceinline__ void cp_async(TIn* smem_dst, const TIn* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if (sizeof(TIn) == 4)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <typename TIn, int EOS, int OUT>
 __global__ void __launch_bounds__(kBlock) k_strat(const TIn* __restrict__ T, const TIn* __restrict__ S,
                                                   const double* __restrict__ z_l, const double* __restrict__ p_level,
                                                   double gravity, double patm, int fill_mode, int nz, i64 ncol,
                                                   double* __restrict__ out) {
-  extern __shared__ double s_coef[];  // [nz][3] gradient coefficients, then [nz] pressure
+  extern __shared__ double s_coef[];  // [nz][3] gradient coefficients, [nz] pressure, then the two rings
   double* s_p = s_coef + 3 * nz;
+  TIn* ringT = reinterpret_cast<TIn*>(s_p + nz) + threadIdx.x;  // [kRing][kBlock], this thread's slot
+  TIn* ringS = ringT + kRing * kBlock;
   gradient_coefficients(z_l, nz, s_coef);
   for (int i = threadIdx.x; i < nz; i += blockDim.x)
     s_p[i] = p_level ? __ldg(p_level + i) : fma(__ldg(z_l + i), 1.0e4, patm);  // derived.py:396
@@ -105,39 +136,27 @@ __global__ void __launch_bounds__(kBlock) k_strat(const TIn* __restrict__ T, con
   const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
   if (c >= ncol) return;
   const i64 slab = (i64)blockIdx.y * nz * ncol + c;
-  const TIn* Tc = T + slab;
-  const TIn* Sc = S + slab;
+  const TIn* gT = T + slab;  // next level to fetch
+  const TIn* gS = S + slab;
   double* oc = out + slab;
-  // rolling window over levels z-2 .. z+2 plus one more level in flight (nz >= 3 is checked by the host)
-  double t_m2 = 0.0, t_m1 = 0.0, t_0 = ldf(Tc), t_p1 = ldf(Tc + ncol), t_p2 = ldf(Tc + 2 * ncol);
-  double s_m2 = 0.0, s_m1 = 0.0, s_0 = ldf(Sc), s_p1 = ldf(Sc + ncol), s_p2 = ldf(Sc + 2 * ncol);
-  double t_p3 = 0.0, s_p3 = 0.0;
-  if (nz > 3) {
-    t_p3 = ldf(Tc + 3 * ncol);
-    s_p3 = ldf(Sc + 3 * ncol);
-  }
-  double carry = nan("");
+  int fetched = 0;
+  auto fetch = [&]() {  // one commit group per level, empty past the bottom
+    if (fetched < nz) {
+      cp_async(ringT + (fetched % kRing) * kBlock, gT);
+      cp_async(ringS + (fetched % kRing) * kBlock, gS);
+      gT += ncol;
+      gS += ncol;
+    }
+    ++fetched;
+    cp_async_commit();
+  };
+  for (int l = 0; l < kRing - 1; ++l) fetch();
   const bool fill_slab = fill_mode == 1 && blockIdx.y == 0;  // adjusted[0] of a 4-D field is its first time step
-  for (int z = 0; z < nz; ++z) {
-    double t_p4 = 0.0, s_p4 = 0.0;
-    if (z + 4 < nz) {
-      t_p4 = ldf(Tc + (i64)(z + 4) * ncol);
-      s_p4 = ldf(Sc + (i64)(z + 4) * ncol);
-    }
-    const double a = s_coef[3 * z], b = s_coef[3 * z + 1], cc = s_coef[3 * z + 2];
-    double dtdz, dsdz;
-    if (z == 0) {  // forward three-point formula
-      dtdz = fma(cc, t_p2, fma(b, t_p1, a * t_0));
-      dsdz = fma(cc, s_p2, fma(b, s_p1, a * s_0));
-    } else if (z == nz - 1) {  // backward three-point formula
-      dtdz = fma(cc, t_0, fma(b, t_m1, a * t_m2));
-      dsdz = fma(cc, s_0, fma(b, s_m1, a * s_m2));
-    } else {
-      dtdz = fma(cc, t_p1, fma(b, t_0, a * t_m1));
-      dsdz = fma(cc, s_p1, fma(b, s_0, a * s_m1));
-    }
+  double carry = nan("");
+  // one output cell: the EOS derivatives at (Tc, Sc, p_z) combined with the vertical gradients
+  auto emit = [&](int z, double Tc, double Sc, double dtdz, double dsdz) {
     double alpha, beta;
-    alpha_beta<EOS>(t_0, s_0, s_p[z], alpha, beta);
+    alpha_beta<EOS>(Tc, Sc, s_p[z], alpha, beta);
     double r;
     if (OUT == kTurnerAngle) {
       const double ratio = (beta * dsdz) / (alpha * dtdz);  // derived.py:753
@@ -146,9 +165,31 @@ __global__ void __launch_bounds__(kBlock) k_strat(const TIn* __restrict__ T, con
       r = gravity * (alpha * dtdz - beta * dsdz);  // derived.py:401
       if (OUT == kN2Adjusted) r = adjust_step(r, fill_slab || (fill_mode == 0 && z == 0), carry);
     }
-    oc[(i64)z * ncol] = r;
-    t_m2 = t_m1; t_m1 = t_0; t_0 = t_p1; t_p1 = t_p2; t_p2 = t_p3; t_p3 = t_p4;
-    s_m2 = s_m1; s_m1 = s_0; s_0 = s_p1; s_p1 = s_p2; s_p2 = s_p3; s_p3 = s_p4;
+    asm volatile("st.global.cs.f64 [%0], %1;" ::"l"(oc + (i64)z * ncol), "d"(r) : "memory");  // streamed, never re-read
+  };
+  // window (a, b, c) = levels (zc-1, zc, zc+1) in registers; nz >= 3 is checked by the host.
+  // numpy.gradient's one-sided formulas at both ends use the same three levels as their neighbours,
+  // so level 0 is emitted with level 1 and level nz-1 with level nz-2.
+  cp_async_wait<kRing - 3>();  // groups 0 and 1 have landed
+  double ta = 0.0, tb = (double)ringT[0], tc = (double)ringT[kBlock];
+  double sa = 0.0, sb = (double)ringS[0], sc = (double)ringS[kBlock];
+  for (int zc = 1; zc < nz - 1; ++zc) {
+    fetch();                      // level zc + kRing - 2; its slot held level zc - 2, long consumed
+    cp_async_wait<kRing - 3>();  // everything up to level zc + 1 has landed
+    ta = tb; tb = tc; tc = (double)ringT[((zc + 1) % kRing) * kBlock];
+    sa = sb; sb = sc; sc = (double)ringS[((zc + 1) % kRing) * kBlock];
+    if (zc == 1) {  // forward three-point formula for the surface level
+      const double a = s_coef[0], b = s_coef[1], cc = s_coef[2];
+      emit(0, ta, sa, fma(cc, tc, fma(b, tb, a * ta)), fma(cc, sc, fma(b, sb, a * sa)));
+    }
+    {
+      const double a = s_coef[3 * zc], b = s_coef[3 * zc + 1], cc = s_coef[3 * zc + 2];
+      emit(zc, tb, sb, fma(cc, tc, fma(b, tb, a * ta)), fma(cc, sc, fma(b, sb, a * sa)));
+    }
+    if (zc == nz - 2) {  // backward three-point formula for the bottom level
+      const double a = s_coef[3 * zc + 3], b = s_coef[3 * zc + 4], cc = s_coef[3 * zc + 5];
+      emit(zc + 1, tc, sc, fma(cc, tc, fma(b, tb, a * ta)), fma(cc, sc, fma(b, sb, a * sa)));
+    }
   }
 }
 
@@ -187,7 +228,7 @@ int launch_strat(int eos, int dtype, const void* T, const void* S, const double*
                  double gravity, double patm, int fill_mode, i64 nouter, int nz, i64 ncol, double* out,
                  cudaStream_t st) {
   const dim3 grid((unsigned)((ncol + kBlock - 1) / kBlock), (unsigned)nouter);
-  const size_t smem = (size_t)4 * nz * sizeof(double);
+  const size_t smem = (size_t)4 * nz * sizeof(double) + (size_t)2 * kRing * kBlock * elem_size(dtype);
 #define ML_STRAT(TIN, E) \
   k_strat<TIN, E, OUT><<<grid, kBlock, smem, st>>>((const TIN*)T, (const TIN*)S, z_l, p_level, gravity, patm, fill_mode, nz, ncol, out)
   if (dtype == ML_F32) {
