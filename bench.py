@@ -278,7 +278,11 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    bound_cpus = 0
     if world > 1:
+        from momlevel_b200 import distributed as mld
+
+        bound_cpus = mld.bind_host_to_device(local_rank)  # pinned e2e buffers on the GPU's own NUMA node
         dist.init_process_group("nccl", device_id=dev)
     if args.force_direct:
         core.force_direct(True)
@@ -381,6 +385,8 @@ def run_ours(args):
         "data": "synthetic", "config": config_of(args), "roofline": roofline, "clocks": clk.summary(),
         "gpu_launches": launches * world, "kernel_family": path,
     }
+    if world > 1:
+        line["host_cpus_bound_per_rank"] = bound_cpus
 
     # ---- extras: the other variants / domains of the same dataset, a few steps each
     if not args.no_extras:

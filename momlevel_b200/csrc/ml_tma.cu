@@ -125,9 +125,11 @@ struct Params {
   double coef;
   int nt, nz;
   int chunk0;             // first time chunk covered by this launch
+  unsigned nchunks;       // time chunks covered by this launch; grid = tiles * nchunks, chunk fastest
+  unsigned tiles;         // column tiles
   i64 ncol;
   double* eta;            // local modes: [nt][ncol]
-  double* partials;       // kGlobal: [nt][gridDim.x];  kSelfRef: [2][gridDim.x] = {volo, masso}
+  double* partials;       // kGlobal: [nt][tiles];  kSelfRef: [2][tiles] = {volo, masso}
 };
 
 // What a launch computes.
@@ -169,8 +171,12 @@ __global__ void ML_TMA_KERNEL_ATTR
   int* s_col = s_key + kTile;                                // [kTile] column handled by each thread (SORT)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int c0 = blockIdx.x * kTile;
-  const int t0 = (P.chunk0 + (int)blockIdx.y) * TC;
+  // The chunks of one tile are neighbours in launch order, so they are resident together and the
+  // time-invariant rows they all read (rho_ref, v_ref, a broadcast operand) come from HBM once and
+  // from L2 for the others; with the tiles fastest those rows were re-read from HBM for every chunk.
+  const unsigned tile = blockIdx.x / P.nchunks;
+  const int c0 = (int)tile * kTile;
+  const int t0 = (P.chunk0 + (int)(blockIdx.x - tile * P.nchunks)) * TC;
   const int nz = P.nz;
 
   // Loads level z of this CTA's tile into its stage.  Called by thread 0 for the first kStages
@@ -379,7 +385,7 @@ __global__ void ML_TMA_KERNEL_ATTR
 #pragma unroll
       for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * TC + tid];
       const i64 row = SELFREF ? tid : (t0 + tid);
-      P.partials[row * gridDim.x + blockIdx.x] = sacc;
+      P.partials[row * P.tiles + tile] = sacc;
     }
   }
 }
@@ -421,7 +427,9 @@ static bool common_eligible(int dtype, int vref_dtype, const void* T, const void
   if (dtype != ML_F32 || vref_dtype != ML_F32) return false;
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
   if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
-  if (nt < 1 || nz < 1 || nz > 512 || nt > 4 * 65535) return false;  // grid.y = time chunks
+  if (nt < 1 || nz < 1 || nz > 512) return false;
+  // grid.x = tiles * time chunks (chunks of at least 4 steps)
+  if ((double)((ncol + kTile - 1) / kTile) * (double)((nt + 3) / 4) > 2147483647.0) return false;
   // TMA global strides must stay below 2^40 bytes
   if ((double)ncol * (double)nz * 4.0 >= 1099511627776.0) return false;
   return encode_fn() != nullptr;
@@ -452,7 +460,10 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
   // is set on every launch (a host-side table lookup) rather than cached in a static
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma)");
-  kern<<<dim3(tiles, chunks), kThreads, smem, st>>>(mT, mS, P);
+  Params Q = P;
+  Q.tiles = tiles;
+  Q.nchunks = chunks;
+  kern<<<tiles * chunks, kThreads, smem, st>>>(mT, mS, Q);
   return launched("k_steric_tma");
 }
 
@@ -516,6 +527,8 @@ static Params base_params(const void* v_ref, int vref_dtype, const double* p_lev
   P.nt = nt;
   P.nz = nz;
   P.chunk0 = 0;
+  P.nchunks = 1;
+  P.tiles = 0;
   P.ncol = ncol;
   P.eta = nullptr;
   P.partials = nullptr;

@@ -14,7 +14,35 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_sizes", "assign_members", "gather_series", "global_sea_level",
-           "steric_global_sharded", "steric_local_members"]
+           "steric_global_sharded", "steric_local_members", "bind_host_to_device"]
+
+
+def bind_host_to_device(device_index):
+    """Pin this process to the CPU cores next to its GPU (NVML's ideal affinity), before host buffers exist.
+
+    With one process per GPU the pinned staging buffers of ``ml_steric_local_host`` should live on
+    the NUMA node the GPU's PCIe root hangs off: pages are placed where the allocating thread runs,
+    and a copy that crosses the socket interconnect shares that link with every other rank.
+    Returns the number of cores bound to, or 0 when NVML or the affinity call is unavailable.
+    """
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pr = torch.cuda.get_device_properties(device_index)
+        busid = f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(busid.encode())
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (os.cpu_count() + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return 0
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:  # noqa: BLE001 -- no NVML, masked device, restricted cpuset: stay unbound
+        return 0
 
 
 def shard_sizes(n, world):

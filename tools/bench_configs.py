@@ -75,7 +75,9 @@ def config3(rank, world, dev):
     ms = max_over_ranks(best, dev, world)
     n_members = 30 if world > 1 else len(members)
     pts = n_members * nt * nz * ny * nx
-    per_member_bytes = nt * nz * ny * nx * 8 + nz * ny * nx * (4 + 8) + ny * nx * 8 * (nt + 1) + (nt // 12 - 1) * nz * ny * nx * 12
+    # algorithmic bytes: T,S once, volcello(t=0) once, rho_ref written once, deptho + eta (the later chunks' reads of
+    # rho_ref / volcello are served by L2 because the chunks of a tile run together)
+    per_member_bytes = nt * nz * ny * nx * 8 + nz * ny * nx * (4 + 8) + ny * nx * 8 * (nt + 1)
     return {"config": 3, "workload": f"SPEAR 1deg {nx}x{ny}x{nz}, {n_members} members x {nt} months, local steric, Wright",
             "n_gpus": world, "members_per_rank_max": len(members), "member_streams": n_streams, "kernel_ms_max_rank": ms,
             "value": pts / (ms * 1e-3), "unit": "grid-points/s",
