@@ -124,7 +124,7 @@ struct Params {
   const double* p_level;
   double coef;
   int nt, nz;
-  int chunk0;             // first time chunk covered by this launch
+  int t_start;            // first time step covered by this launch
   unsigned nchunks;       // time chunks covered by this launch; grid = tiles * nchunks, chunk fastest
   unsigned tiles;         // column tiles
   i64 ncol;
@@ -176,7 +176,7 @@ __global__ void ML_TMA_KERNEL_ATTR
   // from L2 for the others; with the tiles fastest those rows were re-read from HBM for every chunk.
   const unsigned tile = blockIdx.x / P.nchunks;
   const int c0 = (int)tile * kTile;
-  const int t0 = (P.chunk0 + (int)(blockIdx.x - tile * P.nchunks)) * TC;
+  const int t0 = P.t_start + (int)(blockIdx.x - tile * P.nchunks) * TC;
   const int nz = P.nz;
 
   // Loads level z of this CTA's tile into its stage.  Called by thread 0 for the first kStages
@@ -480,38 +480,70 @@ static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const
 #endif
 }
 
-// time steps per register chunk: the largest of {12, 8, 4} that nt fills at least once
-static int plan_tc(int nt) { return nt >= 12 ? 12 : (nt >= 8 ? 8 : 4); }
-
-struct Plan {
+// A launch covers `chunks` register chunks of `tc` time steps starting at `t_start`.  The time axis
+// is cut into 12-step chunks plus ONE remainder chunk of the smallest width in {4, 8, 12} that holds
+// what is left: rows past nt are zero-filled by the TMA unit and cost no bytes, but they do cost
+// arithmetic, so a 10-step window runs as one 12-step chunk (2 idle rows), not as 8 + 8 (6 idle).
+struct Segment {
   CUtensorMap mT, mS;
-  int bc, tc;
-  unsigned tiles, chunks;
+  int tc, t_start;
+  unsigned chunks;
 };
 
-static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P) {
+static int remainder_tc(int steps) { return steps <= 4 ? 4 : (steps <= 8 ? 8 : 12); }
+
+struct Plan {
+  int bc;
+  unsigned tiles;
+  int nseg;
+  Segment seg[2];
+};
+
+static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P, int tc,
+                       int t_start, unsigned chunks) {
+  Segment& g = pl->seg[pl->nseg++];
+  g.tc = tc;
+  g.t_start = t_start;
+  g.chunks = chunks;
+  const bool okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc);
+  const bool okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc);
+  return (okT && okS) ? ML_OK : fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
+}
+
+// segments covering the time steps [t_begin, nt)
+static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P, int t_begin) {
   pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
-  pl->tc = plan_tc(P.nt);
-  const bool okT = t_bcast ? make_map(&pl->mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mT, T, 3, P.ncol, P.nz, P.nt, pl->tc);
-  const bool okS = s_bcast ? make_map(&pl->mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&pl->mS, S, 3, P.ncol, P.nz, P.nt, pl->tc);
-  if (!okT || !okS) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
   pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
-  pl->chunks = (unsigned)((P.nt + pl->tc - 1) / pl->tc);
-  return ML_OK;
+  pl->nseg = 0;
+  const int steps = P.nt - t_begin, full = steps / 12, rest = steps % 12;
+  int rc = ML_OK;
+  if (full > 0) rc = add_segment(pl, T, S, t_bcast, s_bcast, P, 12, t_begin, (unsigned)full);
+  if (rc == ML_OK && rest > 0) rc = add_segment(pl, T, S, t_bcast, s_bcast, P, remainder_tc(rest), t_begin + 12 * full, 1u);
+  return rc;
 }
 
 template <int MODE>
-static int launch_mode(int eos, const Plan& pl, const Params& P, unsigned chunks, cudaStream_t st) {
-#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, MODE>(pl.bc, pl.mT, pl.mS, P, pl.tiles, chunks, st)
+static int launch_segment(int eos, const Plan& pl, const Segment& g, Params P, cudaStream_t st) {
+  P.t_start = g.t_start;
+#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, MODE>(pl.bc, g.mT, g.mS, P, pl.tiles, g.chunks, st)
   if (eos == ML_EOS_WRIGHT) {
-    if (pl.tc == 12) ML_TMA_GO(0, 12);
-    if (pl.tc == 8) ML_TMA_GO(0, 8);
+    if (g.tc == 12) ML_TMA_GO(0, 12);
+    if (g.tc == 8) ML_TMA_GO(0, 8);
     ML_TMA_GO(0, 4);
   }
-  if (pl.tc == 12) ML_TMA_GO(1, 12);
-  if (pl.tc == 8) ML_TMA_GO(1, 8);
+  if (g.tc == 12) ML_TMA_GO(1, 12);
+  if (g.tc == 8) ML_TMA_GO(1, 8);
   ML_TMA_GO(1, 4);
 #undef ML_TMA_GO
+}
+
+template <int MODE>
+static int launch_plan(int eos, const Plan& pl, const Params& P, cudaStream_t st) {
+  for (int i = 0; i < pl.nseg; ++i) {
+    int rc = launch_segment<MODE>(eos, pl, pl.seg[i], P, st);
+    if (rc) return rc;
+  }
+  return ML_OK;
 }
 
 static Params base_params(const void* v_ref, int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol) {
@@ -526,7 +558,7 @@ static Params base_params(const void* v_ref, int vref_dtype, const double* p_lev
   P.coef = 0.0;
   P.nt = nt;
   P.nz = nz;
-  P.chunk0 = 0;
+  P.t_start = 0;
   P.nchunks = 1;
   P.tiles = 0;
   P.ncol = ncol;
@@ -545,9 +577,9 @@ int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_
   P.coef = coef;
   P.eta = eta;
   Plan pl;
-  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
+  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P, 0);
   if (rc) return rc;
-  return launch_mode<kLocal>(eos, pl, P, pl.chunks, st);
+  return launch_plan<kLocal>(eos, pl, P, st);
 }
 
 int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref, int vref_dtype,
@@ -560,17 +592,22 @@ int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bca
   P.coef = coef;
   P.eta = eta;
   P.partials = partials;
-  Plan pl;
-  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
-  if (rc) return rc;
   // the chunk that starts at the reference step: rho_ref, volo, masso and eta in one pass
-  if ((rc = launch_mode<kSelfRef>(eos, pl, P, 1, st))) return rc;
-  if ((rc = reduce_rows(partials, pl.tiles, sums, 2, st))) return rc;
-  if (pl.chunks > 1) {  // later chunks read the rho_ref just written (same stream: ordered)
+  Plan first;
+  first.bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
+  first.tiles = (unsigned)((ncol + kTile - 1) / kTile);
+  first.nseg = 0;
+  const int tc0 = nt >= 12 ? 12 : remainder_tc(nt);
+  int rc = add_segment(&first, T, S, t_bcast, s_bcast, P, tc0, 0, 1u);
+  if (rc) return rc;
+  if ((rc = launch_plan<kSelfRef>(eos, first, P, st))) return rc;
+  if ((rc = reduce_rows(partials, first.tiles, sums, 2, st))) return rc;
+  if (nt > tc0) {  // later chunks read the rho_ref just written (same stream: ordered)
+    Plan rest;
+    if ((rc = make_plan(&rest, T, S, t_bcast, s_bcast, P, tc0))) return rc;
     P.rho_ref = rho_ref;
     P.rho_ref_out = nullptr;
-    P.chunk0 = 1;
-    rc = launch_mode<kLocal>(eos, pl, P, pl.chunks - 1, st);
+    rc = launch_plan<kLocal>(eos, rest, P, st);
   }
   return rc;
 }
@@ -581,9 +618,9 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
   P.partials = partials;
   Plan pl;
-  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P);
+  int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P, 0);
   if (rc) return rc;
-  if ((rc = launch_mode<kGlobal>(eos, pl, P, pl.chunks, st))) return rc;
+  if ((rc = launch_plan<kGlobal>(eos, pl, P, st))) return rc;
   return reduce_rows(partials, pl.tiles, masso, nt, st);
 }
 

@@ -313,6 +313,35 @@ def test_nan_semantics_tma_family(ml):
         assert np.allclose(gres[variant].values, gser, rtol=0, atol=ETA_ATOL)
 
 
+@pytest.mark.parametrize("nt", [1, 4, 5, 8, 9, 12, 13, 16, 21, 24, 25, 37])
+def test_time_axis_partition(ml, nt):
+    """Every way the TMA family cuts the time axis (12-step chunks + one remainder chunk of 4, 8 or 12)
+    gives what the direct family gives for the same call."""
+    from momlevel_b200 import core, synth
+
+    grid = synth.make_grid(6, 8, 64, seed=2, device="cuda")  # 512 columns: two tiles
+    T, S, V = synth.make_fields(grid, nt, seed=40 + nt, dtype=torch.float32)
+    pres = grid["z_l"] * 1.0e4 + 101325.0
+    z_i, depth = grid["z_i"], grid["deptho"]
+    out = {}
+    for direct in (False, True):
+        prev = core.force_direct(direct)
+        try:
+            eta, rho, sums = core.steric_local_selfref(T, S, V, z_i, depth, pres)
+            assert core.last_path() == (1 if direct else 2)
+            eta2, _ = core.steric_local(T, S, rho, V, z_i, depth, pres)
+            masso = core.steric_global(T, S, V, pres)
+            out[direct] = (eta, rho, sums, eta2, masso)
+        finally:
+            core.force_direct(prev)
+    for a, b in zip(out[False], out[True]):
+        assert a.shape == b.shape
+        assert torch.equal(torch.isnan(a), torch.isnan(b))
+        err = torch.nan_to_num(a - b).abs().max()
+        scale = torch.nan_to_num(b).abs().max().clamp_min(1.0)
+        assert float(err / scale) < 1e-13
+
+
 # ------------------------------------------------------- size-independent properties
 
 
