@@ -1,19 +1,22 @@
 // ml_tma.cu -- TMA-staged kernel family for the fused steric kernels (sm_100a).
 //
 // Layout of the work: fields are [t][z][col] fp32 (col = flattened y,x).  A CTA owns a tile
-// of kTile = 256 adjacent columns and a chunk of TC time steps.  One producer warp walks the
-// levels and, for each level, issues ONE 3-D TMA box per field ({256 cols, 1 level, TC steps}
-// = TC KB) into a ring of shared-memory stages guarded by full/empty mbarriers.  Eight
-// consumer warps (one column per thread) read T,S from shared memory, evaluate the EOS in
-// fp64 registers and keep the TC running column sums in registers, so
+// of kTile = 256 adjacent columns and a chunk of TC time steps.  For each level ONE 3-D TMA box
+// per field ({256 cols, 1 level, TC steps} = TC KB) lands in a ring of shared-memory stages
+// guarded by "full" mbarriers; the warp that is last to leave a stage refills it (there is no
+// producer warp).  Eight warps (one column per thread) read T,S from shared memory, evaluate
+// the EOS in fp64 registers and keep the TC running column sums in registers, so
 //   - every byte of T and S crosses HBM exactly once, in 1 KB contiguous rows,
 //   - rho_ref / v_ref (3-D, time-invariant) are fetched once per (level, column, chunk)
-//     with ordinary loads, prefetched one level ahead, and reused for TC steps,
+//     with ordinary loads, prefetched one level ahead, and reused for TC steps; the chunks of
+//     a tile run together, so only the first of them takes these rows from HBM,
 //   - loads cost no registers and no issue slots in the compute warps; the depth of the
 //     ring (not occupancy) hides HBM latency,
 //   - out-of-range columns / time steps of edge tiles are zero-filled by the TMA unit.
 // Levels at which no lane of a warp has any water (dz = 0: land, below the sea floor) are
 // skipped by that warp: their terms are multiplied by dz = 0 in steric.py:163 and vanish.
+// The columns of a tile are sorted by wet depth first (ML_TMA_SORT) so that dry columns share
+// warps with other dry columns instead of riding along in wet ones.
 //
 // Eligibility: fp32 fields, 16-byte aligned bases, ncol % 4 == 0 (TMA global strides are
 // multiples of 16 bytes), ncol >= kTile, no delta_rho output.  Everything else takes the
@@ -31,7 +34,7 @@ constexpr int kTile = 256;                    // columns per CTA = threads per C
 constexpr int kConsumerWarps = kTile / 32;    // 8
 constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
 constexpr int kStages = 4;                    // ring depth: levels in flight per CTA
-// Which column of the tile a thread integrates (local modes):
+// Which column of the tile a thread integrates:
 //   0 = thread i takes column i
 //   1 = columns are ranked by depth within each residue class mod 32 (lane l keeps bank l: no
 //       shared-memory conflicts) and handed to the warps deepest first
