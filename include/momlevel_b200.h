@@ -156,6 +156,19 @@ int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, 
                  int64_t nt, int64_t nz, int64_t ncol, double* delta_rho, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ml_delta_rho_annual -- the density anomaly of ml_delta_rho averaged over each year of 12 monthly
+ * steps with the weights of util.annual_average (src/momlevel/util.py:84-87, applied to the result
+ * Dataset by steric.py:181-182): sum_m w_m d_m / sum_m w_m per cell, missing months skipped and the
+ * weights renormalised (xarray's weighted(...).mean).  The monthly 4-D field is never stored.
+ *   weights           device fp64[nt] (days in month); nt must be a multiple of 12
+ *   delta_rho_annual  [nt/12][nz][ncol] fp64 out
+ * ------------------------------------------------------------------------------------- */
+int ml_delta_rho_annual(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                        const double* rho_ref, const void* v_ref, int vref_dtype,
+                        const double* p_level, const double* weights, int64_t nt, int64_t nz,
+                        int64_t ncol, double* delta_rho_annual, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * ml_steric_local_selfref -- ml_reference_state + ml_steric_local in one pass when the
  * reference state is the first time step of the dataset itself, which is what
  * steric.steric does when no `reference` is supplied (src/momlevel/steric.py:105-107 ->

@@ -331,6 +331,25 @@ def delta_rho(T, S, rho_ref, v_ref, p_level, eos="Wright", t_bcast=False, s_bcas
     return out
 
 
+def delta_rho_annual(T, S, rho_ref, v_ref, p_level, days_in_month, eos="Wright", t_bcast=False, s_bcast=False):
+    """Annual means of ``delta_rho`` weighted by ``days_in_month`` (util.py:84-87 applied to steric.py:151-158).
+
+    ``[nt/12, nz, ...]`` fp64 on the device; the monthly 4-D anomaly is never materialised.
+    """
+    L = _lib.lib()
+    T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
+    rho_ref, v_ref, p, w = _f64(rho_ref), to_device(v_ref), _f64(p_level), _f64(days_in_month)
+    assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and p.numel() == nz
+    assert w.numel() == nt and nt % 12 == 0, "annual averaging needs whole years of monthly data"
+    out = torch.empty((nt // 12, nz) + hshape, dtype=torch.float64, device=T.device)
+    _lib.check(
+        L.ml_delta_rho_annual(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                              rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), w.data_ptr(), nt, nz,
+                              ncol, out.data_ptr(), _stream())
+    )
+    return out
+
+
 def selfref_outputs(T, S, t_bcast=False, s_bcast=False):
     """Empty ``(eta, rho_ref, sums)`` for :func:`steric_local_selfref`, allocated on the current stream."""
     full = S if t_bcast else T

@@ -104,12 +104,16 @@ __global__ void __launch_bounds__(kBlock) k_eos_eval_vec(const TIn* __restrict__
 // delta_rho[t][z][col] = V_ref notnull ? rho(T,S,p_z) - rho_ref : NaN   (steric.py:151-153).
 // One level per trip of blockIdx.y; rho_ref / v_ref are read once per (level, column) and reused
 // for every time step.  VEC = 4 adjacent columns per thread with 128-bit accesses, or 1.
-template <typename TIn, int EOS, int VEC>
+// ANNUAL: out[year][z][col] = sum_m w_m d_m / sum_m w_m over the 12 steps of each year, NaNs skipped
+// and the weights renormalised per cell (xarray's weighted(...).mean, util.py:84-87) -- the 4-D
+// monthly anomaly is never stored.
+template <typename TIn, int EOS, int VEC, bool ANNUAL>
 __global__ void __launch_bounds__(kBlock) k_delta_rho(const TIn* __restrict__ T, const TIn* __restrict__ S,
                                                       i64 t_stride, i64 s_stride,
                                                       const double* __restrict__ rho_ref,
                                                       const void* __restrict__ v_ref, int v_f32,
-                                                      const double* __restrict__ p_level, int nt, int nz, i64 ncol,
+                                                      const double* __restrict__ p_level,
+                                                      const double* __restrict__ weights, int nt, int nz, i64 ncol,
                                                       double* __restrict__ out) {
   const i64 c = VEC * ((i64)blockIdx.x * kBlock + threadIdx.x);
   if (c >= ncol) return;
@@ -126,6 +130,9 @@ __global__ void __launch_bounds__(kBlock) k_delta_rho(const TIn* __restrict__ T,
 #pragma unroll
     for (int j = 0; j < VEC; ++j)
       if (!vref_wet(v_ref, v_f32, i + j)) ref[j] = nan("");
+    double num[VEC], den[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) num[j] = den[j] = 0.0;
     for (int t = 0; t < nt; ++t) {
       double tv[VEC], sv[VEC], r[VEC];
       if (VEC == 4) {
@@ -137,7 +144,22 @@ __global__ void __launch_bounds__(kBlock) k_delta_rho(const TIn* __restrict__ T,
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) r[j] = eos.rho(tv[j], sv[j]) - ref[j];
-      double* o = out + ((i64)t * nz + z) * ncol + c;
+      if (ANNUAL) {
+        const double w = __ldg(weights + t);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (!is_nan_q(r[j])) {
+            num[j] = fma(w, r[j], num[j]);
+            den[j] += w;
+          }
+        if (t % 12 != 11) continue;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          r[j] = num[j] / den[j];  // 0/0 = NaN where every month is missing
+          num[j] = den[j] = 0.0;
+        }
+      }
+      double* o = out + ((i64)(ANNUAL ? t / 12 : t) * nz + z) * ncol + c;
       if (VEC == 4) {
         st4(o, r);
       } else {
@@ -718,9 +740,9 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
   return launch_local_direct<double, 1>(T, S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, eta, delta_rho, st);
 }
 
-int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
-                 const void* v_ref, int vref_dtype, const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
-                 double* delta_rho, void* stream) {
+static int delta_rho_impl(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                          const double* rho_ref, const void* v_ref, int vref_dtype, const double* p_level,
+                          const double* weights, int64_t nt, int64_t nz, int64_t ncol, double* delta_rho, void* stream) {
   int rc = check_common(eos, dtype);
   if (rc) return rc;
   if ((rc = check_bcast(t_bcast, s_bcast))) return rc;
@@ -732,6 +754,7 @@ int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, 
   ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(delta_rho);
   if (nt < 0 || nz <= 0 || ncol < 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (weights && nt % 12 != 0) return fail(ML_ERR_SHAPE, "annual averaging needs whole years of monthly data, got nt=%lld", (long long)nt);
   ML_REQUIRE_ALIGNED(T, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
@@ -748,8 +771,15 @@ int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, 
   i64 gy = cdiv(148 * 16, gx);
   gy = gy < 1 ? 1 : (gy > nz ? nz : gy);
   dim3 grid((unsigned)gx, (unsigned)gy);
-#define ML_LAUNCH_DRHO(TIN, E, V) \
-  k_delta_rho<TIN, E, V><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref, v_f32, p_level, (int)nt, (int)nz, ncol, delta_rho)
+#define ML_LAUNCH_DRHO(TIN, E, V)                                                                                      \
+  do {                                                                                                                 \
+    if (weights)                                                                                                       \
+      k_delta_rho<TIN, E, V, true><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref, v_f32, \
+                                                            p_level, weights, (int)nt, (int)nz, ncol, delta_rho);     \
+    else                                                                                                               \
+      k_delta_rho<TIN, E, V, false><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref,     \
+                                                             v_f32, p_level, nullptr, (int)nt, (int)nz, ncol, delta_rho); \
+  } while (0)
   if (dtype == ML_F32) {
     if (eos == ML_EOS_WRIGHT) { if (vec) ML_LAUNCH_DRHO(float, 0, 4); else ML_LAUNCH_DRHO(float, 0, 1); }
     else { if (vec) ML_LAUNCH_DRHO(float, 1, 4); else ML_LAUNCH_DRHO(float, 1, 1); }
@@ -759,6 +789,22 @@ int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, 
   }
 #undef ML_LAUNCH_DRHO
   return launched("k_delta_rho");
+}
+
+int ml_delta_rho(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
+                 const void* v_ref, int vref_dtype, const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
+                 double* delta_rho, void* stream) {
+  return delta_rho_impl(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, p_level, nullptr, nt, nz, ncol,
+                        delta_rho, stream);
+}
+
+int ml_delta_rho_annual(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast,
+                        const double* rho_ref, const void* v_ref, int vref_dtype, const double* p_level,
+                        const double* weights, int64_t nt, int64_t nz, int64_t ncol, double* delta_rho_annual,
+                        void* stream) {
+  ML_REQUIRE_PTR(weights);
+  return delta_rho_impl(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, p_level, weights, nt, nz, ncol,
+                        delta_rho_annual, stream);
 }
 
 int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,

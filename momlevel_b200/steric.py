@@ -51,6 +51,7 @@ def steric(
             assert type(reference).__module__.startswith("xarray"), "`reference` must be an xarray Dataset"
             reference = xarray_io.from_xarray(reference)
 
+    annual_drho = False  # set when delta_rho is produced as annual means by the fused kernel
     # steric.py:84-91
     dset = dset.rename(varname_map)
     tcoord, zcoord, zbounds = default_coords(coord_names)
@@ -116,7 +117,21 @@ def steric(
             return core.delta_rho(thetao.data, so.data, reference["rho"].data, reference["volcello"].data, pres,
                                   eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
 
-        result["delta_rho"] = DataArray.lazy(_delta_rho, full.shape, full.dims, attrs={
+        drho_shape = full.shape
+        if annual and days_in_month is not None:
+            # steric.py:181-182 averages every result variable, the 4-D anomaly included: its annual means
+            # come out of one fused pass instead of averaging a materialised monthly field
+            weights = np.asarray(days_in_month, dtype=np.float64)
+            assert weights.size == full.shape[0] and weights.size % 12 == 0, \
+                "annual averaging needs whole years of monthly data"
+
+            def _delta_rho():  # noqa: F811
+                return core.delta_rho_annual(thetao.data, so.data, reference["rho"].data, reference["volcello"].data,
+                                             pres, weights, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
+
+            drho_shape = (full.shape[0] // 12,) + tuple(full.shape[1:])
+            annual_drho = True
+        result["delta_rho"] = DataArray.lazy(_delta_rho, drho_shape, full.dims, attrs={
             "long_name": "change in in situ density from reference state", "units": "kg m-3"})
         result["delta_rho"].encoding["dtype"] = dtype
         result[variant] = DataArray(eta, (tcoord,) + hdims)
@@ -131,7 +146,12 @@ def steric(
             result[var] = coord
 
     if annual:
+        fused = result["delta_rho"] if annual_drho else None  # already annual, and still lazy
+        if fused is not None:
+            result = result.drop_vars(["delta_rho"])
         result = annual_average(result, tcoord=tcoord, days_in_month=days_in_month)
+        if fused is not None:
+            result["delta_rho"] = fused
 
     if xarray_in:
         return xarray_io.to_xarray(result, like=dset_x), xarray_io.to_xarray(reference, like=dset_x)

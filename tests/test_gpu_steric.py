@@ -160,6 +160,35 @@ def test_steric_annual_average(ml):
     assert float(summed["delta_rho"]) == pytest.approx(-4.15906613, abs=5e-9)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_annual_delta_rho_is_the_weighted_mean_of_the_monthly_field(ml, dtype):
+    """ml_delta_rho_annual == xarray's weighted(days_in_month).mean over each year of ml_delta_rho's field
+    (util.py:84-87): missing months are skipped and the weights renormalised per cell."""
+    from momlevel_b200 import core, synth
+
+    shape = (24, 6, 9, 32) if dtype == torch.float32 else (12, 5, 7, 13)
+    ds = synth.make_dataset(*shape, seed=8, device="cuda", dtype=dtype)
+    T, S = ds["thetao"].data.clone(), ds["so"].data.clone()
+    V = ds["volcello"].data[0]
+    pres = ds["z_l"].values * 1.0e4 + 101325.0
+    rho_ref, _ = core.reference_state(T[0], S[0], V, pres)
+    wet = torch.nonzero(torch.isfinite(T).all(0) & torch.isfinite(S).all(0) & torch.isfinite(V))
+    (z1, y1, x1), (z2, y2, x2) = wet[0].tolist(), wet[-1].tolist()
+    T[3, z1, y1, x1] = float("nan")       # one month missing in a wet cell
+    S[:12, z2, y2, x2] = float("nan")     # a whole year missing in another
+    w = np.tile(np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], dtype=np.float64), shape[0] // 12)
+    got = core.delta_rho_annual(T, S, rho_ref, V, pres, w).cpu().numpy()
+    monthly = core.delta_rho(T, S, rho_ref, V, pres).cpu().numpy().reshape((shape[0] // 12, 12) + shape[1:])
+    ww = w.reshape(-1, 12)[:, :, None, None, None]
+    valid = ~np.isnan(monthly)
+    with np.errstate(invalid="ignore"):
+        want = np.where(valid, monthly, 0.0).__mul__(ww).sum(1) / (valid * ww).sum(1)
+    assert got.shape == want.shape
+    _close_nan(got, want, atol=1e-12)
+    assert np.isfinite(got[0, z1, y1, x1]) and np.isnan(got[0, z2, y2, x2])
+    assert shape[0] == 12 or np.isfinite(got[1, z2, y2, x2])
+
+
 def test_errors(ml, dset):
     with pytest.raises(ValueError, match="Unknown variant"):
         ml.steric(dset, variant="barosteric")
@@ -337,9 +366,11 @@ def test_time_axis_partition(ml, nt):
     for a, b in zip(out[False], out[True]):
         assert a.shape == b.shape
         assert torch.equal(torch.isnan(a), torch.isnan(b))
-        err = torch.nan_to_num(a - b).abs().max()
-        scale = torch.nan_to_num(b).abs().max().clamp_min(1.0)
-        assert float(err / scale) < 1e-13
+        err = float(torch.nan_to_num(a - b).abs().max())
+        scale = float(torch.nan_to_num(b).abs().max())
+        # heights: the two families round rho - rho_ref differently (one FMA against two operations), which
+        # shows as ~1e-12 m where the height itself is a rounding residue; everything else to fp64 accuracy
+        assert err <= 1e-11 + 1e-13 * scale
 
 
 # ------------------------------------------------------- size-independent properties
