@@ -526,6 +526,64 @@ def test_full_size_om4p25_properties(ml):
     _close_nan(reference["rho"].data[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
 
 
+def test_full_size_spear_member(ml):
+    """BASELINE config 3, one ensemble member at full size (360x320x75, 120 months): ten register chunks,
+    a slab against the oracle, step 0 exactly zero, and the member loop on streams against plain calls."""
+    from momlevel_b200 import core, synth
+    from momlevel_b200 import distributed as mld
+
+    nt, nz, ny, nx = synth.CONFIGS["spear1deg"]
+    grid = synth.make_grid(nz, ny, nx, seed=7, device="cuda")
+    T, S, V = synth.make_fields(grid, nt, seed=1000, dtype=torch.float32)
+    pres = grid["z_l"] * 1.0e4 + 101325.0
+    eta, rho, sums = core.steric_local_selfref(T, S, V, grid["z_i"], grid["deptho"], pres)
+    assert core.last_path() == 2
+    wet = ~torch.isnan(V[0])
+    assert torch.all(eta[0][wet] == 0.0) and torch.equal(torch.isnan(eta[77]), ~wet)
+    ys = slice(150, 154)
+    f64 = lambda x: x[..., ys, :].double().cpu().numpy()  # noqa: E731
+    z_l, z_i = grid["z_l"].cpu().numpy(), grid["z_i"].cpu().numpy()
+    V4 = np.broadcast_to(f64(V), (nt,) + f64(V).shape)
+    oref = osteric.reference_state(f64(T), f64(S), V4, grid["areacello"][ys].cpu().numpy(), z_l)
+    oeta, _ = osteric.steric_local(f64(T), f64(S), z_l, z_i, grid["deptho"][ys].cpu().numpy(), oref)
+    _close_nan(eta[:, ys, :].cpu().numpy(), oeta, atol=ETA_ATOL)
+    _close_nan(rho[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
+    (e2, r2, s2), = mld.steric_local_members([(T, S, V)], grid["z_i"], grid["deptho"], pres)
+    assert torch.equal(torch.nan_to_num(e2), torch.nan_to_num(eta)) and torch.equal(s2, sums)
+
+
+def test_full_size_om4p125_window(ml):
+    """BASELINE config 4 at full grid size (2880x2240x75), a 10-step window of the daily series: the global
+    mass series of the fused kernel against the 4-D route (ml_eos_eval + a torch reduction) and, on a slab
+    of rows, against the oracle's masses."""
+    from momlevel_b200 import core, synth
+
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100e9:
+        pytest.skip("needs ~70 GB of free HBM")
+    nz, ny, nx = synth.CONFIGS["om4p125"][1:]
+    nt = 10  # 12 + remainder logic: one 12-wide chunk with two idle rows
+    grid = synth.make_grid(nz, ny, nx, seed=11, device="cuda")
+    T, S, V = synth.make_fields(grid, nt, seed=55, dtype=torch.float32)
+    pres = grid["z_l"] * 1.0e4 + 101325.0
+    masso = core.steric_global(T, S, V, pres)
+    assert core.last_path() == 2 and masso.shape == (nt,)
+    # the reference's own route for one step: rho as a field, times volcello, skipna sum (derived.py:435-438)
+    for t in (0, nt - 1):
+        rho = core.eos_eval("Wright", "density", T[t], S[t], pres, z_axis=0)
+        want = torch.nansum(rho * V.double())
+        assert float((masso[t] - want).abs() / want) < 1e-12
+        del rho
+    ys = slice(1000, 1002)
+    f64 = lambda x: x[..., ys, :].double().cpu().numpy()  # noqa: E731
+    z_l = grid["z_l"].cpu().numpy()
+    V4 = np.broadcast_to(f64(V), (nt,) + f64(V).shape)
+    oref = osteric.reference_state(f64(T), f64(S), V4, grid["areacello"][ys].cpu().numpy(), z_l)
+    _, _, omass = osteric.steric_global(f64(T), f64(S), z_l, oref)
+    got = core.steric_global(T[..., ys, :].contiguous(), S[..., ys, :].contiguous(), V[:, ys, :].contiguous(), pres)
+    assert np.allclose(got.cpu().numpy(), omass, rtol=1e-12, atol=0)
+
+
 @pytest.mark.parametrize("shape", [(3, 10, 37, 53), (5, 9, 16, 64)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
 def test_delta_rho_entry_equals_fused_output(ml, shape, dtype):
