@@ -423,6 +423,17 @@ def run_ours(args):
         ms = timed(lambda: core.calc_n2(T[:half], S[:half], z_l, adjust_negative=True))
         extras["calc_n2_adjusted_gpts"] = half * N / ms / 1e6
         extras["steric_local_selfref_call_gpts"] = points / k3_avg_ms / 1e6
+        # the public call with everything around the kernel: validation, variant select, result Datasets,
+        # the read-back of volo / masso (wall clock, synchronised on both sides)
+        dset = synth.dataset_from_fields(grid, T, S, V)
+        ml.steric(dset)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ml.steric(dset)
+        torch.cuda.synchronize()
+        extras["steric_public_api_wall_gpts"] = points / ((time.perf_counter() - t0) / 3) / 1e9
+        del dset
         line["extras_Gpts_per_s"] = extras
         torch.cuda.empty_cache()
 

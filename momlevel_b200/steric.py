@@ -8,6 +8,7 @@ writes only the 2-D field.
 """
 
 import numpy as np
+import torch
 
 from . import core
 from .labeled import DataArray, Dataset
@@ -110,7 +111,8 @@ def steric(
         args = (thetao.data, so.data, reference["rho"].data, reference["volcello"].data, dset[zbounds].data,
                 dset["deptho"].data, pres)
         kw = dict(rhozero=rhozero, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
-        _check_depths(dset, zcoord, zbounds)
+        if fused_eta is None:  # the fused pass has checked already
+            _check_depths(dset, zcoord, zbounds)
         eta = fused_eta if fused_eta is not None else core.steric_local(*args, want_delta_rho=False, **kw)[0]
 
         def _delta_rho():
@@ -158,11 +160,19 @@ def steric(
     return (result, reference)
 
 
+def _all_nonnegative(arr):
+    """``np.all(nan_to_num(x, nan=0) >= 0)`` without leaving the device a tensor lives on (NaN passes)."""
+    data = arr.data
+    if isinstance(data, torch.Tensor):
+        return not bool((data < 0).any())
+    return not bool(np.any(np.asarray(data) < 0))
+
+
 def _check_depths(dset, zcoord, zbounds):
-    """derived.py:284-292: calc_dz's sign checks, on metadata-sized arrays."""
-    assert bool(np.all(np.nan_to_num(dset["deptho"].values, nan=0.0) >= 0)), "Depth values must all be positive-definite"
-    assert bool(np.all(dset[zcoord].values >= 0)), "Vertical coordinate levels must all be positive-definite"
-    assert bool(np.all(dset[zbounds].values >= 0)), "Vertical coordinate interfaces must all be positive-definite"
+    """derived.py:284-292: calc_dz's sign checks."""
+    assert _all_nonnegative(dset["deptho"]), "Depth values must all be positive-definite"
+    assert _all_nonnegative(dset[zcoord]), "Vertical coordinate levels must all be positive-definite"
+    assert _all_nonnegative(dset[zbounds]), "Vertical coordinate interfaces must all be positive-definite"
 
 
 def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):

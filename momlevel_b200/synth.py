@@ -16,7 +16,7 @@ import torch
 
 from .labeled import DataArray, Dataset
 
-__all__ = ["vertical_grid", "make_grid", "make_fields", "make_dataset", "CONFIGS"]
+__all__ = ["vertical_grid", "make_grid", "make_fields", "make_dataset", "dataset_from_fields", "CONFIGS"]
 
 OCEAN_AREA = 3.6111092e14
 
@@ -99,10 +99,9 @@ def make_fields(grid, nt, seed=123, device=None, dtype=torch.float32, t_first=0)
     return T, S, V.to(dtype)
 
 
-def make_dataset(nt, nz, ny, nx, seed=123, device="cpu", dtype=torch.float32):
-    """A labelled Dataset shaped like MOM6 output (``volcello`` is a time-expanded view)."""
-    grid = make_grid(nz, ny, nx, seed=seed, device=device)
-    T, S, V = make_fields(grid, nt, seed=seed, dtype=dtype)
+def dataset_from_fields(grid, T, S, V):
+    """Wrap resident fields in a labelled Dataset shaped like MOM6 output (``volcello`` is a time-expanded view)."""
+    nt, nz, ny, nx = T.shape
     dims = ("time", "z_l", "yh", "xh")
     ds = Dataset()
     ds["time"] = DataArray(np.arange(nt, dtype=np.float64), ("time",))
@@ -116,3 +115,10 @@ def make_dataset(nt, nz, ny, nx, seed=123, device="cpu", dtype=torch.float32):
     ds["deptho"] = DataArray(grid["deptho"], ("yh", "xh"))
     ds["areacello"] = DataArray(grid["areacello"], ("yh", "xh"))
     return ds
+
+
+def make_dataset(nt, nz, ny, nx, seed=123, device="cpu", dtype=torch.float32):
+    """A labelled Dataset shaped like MOM6 output."""
+    grid = make_grid(nz, ny, nx, seed=seed, device=device)
+    T, S, V = make_fields(grid, nt, seed=seed, dtype=dtype)
+    return dataset_from_fields(grid, T, S, V)
