@@ -481,6 +481,8 @@ def run_ours(args):
 
 def main():
     args = parse_args()
+    # stdout carries the one JSON line; NCCL's version / debug banner (NCCL_DEBUG=VERSION on the GPU boxes) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     if args.impl == "reference":
         run_reference(args)
     else:
