@@ -186,6 +186,28 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
                             double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ml_steric_local_variants -- steric, thermosteric and halosteric height from ONE pass over T, S.
+ * steric.py:115-121 selects per call which operand of the EOS is held at its reference value;
+ * BASELINE config 2 asks for all three, and three calls move the fields through HBM three times.
+ * Here the reference slab's rows are staged next to the time rows and a point costs three densities:
+ *   rho(T,S) - rho_ref,  rho(T,S_ref) - rho_ref,  rho(T_ref,S) - rho_ref        (steric.py:128,151-153)
+ *   T, S          [nt][nz][ncol] of `dtype`
+ *   T_ref, S_ref  [nz][ncol] of `dtype`: reference["thetao"], reference["so"]; when they are step 0
+ *                 of T, S themselves (the same pointers) the heights of step 0 are exactly zero
+ *   rho_ref       [nz][ncol] fp64 in, or NULL: evaluate it from T_ref, S_ref (reference.py:71-80),
+ *                 store it in rho_ref_out [nz][ncol] and put {volo, masso} into sums (workspace as
+ *                 for ml_reference_state)
+ *   eta_*         [nt][ncol] fp64 out each; a NULL pointer skips that variant's store
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, const void* T_ref,
+                             const void* S_ref, const double* rho_ref, const void* v_ref,
+                             int vref_dtype, const double* z_i, const double* deptho,
+                             const double* p_level, double neg_inv_rhozero, int64_t nt, int64_t nz,
+                             int64_t ncol, double* eta_steric, double* eta_thermosteric,
+                             double* eta_halosteric, double* rho_ref_out, double* sums,
+                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * ml_steric_global -- fused EOS -> sum_{z,col} rho * v_ref per time step.
  * Replaces calc_masso(rho, reference["volcello"]) in the global branch
  * (src/momlevel/steric.py:135, derived.py:435-438); the ln() formula (steric.py:136-142)

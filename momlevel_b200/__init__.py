@@ -11,9 +11,9 @@ reached through a C ABI; there is no CPU implementation in this package.
 from . import core, derived, dynamic, eos, reference, spice, test_data, util
 from .dynamic import inverse_barometer
 from .labeled import DataArray, Dataset
-from .steric import halosteric, steric, thermosteric
+from .steric import halosteric, steric, steric_variants, thermosteric
 
 __version__ = "0.1.0"
 
 __all__ = ["core", "derived", "dynamic", "inverse_barometer", "eos", "reference", "spice", "test_data", "util", "DataArray", "Dataset",
-           "halosteric", "steric", "thermosteric"]
+           "halosteric", "steric", "steric_variants", "thermosteric"]

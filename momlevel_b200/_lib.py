@@ -38,6 +38,8 @@ EXPORTS = {
     "ml_delta_rho_annual": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ml_steric_local_selfref": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _vp, _d, _i64, _i64, _i64, _vp, _vp, _vp,
                                      _vp, _sz, _vp]),
+    "ml_steric_local_variants": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _d, _i64, _i64, _i64, _vp, _vp,
+                                      _vp, _vp, _vp, _vp, _sz, _vp]),
     "ml_steric_global": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "ml_host_release": (_i, []),
     "ml_calc_n2": (_i, [_i, _i, _vp, _vp, _vp, _d, _d, _i, _i, _i64, _i64, _i64, _vp, _vp]),

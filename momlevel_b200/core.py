@@ -386,6 +386,44 @@ def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos=
     return eta, rho, sums
 
 
+def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=None, rho_ref=None, rhozero=1035.0,
+                          eos="Wright"):
+    """Steric, thermosteric and halosteric height from one pass over T, S (steric.py:115-121, :150-166).
+
+    ``T_ref, S_ref`` default to step 0 of ``T, S`` (what ``steric()`` does without ``reference=``); with
+    ``rho_ref=None`` the reference density is evaluated on the way.  Returns
+    ``({"steric": eta, "thermosteric": eta, "halosteric": eta}, rho_ref, sums or None)`` on the device.
+    """
+    L = _lib.lib()
+    T, S, nt, nz, ncol, hshape = _steric_operands(T, S, False, False)
+    Tr = T[0] if T_ref is None else to_device(T_ref).to(T.dtype)
+    Sr = S[0] if S_ref is None else to_device(S_ref).to(S.dtype)
+    assert Tr.is_contiguous() and Sr.is_contiguous() and Tr.numel() == nz * ncol and Sr.numel() == nz * ncol
+    v_ref = to_device(v_ref)
+    z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
+    assert v_ref.numel() == nz * ncol and depth.numel() == ncol and z_i.numel() == nz + 1 and p.numel() == nz
+    eta = torch.empty((3, nt) + hshape, dtype=torch.float64, device=T.device)
+    sums, ws, nbytes = None, None, 0
+    if rho_ref is None:
+        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+        sums = torch.empty(2, dtype=torch.float64, device=T.device)
+        ws, nbytes = _workspace(2, nz, ncol, T.device)
+        rho_in = None
+    else:
+        rho = _f64(rho_ref)
+        assert rho.numel() == nz * ncol
+        rho_in = rho.data_ptr()
+    _lib.check(
+        L.ml_steric_local_variants(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), Tr.data_ptr(), Sr.data_ptr(),
+                                   rho_in, v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(),
+                                   p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, eta[0].data_ptr(), eta[1].data_ptr(),
+                                   eta[2].data_ptr(), rho.data_ptr() if rho_ref is None else None,
+                                   sums.data_ptr() if sums is not None else None,
+                                   ws.data_ptr() if ws is not None else None, nbytes, _stream())
+    )
+    return {"steric": eta[0], "thermosteric": eta[1], "halosteric": eta[2]}, rho, sums
+
+
 def steric_global(T, S, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):
     """``calc_masso(rho, reference.volcello)`` of the global branch (steric.py:135) -> ``masso[nt]``."""
     L = _lib.lib()

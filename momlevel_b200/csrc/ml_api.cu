@@ -807,6 +807,63 @@ int ml_delta_rho_annual(int eos, int dtype, const void* T, const void* S, int t_
                         delta_rho_annual, stream);
 }
 
+int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, const void* T_ref, const void* S_ref,
+                             const double* rho_ref, const void* v_ref, int vref_dtype, const double* z_i,
+                             const double* deptho, const double* p_level, double neg_inv_rhozero, int64_t nt,
+                             int64_t nz, int64_t ncol, double* eta_steric, double* eta_thermosteric,
+                             double* eta_halosteric, double* rho_ref_out, double* sums, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  int rc = check_common(eos, dtype);
+  if (rc) return rc;
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(T_ref);
+  ML_REQUIRE_PTR(S_ref);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(z_i);
+  ML_REQUIRE_PTR(deptho);
+  ML_REQUIRE_PTR(p_level);
+  if (rho_ref == nullptr) {  // the reference density is evaluated here and handed back
+    ML_REQUIRE_PTR(rho_ref_out);
+    ML_REQUIRE_PTR(sums);
+    if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
+      return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
+    ML_REQUIRE_ALIGNED(workspace, 8);
+  }
+  if (nt <= 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  ML_REQUIRE_ALIGNED(T, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(T_ref, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(S_ref, elem_size(dtype));
+  ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* const eta[3] = {eta_steric, eta_thermosteric, eta_halosteric};
+  if (!tls().force_direct && tma::variants_eligible(dtype, T, S, T_ref, S_ref, v_ref, vref_dtype, nt, nz, ncol)) {
+    tls().last_path = ML_PATH_TMA;
+    return tma::launch_variants(eos, T, S, T_ref, S_ref, rho_ref, v_ref, z_i, deptho, p_level, neg_inv_rhozero, (int)nt,
+                                (int)nz, ncol, eta, rho_ref_out, sums, (double*)workspace, st);
+  }
+  // any other layout: the reference state if asked for, then one single-variant call per requested height
+  // (steric.py:115-121: thermosteric holds S at the reference slab, halosteric holds T)
+  if (rho_ref == nullptr) {
+    rc = reference_state_impl(eos, dtype, T_ref, S_ref, v_ref, vref_dtype, p_level, nz, ncol, rho_ref_out, sums,
+                              workspace, workspace_bytes, stream);
+    if (rc) return rc;
+    rho_ref = rho_ref_out;
+  }
+  if (eta_steric && (rc = ml_steric_local(eos, dtype, T, S, 0, 0, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
+                                          neg_inv_rhozero, nt, nz, ncol, eta_steric, nullptr, stream)))
+    return rc;
+  if (eta_thermosteric && (rc = ml_steric_local(eos, dtype, T, S_ref, 0, 1, rho_ref, v_ref, vref_dtype, z_i, deptho,
+                                                p_level, neg_inv_rhozero, nt, nz, ncol, eta_thermosteric, nullptr, stream)))
+    return rc;
+  if (eta_halosteric && (rc = ml_steric_local(eos, dtype, T_ref, S, 1, 0, rho_ref, v_ref, vref_dtype, z_i, deptho,
+                                              p_level, neg_inv_rhozero, nt, nz, ncol, eta_halosteric, nullptr, stream)))
+    return rc;
+  return ML_OK;
+}
+
 int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
                      int vref_dtype, const double* p_level, int64_t nt, int64_t nz, int64_t ncol, double* masso,
                      void* workspace, size_t workspace_bytes, void* stream) {

@@ -34,16 +34,14 @@ constexpr int kTile = 256;                    // columns per CTA = threads per C
 constexpr int kConsumerWarps = kTile / 32;    // 8
 constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
 constexpr int kStages = 4;                    // ring depth: levels in flight per CTA
-// Which column of the tile a thread integrates:
-//   0 = thread i takes column i
-//   1 = columns are ranked by depth within each residue class mod 32 (lane l keeps bank l: no
-//       shared-memory conflicts) and handed to the warps deepest first
-//   2 = columns are ranked by depth across the whole tile
-// A warp skips a level when none of its lanes has water there, so packing columns of similar
-// depth (and land) into the same warps removes the fp64 work of dry lanes that ride along in
-// partly wet warps -- 0.90 -> 0.72 (1) / 0.58 (2) of all warp-levels on the synthetic ocean.
+// Which column of the tile a thread integrates: 0 = thread i takes column i; otherwise the columns
+// are ranked by wet depth across the tile first (sorted_column below).  A warp skips a level when
+// none of its lanes has water there, so packing columns of similar depth (and land) into the same
+// warps removes the fp64 work of dry lanes that ride along in partly wet warps -- 0.90 -> 0.58 of all
+// (warp, level) pairs on the synthetic ocean.  (Ranking within residue classes mod 32 keeps the
+// shared-memory reads conflict-free but only reaches 0.72 and was slower: profiles/r01_experiments.md.)
 #ifndef ML_TMA_SORT
-#define ML_TMA_SORT 2
+#define ML_TMA_SORT 1
 #endif
 // Ceiling experiments (tools/k3_sweep.sh; results are WRONG by construction, never shipped):
 //   1 = compute only: the ring is filled once and re-read, nothing streams from HBM
@@ -116,6 +114,45 @@ __device__ __forceinline__ double level_dz(double depth, double ztop, double zbo
 }
 __device__ __forceinline__ bool nonzero(double x) {  // x != 0 without touching the fp64 pipe
   return ((((unsigned)__double2hiint(x)) << 1) | (unsigned)__double2loint(x)) != 0u;
+}
+
+// number of levels whose upper interface lies above the sea floor (those with dz > 0); NaN depth = land = 0
+__device__ __forceinline__ int wet_levels(double depth, const double* s_zi, int nz) {
+  int lo = 0, hi = nz;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_zi[mid] < depth) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// Column of the tile that thread `tid` integrates, given every thread's key (wet levels of column
+// `tid`): a bitonic sort of the 256 (key, column) words, deepest first -- unique words, so one fixed
+// order -- in registers (shuffles) and one shared-memory array.  Sorted position p goes to warp slot
+// 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the two warps an SM sub-partition hosts (w and
+// w + 4) carry a deep and a shallow band.  Every thread of the CTA must call it.
+__device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_col) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  unsigned v = ((unsigned)key << 8) | (unsigned)(kTile - 1 - tid);
+  for (int k = 2; k <= kTile; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      unsigned o;
+      if (j >= 32) {
+        __syncthreads();
+        s_key[tid] = v;
+        __syncthreads();
+        o = s_key[tid ^ j];
+      } else {
+        o = __shfl_xor_sync(0xffffffffu, v, j);
+      }
+      const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = 256): descending
+      v = (lower == desc) ? max(v, o) : min(v, o);
+    }
+  }
+  const int band = tid >> 5;
+  s_col[(band < 4 ? band : 11 - band) * 32 + lane] = kTile - 1 - (int)(v & 255u);
+  __syncthreads();
+  return s_col[tid];
 }
 
 struct Params {
@@ -212,57 +249,17 @@ __global__ void ML_TMA_KERNEL_ATTR
 
   int col = tid;  // column of the tile this thread integrates
   if (SORT != 0) {
-    // key = number of wet levels of the column: levels whose upper interface lies above the sea
-    // floor (local modes, dz > 0) or whose reference volume is present (global mode)
+    // key = number of wet levels of the column: levels above the sea floor (local modes) or levels
+    // whose reference volume is present (global mode, which has no deptho)
     const i64 cg = (i64)c0 + tid;
     int key = 0;
     if (GLOBAL) {
       if (cg < P.ncol)
         for (int z = 0; z < nz; ++z) key += vraw_isnan(ld_vraw(P.v_ref, (i64)z * P.ncol + cg)) ? 0 : 1;
     } else {
-      const double dep = cg < P.ncol ? __ldg(P.deptho + cg) : 0.0;
-      int lo = 0, hi = nz;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_zi[mid] < dep) lo = mid + 1; else hi = mid;  // NaN depth (land): never true -> key 0
-      }
-      key = lo;
+      key = wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
     }
-    if (SORT == 1) {
-      s_key[tid] = key;
-      __syncthreads();
-      int rank = 0;  // position among the 8 columns of this lane's residue class, deepest first
-#pragma unroll
-      for (int j = 0; j < kConsumerWarps; ++j) {
-        const int k = s_key[j * 32 + lane];
-        rank += (k > key || (k == key && j < warp)) ? 1 : 0;
-      }
-      s_col[(rank < 4 ? rank : 11 - rank) * 32 + lane] = tid;
-    } else {
-      // bitonic sort of the 256 (key, column) words, deepest first; unique words -> one fixed order
-      unsigned v = ((unsigned)key << 8) | (unsigned)(kTile - 1 - tid);
-      for (int k = 2; k <= kTile; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-          unsigned o;
-          if (j >= 32) {
-            __syncthreads();
-            reinterpret_cast<unsigned*>(s_key)[tid] = v;
-            __syncthreads();
-            o = reinterpret_cast<unsigned*>(s_key)[tid ^ j];
-          } else {
-            o = __shfl_xor_sync(0xffffffffu, v, j);
-          }
-          const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = 256): descending
-          v = (lower == desc) ? max(v, o) : min(v, o);
-        }
-      }
-      // sorted position p goes to warp slot 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the
-      // two warps an SM sub-partition hosts (w and w + 4) carry a deep and a shallow band
-      const int band = tid >> 5;
-      s_col[(band < 4 ? band : 11 - band) * 32 + lane] = kTile - 1 - (int)(v & 255u);
-    }
-    __syncthreads();
-    col = s_col[tid];
+    col = sorted_column(key, reinterpret_cast<unsigned*>(s_key), s_col);
   }
 
   {
@@ -389,6 +386,184 @@ __global__ void ML_TMA_KERNEL_ATTR
       for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * TC + tid];
       const i64 row = SELFREF ? tid : (t0 + tid);
       P.partials[row * P.tiles + tile] = sacc;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ all three variants
+// steric, thermosteric and halosteric height from ONE pass over T and S (SURVEY.md section 2,
+// kernel K3 "1-3 variants per pass"): steric.py:115-121 only changes which operand of the EOS is
+// held at its reference value, so with the reference slab's T0, S0 rows staged next to the time
+// rows a point costs three densities instead of three trips through HBM,
+//   d_steric = rho(T, S) - rho_ref,  d_thermo = rho(T, S0) - rho_ref,  d_halo = rho(T0, S) - rho_ref.
+// Chunks are kVT = 4 steps wide (3 variants x 4 steps = the 12 sums per thread the single-variant
+// kernels carry), the ring is kVStages = 8 levels deep (10 KB each), everything else -- refill by
+// the last warp out, depth-sorted tile, skipna accumulation -- is as in k_steric_tma.  The loop over
+// the steps is fully unrolled.  Measured: 290 G points/s for the three heights against 271 for three
+// calls -- a density evaluation is bound by instruction issue (about 40 instructions around its 18
+// fp64 ones), not by HBM, so sharing the loads buys 7 %; pinning S or T algebraically (6 and 4 fused
+// multiply-adds instead of 13 before the division) changed nothing and was dropped.
+constexpr int kVT = 4;
+constexpr int kVStages = 8;
+constexpr int kVRows = 2 * kVT + 2;  // T rows, S rows, T0 row, S0 row
+constexpr uint32_t kVStageBytes = (uint32_t)kVRows * kTile * sizeof(float);
+
+struct VParams {
+  const double* rho_ref;  // reference density to read, or NULL: evaluate it from T0, S0 (and write rho_ref_out)
+  double* rho_ref_out;
+  const float* v_ref;
+  const double* z_i;
+  const double* deptho;
+  const double* p_level;
+  double coef;
+  int nt, nz;
+  int self_reference;     // T0, S0 are step 0 of T, S: the heights of step 0 are exactly zero (steric.py:105-107)
+  unsigned nchunks, tiles;
+  i64 ncol;
+  double* eta[3];         // steric, thermosteric, halosteric: each [nt][ncol]
+  double* partials;       // [2][tiles] = {volo, masso} when rho_ref is evaluated here
+};
+
+template <int EOS>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_steric_variants(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS,
+                      const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapS0,
+                      const VParams P) {
+  constexpr int kStageFloats = (int)(kVStageBytes / sizeof(float));
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kVStages * kVStageBytes);
+  int* released = reinterpret_cast<int*>(full + kVStages);
+  double* red = reinterpret_cast<double*>(full + 2 * kVStages);  // [kConsumerWarps][2]
+  double* s_p = red + kConsumerWarps * 2;
+  double* s_zi = s_p + P.nz;
+  unsigned* s_key = reinterpret_cast<unsigned*>(s_zi + P.nz + 1);
+  int* s_col = reinterpret_cast<int*>(s_key + kTile);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned tile = blockIdx.x / P.nchunks;
+  const int c0 = (int)tile * kTile;
+  const int t0 = (int)(blockIdx.x - tile * P.nchunks) * kVT;
+  const int nz = P.nz;
+  const bool compute_ref = P.rho_ref == nullptr;
+  const bool owns_ref = compute_ref && t0 == 0;  // one chunk per tile stores rho_ref and reduces volo / masso
+
+  auto refill_stage = [&](int z) {
+    const int s = z % kVStages;
+    float* d = stage_base + (size_t)s * kStageFloats;
+    mbar_expect_tx(full + s, kVStageBytes);
+    tma_load_3d(d, &mapT, full + s, c0, z, t0);
+    tma_load_3d(d + kVT * kTile, &mapS, full + s, c0, z, t0);
+    tma_load_2d(d + 2 * kVT * kTile, &mapT0, full + s, c0, z);
+    tma_load_2d(d + (2 * kVT + 1) * kTile, &mapS0, full + s, c0, z);
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < kVStages; ++s) {
+      mbar_init(full + s, 1);
+      released[s] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int z = 0; z < kVStages && z < nz; ++z) refill_stage(z);
+  }
+  for (int i = tid; i < nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
+  for (int i = tid; i <= nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
+  __syncthreads();
+
+  int col = tid;
+  if (ML_TMA_SORT != 0) {
+    const i64 cg = (i64)c0 + tid;
+    col = sorted_column(wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz), s_key, s_col);
+  }
+  const i64 c = (i64)c0 + col;
+  const bool in = c < P.ncol;
+  const i64 cc = in ? c : (P.ncol - 1);
+  Eos<EOS> eos;
+  double acc[3][kVT];
+#pragma unroll
+  for (int v = 0; v < 3; ++v)
+#pragma unroll
+    for (int k = 0; k < kVT; ++k) acc[v][k] = 0.0;
+  double vol = 0.0, mass = 0.0;
+  double depth = __ldg(P.deptho + cc);
+  if (isnan(depth)) depth = 0.0;  // derived.py:295
+  double rref_n = 0.0;
+  unsigned v_n = ld_vraw(P.v_ref, cc);
+  if (!compute_ref) rref_n = __ldg(P.rho_ref + cc);
+  const bool surface_wet = !vraw_isnan(v_n);  // steric.py:166
+  const bool zero_step = P.self_reference != 0 && t0 == 0;  // row 0 of this chunk is the reference step itself
+
+  for (int z = 0; z < nz; ++z) {
+    const unsigned v_z = v_n;
+    double rref_z = rref_n;
+    if (z + 1 < nz) {
+      const i64 j = (i64)(z + 1) * P.ncol + cc;
+      v_n = ld_vraw(P.v_ref, j);
+      if (!compute_ref) rref_n = __ldg(P.rho_ref + j);
+    }
+    const int s = z % kVStages;
+    const float* st = stage_base + (size_t)s * kStageFloats + col;
+    mbar_wait(full + s, (uint32_t)(z / kVStages) & 1u);
+    eos.set_level(s_p[z]);
+    const float t0f = st[2 * kVT * kTile], s0f = st[(2 * kVT + 1) * kTile];
+    const double T0 = (double)t0f, S0 = (double)s0f;
+    const bool dry = vraw_isnan(v_z);
+    // reference.py:71 evaluates the EOS everywhere; a warp over land has nothing to evaluate
+    const bool any_ref = __any_sync(0xffffffffu, !(isnan(t0f) || isnan(s0f)));
+    double w = level_dz(depth, s_zi[z], s_zi[z + 1]);
+    if (dry) w = 0.0;  // steric.py:151-153
+    if (compute_ref) rref_z = nan("");
+    else if (isnan(rref_z)) w = 0.0;
+    if (compute_ref && any_ref) rref_z = eos.rho(T0, S0);
+    if (__any_sync(0xffffffffu, nonzero(w))) {
+#pragma unroll
+      for (int kk = 0; kk < kVT; ++kk) {
+        if (kk == 0 && zero_step) continue;  // the reference step: all three heights are exactly zero
+        const double Tv = (double)st[kk * kTile];
+        const double Sv = (double)st[(kVT + kk) * kTile];
+        fma_skipnan(acc[0][kk], w, eos.rho(Tv, Sv) - rref_z);
+        fma_skipnan(acc[1][kk], w, eos.rho(Tv, S0) - rref_z);  // S held at the reference slab
+        fma_skipnan(acc[2][kk], w, eos.rho(T0, Sv) - rref_z);  // T held at the reference slab
+      }
+    }
+    if (owns_ref && in) {
+      if (P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = rref_z;
+      if (!dry) {  // volo, masso: skipna sums (derived.py:787-789, :435-438)
+        const double vv = vraw_value(v_z);
+        vol += vv;
+        const double m = rref_z * vv;
+        if (!is_nan_q(m)) mass += m;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int before = atomicAdd(released + s, 1);
+      if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kVStages < nz) refill_stage(z + kVStages);
+    }
+  }
+  if (in) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+      if (P.eta[v] != nullptr) {
+#pragma unroll
+        for (int k = 0; k < kVT; ++k)
+          if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[v][k] : nan("");
+      }
+  }
+  if (owns_ref) {  // uniform per CTA
+    vol = warp_sum(vol);
+    mass = warp_sum(mass);
+    if (lane == 0) {
+      red[warp * 2 + 0] = vol;
+      red[warp * 2 + 1] = mass;
+    }
+    __syncthreads();
+    if (tid < 2) {
+      double sacc = 0.0;
+#pragma unroll
+      for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * 2 + tid];
+      P.partials[(i64)tid * P.tiles + tile] = sacc;
     }
   }
 }
@@ -625,6 +800,53 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   if (rc) return rc;
   if ((rc = launch_plan<kGlobal>(eos, pl, P, st))) return rc;
   return reduce_rows(partials, pl.tiles, masso, nt, st);
+}
+
+bool variants_eligible(int dtype, const void* T, const void* S, const void* T_ref, const void* S_ref, const void* v_ref,
+                       int vref_dtype, int64_t nt, int64_t nz, int64_t ncol) {
+  if ((reinterpret_cast<uintptr_t>(T_ref) | reinterpret_cast<uintptr_t>(S_ref)) & 15u) return false;
+  return common_eligible(dtype, vref_dtype, T, S, nt, nz, ncol);
+}
+
+int launch_variants(int eos, const void* T, const void* S, const void* T_ref, const void* S_ref, const double* rho_ref,
+                    const void* v_ref, const double* z_i, const double* deptho, const double* p_level, double coef,
+                    int nt, int nz, int64_t ncol, double* const eta[3], double* rho_ref_out, double* sums,
+                    double* partials, cudaStream_t st) {
+  VParams P;
+  P.rho_ref = rho_ref;
+  P.rho_ref_out = rho_ref_out;
+  P.v_ref = static_cast<const float*>(v_ref);
+  P.z_i = z_i;
+  P.deptho = deptho;
+  P.p_level = p_level;
+  P.coef = coef;
+  P.nt = nt;
+  P.nz = nz;
+  P.self_reference = (T_ref == T && S_ref == S) ? 1 : 0;
+  P.nchunks = (unsigned)((nt + kVT - 1) / kVT);
+  P.tiles = (unsigned)((ncol + kTile - 1) / kTile);
+  P.ncol = ncol;
+  for (int v = 0; v < 3; ++v) P.eta[v] = eta[v];
+  P.partials = partials;
+  CUtensorMap mT, mS, mT0, mS0;
+  if (!make_map(&mT, T, 3, ncol, nz, nt, kVT) || !make_map(&mS, S, 3, ncol, nz, nt, kVT) ||
+      !make_map(&mT0, T_ref, 2, ncol, nz, 1, 1) || !make_map(&mS0, S_ref, 2, ncol, nz, 1, 1))
+    return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
+  const size_t smem = (size_t)kVStages * kVStageBytes + 2 * kVStages * sizeof(uint64_t) +
+                      (size_t)kConsumerWarps * 2 * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) +
+                      2 * kTile * sizeof(int) + 128;
+  cudaError_t e;
+#define ML_TMA_VARIANTS(E)                                                                                  \
+  do {                                                                                                      \
+    e = cudaFuncSetAttribute(k_steric_variants<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_variants)");                  \
+    k_steric_variants<E><<<P.tiles * P.nchunks, kThreads, smem, st>>>(mT, mS, mT0, mS0, P);                \
+  } while (0)
+  if (eos == ML_EOS_WRIGHT) ML_TMA_VARIANTS(0); else ML_TMA_VARIANTS(1);
+#undef ML_TMA_VARIANTS
+  int rc = launched("k_steric_variants");
+  if (rc || rho_ref != nullptr) return rc;
+  return reduce_rows(partials, P.tiles, sums, 2, st);
 }
 
 }  // namespace tma

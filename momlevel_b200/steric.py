@@ -15,7 +15,7 @@ from .labeled import DataArray, Dataset
 from .reference import _pressure, setup_reference_state
 from .util import annual_average, default_coords, validate_dataset
 
-__all__ = ["halosteric", "steric", "thermosteric"]
+__all__ = ["halosteric", "steric", "steric_variants", "thermosteric"]
 
 
 def steric(
@@ -175,20 +175,11 @@ def _check_depths(dset, zcoord, zbounds):
     assert _all_nonnegative(dset[zbounds]), "Vertical coordinate interfaces must all be positive-definite"
 
 
-def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
-    """``setup_reference_state(dset)`` (reference.py:57-83) with the local column integral fused in."""
-    from .util import eos_func_from_str
-
-    eos_func_from_str(eos)
-    _check_depths(dset, zcoord, zbounds)
+def _reference_from_pass(dset, tcoord, eos, rho, sums):
+    """The reference Dataset of reference.py:57-83 around a rho_ref / {volo, masso} pair a fused pass produced."""
     reference = Dataset()
     for name in ("thetao", "so", "volcello"):
         reference[name] = dset[name].isel({tcoord: 0}).squeeze().reset_coords(drop=True)
-    T = reference["thetao"].data if variant == "halosteric" else dset["thetao"].data
-    S = reference["so"].data if variant == "thermosteric" else dset["so"].data
-    eta, rho, sums = core.steric_local_selfref(
-        T, S, reference["volcello"].data, dset[zbounds].data, dset["deptho"].data, pres, rhozero=rhozero, eos=eos,
-        t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric")
     volo, masso = (float(x) for x in sums.cpu())
     reference["rho"] = DataArray(rho, reference["thetao"].dims, attrs={
         "standard_name": "sea_water_density", "long_name": "In situ sea water density",
@@ -200,7 +191,78 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
     reference["rhoga"] = DataArray(np.float64(masso) / np.float64(volo), (), attrs={
         "long_name": "Global Average Sea Water Density", "units": "kg m-3"})
     reference["areacello"] = dset["areacello"]
-    return reference, eta
+    return reference
+
+
+def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
+    """``setup_reference_state(dset)`` (reference.py:57-83) with the local column integral fused in."""
+    from .util import eos_func_from_str
+
+    eos_func_from_str(eos)
+    _check_depths(dset, zcoord, zbounds)
+    T0 = dset["thetao"].isel({tcoord: 0}).squeeze().data
+    S0 = dset["so"].isel({tcoord: 0}).squeeze().data
+    V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
+    T = T0 if variant == "halosteric" else dset["thetao"].data
+    S = S0 if variant == "thermosteric" else dset["so"].data
+    eta, rho, sums = core.steric_local_selfref(
+        T, S, V0, dset[zbounds].data, dset["deptho"].data, pres, rhozero=rhozero, eos=eos,
+        t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric")
+    return _reference_from_pass(dset, tcoord, eos, rho, sums), eta
+
+
+VARIANTS = ("steric", "thermosteric", "halosteric")
+
+
+def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rhozero=1035.0, patm=101325.0,
+                    equation_of_state="Wright", dtype="float32", strict=True, verbose=False):
+    """Steric, thermosteric and halosteric height (``domain="local"``) from one pass over the dataset.
+
+    Equivalent to ``steric(dset)``, ``thermosteric(dset, reference=ref)`` and ``halosteric(dset, reference=ref)``
+    (steric.py:115-121 only changes which operand of the equation of state is held at its reference value),
+    but T and S cross HBM once instead of three times.  Arguments as :func:`steric`.  Returns
+    ``(result, reference)``; ``result`` holds the three height variables (no ``delta_rho``: there is one per
+    variant -- ask :func:`steric` for the variant whose 4-D anomaly is wanted).
+    """
+    from .util import eos_func_from_str
+
+    dset = dset.rename(varname_map)
+    tcoord, zcoord, zbounds = default_coords(coord_names)
+    validate_dataset(dset, strict=strict, additional_vars=[zbounds, "deptho"])
+    pres = _pressure(dset, zcoord, patm)
+    eos_func_from_str(equation_of_state)
+    _check_depths(dset, zcoord, zbounds)
+    full = dset["thetao"]
+    if full.dims[0] != tcoord or full.dims[1] != zcoord or dset["so"].dims != full.dims:
+        raise ValueError(f"expecting fields laid out ({tcoord}, {zcoord}, y, x), got {full.dims}")
+    args = (full.data, dset["so"].data)
+    tail = (dset[zbounds].data, dset["deptho"].data, pres)
+    kw = dict(rhozero=rhozero, eos=equation_of_state)
+    if reference is not None:
+        assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
+        if verbose:
+            print("Using supplied reference state")
+        validate_dataset(reference, reference=True, strict=strict)
+        etas, _, _ = core.steric_local_variants(*args, reference["volcello"].data, *tail, T_ref=reference["thetao"].data,
+                                                S_ref=reference["so"].data, rho_ref=reference["rho"].data, **kw)
+    else:
+        if verbose:
+            print("Generating reference state from first timestep")
+        V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
+        etas, rho, sums = core.steric_local_variants(*args, V0, *tail, **kw)
+        reference = _reference_from_pass(dset, tcoord, equation_of_state, rho, sums)
+        validate_dataset(reference, reference=True, strict=strict)
+    result = Dataset()
+    for variant in VARIANTS:
+        result[variant] = DataArray(etas[variant], (tcoord,) + full.dims[2:], attrs={
+            "long_name": f"{variant.capitalize()} height adjustment", "units": "m"})  # steric.py:169-172
+        result[variant].encoding["dtype"] = dtype
+    for var in set(result.dims):
+        if var in dset.variables:
+            coord = dset[var].copy(deep=False)
+            coord.attrs = dict(dset[var].attrs)
+            result[var] = coord
+    return (result, reference)
 
 
 def halosteric(*args, **kwargs):

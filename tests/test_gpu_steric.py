@@ -373,6 +373,45 @@ def test_time_axis_partition(ml, nt):
         assert err <= 1e-11 + 1e-13 * scale
 
 
+@pytest.mark.parametrize("shape,dtype", [((13, 12, 16, 64), torch.float32),   # TMA family, 4-step chunks + a short one
+                                         ((5, 75, 8, 96), torch.float32),     # full 75-level column
+                                         ((3, 10, 37, 53), torch.float32),    # ragged: single-variant fallback
+                                         ((6, 9, 16, 64), torch.float64)])    # fp64 storage: fallback
+@pytest.mark.parametrize("eos", ["Wright", "linear"])
+def test_all_variants_in_one_pass(ml, shape, dtype, eos):
+    """steric_variants == steric + thermosteric + halosteric called one by one, and the oracle."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(*shape, seed=31, device="cuda", dtype=dtype)
+    ds["thetao"].data[shape[0] // 2, 1, 3, 5] = float("nan")  # a hole at one step
+    res, ref = ml.steric_variants(ds, equation_of_state=eos)
+    path = core.last_path()
+    assert path == (2 if dtype == torch.float32 and (shape[2] * shape[3]) % 4 == 0 and shape[2] * shape[3] >= 256 else 1)
+    one, ref1 = ml.steric(ds, equation_of_state=eos)
+    _close_nan(ref["rho"].values, ref1["rho"].values, rtol=1e-15)
+    assert float(ref["volo"]) == pytest.approx(float(ref1["volo"]), rel=1e-13)
+    assert float(ref["masso"]) == pytest.approx(float(ref1["masso"]), rel=1e-13)
+    singles = {"steric": one}
+    singles["thermosteric"], _ = ml.thermosteric(ds, equation_of_state=eos, reference=ref1)
+    singles["halosteric"], _ = ml.halosteric(ds, equation_of_state=eos, reference=ref1)
+    wet = ~torch.isnan(ref["volcello"].data[0])
+    for variant in ("steric", "thermosteric", "halosteric"):
+        got = res[variant]
+        assert got.dims == ("time", "yh", "xh") and got.attrs["long_name"] == f"{variant.capitalize()} height adjustment"
+        _close_nan(got.values, singles[variant][variant].values, atol=1e-12)
+        if path == 2:
+            assert torch.all(got.data[0][wet] == 0.0)  # the reference step, exactly as in the reference
+        else:  # the fallback subtracts a rounded rho_ref: the residue of one rounding, integrated
+            assert float(got.data[0][wet].abs().max()) < 1e-12
+        ref_o, eta_o, _, _, _, _ = _oracle_case(ds, variant, eos)
+        _close_nan(got.values, eta_o, atol=ETA_ATOL)
+    # a supplied reference takes the same kernel with rho_ref read instead of evaluated
+    again, _ = ml.steric_variants(ds, equation_of_state=eos, reference=ref)
+    assert core.last_path() == path
+    for variant in ("steric", "thermosteric", "halosteric"):
+        _close_nan(again[variant].values, res[variant].values, atol=1e-12)
+
+
 # ------------------------------------------------------- size-independent properties
 
 
