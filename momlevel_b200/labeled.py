@@ -325,8 +325,9 @@ class Dataset:
     # --------------------------------------------------------------------- operations
     def rename(self, name_dict=None):
         """``Dataset.rename`` (steric.py:84); ``None`` is the identity."""
+        if not name_dict:
+            return self  # nothing to rename: the callers only read
         out = Dataset(attrs=self.attrs)
-        name_dict = name_dict or {}
         for k, v in self._vars.items():
             nv = DataArray(v, tuple(name_dict.get(d, d) for d in v.dims)) if not v.is_lazy else v
             nv.encoding = dict(v.encoding)

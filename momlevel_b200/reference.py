@@ -5,6 +5,7 @@ sums in a single pass over the ``time_index`` slab.
 """
 
 import numpy as np
+import torch
 
 from . import core, util
 from .labeled import DataArray, Dataset
@@ -18,6 +19,9 @@ def _pressure(dset, zcoord, patm):
         if getattr(patm, "ndim", np.ndim(patm)) != 0:
             raise NotImplementedError("momlevel_b200 supports a scalar `patm` only")
         patm = float(patm)
+    z = dset[zcoord].data
+    if isinstance(z, torch.Tensor) and z.is_cuda:  # stays on the device: no read-back in front of the launch
+        return (z.to(torch.float64) * 1.0e4) + float(patm)
     return (np.asarray(dset[zcoord].values, dtype=np.float64) * 1.0e4) + float(patm)
 
 

@@ -170,6 +170,13 @@ def _all_nonnegative(arr):
 
 def _check_depths(dset, zcoord, zbounds):
     """derived.py:284-292: calc_dz's sign checks."""
+    arrs = [dset["deptho"].data, dset[zcoord].data, dset[zbounds].data]
+    if all(isinstance(a, torch.Tensor) and a.is_cuda for a in arrs):  # one read-back for the three flags
+        neg = torch.stack([(a < 0).any() for a in arrs]).cpu()
+        assert not bool(neg[0]), "Depth values must all be positive-definite"
+        assert not bool(neg[1]), "Vertical coordinate levels must all be positive-definite"
+        assert not bool(neg[2]), "Vertical coordinate interfaces must all be positive-definite"
+        return
     assert _all_nonnegative(dset["deptho"]), "Depth values must all be positive-definite"
     assert _all_nonnegative(dset[zcoord]), "Vertical coordinate levels must all be positive-definite"
     assert _all_nonnegative(dset[zbounds]), "Vertical coordinate interfaces must all be positive-definite"
