@@ -236,7 +236,17 @@ int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const
                          int steps_per_window, double* eta, double* rho_ref_out,
                          double* sums_out);
 
-/* Frees the device staging buffers, streams and events that ml_steric_local_host keeps per
+/* ---------------------------------------------------------------------------------------
+ * ml_steric_global_host -- the masses of ml_steric_global for fields in HOST memory (a daily global
+ * series does not fit in HBM: BASELINE config 4 is 1.4 TB), streamed through the same two windows.
+ *   T, S    host [nt][nz][ncol] of `dtype`;  v_ref host [nz][ncol] of `dtype` (reference["volcello"])
+ *   masso   host fp64[nt] out; the ln() formula of steric.py:136-142 stays with the caller
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_global_host(int eos, int dtype, const void* T, const void* S, const void* v_ref,
+                          const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
+                          int steps_per_window, double* masso);
+
+/* Frees the device staging buffers, streams and events that the *_host entry points keep per
  * host thread between calls. */
 int ml_host_release(void);
 

@@ -8,12 +8,12 @@ All field arithmetic runs in hand-written sm_100a CUDA kernels (libmomlevel_b200
 reached through a C ABI; there is no CPU implementation in this package.
 """
 
-from . import core, derived, dynamic, eos, reference, spice, test_data, util
+from . import core, derived, distributed, dynamic, eos, reference, spice, test_data, util
 from .dynamic import inverse_barometer
 from .labeled import DataArray, Dataset
 from .steric import halosteric, steric, steric_variants, thermosteric
 
 __version__ = "0.1.0"
 
-__all__ = ["core", "derived", "dynamic", "inverse_barometer", "eos", "reference", "spice", "test_data", "util", "DataArray", "Dataset",
+__all__ = ["core", "derived", "distributed", "dynamic", "inverse_barometer", "eos", "reference", "spice", "test_data", "util", "DataArray", "Dataset",
            "halosteric", "steric", "steric_variants", "thermosteric"]

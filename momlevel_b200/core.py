@@ -475,3 +475,29 @@ def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
                                eta.data_ptr(), rho.data_ptr() if rho is not None else None, sums.data_ptr())
     )
     return eta, rho, (float(sums[0]), float(sums[1]))
+
+
+def steric_global_host(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
+    """Per-step masses of the global branch (steric.py:135) for HOST arrays, streamed through device windows.
+
+    Returns ``masso[nt]`` as a CPU tensor; ``distributed.global_sea_level`` applies the ``ln`` formula.
+    """
+    L = _lib.lib()
+    _device()
+
+    def host(x):
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        assert t.device.type == "cpu"
+        return t.contiguous()
+
+    T, S, v_ref = host(T), host(S), host(v_ref)
+    dt = _field_dtype(T, S, v_ref)
+    T, S, v_ref = T.to(dt), S.to(dt), v_ref.to(dt)
+    assert T.shape == S.shape and tuple(v_ref.shape) == tuple(T.shape[1:])
+    nt, nz = T.shape[0], T.shape[1]
+    ncol = int(np.prod(T.shape[2:], dtype=np.int64))
+    p = host(np.asarray(p_level, dtype=np.float64))
+    masso = torch.empty(nt, dtype=torch.float64)
+    _lib.check(L.ml_steric_global_host(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), v_ref.data_ptr(),
+                                       p.data_ptr(), nt, nz, ncol, int(steps_per_window), masso.data_ptr()))
+    return masso

@@ -1,4 +1,4 @@
-// ml_hostpath.cu -- ml_steric_local_host: the steric path on HOST buffers.
+// ml_hostpath.cu -- ml_steric_local_host / ml_steric_global_host: the steric path on HOST buffers.
 //
 // What momlevel.steric(dset) does for variant="steric", domain="local" when the Dataset
 // lives in host memory (src/momlevel/steric.py:84-184 with the reference state taken from
@@ -155,6 +155,66 @@ extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const voi
   ML_CUDA(cudaMemcpyAsync(eta, dEta, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  ML_CUDA(cudaStreamSynchronize(r.comp));
+  ML_CUDA(cudaStreamSynchronize(r.copy));
+  return ML_OK;
+}
+
+// The global branch (src/momlevel/steric.py:134-147) on host buffers: per-step masses
+// M(t) = sum rho(t) * volcello_ref (derived.py:435-438) with T, S streamed through the same two
+// windows; the ln() formula stays with the caller, as for ml_steric_global.
+extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const void* S, const void* v_ref,
+                                     const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
+                                     int steps_per_window, double* masso) {
+  using namespace ml;
+  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  ML_REQUIRE_PTR(T);
+  ML_REQUIRE_PTR(S);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(p_level);
+  ML_REQUIRE_PTR(masso);
+  if (nt <= 0 || nz <= 0 || ncol <= 0 || steps_per_window < 1)
+    return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld window=%d", (long long)nt, (long long)nz,
+                (long long)ncol, steps_per_window);
+  const size_t es = (size_t)elem_size(dtype);
+  const size_t lvl = (size_t)nz * (size_t)ncol;
+  const int64_t spw = steps_per_window < nt ? steps_per_window : nt;
+  const size_t win_bytes = (size_t)spw * lvl * es;
+  const size_t ws_bytes = ml_workspace_bytes(spw, nz, ncol);
+
+  Resources& r = resources();
+  ML_CUDA(r.prepare());
+  void *dT[2], *dS[2], *dV, *dM, *dP, *dWs;
+  for (int b = 0; b < 2; ++b) {
+    ML_CUDA(r.alloc(2 * b, &dT[b], win_bytes));
+    ML_CUDA(r.alloc(2 * b + 1, &dS[b], win_bytes));
+  }
+  ML_CUDA(r.alloc(4, &dV, lvl * es));
+  ML_CUDA(r.alloc(6, &dM, (size_t)nt * sizeof(double)));
+  ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
+  ML_CUDA(r.alloc(11, &dWs, ws_bytes));
+  ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(dV, v_ref, lvl * es, cudaMemcpyHostToDevice, r.copy));
+
+  const int64_t nwin = (nt + spw - 1) / spw;
+  for (int64_t w = 0; w < nwin; ++w) {
+    const int b = (int)(w & 1);
+    const int64_t t_first = w * spw;
+    const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
+    const size_t off = (size_t)t_first * lvl * es;
+    const size_t bytes = (size_t)nt_w * lvl * es;
+    if (w >= 2) ML_CUDA(cudaStreamWaitEvent(r.copy, r.freed[b], 0));
+    ML_CUDA(cudaMemcpyAsync(dT[b], (const char*)T + off, bytes, cudaMemcpyHostToDevice, r.copy));
+    ML_CUDA(cudaMemcpyAsync(dS[b], (const char*)S + off, bytes, cudaMemcpyHostToDevice, r.copy));
+    ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
+    ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
+    int rc = ml_steric_global(eos, dtype, dT[b], dS[b], 0, 0, dV, dtype, (const double*)dP, nt_w, nz, ncol,
+                              (double*)dM + t_first, dWs, ws_bytes, r.comp);
+    if (rc) return rc;
+    ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
+  }
+  ML_CUDA(cudaMemcpyAsync(masso, dM, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   ML_CUDA(cudaStreamSynchronize(r.comp));
   ML_CUDA(cudaStreamSynchronize(r.copy));
   return ML_OK;

@@ -659,3 +659,21 @@ def test_host_entry_matches_device_path(ml):
         _close_nan(rho.numpy(), reference["rho"].values, rtol=1e-15)
         assert volo == pytest.approx(float(reference["volo"]), rel=1e-14)
         assert masso == pytest.approx(float(reference["masso"]), rel=1e-14)
+
+
+def test_global_host_entry_matches_device_path(ml):
+    """ml_steric_global_host: the masses of a host-resident series, any window width, against the device call."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(7, 12, 20, 32, seed=6, device="cpu", dtype=torch.float32)
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    T, S, V = ds["thetao"].data, ds["so"].data, ds["volcello"].data[0].contiguous()
+    want = core.steric_global(T.cuda(), S.cuda(), V.cuda(), pres).cpu()
+    for spw in (1, 3, 7, 12):
+        got = core.steric_global_host(T, S, V, pres, steps_per_window=spw)
+        assert got.shape == (7,) and torch.allclose(got, want, rtol=1e-14, atol=0)
+    # the public route: steric(domain="global") on the same data
+    res, ref = ml.steric(ds, domain="global")
+    eta, href = ml.distributed.global_sea_level(got.numpy(), float(ref["volo"]), float(ref["rhoga"]),
+                                                float(ref["areacello"].sum()))
+    assert np.allclose(eta, res["steric"].values, rtol=0, atol=1e-12)
