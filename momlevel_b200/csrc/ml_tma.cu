@@ -33,7 +33,13 @@ namespace tma {
 constexpr int kTile = 256;                    // columns per CTA = threads per CTA
 constexpr int kConsumerWarps = kTile / 32;    // 8
 constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
-constexpr int kStages = 4;                    // ring depth: levels in flight per CTA
+// Ring depth (levels in flight per CTA) and resident CTAs per SM, by mode.  The local modes run two
+// CTAs per SM with a 4-level ring and ~120 registers per thread.  The global kernel carries no
+// rho_ref / dz operands and fits 64 registers, so it runs four CTAs per SM with a 2-level ring (the
+// same bytes in flight per SM): +4.5 % (profiles/r01_experiments.md).  The self-reference mode reads
+// row 0 of the NEXT level while it works on this one and loses 15 % with a 2-level ring.
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 1 /* kGlobal */ ? 2 : 4; }
+__host__ __device__ constexpr int ctas_per_sm_of(int mode) { return mode == 1 /* kGlobal */ ? 4 : 2; }
 // Which column of the tile a thread integrates: 0 = thread i takes column i; otherwise the columns
 // are ranked by wet depth across the tile first (sorted_column below).  A warp skips a level when
 // none of its lanes has water there, so packing columns of similar depth (and land) into the same
@@ -185,7 +191,7 @@ enum Mode { kLocal = 0, kGlobal = 1, kSelfRef = 2 };
 #ifdef ML_TMA_MAXNREG  // experiment builds: explicit register cap instead of the occupancy hint
 #define ML_TMA_KERNEL_ATTR __maxnreg__(ML_TMA_MAXNREG)
 #else
-#define ML_TMA_KERNEL_ATTR __launch_bounds__(kThreads, 2)
+#define ML_TMA_KERNEL_ATTR __launch_bounds__(kThreads, ctas_per_sm_of(MODE))
 #endif
 
 template <int EOS, int TC, int BC, int MODE>
@@ -193,6 +199,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
+  constexpr int kStages = stages_of(MODE);
   constexpr int SORT = ML_TMA_SORT;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
@@ -624,7 +631,8 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
 }
 
 template <int TC>
-inline size_t smem_bytes(int bc, int nz) {
+inline size_t smem_bytes(int bc, int nz, int mode) {
+  const int kStages = stages_of(mode);
   return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
@@ -633,7 +641,7 @@ template <int EOS, int TC, int BC, int MODE>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
   auto kern = k_steric_tma<EOS, TC, BC, MODE>;
-  const size_t smem = smem_bytes<TC>(BC, P.nz);
+  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE);
   // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
   // is set on every launch (a host-side table lookup) rather than cached in a static
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
