@@ -144,3 +144,52 @@ def test_annual_average_weights():
     expect = [(vals[:12] * w[:12]).sum() / w[:12].sum(), (vals[12:] * w[12:]).sum() / w[12:].sum()]
     assert out["x"].shape == (2, 3)
     assert np.allclose(out["x"].values[:, 0], expect, rtol=1e-15)
+
+
+def test_dataset_hands_out_index_coordinates_and_rename_identity():
+    # like xarray, a variable taken out of a Dataset knows the values of its dimension coordinates
+    # (derived.calc_n2 reads thetao[zcoord], derived.py:396)
+    t = dset["thetao"]
+    assert set(t.coords) >= {"time", "z_l", "yh", "xh"}
+    assert np.array_equal(np.asarray(t.coords["z_l"].values), np.asarray(dset["z_l"].values))
+    assert "z_l" not in dset["z_l"].coords  # an index variable does not carry itself
+    assert dset.rename(None) is dset and dset.rename({}) is dset
+    renamed = dset.rename({"thetao": "temp"})
+    assert "temp" in renamed.variables and "thetao" not in renamed.variables and "thetao" in dset.variables
+
+
+def test_column_diagnostics_argument_errors_fire_before_any_compute():
+    from momlevel_b200 import derived
+
+    bare = DataArray(np.zeros((2, 3, 4)), ("time", "z_l", "xh"))  # no level values attached
+    with pytest.raises(KeyError):
+        derived.calc_n2(bare, bare)
+    with pytest.raises(NotImplementedError):
+        derived.calc_n2(dset["thetao"], dset["so"], interfaces=dset["z_i"])  # needs xgcm (derived.py:391-395)
+    with pytest.raises(ValueError):
+        derived.calc_n2(dset["thetao"], dset["so"], eos="teos10")  # util.py:243-249
+    with pytest.raises(ValueError):
+        derived.calc_n2(dset["thetao"], dset["so"][0])
+
+
+def test_steric_variants_validates_like_steric():
+    with pytest.raises(ValueError, match="Errors found in dataset."):
+        momlevel.steric_variants(dset.drop_vars(["deptho"]))
+    bad = dset.copy()
+    bad["areacello"] = dset["areacello"] * 2.0
+    with pytest.raises(ValueError, match="Errors found in dataset."):
+        momlevel.steric_variants(bad)
+    with pytest.raises(ValueError, match="Unknown equation of state"):
+        momlevel.steric_variants(dset, equation_of_state="teos10")
+
+
+def test_bind_host_to_device_is_harmless_without_a_gpu():
+    import os
+
+    from momlevel_b200 import distributed
+
+    before = os.sched_getaffinity(0)
+    n = distributed.bind_host_to_device(0)
+    assert n == 0 or n == len(os.sched_getaffinity(0))
+    if n == 0:
+        assert os.sched_getaffinity(0) == before
