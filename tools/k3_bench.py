@@ -27,5 +27,6 @@ res["local"] = pts / timed(lambda: core.steric_local(T, S, rho_ref, V, z_i, dept
 res["global"] = pts / timed(lambda: core.steric_global(T, S, V, pres)) / 1e6
 if "--all" in sys.argv:
     res["thermo"] = pts / timed(lambda: core.steric_local(T, S[0], rho_ref, V, z_i, depth, pres, s_bcast=True)) / 1e6
+    res["halo"] = pts / timed(lambda: core.steric_local(T[0], S, rho_ref, V, z_i, depth, pres, t_bcast=True)) / 1e6
     res["linear"] = pts / timed(lambda: core.steric_local(T, S, rho_ref, V, z_i, depth, pres, eos="linear")) / 1e6
 print(json.dumps({k: (round(v, 1) if isinstance(v, float) else v) for k, v in res.items()}), flush=True)
