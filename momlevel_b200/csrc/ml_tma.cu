@@ -412,10 +412,11 @@ __global__ void ML_TMA_KERNEL_ATTR
 // Chunks are kVT = 4 steps wide (3 variants x 4 steps = the 12 sums per thread the single-variant
 // kernels carry), the ring is kVStages = 8 levels deep (10 KB each), everything else -- refill by
 // the last warp out, depth-sorted tile, skipna accumulation -- is as in k_steric_tma.  The loop over
-// the steps is fully unrolled.  Measured: 290 G points/s for the three heights against 271 for three
-// calls -- a density evaluation is bound by instruction issue (about 40 instructions around its 18
-// fp64 ones), not by HBM, so sharing the loads buys 7 %; pinning S or T algebraically (6 and 4 fused
-// multiply-adds instead of 13 before the division) changed nothing and was dropped.
+// the steps is fully unrolled.  Measured: 290 G points/s for the three heights -- a density
+// evaluation is bound by instruction issue (about 40 instructions around its 18 fp64 ones), not by
+// HBM, so sharing the loads buys little.  The pinned operand is folded into the coefficients as in
+// the single-variant kernels (same arithmetic, so the heights agree with theirs); in THIS kernel that
+// did not change the time (128 registers either way).
 constexpr int kVT = 4;
 constexpr int kVStages = 8;
 constexpr int kVRows = 2 * kVT + 2;  // T rows, S rows, T0 row, S0 row
@@ -530,14 +531,16 @@ __global__ void __launch_bounds__(kThreads, 2)
     else if (isnan(rref_z)) w = 0.0;
     if (compute_ref && any_ref) rref_z = eos.rho(T0, S0);
     if (__any_sync(0xffffffffu, nonzero(w))) {
+      // the pinned operand of the thermo- / halosteric evaluation goes into the coefficients once per level
+      const typename Eos<EOS>::Pinned ps = eos.pin_s(S0), pt = eos.pin_t(T0);
 #pragma unroll
       for (int kk = 0; kk < kVT; ++kk) {
         if (kk == 0 && zero_step) continue;  // the reference step: all three heights are exactly zero
         const double Tv = (double)st[kk * kTile];
         const double Sv = (double)st[(kVT + kk) * kTile];
         fma_skipnan(acc[0][kk], w, eos.rho(Tv, Sv) - rref_z);
-        fma_skipnan(acc[1][kk], w, eos.rho(Tv, S0) - rref_z);  // S held at the reference slab
-        fma_skipnan(acc[2][kk], w, eos.rho(T0, Sv) - rref_z);  // T held at the reference slab
+        fma_skipnan(acc[1][kk], w, eos.rho_pinned_s(ps, Tv) - rref_z);  // S held at the reference slab
+        fma_skipnan(acc[2][kk], w, eos.rho_pinned_t(pt, Sv) - rref_z);  // T held at the reference slab
       }
     }
     if (owns_ref && in) {
