@@ -259,6 +259,25 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     # the device-resident and the host-streamed paths must agree
     err = (eta_h.to(dev) - eta).abs()
     line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
+    # BASELINE config 2 names all three variants: the same transfer feeding three integrations per window
+    # (grid points counted once; three heights come back)
+    try:
+        outs = {"steric": eta_h, "thermosteric": torch.empty_like(eta_h, pin_memory=True),
+                "halosteric": torch.empty_like(eta_h, pin_memory=True)}
+        core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, variants=True, eta_out=outs)
+        barrier()
+        t0 = time.perf_counter()
+        core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, variants=True, eta_out=outs)
+        torch.cuda.synchronize()
+        dt3 = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt3, op=dist.ReduceOp.MAX)
+        line["e2e"]["all_three_variants"] = {"value": world * points / float(dt3[0]), "unit": UNIT,
+                                             "ms_per_step": float(dt3[0]) * 1e3,
+                                             "d2h_bytes_per_step": 3 * eta_h.numel() * 8 + 16,
+                                             "api": "core.steric_local_host(variants=True) -> ml_steric_local_variants_host"}
+    except (RuntimeError, MemoryError) as exc:  # the two extra pageable height fields are a few hundred MB
+        line["e2e"]["all_three_variants"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     return (Th.numpy(), Sh.numpy(), Vh.numpy(), grid["areacello"].cpu().numpy(), d_h, grid["z_l"].cpu().numpy(), z_h)
 
 

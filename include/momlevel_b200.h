@@ -186,11 +186,13 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
                             double* sums, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * ml_steric_local_variants -- steric, thermosteric and halosteric height from ONE pass over T, S.
+ * ml_steric_local_variants -- steric, thermosteric and halosteric height in one call.
  * steric.py:115-121 selects per call which operand of the EOS is held at its reference value;
- * BASELINE config 2 asks for all three, and three calls move the fields through HBM three times.
- * Here the reference slab's rows are staged next to the time rows and a point costs three densities:
+ * BASELINE config 2 asks for all three:
  *   rho(T,S) - rho_ref,  rho(T,S_ref) - rho_ref,  rho(T_ref,S) - rho_ref        (steric.py:128,151-153)
+ * One launch per requested height over device-resident fields (a fused three-variant kernel was
+ * measured and dropped: the evaluation, not HBM, bounds these kernels); the host entry point
+ * ml_steric_local_variants_host is where sharing pays, one PCIe transfer feeding all three.
  *   T, S          [nt][nz][ncol] of `dtype`
  *   T_ref, S_ref  [nz][ncol] of `dtype`: reference["thetao"], reference["so"]; when they are step 0
  *                 of T, S themselves (the same pointers) the heights of step 0 are exactly zero
@@ -245,6 +247,18 @@ int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const
 int ml_steric_global_host(int eos, int dtype, const void* T, const void* S, const void* v_ref,
                           const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
                           int steps_per_window, double* masso);
+
+/* ---------------------------------------------------------------------------------------
+ * ml_steric_local_variants_host -- ml_steric_local_host that also returns the thermosteric and
+ * halosteric heights: the fields cross PCIe once (the transfer is what bounds the host path) and each
+ * window is integrated three times on the device.  eta_thermosteric / eta_halosteric are host
+ * [nt][ncol] fp64 outputs and may be NULL; the other arguments are those of ml_steric_local_host.
+ * ------------------------------------------------------------------------------------- */
+int ml_steric_local_variants_host(int eos, int dtype, const void* T, const void* S, const void* v0,
+                                  const double* z_i, const double* deptho, const double* p_level,
+                                  double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                                  int steps_per_window, double* eta_steric, double* eta_thermosteric,
+                                  double* eta_halosteric, double* rho_ref_out, double* sums_out);
 
 /* Frees the device staging buffers, streams and events that the *_host entry points keep per
  * host thread between calls. */

@@ -47,6 +47,8 @@ EXPORTS = {
     "ml_stability_angle": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ml_wave_speed": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _vp, _vp]),
     "ml_steric_global_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
+    "ml_steric_local_variants_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i64, _i64, _i64, _i, _vp, _vp, _vp, _vp,
+                                           _vp]),
     "ml_steric_local_host": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i64, _i64, _i64, _i, _vp, _vp, _vp]),
 }
 

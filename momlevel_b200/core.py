@@ -388,7 +388,7 @@ def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos=
 
 def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=None, rho_ref=None, rhozero=1035.0,
                           eos="Wright"):
-    """Steric, thermosteric and halosteric height from one pass over T, S (steric.py:115-121, :150-166).
+    """Steric, thermosteric and halosteric height in one call (steric.py:115-121, :150-166).
 
     ``T_ref, S_ref`` default to step 0 of ``T, S`` (what ``steric()`` does without ``reference=``); with
     ``rho_ref=None`` the reference density is evaluated on the way.  Returns
@@ -441,40 +441,51 @@ def steric_global(T, S, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=Fal
     return masso
 
 
+def _host_tensor(x):
+    t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+    assert t.device.type == "cpu"
+    return t.contiguous()
+
+
 def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", steps_per_window=1,
-                      want_rho_ref=False, eta_out=None):
-    """End-to-end host call: HOST arrays in (numpy or CPU torch, pinned for speed), numpy out.
+                      want_rho_ref=False, eta_out=None, variants=False):
+    """End-to-end host call: HOST arrays in (numpy or CPU torch, pinned for speed), CPU tensors out.
 
     ``reference_state`` + ``steric_local`` for variant="steric" with the reference taken
     from time step 0; copies are pipelined against the kernels inside the library.
-    Returns ``(eta [nt,...], rho_ref or None, (volo, masso))``.
+    Returns ``(eta [nt,...], rho_ref or None, (volo, masso))``.  With ``variants=True`` ``eta`` is a dict
+    ``{"steric", "thermosteric", "halosteric"}``: the fields cross PCIe once and every window is
+    integrated three times on the device (``ml_steric_local_variants_host``).  ``eta_out`` may hand in
+    the output tensor (or, with ``variants``, a dict of them) -- pinned memory keeps the read-back asynchronous.
     """
     L = _lib.lib()
     _device()
-
-    def host(x):
-        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
-        assert t.device.type == "cpu"
-        return t.contiguous()
-
-    T, S, V0 = host(T), host(S), host(V0)
+    T, S, V0 = _host_tensor(T), _host_tensor(S), _host_tensor(V0)
     dt = _field_dtype(T, S, V0)
     T, S, V0 = T.to(dt), S.to(dt), V0.to(dt)
     nt, nz = T.shape[0], T.shape[1]
     hshape = tuple(T.shape[2:])
     ncol = int(np.prod(hshape, dtype=np.int64))
-    z_i = host(np.asarray(z_i, dtype=np.float64))
-    depth = host(np.asarray(deptho, dtype=np.float64))
-    p = host(np.asarray(p_level, dtype=np.float64))
-    eta = eta_out if eta_out is not None else torch.empty((nt,) + hshape, dtype=torch.float64)
+    z_i = _host_tensor(np.asarray(z_i, dtype=np.float64))
+    depth = _host_tensor(np.asarray(deptho, dtype=np.float64))
+    p = _host_tensor(np.asarray(p_level, dtype=np.float64))
+    outs = eta_out if isinstance(eta_out, dict) else {"steric": eta_out}
+    eta = outs.get("steric")
+    if eta is None:
+        eta = torch.empty((nt,) + hshape, dtype=torch.float64)
     rho = torch.empty((nz,) + hshape, dtype=torch.float64) if want_rho_ref else None
     sums = torch.empty(2, dtype=torch.float64)
-    _lib.check(
-        L.ml_steric_local_host(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), V0.data_ptr(), z_i.data_ptr(),
-                               depth.data_ptr(), p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, int(steps_per_window),
-                               eta.data_ptr(), rho.data_ptr() if rho is not None else None, sums.data_ptr())
-    )
-    return eta, rho, (float(sums[0]), float(sums[1]))
+    head = (_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), V0.data_ptr(), z_i.data_ptr(), depth.data_ptr(),
+            p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, int(steps_per_window))
+    tail = (rho.data_ptr() if rho is not None else None, sums.data_ptr())
+    if not variants:
+        _lib.check(L.ml_steric_local_host(*head, eta.data_ptr(), *tail))
+        return eta, rho, (float(sums[0]), float(sums[1]))
+    eta_t, eta_h = outs.get("thermosteric"), outs.get("halosteric")
+    eta_t = torch.empty_like(eta) if eta_t is None else eta_t
+    eta_h = torch.empty_like(eta) if eta_h is None else eta_h
+    _lib.check(L.ml_steric_local_variants_host(*head, eta.data_ptr(), eta_t.data_ptr(), eta_h.data_ptr(), *tail))
+    return {"steric": eta, "thermosteric": eta_t, "halosteric": eta_h}, rho, (float(sums[0]), float(sums[1]))
 
 
 def steric_global_host(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
@@ -484,12 +495,7 @@ def steric_global_host(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
     """
     L = _lib.lib()
     _device()
-
-    def host(x):
-        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
-        assert t.device.type == "cpu"
-        return t.contiguous()
-
+    host = _host_tensor
     T, S, v_ref = host(T), host(S), host(v_ref)
     dt = _field_dtype(T, S, v_ref)
     T, S, v_ref = T.to(dt), S.to(dt), v_ref.to(dt)

@@ -837,15 +837,28 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
   ML_REQUIRE_ALIGNED(T_ref, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S_ref, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
-  cudaStream_t st = (cudaStream_t)stream;
-  double* const eta[3] = {eta_steric, eta_thermosteric, eta_halosteric};
-  if (!tls().force_direct && tma::variants_eligible(dtype, T, S, T_ref, S_ref, v_ref, vref_dtype, nt, nz, ncol)) {
-    tls().last_path = ML_PATH_TMA;
-    return tma::launch_variants(eos, T, S, T_ref, S_ref, rho_ref, v_ref, z_i, deptho, p_level, neg_inv_rhozero, (int)nt,
-                                (int)nz, ncol, eta, rho_ref_out, sums, (double*)workspace, st);
+  // steric.py:115-121: thermosteric holds S at the reference slab, halosteric holds T.  Three launches that
+  // share nothing but the reference state: a fused three-variant kernel was measured and dropped (a density
+  // evaluation is bound by instruction issue, not by HBM, so sharing the loads gained nothing:
+  // profiles/r01_experiments.md), and the single-variant kernels fold the pinned operand into the coefficients.
+  if (rho_ref == nullptr && T_ref == T && S_ref == S) {
+    // the reference state is step 0 of the dataset itself: every variant goes through the fused
+    // self-reference pass, which also makes its step-0 height exactly zero (as in the reference);
+    // rho_ref, volo and masso come out of the first of them
+    const void* Ts[3] = {T, T, T_ref};
+    const void* Ss[3] = {S, S_ref, S};
+    double* const eta[3] = {eta_steric, eta_thermosteric, eta_halosteric};
+    bool have_ref = false;
+    for (int v = 0; v < 3; ++v) {
+      if (eta[v] == nullptr) continue;
+      rc = ml_steric_local_selfref(eos, dtype, Ts[v], Ss[v], v == 2, v == 1, v_ref, vref_dtype, z_i, deptho, p_level,
+                                   neg_inv_rhozero, nt, nz, ncol, eta[v], rho_ref_out, sums, workspace, workspace_bytes,
+                                   stream);
+      if (rc) return rc;
+      have_ref = true;
+    }
+    if (have_ref) return ML_OK;
   }
-  // any other layout: the reference state if asked for, then one single-variant call per requested height
-  // (steric.py:115-121: thermosteric holds S at the reference slab, halosteric holds T)
   if (rho_ref == nullptr) {
     rc = reference_state_impl(eos, dtype, T_ref, S_ref, v_ref, vref_dtype, p_level, nz, ncol, rho_ref_out, sums,
                               workspace, workspace_bytes, stream);

@@ -16,7 +16,7 @@ namespace {
 // OM4p25 needs ~5 GB of windows; allocating and freeing them costs tens of milliseconds per call)
 // and released by ml_host_release() or at thread exit.
 struct Resources {
-  static constexpr int kSlots = 12;
+  static constexpr int kSlots = 16;
   void* buf[kSlots] = {nullptr};
   size_t cap[kSlots] = {0};
   int device = -1;
@@ -82,10 +82,11 @@ extern "C" int ml_host_release(void) {
   return ML_OK;
 }
 
-extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
-                                    const double* z_i, const double* deptho, const double* p_level,
-                                    double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
-                                    int steps_per_window, double* eta, double* rho_ref_out, double* sums_out) {
+// eta_thermo / eta_halo: optional extra heights from the same transfer (NULL = steric only)
+static int steric_local_host_impl(int eos, int dtype, const void* T, const void* S, const void* v0, const double* z_i,
+                                  const double* deptho, const double* p_level, double neg_inv_rhozero, int64_t nt,
+                                  int64_t nz, int64_t ncol, int steps_per_window, double* eta, double* eta_thermo,
+                                  double* eta_halo, double* rho_ref_out, double* sums_out) {
   using namespace ml;
   if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
   if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
@@ -121,6 +122,16 @@ extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const voi
   ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
   ML_CUDA(r.alloc(10, &dSums, 2 * sizeof(double)));
   ML_CUDA(r.alloc(11, &dWs, ws_bytes));
+  // the other two variants hold one field at the reference slab (steric.py:115-121), so step 0 of T and S
+  // stays on the device for the whole call, next to one more height field per variant
+  const bool variants = eta_thermo != nullptr || eta_halo != nullptr;
+  void *dT0 = nullptr, *dS0 = nullptr, *dEtaT = nullptr, *dEtaH = nullptr;
+  if (variants) {
+    ML_CUDA(r.alloc(12, &dT0, lvl * es));
+    ML_CUDA(r.alloc(13, &dS0, lvl * es));
+    if (eta_thermo) ML_CUDA(r.alloc(14, &dEtaT, (size_t)nt * ncol * sizeof(double)));
+    if (eta_halo) ML_CUDA(r.alloc(15, &dEtaH, (size_t)nt * ncol * sizeof(double)));
+  }
 
   ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
@@ -150,14 +161,56 @@ extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const voi
                            (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
                            (double*)dEta + (size_t)t_first * ncol, nullptr, r.comp);
     if (rc) return rc;
+    if (variants) {
+      if (w == 0) {  // keep the reference slabs before window 0 is recycled
+        ML_CUDA(cudaMemcpyAsync(dT0, dT[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
+        ML_CUDA(cudaMemcpyAsync(dS0, dS[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
+      }
+      // window 0 starts at the reference step: the fused self-reference pass again, so that the step-0
+      // heights of these variants are exactly zero as well (it rewrites rho_ref / sums with the same values)
+      for (int v = 0; v < 2; ++v) {
+        double* out = (double*)(v == 0 ? dEtaT : dEtaH);
+        if ((v == 0 ? eta_thermo : eta_halo) == nullptr) continue;
+        const void* Tv = v == 0 ? dT[b] : dT0;
+        const void* Sv = v == 0 ? dS0 : dS[b];
+        if (w == 0)
+          rc = ml_steric_local_selfref(eos, dtype, Tv, Sv, v == 1, v == 0, dV, dtype, (const double*)dZi,
+                                       (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol, out,
+                                       (double*)dRho, (double*)dSums, dWs, ws_bytes, r.comp);
+        else
+          rc = ml_steric_local(eos, dtype, Tv, Sv, v == 1, v == 0, (const double*)dRho, dV, dtype, (const double*)dZi,
+                               (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
+                               out + (size_t)t_first * ncol, nullptr, r.comp);
+        if (rc) return rc;
+      }
+    }
     ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
   }
   ML_CUDA(cudaMemcpyAsync(eta, dEta, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  if (eta_thermo) ML_CUDA(cudaMemcpyAsync(eta_thermo, dEtaT, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  if (eta_halo) ML_CUDA(cudaMemcpyAsync(eta_halo, dEtaH, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   ML_CUDA(cudaStreamSynchronize(r.comp));
   ML_CUDA(cudaStreamSynchronize(r.copy));
   return ML_OK;
+}
+
+extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
+                                    const double* z_i, const double* deptho, const double* p_level,
+                                    double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                                    int steps_per_window, double* eta, double* rho_ref_out, double* sums_out) {
+  return steric_local_host_impl(eos, dtype, T, S, v0, z_i, deptho, p_level, neg_inv_rhozero, nt, nz, ncol,
+                                steps_per_window, eta, nullptr, nullptr, rho_ref_out, sums_out);
+}
+
+extern "C" int ml_steric_local_variants_host(int eos, int dtype, const void* T, const void* S, const void* v0,
+                                             const double* z_i, const double* deptho, const double* p_level,
+                                             double neg_inv_rhozero, int64_t nt, int64_t nz, int64_t ncol,
+                                             int steps_per_window, double* eta_steric, double* eta_thermosteric,
+                                             double* eta_halosteric, double* rho_ref_out, double* sums_out) {
+  return steric_local_host_impl(eos, dtype, T, S, v0, z_i, deptho, p_level, neg_inv_rhozero, nt, nz, ncol,
+                                steps_per_window, eta_steric, eta_thermosteric, eta_halosteric, rho_ref_out, sums_out);
 }
 
 // The global branch (src/momlevel/steric.py:134-147) on host buffers: per-step masses

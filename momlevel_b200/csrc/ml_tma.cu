@@ -403,187 +403,6 @@ __global__ void ML_TMA_KERNEL_ATTR
   }
 }
 
-// ------------------------------------------------------------------ all three variants
-// steric, thermosteric and halosteric height from ONE pass over T and S (SURVEY.md section 2,
-// kernel K3 "1-3 variants per pass"): steric.py:115-121 only changes which operand of the EOS is
-// held at its reference value, so with the reference slab's T0, S0 rows staged next to the time
-// rows a point costs three densities instead of three trips through HBM,
-//   d_steric = rho(T, S) - rho_ref,  d_thermo = rho(T, S0) - rho_ref,  d_halo = rho(T0, S) - rho_ref.
-// Chunks are kVT = 4 steps wide (3 variants x 4 steps = the 12 sums per thread the single-variant
-// kernels carry), the ring is kVStages = 8 levels deep (10 KB each), everything else -- refill by
-// the last warp out, depth-sorted tile, skipna accumulation -- is as in k_steric_tma.  The loop over
-// the steps is fully unrolled.  Measured: 290 G points/s for the three heights -- a density
-// evaluation is bound by instruction issue (about 40 instructions around its 18 fp64 ones), not by
-// HBM, so sharing the loads buys little.  The pinned operand is folded into the coefficients as in
-// the single-variant kernels (same arithmetic, so the heights agree with theirs); in THIS kernel that
-// did not change the time (128 registers either way).
-constexpr int kVT = 4;
-constexpr int kVStages = 8;
-constexpr int kVRows = 2 * kVT + 2;  // T rows, S rows, T0 row, S0 row
-constexpr uint32_t kVStageBytes = (uint32_t)kVRows * kTile * sizeof(float);
-
-struct VParams {
-  const double* rho_ref;  // reference density to read, or NULL: evaluate it from T0, S0 (and write rho_ref_out)
-  double* rho_ref_out;
-  const float* v_ref;
-  const double* z_i;
-  const double* deptho;
-  const double* p_level;
-  double coef;
-  int nt, nz;
-  int self_reference;     // T0, S0 are step 0 of T, S: the heights of step 0 are exactly zero (steric.py:105-107)
-  unsigned nchunks, tiles;
-  i64 ncol;
-  double* eta[3];         // steric, thermosteric, halosteric: each [nt][ncol]
-  double* partials;       // [2][tiles] = {volo, masso} when rho_ref is evaluated here
-};
-
-template <int EOS>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_steric_variants(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS,
-                      const __grid_constant__ CUtensorMap mapT0, const __grid_constant__ CUtensorMap mapS0,
-                      const VParams P) {
-  constexpr int kStageFloats = (int)(kVStageBytes / sizeof(float));
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kVStages * kVStageBytes);
-  int* released = reinterpret_cast<int*>(full + kVStages);
-  double* red = reinterpret_cast<double*>(full + 2 * kVStages);  // [kConsumerWarps][2]
-  double* s_p = red + kConsumerWarps * 2;
-  double* s_zi = s_p + P.nz;
-  unsigned* s_key = reinterpret_cast<unsigned*>(s_zi + P.nz + 1);
-  int* s_col = reinterpret_cast<int*>(s_key + kTile);
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const unsigned tile = blockIdx.x / P.nchunks;
-  const int c0 = (int)tile * kTile;
-  const int t0 = (int)(blockIdx.x - tile * P.nchunks) * kVT;
-  const int nz = P.nz;
-  const bool compute_ref = P.rho_ref == nullptr;
-  const bool owns_ref = compute_ref && t0 == 0;  // one chunk per tile stores rho_ref and reduces volo / masso
-
-  auto refill_stage = [&](int z) {
-    const int s = z % kVStages;
-    float* d = stage_base + (size_t)s * kStageFloats;
-    mbar_expect_tx(full + s, kVStageBytes);
-    tma_load_3d(d, &mapT, full + s, c0, z, t0);
-    tma_load_3d(d + kVT * kTile, &mapS, full + s, c0, z, t0);
-    tma_load_2d(d + 2 * kVT * kTile, &mapT0, full + s, c0, z);
-    tma_load_2d(d + (2 * kVT + 1) * kTile, &mapS0, full + s, c0, z);
-  };
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < kVStages; ++s) {
-      mbar_init(full + s, 1);
-      released[s] = 0;
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    for (int z = 0; z < kVStages && z < nz; ++z) refill_stage(z);
-  }
-  for (int i = tid; i < nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
-  for (int i = tid; i <= nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
-  __syncthreads();
-
-  int col = tid;
-  if (ML_TMA_SORT != 0) {
-    const i64 cg = (i64)c0 + tid;
-    col = sorted_column(wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz), s_key, s_col);
-  }
-  const i64 c = (i64)c0 + col;
-  const bool in = c < P.ncol;
-  const i64 cc = in ? c : (P.ncol - 1);
-  Eos<EOS> eos;
-  double acc[3][kVT];
-#pragma unroll
-  for (int v = 0; v < 3; ++v)
-#pragma unroll
-    for (int k = 0; k < kVT; ++k) acc[v][k] = 0.0;
-  double vol = 0.0, mass = 0.0;
-  double depth = __ldg(P.deptho + cc);
-  if (isnan(depth)) depth = 0.0;  // derived.py:295
-  double rref_n = 0.0;
-  unsigned v_n = ld_vraw(P.v_ref, cc);
-  if (!compute_ref) rref_n = __ldg(P.rho_ref + cc);
-  const bool surface_wet = !vraw_isnan(v_n);  // steric.py:166
-  const bool zero_step = P.self_reference != 0 && t0 == 0;  // row 0 of this chunk is the reference step itself
-
-  for (int z = 0; z < nz; ++z) {
-    const unsigned v_z = v_n;
-    double rref_z = rref_n;
-    if (z + 1 < nz) {
-      const i64 j = (i64)(z + 1) * P.ncol + cc;
-      v_n = ld_vraw(P.v_ref, j);
-      if (!compute_ref) rref_n = __ldg(P.rho_ref + j);
-    }
-    const int s = z % kVStages;
-    const float* st = stage_base + (size_t)s * kStageFloats + col;
-    mbar_wait(full + s, (uint32_t)(z / kVStages) & 1u);
-    eos.set_level(s_p[z]);
-    const float t0f = st[2 * kVT * kTile], s0f = st[(2 * kVT + 1) * kTile];
-    const double T0 = (double)t0f, S0 = (double)s0f;
-    const bool dry = vraw_isnan(v_z);
-    // reference.py:71 evaluates the EOS everywhere; a warp over land has nothing to evaluate
-    const bool any_ref = __any_sync(0xffffffffu, !(isnan(t0f) || isnan(s0f)));
-    double w = level_dz(depth, s_zi[z], s_zi[z + 1]);
-    if (dry) w = 0.0;  // steric.py:151-153
-    if (compute_ref) rref_z = nan("");
-    else if (isnan(rref_z)) w = 0.0;
-    if (compute_ref && any_ref) rref_z = eos.rho(T0, S0);
-    if (__any_sync(0xffffffffu, nonzero(w))) {
-      // the pinned operand of the thermo- / halosteric evaluation goes into the coefficients once per level
-      const typename Eos<EOS>::Pinned ps = eos.pin_s(S0), pt = eos.pin_t(T0);
-#pragma unroll
-      for (int kk = 0; kk < kVT; ++kk) {
-        if (kk == 0 && zero_step) continue;  // the reference step: all three heights are exactly zero
-        const double Tv = (double)st[kk * kTile];
-        const double Sv = (double)st[(kVT + kk) * kTile];
-        fma_skipnan(acc[0][kk], w, eos.rho(Tv, Sv) - rref_z);
-        fma_skipnan(acc[1][kk], w, eos.rho_pinned_s(ps, Tv) - rref_z);  // S held at the reference slab
-        fma_skipnan(acc[2][kk], w, eos.rho_pinned_t(pt, Sv) - rref_z);  // T held at the reference slab
-      }
-    }
-    if (owns_ref && in) {
-      if (P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = rref_z;
-      if (!dry) {  // volo, masso: skipna sums (derived.py:787-789, :435-438)
-        const double vv = vraw_value(v_z);
-        vol += vv;
-        const double m = rref_z * vv;
-        if (!is_nan_q(m)) mass += m;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) {
-      const int before = atomicAdd(released + s, 1);
-      if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kVStages < nz) refill_stage(z + kVStages);
-    }
-  }
-  if (in) {
-#pragma unroll
-    for (int v = 0; v < 3; ++v)
-      if (P.eta[v] != nullptr) {
-#pragma unroll
-        for (int k = 0; k < kVT; ++k)
-          if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[v][k] : nan("");
-      }
-  }
-  if (owns_ref) {  // uniform per CTA
-    vol = warp_sum(vol);
-    mass = warp_sum(mass);
-    if (lane == 0) {
-      red[warp * 2 + 0] = vol;
-      red[warp * 2 + 1] = mass;
-    }
-    __syncthreads();
-    if (tid < 2) {
-      double sacc = 0.0;
-#pragma unroll
-      for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * 2 + tid];
-      P.partials[(i64)tid * P.tiles + tile] = sacc;
-    }
-  }
-}
-
 // ----------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -817,53 +636,6 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   if (rc) return rc;
   if ((rc = launch_plan<kGlobal>(eos, pl, P, st))) return rc;
   return reduce_rows(partials, pl.tiles, masso, nt, st);
-}
-
-bool variants_eligible(int dtype, const void* T, const void* S, const void* T_ref, const void* S_ref, const void* v_ref,
-                       int vref_dtype, int64_t nt, int64_t nz, int64_t ncol) {
-  if ((reinterpret_cast<uintptr_t>(T_ref) | reinterpret_cast<uintptr_t>(S_ref)) & 15u) return false;
-  return common_eligible(dtype, vref_dtype, T, S, nt, nz, ncol);
-}
-
-int launch_variants(int eos, const void* T, const void* S, const void* T_ref, const void* S_ref, const double* rho_ref,
-                    const void* v_ref, const double* z_i, const double* deptho, const double* p_level, double coef,
-                    int nt, int nz, int64_t ncol, double* const eta[3], double* rho_ref_out, double* sums,
-                    double* partials, cudaStream_t st) {
-  VParams P;
-  P.rho_ref = rho_ref;
-  P.rho_ref_out = rho_ref_out;
-  P.v_ref = static_cast<const float*>(v_ref);
-  P.z_i = z_i;
-  P.deptho = deptho;
-  P.p_level = p_level;
-  P.coef = coef;
-  P.nt = nt;
-  P.nz = nz;
-  P.self_reference = (T_ref == T && S_ref == S) ? 1 : 0;
-  P.nchunks = (unsigned)((nt + kVT - 1) / kVT);
-  P.tiles = (unsigned)((ncol + kTile - 1) / kTile);
-  P.ncol = ncol;
-  for (int v = 0; v < 3; ++v) P.eta[v] = eta[v];
-  P.partials = partials;
-  CUtensorMap mT, mS, mT0, mS0;
-  if (!make_map(&mT, T, 3, ncol, nz, nt, kVT) || !make_map(&mS, S, 3, ncol, nz, nt, kVT) ||
-      !make_map(&mT0, T_ref, 2, ncol, nz, 1, 1) || !make_map(&mS0, S_ref, 2, ncol, nz, 1, 1))
-    return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
-  const size_t smem = (size_t)kVStages * kVStageBytes + 2 * kVStages * sizeof(uint64_t) +
-                      (size_t)kConsumerWarps * 2 * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) +
-                      2 * kTile * sizeof(int) + 128;
-  cudaError_t e;
-#define ML_TMA_VARIANTS(E)                                                                                  \
-  do {                                                                                                      \
-    e = cudaFuncSetAttribute(k_steric_variants<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_variants)");                  \
-    k_steric_variants<E><<<P.tiles * P.nchunks, kThreads, smem, st>>>(mT, mS, mT0, mS0, P);                \
-  } while (0)
-  if (eos == ML_EOS_WRIGHT) ML_TMA_VARIANTS(0); else ML_TMA_VARIANTS(1);
-#undef ML_TMA_VARIANTS
-  int rc = launched("k_steric_variants");
-  if (rc || rho_ref != nullptr) return rc;
-  return reduce_rows(partials, P.tiles, sums, 2, st);
 }
 
 }  // namespace tma

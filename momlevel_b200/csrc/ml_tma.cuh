@@ -24,15 +24,6 @@ int launch_global(int eos, int dtype, const void* T, const void* S, int t_bcast,
                   int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
                   cudaStream_t st);
 
-// all three variants (steric, thermosteric, halosteric) from one pass over T, S; rho_ref == NULL: evaluate the
-// reference density from T_ref, S_ref, store it in rho_ref_out and reduce volo / masso into sums
-bool variants_eligible(int dtype, const void* T, const void* S, const void* T_ref, const void* S_ref, const void* v_ref,
-                       int vref_dtype, int64_t nt, int64_t nz, int64_t ncol);
-int launch_variants(int eos, const void* T, const void* S, const void* T_ref, const void* S_ref, const double* rho_ref,
-                    const void* v_ref, const double* z_i, const double* deptho, const double* p_level, double coef,
-                    int nt, int nz, int64_t ncol, double* const eta[3], double* rho_ref_out, double* sums,
-                    double* partials, cudaStream_t st);
-
 // fixed-order second reduction stage (defined in ml_api.cu): out[r] = sum_b partials[r][b]
 int reduce_rows(const double* partials, int64_t nblk, double* out, int nrows, cudaStream_t st);
 

@@ -223,11 +223,11 @@ VARIANTS = ("steric", "thermosteric", "halosteric")
 
 def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rhozero=1035.0, patm=101325.0,
                     equation_of_state="Wright", dtype="float32", strict=True, verbose=False):
-    """Steric, thermosteric and halosteric height (``domain="local"``) from one pass over the dataset.
+    """Steric, thermosteric and halosteric height (``domain="local"``) from one call.
 
-    Equivalent to ``steric(dset)``, ``thermosteric(dset, reference=ref)`` and ``halosteric(dset, reference=ref)``
-    (steric.py:115-121 only changes which operand of the equation of state is held at its reference value),
-    but T and S cross HBM once instead of three times.  Arguments as :func:`steric`.  Returns
+    Equivalent to ``steric(dset)``, ``thermosteric(dset)`` and ``halosteric(dset)`` (steric.py:115-121 only
+    changes which operand of the equation of state is held at its reference value) with the validation, the
+    reference state and the result assembly done once.  Arguments as :func:`steric`.  Returns
     ``(result, reference)``; ``result`` holds the three height variables (no ``delta_rho``: there is one per
     variant -- ask :func:`steric` for the variant whose 4-D anomaly is wanted).
     """

@@ -678,3 +678,25 @@ def test_global_host_entry_matches_device_path(ml):
     eta, href = ml.distributed.global_sea_level(got.numpy(), float(ref["volo"]), float(ref["rhoga"]),
                                                 float(ref["areacello"].sum()))
     assert np.allclose(eta, res["steric"].values, rtol=0, atol=1e-12)
+
+
+def test_host_entry_all_variants_from_one_transfer(ml):
+    """ml_steric_local_variants_host: three heights from one pass of the fields over PCIe == three device calls."""
+    from momlevel_b200 import synth
+
+    ds = synth.make_dataset(7, 12, 20, 32, seed=5, device="cpu", dtype=torch.float32)
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    want = {}
+    want["steric"], ref = ml.steric(ds)
+    want["thermosteric"], _ = ml.thermosteric(ds)
+    want["halosteric"], _ = ml.halosteric(ds)
+    for spw in (1, 3, 7):
+        etas, rho, (volo, masso) = ml.core.steric_local_host(
+            ds["thetao"].data, ds["so"].data, ds["volcello"].data[0], ds["z_i"].values, ds["deptho"].values, pres,
+            steps_per_window=spw, want_rho_ref=True, variants=True)
+        for variant in ("steric", "thermosteric", "halosteric"):
+            _close_nan(etas[variant].numpy(), want[variant][variant].values, atol=1e-12)
+            wet = ~np.isnan(ref["volcello"].values[0])
+            assert np.all(etas[variant].numpy()[0][wet] == 0.0)  # step 0 is the reference state, for every variant
+        _close_nan(rho.numpy(), ref["rho"].values, rtol=1e-15)
+        assert masso == pytest.approx(float(ref["masso"]), rel=1e-14)
