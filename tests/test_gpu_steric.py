@@ -700,3 +700,38 @@ def test_host_entry_all_variants_from_one_transfer(ml):
             assert np.all(etas[variant].numpy()[0][wet] == 0.0)  # step 0 is the reference state, for every variant
         _close_nan(rho.numpy(), ref["rho"].values, rtol=1e-15)
         assert masso == pytest.approx(float(ref["masso"]), rel=1e-14)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shapes_tma_against_direct(ml, seed):
+    """Shapes drawn at random around the TMA family's edges -- a last tile with a few columns, one or two
+    levels, a single step, more levels than the ring is deep -- must agree with the direct family."""
+    from momlevel_b200 import core, synth
+
+    rng = np.random.default_rng(1000 + seed)
+    nt = int(rng.choice([1, 2, 3, 5, 11, 12, 13, 17, 29]))
+    nz = int(rng.choice([1, 2, 3, 4, 5, 9, 33, 75, 130]))
+    ny = int(rng.integers(1, 9))
+    nx = 4 * int(rng.integers(64 // ny + 1, 200))  # ncol % 4 == 0 and >= 256
+    grid = synth.make_grid(nz, ny, nx, seed=seed, device="cuda")
+    T, S, V = synth.make_fields(grid, nt, seed=seed, dtype=torch.float32)
+    if nt > 1 and nz > 1:
+        T[nt - 1, nz // 2, 0, nx // 2] = float("nan")
+    pres = grid["z_l"] * 1.0e4 + 101325.0
+    out = {}
+    for direct in (False, True):
+        prev = core.force_direct(direct)
+        try:
+            eta, rho, sums = core.steric_local_selfref(T, S, V, grid["z_i"], grid["deptho"], pres)
+            assert core.last_path() == (1 if direct else 2), (nt, nz, ny, nx)
+            eta_t, _ = core.steric_local(T, S[0], rho, V, grid["z_i"], grid["deptho"], pres, s_bcast=True)
+            eta_h, _ = core.steric_local(T[0], S, rho, V, grid["z_i"], grid["deptho"], pres, t_bcast=True)
+            masso = core.steric_global(T, S, V, pres)
+            out[direct] = (eta, rho, sums, eta_t, eta_h, masso)
+        finally:
+            core.force_direct(prev)
+    for a, b in zip(out[False], out[True]):
+        assert a.shape == b.shape and torch.equal(torch.isnan(a), torch.isnan(b)), (nt, nz, ny, nx)
+        err = float(torch.nan_to_num(a - b).abs().max())
+        scale = float(torch.nan_to_num(b).abs().max())
+        assert err <= 1e-11 + 1e-13 * scale, (nt, nz, ny, nx, err)
