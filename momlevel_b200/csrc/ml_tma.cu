@@ -162,6 +162,8 @@ __device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_co
 }
 
 struct Params {
+  const float* T;         // the fields themselves (the streaming path goes through the tensor maps;
+  const float* S;         //  these are for the repair pass of a column that met a missing value)
   const double* rho_ref;  // kLocal: read
   double* rho_ref_out;    // kSelfRef: written (may be NULL)
   const float* v_ref;     // fp32 volcello of the reference state
@@ -326,6 +328,7 @@ __global__ void ML_TMA_KERNEL_ATTR
       }
       eos.set_level(s_p[z]);
       const bool live = nonzero(w);
+      if (!live) sub = 0.0;  // a dry lane adds 0 * (rho of a borrowed column - sub): keep a missing rho_ref out of it
       const unsigned live_lanes = __ballot_sync(0xffffffffu, live);
       // kSelfRef: row 0 of the NEXT level (clamped at the bottom level, where the value is
       // recomputed and discarded) -- wait for it up front so that the reference point and the
@@ -337,7 +340,14 @@ __global__ void ML_TMA_KERNEL_ATTR
       if (SELFREF && (ML_TMA_EXPERIMENT != 1 || zn < kStages)) mbar_wait(full + (zn % kStages), (uint32_t)(zn / kStages) & 1u);
       if (ML_TMA_EXPERIMENT != 1 || z < kStages) mbar_wait(full + s, (uint32_t)(z / kStages) & 1u);
       if (ML_TMA_EXPERIMENT != 2 && live_lanes != 0u) {
-        const float* sT = stage_base + (size_t)s * kStageFloats + col;
+        // A lane whose cell is dry (w = 0: land, below the sea floor) holds missing values and would
+        // put NaN into its sums (0 * NaN), so it evaluates the column of the warp's first wet lane
+        // instead -- the same shared-memory words, a broadcast -- and adds 0 * (a finite number).
+        // The sums are then plain FMAs: the four ALU instructions of a per-point NaN test were 6-10 %
+        // of the thermo- / halosteric kernels.  A hole at a WET cell does reach the sums; it is
+        // caught after the sweep and that column is redone with the skipna rule (repair pass below).
+        const int first_wet = __shfl_sync(0xffffffffu, col, __ffs(live_lanes) - 1);  // every lane takes part
+        const float* sT = stage_base + (size_t)s * kStageFloats + (live ? col : first_wet);
         const float* sS = sT + kRowsT * kTile;
         if (SELFREF) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
         // a time-invariant operand is folded into the polynomial's coefficients once per level
@@ -350,8 +360,7 @@ __global__ void ML_TMA_KERNEL_ATTR
           const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
           const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
           const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
-          const double d = GLOBAL ? rho : rho - sub;
-          fma_skipnan(acc[kk], w, d);
+          acc[kk] = fma(w, GLOBAL ? rho : rho - sub, acc[kk]);
         }
       } else if (SELFREF) {
         // a warp without water still owes rho_ref of the next level (reference.py:71 evaluates the
@@ -367,6 +376,37 @@ __global__ void ML_TMA_KERNEL_ATTR
         const int before = atomicAdd(released + s, 1);
         if (ML_TMA_EXPERIMENT != 1 && (before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz)
           refill_stage(z + kStages);
+      }
+    }
+    // Repair pass (rare: consistent model output has no holes at wet cells).  xarray's sum skips a
+    // missing term (steric.py:163, derived.py:435-438); the sweep above does not, so a column whose
+    // sums turned NaN is integrated again from global memory with the skipna rule.
+    bool poisoned = false;
+#pragma unroll
+    for (int k = 0; k < TC; ++k) poisoned |= is_nan_q(acc[k]);
+    if (poisoned && in) {
+#pragma unroll
+      for (int k = 0; k < TC; ++k) acc[k] = 0.0;
+      const i64 lvl = (i64)nz * P.ncol;
+      for (int z = 0; z < nz; ++z) {
+        const i64 j = (i64)z * P.ncol + c;
+        const unsigned v = ld_vraw(P.v_ref, j);
+        double w, sub = 0.0;
+        if (GLOBAL) {
+          w = vraw_isnan(v) ? 0.0 : vraw_value(v);
+        } else {
+          w = vraw_isnan(v) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
+          sub = SELFREF ? P.rho_ref_out[j] : __ldg(P.rho_ref + j);  // kSelfRef: this thread stored it above
+        }
+        if (!nonzero(w)) continue;
+        eos.set_level(s_p[z]);
+#pragma unroll
+        for (int k = SELFREF ? 1 : 0; k < TC; ++k) {
+          if (t0 + k >= P.nt) continue;
+          const double Tv = (double)__ldg(P.T + (BC == 1 ? 0 : (i64)(t0 + k) * lvl) + j);
+          const double Sv = (double)__ldg(P.S + (BC == 2 ? 0 : (i64)(t0 + k) * lvl) + j);
+          fma_skipnan(acc[k], w, GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub);
+        }
       }
     }
     if (!GLOBAL) {
@@ -560,8 +600,11 @@ static int launch_plan(int eos, const Plan& pl, const Params& P, cudaStream_t st
   return ML_OK;
 }
 
-static Params base_params(const void* v_ref, int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol) {
+static Params base_params(const void* T, const void* S, const void* v_ref, int vref_dtype, const double* p_level,
+                          int nt, int nz, int64_t ncol) {
   Params P;
+  P.T = static_cast<const float*>(T);
+  P.S = static_cast<const float*>(S);
   P.rho_ref = nullptr;
   P.rho_ref_out = nullptr;
   P.v_ref = static_cast<const float*>(v_ref);
@@ -584,7 +627,7 @@ static Params base_params(const void* v_ref, int vref_dtype, const double* p_lev
 int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
                  const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
                  double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st) {
-  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  Params P = base_params(T, S, v_ref, vref_dtype, p_level, nt, nz, ncol);
   P.rho_ref = rho_ref;
   P.z_i = z_i;
   P.deptho = deptho;
@@ -599,7 +642,7 @@ int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_
 int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref, int vref_dtype,
                    const double* z_i, const double* deptho, const double* p_level, double coef, int nt, int nz,
                    int64_t ncol, double* eta, double* rho_ref, double* sums, double* partials, cudaStream_t st) {
-  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  Params P = base_params(T, S, v_ref, vref_dtype, p_level, nt, nz, ncol);
   P.rho_ref_out = rho_ref;
   P.z_i = z_i;
   P.deptho = deptho;
@@ -629,7 +672,7 @@ int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bca
 int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref,
                   int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
                   cudaStream_t st) {
-  Params P = base_params(v_ref, vref_dtype, p_level, nt, nz, ncol);
+  Params P = base_params(T, S, v_ref, vref_dtype, p_level, nt, nz, ncol);
   P.partials = partials;
   Plan pl;
   int rc = make_plan(&pl, T, S, t_bcast, s_bcast, P, 0);
