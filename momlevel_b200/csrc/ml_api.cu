@@ -841,39 +841,44 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
   // share nothing but the reference state: a fused three-variant kernel was measured and dropped (a density
   // evaluation is bound by instruction issue, not by HBM, so sharing the loads gained nothing:
   // profiles/r01_experiments.md), and the single-variant kernels fold the pinned operand into the coefficients.
-  if (rho_ref == nullptr && T_ref == T && S_ref == S) {
-    // the reference state is step 0 of the dataset itself: every variant goes through the fused
-    // self-reference pass, which also makes its step-0 height exactly zero (as in the reference);
-    // rho_ref, volo and masso come out of the first of them
-    const void* Ts[3] = {T, T, T_ref};
-    const void* Ss[3] = {S, S_ref, S};
-    double* const eta[3] = {eta_steric, eta_thermosteric, eta_halosteric};
-    bool have_ref = false;
-    for (int v = 0; v < 3; ++v) {
-      if (eta[v] == nullptr) continue;
-      rc = ml_steric_local_selfref(eos, dtype, Ts[v], Ss[v], v == 2, v == 1, v_ref, vref_dtype, z_i, deptho, p_level,
-                                   neg_inv_rhozero, nt, nz, ncol, eta[v], rho_ref_out, sums, workspace, workspace_bytes,
-                                   stream);
-      if (rc) return rc;
-      have_ref = true;
-    }
-    if (have_ref) return ML_OK;
-  }
+  const bool self_reference = rho_ref == nullptr && T_ref == T && S_ref == S;  // the reference state is step 0
+  bool steric_done = false;
   if (rho_ref == nullptr) {
-    rc = reference_state_impl(eos, dtype, T_ref, S_ref, v_ref, vref_dtype, p_level, nz, ncol, rho_ref_out, sums,
-                              workspace, workspace_bytes, stream);
+    if (self_reference && eta_steric) {  // reference state and steric height in one fused pass
+      rc = ml_steric_local_selfref(eos, dtype, T, S, 0, 0, v_ref, vref_dtype, z_i, deptho, p_level, neg_inv_rhozero, nt,
+                                   nz, ncol, eta_steric, rho_ref_out, sums, workspace, workspace_bytes, stream);
+      steric_done = true;
+    } else {
+      rc = reference_state_impl(eos, dtype, T_ref, S_ref, v_ref, vref_dtype, p_level, nz, ncol, rho_ref_out, sums,
+                                workspace, workspace_bytes, stream);
+    }
     if (rc) return rc;
     rho_ref = rho_ref_out;
   }
-  if (eta_steric && (rc = ml_steric_local(eos, dtype, T, S, 0, 0, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
-                                          neg_inv_rhozero, nt, nz, ncol, eta_steric, nullptr, stream)))
-    return rc;
-  if (eta_thermosteric && (rc = ml_steric_local(eos, dtype, T, S_ref, 0, 1, rho_ref, v_ref, vref_dtype, z_i, deptho,
-                                                p_level, neg_inv_rhozero, nt, nz, ncol, eta_thermosteric, nullptr, stream)))
-    return rc;
-  if (eta_halosteric && (rc = ml_steric_local(eos, dtype, T_ref, S, 1, 0, rho_ref, v_ref, vref_dtype, z_i, deptho,
-                                              p_level, neg_inv_rhozero, nt, nz, ncol, eta_halosteric, nullptr, stream)))
-    return rc;
+  // one single-variant launch per remaining height; with a self-reference the TMA family is told that step 0 is
+  // the reference state itself, so that height is exactly zero there as in the reference (rho - rho_ref == 0)
+  struct Variant {
+    double* eta;
+    const void *T, *S;
+    int t_bcast, s_bcast;
+  };
+  const Variant todo[3] = {{steric_done ? nullptr : eta_steric, T, S, 0, 0},
+                           {eta_thermosteric, T, S_ref, 0, 1},
+                           {eta_halosteric, T_ref, S, 1, 0}};
+  for (const Variant& v : todo) {
+    if (v.eta == nullptr) continue;
+    if (!tls().force_direct && tma::local_eligible(dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, nt,
+                                                   nz, ncol, v.eta, nullptr)) {
+      tls().last_path = ML_PATH_TMA;
+      rc = tma::launch_local(eos, dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho,
+                             p_level, neg_inv_rhozero, (int)nt, (int)nz, ncol, v.eta, nullptr, (cudaStream_t)stream,
+                             self_reference ? 1 : 0);
+    } else {
+      rc = ml_steric_local(eos, dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
+                           neg_inv_rhozero, nt, nz, ncol, v.eta, nullptr, stream);
+    }
+    if (rc) return rc;
+  }
   return ML_OK;
 }
 

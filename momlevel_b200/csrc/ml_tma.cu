@@ -173,6 +173,7 @@ struct Params {
   double coef;
   int nt, nz;
   int t_start;            // first time step covered by this launch
+  int first_is_reference; // kLocal: step 0 of the field IS the reference state -> its height is exactly zero
   unsigned nchunks;       // time chunks covered by this launch; grid = tiles * nchunks, chunk fastest
   unsigned tiles;         // column tiles
   i64 ncol;
@@ -290,6 +291,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     unsigned v_n = ld_vraw(P.v_ref, cc);
     if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
     const bool surface_wet = !vraw_isnan(v_n);  // steric.py:166
+    const bool zero_first = MODE == kLocal && P.first_is_reference != 0 && t0 == 0;
     // kSelfRef: the reference density of level z+1 is evaluated together with the points of
     // level z (from row 0 of the next stage, inside the same unrolled block so the scheduler
     // interleaves it), stored for the caller and used one iteration later.
@@ -357,6 +359,7 @@ __global__ void ML_TMA_KERNEL_ATTR
         if (BC == 2) pin = eos.pin_s((double)sS[0]);
 #pragma unroll
         for (int kk = SELFREF ? 1 : 0; kk < TC; ++kk) {  // kSelfRef: step 0 is the reference itself
+          if (MODE == kLocal && kk == 0 && zero_first) continue;  // ... and so it is here, by the caller's word
           const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
           const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
           const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
@@ -402,7 +405,7 @@ __global__ void ML_TMA_KERNEL_ATTR
         eos.set_level(s_p[z]);
 #pragma unroll
         for (int k = SELFREF ? 1 : 0; k < TC; ++k) {
-          if (t0 + k >= P.nt) continue;
+          if (t0 + k >= P.nt || (k == 0 && zero_first)) continue;
           const double Tv = (double)__ldg(P.T + (BC == 1 ? 0 : (i64)(t0 + k) * lvl) + j);
           const double Sv = (double)__ldg(P.S + (BC == 2 ? 0 : (i64)(t0 + k) * lvl) + j);
           fma_skipnan(acc[k], w, GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub);
@@ -616,6 +619,7 @@ static Params base_params(const void* T, const void* S, const void* v_ref, int v
   P.nt = nt;
   P.nz = nz;
   P.t_start = 0;
+  P.first_is_reference = 0;
   P.nchunks = 1;
   P.tiles = 0;
   P.ncol = ncol;
@@ -626,8 +630,10 @@ static Params base_params(const void* T, const void* S, const void* v_ref, int v
 
 int launch_local(int eos, int, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
                  const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
-                 double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st) {
+                 double coef, int nt, int nz, int64_t ncol, double* eta, double*, cudaStream_t st,
+                 int first_is_reference) {
   Params P = base_params(T, S, v_ref, vref_dtype, p_level, nt, nz, ncol);
+  P.first_is_reference = first_is_reference;
   P.rho_ref = rho_ref;
   P.z_i = z_i;
   P.deptho = deptho;

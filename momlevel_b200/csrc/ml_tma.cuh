@@ -11,7 +11,8 @@ bool local_eligible(int dtype, const void* T, const void* S, int t_bcast, int s_
                     const double* delta_rho);
 int launch_local(int eos, int dtype, const void* T, const void* S, int t_bcast, int s_bcast, const double* rho_ref,
                  const void* v_ref, int vref_dtype, const double* z_i, const double* deptho, const double* p_level,
-                 double coef, int nt, int nz, int64_t ncol, double* eta, double* delta_rho, cudaStream_t st);
+                 double coef, int nt, int nz, int64_t ncol, double* eta, double* delta_rho, cudaStream_t st,
+                 int first_is_reference = 0);  // step 0 of the fields is the reference state: its height is exactly 0
 
 // kSelfRef: reference state (rho_ref, volo, masso) and eta from one pass; reference = step 0
 int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bcast, const void* v_ref, int vref_dtype,
