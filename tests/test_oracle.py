@@ -258,3 +258,42 @@ def test_stability_angle_and_wave_speed_kats():
     assert broadcast.sum() == pytest.approx(524.30956095, abs=5e-8)
     # no missing values here: the broadcast repeats the column sums over the five levels
     assert np.array_equal(broadcast[2], np.moveaxis(c1, 0, -1))
+
+
+# ------------------------------------------------------------------ properties of the oracle itself
+
+
+def test_dz_partitions_the_water_column():
+    # derived.py:295-318: the clipped thicknesses of a column add up to its depth (capped by the grid's bottom)
+    rng = np.random.default_rng(5)
+    z_i = np.concatenate([[0.0], np.cumsum(rng.uniform(1.0, 300.0, 20))])
+    z_l = 0.5 * (z_i[1:] + z_i[:-1])
+    depth = rng.uniform(0.0, 1.2 * z_i[-1], (7, 9))
+    depth[0, 0] = np.nan  # land: filled with 0 (derived.py:295)
+    dz = steric.calc_dz(z_l, z_i, depth)
+    assert dz.shape == (20, 7, 9) and np.all(dz >= 0)
+    assert np.allclose(dz.sum(0), np.minimum(np.nan_to_num(depth), z_i[-1]), rtol=0, atol=1e-9)
+    frac = steric.calc_dz(z_l, z_i, depth, fraction=True)
+    wet = np.isfinite(frac)  # derived.py:320-323: empty cells become NaN, not 0
+    assert np.array_equal(wet, dz > 0) and np.all((frac[wet] > 0) & (frac[wet] <= 1))
+
+
+def test_linear_eos_heights_are_additive():
+    # with a linear equation of state rho(T,S) - rho0 = [rho(T,S0) - rho0] + [rho(T0,S) - rho0]
+    d = testdata.generate_test_data()
+    ref = steric.reference_state(d["thetao"], d["so"], d["volcello"], d["areacello"], d["z_l"], eos="linear")
+    eta = {v: steric.steric_local(d["thetao"], d["so"], d["z_l"], d["z_i"], d["deptho"], ref, eos="linear", variant=v)[0]
+           for v in steric.VARIANTS}
+    assert np.allclose(eta["steric"], eta["thermosteric"] + eta["halosteric"], rtol=0, atol=1e-12)
+    assert np.all(eta["steric"][0] == 0.0)  # step 0 is the reference state
+
+
+def test_adjusted_n2_is_positive_and_idempotent():
+    d = testdata.generate_test_data()
+    n2 = stratification.calc_n2(d["thetao"], d["so"], d["z_l"])
+    adj = stratification.adjust_negative_n2(n2)
+    assert np.all(adj[np.isfinite(adj)] > 0)
+    assert np.array_equal(stratification.adjust_negative_n2(adj), adj, equal_nan=True)
+    # values that were positive are untouched
+    keep = n2 > 0
+    assert np.array_equal(adj[keep], n2[keep])
