@@ -57,13 +57,19 @@ def steric(
     dset = dset.rename(varname_map)
     tcoord, zcoord, zbounds = default_coords(coord_names)
     additional_vars = None if domain == "global" else [zbounds, "deptho"]
-    validate_dataset(dset, strict=strict, additional_vars=additional_vars)
+    # The fused default path on device-resident fields reads every value-dependent check back together with
+    # volo / masso AFTER the kernel is queued (one synchronisation instead of five in front of the launch);
+    # an invalid dataset raises exactly what it raised before, a few milliseconds later.
+    deferred = (reference is None and domain == "local" and variant in VARIANTS
+                and _on_one_cuda_device(dset, ("thetao", "so", "volcello", "areacello", "deptho", zcoord, zbounds)))
+    validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=False if deferred else None)
 
     # steric.py:96
     pres = _pressure(dset, zcoord, patm)
 
     # steric.py:98-112
     fused_eta = None
+    area_total = None  # areacello.sum(), when the fused path has already read it back
     if reference is not None:
         assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
         if verbose:
@@ -71,12 +77,13 @@ def steric(
     else:
         if domain != "global" and variant in ("steric", "thermosteric", "halosteric"):
             # reference state and column integral in one pass over T, S (ml_steric_local_selfref)
-            reference, fused_eta = _selfref(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord, zbounds)
+            reference, fused_eta, area_total = _selfref(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord,
+                                                        zbounds, deferred, strict, additional_vars)
         else:
             reference = setup_reference_state(dset, patm=patm, eos=equation_of_state, coord_names=coord_names)
         if verbose:
             print("Generating reference state from first timestep")
-    validate_dataset(reference, reference=True, strict=strict)
+    validate_dataset(reference, reference=True, strict=strict, area_total=area_total)
 
     # steric.py:115-125: which field, if any, is held at its reference value
     if variant == "thermosteric":
@@ -201,12 +208,27 @@ def _reference_from_pass(dset, tcoord, eos, rho, sums):
     return reference
 
 
-def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
-    """``setup_reference_state(dset)`` (reference.py:57-83) with the local column integral fused in."""
+def _on_one_cuda_device(dset, names):
+    try:
+        devs = {dset[n].data.device for n in names if isinstance(dset[n].data, torch.Tensor)}
+        return len(devs) == 1 and next(iter(devs)).type == "cuda" and all(
+            isinstance(dset[n].data, torch.Tensor) for n in names)
+    except (KeyError, AttributeError):
+        return False
+
+
+def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferred=False, strict=True,
+             additional_vars=None):
+    """``setup_reference_state(dset)`` (reference.py:57-83) with the local column integral fused in.
+
+    Returns ``(reference, eta, area_total)``; ``area_total`` is ``areacello.sum()`` when the value checks were
+    deferred (read back with volo / masso after the launch), else ``None``.
+    """
     from .util import eos_func_from_str
 
     eos_func_from_str(eos)
-    _check_depths(dset, zcoord, zbounds)
+    if not deferred:
+        _check_depths(dset, zcoord, zbounds)
     T0 = dset["thetao"].isel({tcoord: 0}).squeeze().data
     S0 = dset["so"].isel({tcoord: 0}).squeeze().data
     V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
@@ -215,7 +237,19 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
     eta, rho, sums = core.steric_local_selfref(
         T, S, V0, dset[zbounds].data, dset["deptho"].data, pres, rhozero=rhozero, eos=eos,
         t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric")
-    return _reference_from_pass(dset, tcoord, eos, rho, sums), eta
+    area_total = None
+    if deferred:  # the value checks ride behind the kernel and come back with volo / masso
+        arrs = (dset["deptho"].data, dset[zcoord].data, dset[zbounds].data)
+        flags = torch.stack([torch.nansum(dset["areacello"].data.to(torch.float64))]
+                            + [(a < 0).any().to(torch.float64) for a in arrs])
+        host = torch.cat([flags, sums]).cpu()  # the one synchronisation of the call
+        area_total = float(host[0])
+        validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=area_total)  # util.py:783-792
+        assert not bool(host[1]), "Depth values must all be positive-definite"  # derived.py:284-292
+        assert not bool(host[2]), "Vertical coordinate levels must all be positive-definite"
+        assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
+        sums = host[4:6]
+    return _reference_from_pass(dset, tcoord, eos, rho, sums), eta, area_total
 
 
 VARIANTS = ("steric", "thermosteric", "halosteric")

@@ -42,17 +42,22 @@ def _total(arr):
     return float(s.values) if hasattr(s, "values") else float(s)
 
 
-def validate_areacello(areacello, reference=3.6111092e14, tolerance=0.02):
-    """util.py:669-694: ocean area within ``tolerance`` of the real-world total."""
-    error = (_total(areacello) - reference) / reference
+def validate_areacello(areacello, reference=3.6111092e14, tolerance=0.02, total=None):
+    """util.py:669-694: ocean area within ``tolerance`` of the real-world total.
+
+    ``total`` hands in ``areacello.sum()`` when the caller has already read it back from the device.
+    """
+    error = ((_total(areacello) if total is None else float(total)) - reference) / reference
     return bool(np.abs(error) < tolerance)
 
 
-def validate_dataset(dset, reference=False, strict=True, additional_vars=None):
+def validate_dataset(dset, reference=False, strict=True, additional_vars=None, area_total=None):
     """util.py:697-814: presence and rank of the required variables.
 
     All problems are collected, printed, and reported as one ``ValueError``; a bad
-    ``areacello`` is only a warning when ``strict`` is False.
+    ``areacello`` is only a warning when ``strict`` is False.  ``area_total`` (not in the reference) lets a
+    caller that reads device values back in one go supply ``areacello.sum()``; ``False`` leaves the area
+    check to a later call.
     """
     dset_varlist = list(dset.variables)
     exceptions = []
@@ -86,8 +91,8 @@ def validate_dataset(dset, reference=False, strict=True, additional_vars=None):
         if var in dset_varlist:
             _collect(len(dset[var].dims) == 2, f"Variable {var} must have exactly 2 dimensions (y,x)")
 
-    if "areacello" in dset_varlist:
-        if not validate_areacello(dset["areacello"]):
+    if "areacello" in dset_varlist and area_total is not False:
+        if not validate_areacello(dset["areacello"], total=area_total):
             message = "Variable `areacello` field is out of range. It may not be masked."
             if not strict:
                 warnings.warn(message)

@@ -29,4 +29,4 @@ print(f"core.steric_local_selfref: {t * 1e3:.3f} ms wall  -> {pts / t / 1e9:.1f}
 pr = cProfile.Profile(); pr.enable()
 for _ in range(5): ml.steric(ds)
 torch.cuda.synchronize(); pr.disable()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+pstats.Stats(pr).sort_stats("tottime").print_stats(28)
