@@ -735,3 +735,32 @@ def test_random_shapes_tma_against_direct(ml, seed):
         err = float(torch.nan_to_num(a - b).abs().max())
         scale = float(torch.nan_to_num(b).abs().max())
         assert err <= 1e-11 + 1e-13 * scale, (nt, nz, ny, nx, err)
+
+
+def test_deferred_value_checks_raise_what_the_eager_ones_do(ml):
+    """Device-resident datasets take the fused path whose value checks are read back after the launch:
+    same exceptions, same warning (util.py:783-792, derived.py:284-292)."""
+    from momlevel_b200 import synth
+
+    def fresh():
+        return synth.make_dataset(3, 6, 16, 64, seed=12, device="cuda", dtype=torch.float32)
+
+    ds = fresh()
+    ds["areacello"] = ml.DataArray(ds["areacello"].data * 2.0, ("yh", "xh"))
+    with pytest.raises(ValueError, match="Errors found in dataset."):
+        ml.steric(ds)
+    with pytest.warns(UserWarning, match="areacello"):
+        res, _ = ml.steric(ds, strict=False)
+    assert res["steric"].shape == (3, 16, 64)
+    ds = fresh()
+    depth = ds["deptho"].data.clone()
+    depth[3, 5] = -10.0
+    ds["deptho"] = ml.DataArray(depth, ("yh", "xh"))
+    with pytest.raises(AssertionError, match="Depth values"):
+        ml.steric(ds)
+    ds = fresh()
+    z_i = ds["z_i"].data.clone()
+    z_i[0] = -1.0
+    ds["z_i"] = ml.DataArray(z_i, ("z_i",))
+    with pytest.raises(AssertionError, match="interfaces"):
+        ml.thermosteric(ds)
