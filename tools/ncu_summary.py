@@ -11,7 +11,7 @@ from collections import Counter
 
 KEYS = r"""Kernel Name|gpu__time_duration.sum|dram__bytes_(read|write).sum$|launch__registers_per_thread$|launch__grid_size|
 launch__block_size|launch__occupancy_limit_(registers|shared_mem|warps)|sm__warps_active.avg.pct_of_peak_sustained_active|
-sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active|sm__inst_executed_pipe_(xu|alu|lsu|fma).avg.pct_of_peak_sustained_active|
+sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active|sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active|smsp__sass_thread_inst_executed_op_d(fma|add|mul)_pred_on.sum.per_cycle_elapsed$|sm__sass_thread_inst_executed_op_dfma_pred_on.sum.peak_sustained$|sm__inst_executed_pipe_(xu|alu|lsu|fma).avg.pct_of_peak_sustained_active|
 smsp__issue_active.avg.pct_of_peak_sustained_active|smsp__inst_executed.sum$|
 smsp__average_warps_issue_stalled_.*_per_issue_active.ratio|gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed|
 dram__throughput.avg.pct_of_peak_sustained_elapsed|lts__t_bytes.sum$|smsp__cycles_active.avg$|
