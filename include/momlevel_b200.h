@@ -178,6 +178,10 @@ int ml_delta_rho_annual(int eos, int dtype, const void* T, const void* S, int t_
  *   T, S        as ml_steric_local; a broadcast operand IS the reference slab of that field
  *   v_ref       [nz][ncol] volcello at step 0
  *   rho_ref     [nz][ncol] fp64 out;  sums device fp64[2] out {volo, masso}
+ *               rho_ref may be NULL when the caller does not need the field and one fused chunk serves the
+ *               call (fp32, 16-byte aligned fields, ncol % 4 == 0, ncol >= 256, nt <= 12): the store is
+ *               7 % of the traffic of a 12-step call, and ml_reference_state produces the field on demand.
+ *               Any other call with rho_ref == NULL returns ML_ERR_NULL.
  * ------------------------------------------------------------------------------------- */
 int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, int t_bcast,
                             int s_bcast, const void* v_ref, int vref_dtype, const double* z_i,

@@ -361,28 +361,44 @@ def selfref_outputs(T, S, t_bcast=False, s_bcast=False):
 
 
 def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False, s_bcast=False,
-                         out=None):
+                         out=None, want_rho_ref=True):
     """``setup_reference_state`` + the local branch in one pass; reference = step 0 (steric.py:105-107).
 
     A broadcast operand is the step-0 slab of that field.  Returns
     ``(eta [nt,...], rho_ref [nz,...], sums fp64[2] = {volo, masso})`` on the device; ``out`` may
     hand in those three tensors (see :func:`selfref_outputs`) when the caller manages streams.
+    ``want_rho_ref=False`` asks the library not to store the reference density (7 % of the traffic of a
+    12-step call); ``rho_ref`` is then ``None`` unless the layout needs it internally (more than 12 steps, or
+    fields the TMA family does not take), in which case it is produced anyway.
     """
     L = _lib.lib()
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     v_ref = to_device(v_ref)
     z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
     assert v_ref.numel() == nz * ncol and depth.numel() == ncol and z_i.numel() == nz + 1 and p.numel() == nz
-    eta, rho, sums = out if out is not None else selfref_outputs(T, S, t_bcast, s_bcast)
-    assert eta.dtype == rho.dtype == sums.dtype == torch.float64 and eta.is_contiguous() and rho.is_contiguous()
-    assert eta.numel() == nt * ncol and rho.numel() == nz * ncol and sums.numel() == 2
+    if out is not None:
+        eta, rho, sums = out
+    else:
+        eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
+        sums = torch.empty(2, dtype=torch.float64, device=T.device)
+        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device) if want_rho_ref else None
+    assert eta.dtype == sums.dtype == torch.float64 and eta.is_contiguous()
+    assert eta.numel() == nt * ncol and sums.numel() == 2
+    assert rho is None or (rho.dtype == torch.float64 and rho.is_contiguous() and rho.numel() == nz * ncol)
     ws, nbytes = _workspace(2, nz, ncol, T.device)
-    _lib.check(
-        L.ml_steric_local_selfref(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
-                                  v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(), p.data_ptr(),
-                                  -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(), rho.data_ptr(), sums.data_ptr(),
-                                  ws.data_ptr(), nbytes, _stream())
-    )
+
+    def call(rho_t):
+        return L.ml_steric_local_selfref(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                                         v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(), p.data_ptr(),
+                                         -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(),
+                                         rho_t.data_ptr() if rho_t is not None else None, sums.data_ptr(),
+                                         ws.data_ptr(), nbytes, _stream())
+
+    rc = call(rho)
+    if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
+        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+        rc = call(rho)
+    _lib.check(rc)
     return eta, rho, sums
 
 

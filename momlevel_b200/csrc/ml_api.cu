@@ -674,7 +674,6 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   ML_REQUIRE_PTR(deptho);
   ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(eta);
-  ML_REQUIRE_PTR(rho_ref);
   ML_REQUIRE_PTR(sums);
   if (nt <= 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
   if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
@@ -684,8 +683,14 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
   cudaStream_t st = (cudaStream_t)stream;
-  if (!tls().force_direct &&
-      tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref, vref_dtype, nt, nz, ncol, eta, nullptr)) {
+  const bool tma_ok = !tls().force_direct && tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref,
+                                                                 vref_dtype, nt, nz, ncol, eta, nullptr);
+  // rho_ref is an output the caller may not want (8 bytes per reference point, 7 % of the traffic of a
+  // 12-step call).  It can be left out when one fused chunk serves the whole call; longer series and the
+  // direct family read it back for the later steps.
+  if (rho_ref == nullptr && !(tma_ok && nt <= 12))
+    return fail(ML_ERR_NULL, "rho_ref is NULL: it may only be omitted for fp32, aligned fields of at most 12 steps");
+  if (tma_ok) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_selfref(eos, T, S, t_bcast, s_bcast, v_ref, vref_dtype, z_i, deptho, p_level, neg_inv_rhozero,
                                (int)nt, (int)nz, ncol, eta, rho_ref, sums, (double*)workspace, st);

@@ -399,10 +399,12 @@ __global__ void ML_TMA_KERNEL_ATTR
           w = vraw_isnan(v) ? 0.0 : vraw_value(v);
         } else {
           w = vraw_isnan(v) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
-          sub = SELFREF ? P.rho_ref_out[j] : __ldg(P.rho_ref + j);  // kSelfRef: this thread stored it above
+          if (!SELFREF) sub = __ldg(P.rho_ref + j);
         }
         if (!nonzero(w)) continue;
         eos.set_level(s_p[z]);
+        if (SELFREF)  // the reference density again, from step 0 of this column (same arithmetic as in the sweep)
+          sub = eos.rho((double)__ldg(P.T + j), (double)__ldg(P.S + j));
 #pragma unroll
         for (int k = SELFREF ? 1 : 0; k < TC; ++k) {
           if (t0 + k >= P.nt || (k == 0 && zero_first)) continue;

@@ -115,12 +115,13 @@ def steric(
         result[variant] = DataArray(sealevel, (tcoord,))
     else:
         # steric.py:150-166
-        args = (thetao.data, so.data, reference["rho"].data, reference["volcello"].data, dset[zbounds].data,
-                dset["deptho"].data, pres)
-        kw = dict(rhozero=rhozero, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
-        if fused_eta is None:  # the fused pass has checked already
+        if fused_eta is not None:  # the fused pass has checked the depths and integrated already
+            eta = fused_eta
+        else:
             _check_depths(dset, zcoord, zbounds)
-        eta = fused_eta if fused_eta is not None else core.steric_local(*args, want_delta_rho=False, **kw)[0]
+            eta = core.steric_local(thetao.data, so.data, reference["rho"].data, reference["volcello"].data,
+                                    dset[zbounds].data, dset["deptho"].data, pres, want_delta_rho=False,
+                                    rhozero=rhozero, eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)[0]
 
         def _delta_rho():
             return core.delta_rho(thetao.data, so.data, reference["rho"].data, reference["volcello"].data, pres,
@@ -189,15 +190,24 @@ def _check_depths(dset, zcoord, zbounds):
     assert _all_nonnegative(dset[zbounds]), "Vertical coordinate interfaces must all be positive-definite"
 
 
-def _reference_from_pass(dset, tcoord, eos, rho, sums):
-    """The reference Dataset of reference.py:57-83 around a rho_ref / {volo, masso} pair a fused pass produced."""
+def _reference_from_pass(dset, tcoord, eos, rho, sums, pres=None):
+    """The reference Dataset of reference.py:57-83 around a rho_ref / {volo, masso} pair a fused pass produced.
+
+    ``rho=None``: the pass did not store the reference density (its volume-weighted sums are all the height
+    needs); ``reference["rho"]`` then evaluates it on first access, like ``delta_rho`` in the result.
+    """
     reference = Dataset()
     for name in ("thetao", "so", "volcello"):
         reference[name] = dset[name].isel({tcoord: 0}).squeeze().reset_coords(drop=True)
     volo, masso = (float(x) for x in sums.cpu())
-    reference["rho"] = DataArray(rho, reference["thetao"].dims, attrs={
-        "standard_name": "sea_water_density", "long_name": "In situ sea water density",
-        "comment": f"calculated with the {eos} equation of state", "units": "kg m-3"})
+    rho_attrs = {"standard_name": "sea_water_density", "long_name": "In situ sea water density",
+                 "comment": f"calculated with the {eos} equation of state", "units": "kg m-3"}
+    if rho is None:
+        T0, S0, V0 = (reference[k].data for k in ("thetao", "so", "volcello"))
+        reference["rho"] = DataArray.lazy(lambda: core.reference_state(T0, S0, V0, pres, eos=eos)[0],
+                                          reference["thetao"].shape, reference["thetao"].dims, attrs=rho_attrs)
+    else:
+        reference["rho"] = DataArray(rho, reference["thetao"].dims, attrs=rho_attrs)
     reference["volo"] = DataArray(np.float64(volo), (), attrs={
         "standard_name": "sea_water_volume", "long_name": "Sea Water Volume", "units": "m3"})
     reference["masso"] = DataArray(np.float64(masso), (), attrs={
@@ -236,7 +246,7 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferre
     S = S0 if variant == "thermosteric" else dset["so"].data
     eta, rho, sums = core.steric_local_selfref(
         T, S, V0, dset[zbounds].data, dset["deptho"].data, pres, rhozero=rhozero, eos=eos,
-        t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric")
+        t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric", want_rho_ref=False)
     area_total = None
     if deferred:  # the value checks ride behind the kernel and come back with volo / masso
         arrs = (dset["deptho"].data, dset[zcoord].data, dset[zbounds].data)
@@ -249,7 +259,7 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferre
         assert not bool(host[2]), "Vertical coordinate levels must all be positive-definite"
         assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
         sums = host[4:6]
-    return _reference_from_pass(dset, tcoord, eos, rho, sums), eta, area_total
+    return _reference_from_pass(dset, tcoord, eos, rho, sums, pres), eta, area_total
 
 
 VARIANTS = ("steric", "thermosteric", "halosteric")

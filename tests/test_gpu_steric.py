@@ -764,3 +764,34 @@ def test_deferred_value_checks_raise_what_the_eager_ones_do(ml):
     ds["z_i"] = ml.DataArray(z_i, ("z_i",))
     with pytest.raises(AssertionError, match="interfaces"):
         ml.thermosteric(ds)
+
+
+def test_reference_density_is_produced_on_demand(ml):
+    """The fused default call does not store rho_ref (ml_steric_local_selfref with rho_ref = NULL); the
+    reference Dataset evaluates it on first access, bit-identical to the stored one, and longer series or
+    layouts that need the field internally still get it."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(12, 10, 16, 64, seed=14, device="cuda", dtype=torch.float32)
+    T, S, V = ds["thetao"].data, ds["so"].data, ds["volcello"].data[0]
+    pres = ds["z_l"].data * 1.0e4 + 101325.0
+    eta1, rho1, sums1 = core.steric_local_selfref(T, S, V, ds["z_i"].data, ds["deptho"].data, pres)
+    eta0, rho0, sums0 = core.steric_local_selfref(T, S, V, ds["z_i"].data, ds["deptho"].data, pres, want_rho_ref=False)
+    assert rho0 is None and rho1 is not None and core.last_path() == 2
+    assert torch.equal(torch.nan_to_num(eta0), torch.nan_to_num(eta1)) and torch.equal(sums0, sums1)
+    result, reference = ml.steric(ds)
+    assert reference["rho"].is_lazy and reference["rho"].dims == ("z_l", "yh", "xh")
+    assert torch.equal(torch.nan_to_num(reference["rho"].data), torch.nan_to_num(rho1))  # evaluated here
+    again, _ = ml.thermosteric(ds, reference=reference)  # and usable as a supplied reference
+    want, _ = ml.thermosteric(ds)
+    _close_nan(again["thermosteric"].values, want["thermosteric"].values, atol=1e-12)
+    # 13 steps: the later chunk reads rho_ref, so it is produced whether asked for or not
+    ds13 = synth.make_dataset(13, 10, 16, 64, seed=14, device="cuda", dtype=torch.float32)
+    out = core.steric_local_selfref(ds13["thetao"].data, ds13["so"].data, ds13["volcello"].data[0], ds13["z_i"].data,
+                                    ds13["deptho"].data, pres, want_rho_ref=False)
+    assert out[1] is not None
+    # a ragged grid takes the direct family, which needs the field as well
+    dsr = synth.make_dataset(3, 10, 37, 53, seed=14, device="cuda", dtype=torch.float32)
+    out = core.steric_local_selfref(dsr["thetao"].data, dsr["so"].data, dsr["volcello"].data[0], dsr["z_i"].data,
+                                    dsr["deptho"].data, pres, want_rho_ref=False)
+    assert out[1] is not None and core.last_path() == 1
