@@ -251,14 +251,37 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    h2d = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
+    dense = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
+    # what the library copied: level rows cross PCIe either as they are or as the cells the reference reads
+    # (volcello present, steric.py:151-153), whichever side has time left -- the share differs from run to run
+    h2d, packed_rows = core.host_last_transfer()
     d2h = eta_h.numel() * 8 + 16
     line["e2e"] = {"value": world * points / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
-                   "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)"}
+                   "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)",
+                   "host_input_bytes_per_step": dense, "level_rows_sent_packed": packed_rows,
+                   "host_pack_threads": max(1, min(len(os.sched_getaffinity(0)) - 1, 64)), "host_pack_simd": core.host_pack_simd()}
     # the device-resident and the host-streamed paths must agree
     err = (eta_h.to(dev) - eta).abs()
     line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
+    # A/B: every row as it is (the PCIe-bound transfer of the whole fields)
+    core.host_packing(0)
+    try:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt0 = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(dt0, op=dist.ReduceOp.MAX)
+        line["e2e"]["every_row_dense"] = {"value": world * points / float(dt0[0]), "unit": UNIT,
+                                          "ms_per_step": float(dt0[0]) * 1e3,
+                                          "h2d_bytes_per_step": core.host_last_transfer()[0],
+                                          "max_abs_diff_vs_resident_m": float(torch.nan_to_num((eta_h.to(dev) - eta).abs()).max())}
+    finally:
+        core.host_packing(1)
     # BASELINE config 2 names all three variants: the same transfer feeding three integrations per window
     # (grid points counted once; three heights come back)
     try:

@@ -268,6 +268,38 @@ int ml_steric_local_variants_host(int eos, int dtype, const void* T, const void*
  * host thread between calls. */
 int ml_host_release(void);
 
+/* ---------------------------------------------------------------------------------------
+ * Wet-cell packing of the host path.  The reference never uses T or S where the reference
+ * volcello is missing: delta_rho is NaN there (src/momlevel/steric.py:151-153), the column sum
+ * skips it (:163) and so do volo / masso (derived.py:435-438, 787-789).  ml_steric_local_host and
+ * ml_steric_local_variants_host therefore move a level row either as it is (DMA straight from the
+ * caller's buffer) or as its present cells only (compressed by host threads into pinned staging,
+ * expanded on the device with NaN in the absent cells), whichever side -- PCIe or the host cores --
+ * has time left; the heights are bit-identical either way.  fp32 fields only; a call that asks for
+ * rho_ref_out moves every row as it is (rho_ref is defined on absent cells too).
+ *   ml_host_set_packing(mode, threads)  mode 0 = never pack, 1 = balance dynamically (default),
+ *                                       2 = pack every row that has absent cells; threads <= 0 keeps
+ *                                       the default (the calling thread's CPU affinity count - 1).
+ *                                       Applies to the calling host thread.
+ *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed
+ *   ml_host_last_h2d_bytes()            bytes the last host call of this thread copied host -> device
+ * The two loops underneath are exported for testing (csrc/ml_pack.cpp, no CUDA inside):
+ *   ml_pack_index_rows  v [nrows][ncol] fp32 -> words / before [nrows][ceil(ncol/32)]: bit i of a word
+ *                       = column 32 g + i is not NaN; before = present cells of the row in front of the
+ *                       group; row_count [nrows]; returns the total
+ *   ml_pack_rows        present cells of groups [g0, g1) of one T row and one S row, written to
+ *                       t_out / s_out (the row's packed base) at offset before[g0]
+ *   ml_pack_simd        512 when the AVX-512 bodies are in use, 0 for the scalar ones
+ * ------------------------------------------------------------------------------------- */
+int ml_host_set_packing(int mode, int threads);
+double ml_host_last_packed_fraction(void);
+uint64_t ml_host_last_h2d_bytes(void);
+uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t ncol, uint32_t* words,
+                            uint32_t* before, uint64_t* row_count);
+void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,
+                  int64_t g0, int64_t g1, int64_t ncol, float* t_out, float* s_out);
+int ml_pack_simd(void);
+
 /* =======================================================================================
  * Stratification diagnostics that share the vertical sweep of the steric path (csrc/ml_strat.cu).
  * T, S are [nouter][nz][ncol] of `dtype`, z_l is [nz] fp64 (3 <= nz <= 512: the vertical

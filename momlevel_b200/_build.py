@@ -13,7 +13,7 @@ import sys
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libmomlevel_b200.so"
-SOURCES = ["ml_api.cu", "ml_tma.cu", "ml_hostpath.cu", "ml_strat.cu"]
+SOURCES = ["ml_api.cu", "ml_tma.cu", "ml_hostpath.cu", "ml_strat.cu", "ml_pack.cpp"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -22,7 +22,7 @@ NVCC_FLAGS = [
     "-std=c++17",
     "-shared",
     "-Xcompiler",
-    "-fPIC",
+    "-fPIC,-pthread",
 ]
 
 
@@ -36,7 +36,7 @@ def _nvcc():
 def needs_build():
     if not LIB.exists():
         return True
-    newest = max(p.stat().st_mtime for p in list(CSRC.glob("*.cu*")) + [PKG.parent / "include" / "momlevel_b200.h"])
+    newest = max(p.stat().st_mtime for p in list(CSRC.glob("*.c*")) + [PKG.parent / "include" / "momlevel_b200.h"])
     return newest > LIB.stat().st_mtime
 
 

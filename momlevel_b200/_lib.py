@@ -42,6 +42,12 @@ EXPORTS = {
                                       _vp, _vp, _vp, _vp, _sz, _vp]),
     "ml_steric_global": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "ml_host_release": (_i, []),
+    "ml_host_set_packing": (_i, [_i, _i]),
+    "ml_host_last_packed_fraction": (_d, []),
+    "ml_host_last_h2d_bytes": (ctypes.c_uint64, []),
+    "ml_pack_index_rows": (ctypes.c_uint64, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "ml_pack_rows": (None, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "ml_pack_simd": (_i, []),
     "ml_calc_n2": (_i, [_i, _i, _vp, _vp, _vp, _d, _d, _i, _i, _i64, _i64, _i64, _vp, _vp]),
     "ml_adjust_negative_n2": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp]),
     "ml_stability_angle": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),

@@ -23,6 +23,9 @@ __all__ = [
     "delta_rho",
     "steric_global",
     "steric_local_host",
+    "host_packing",
+    "host_last_transfer",
+    "host_pack_simd",
     "last_path",
     "launch_count",
     "force_direct",
@@ -502,6 +505,24 @@ def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
     eta_h = torch.empty_like(eta) if eta_h is None else eta_h
     _lib.check(L.ml_steric_local_variants_host(*head, eta.data_ptr(), eta_t.data_ptr(), eta_h.data_ptr(), *tail))
     return {"steric": eta, "thermosteric": eta_t, "halosteric": eta_h}, rho, (float(sums[0]), float(sums[1]))
+
+
+def host_packing(mode=1, threads=0):
+    """How the ``*_host`` calls of this thread move level rows: 0 = as they are, 1 = compressed to their
+    present cells where the host cores have time for it (default), 2 = every row with absent cells compressed.
+    The results do not depend on it (``ml_host_set_packing``)."""
+    _lib.check(_lib.lib().ml_host_set_packing(int(mode), int(threads)))
+
+
+def host_last_transfer():
+    """``(host->device bytes, share of level rows that crossed packed)`` of this thread's last ``*_host`` call."""
+    L = _lib.lib()
+    return int(L.ml_host_last_h2d_bytes()), float(L.ml_host_last_packed_fraction())
+
+
+def host_pack_simd():
+    """512 when the host-side packing loops run their AVX-512 bodies, 0 for the scalar ones."""
+    return int(_lib.lib().ml_pack_simd())
 
 
 def steric_global_host(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):

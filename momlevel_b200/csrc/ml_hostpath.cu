@@ -6,32 +6,122 @@
 // windows, the host->device copy of window k+1 running on a copy stream while the kernels of
 // window k run on the compute stream.  Pinned (page-locked) host buffers make the copies
 // truly asynchronous; pageable buffers work but serialise inside the driver.
+#include <sched.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "ml_host.cuh"
 
 namespace {
 
-// Device staging buffers, streams and events are kept per host thread between calls (a year of
-// OM4p25 needs ~5 GB of windows; allocating and freeing them costs tens of milliseconds per call)
-// and released by ml_host_release() or at thread exit.
+// Worker threads of the packed transfer (below).  start() hands every worker the same job, the caller does
+// its own share of the window meanwhile and then wait()s.
+class Pool {
+ public:
+  ~Pool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+    }
+    cv_start_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  void ensure(int n) {
+    std::lock_guard<std::mutex> l(m_);
+    while ((int)th_.size() < n) {
+      const int id = (int)th_.size();
+      const uint64_t born = gen_;
+      th_.emplace_back([this, id, born] { loop(id, born); });
+    }
+  }
+  void start(int active, std::function<void(int)> job) {
+    std::lock_guard<std::mutex> l(m_);
+    job_ = std::move(job);
+    active_ = std::min(active, (int)th_.size());
+    running_ = active_;
+    ++gen_;
+    cv_start_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> l(m_);
+    cv_done_.wait(l, [this] { return running_ == 0; });
+  }
+
+ private:
+  void loop(int id, uint64_t seen) {
+    for (;;) {
+      std::function<void(int)> job;
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_start_.wait(l, [&] { return stop_ || gen_ != seen; });
+        if (stop_) return;
+        seen = gen_;
+        if (id >= active_) continue;
+        job = job_;
+      }
+      job(id);
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--running_ == 0) cv_done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_start_, cv_done_;
+  std::function<void(int)> job_;
+  uint64_t gen_ = 0;
+  int active_ = 0, running_ = 0;
+  bool stop_ = false;
+};
+
+// Device staging buffers, pinned host staging, streams, events and the worker threads are kept per host
+// thread between calls (a year of OM4p25 needs ~5 GB of windows; allocating and freeing them costs tens of
+// milliseconds per call) and released by ml_host_release() or at thread exit.
 struct Resources {
-  static constexpr int kSlots = 16;
+  static constexpr int kSlots = 28;
+  static constexpr int kHostSlots = 8;
+  static constexpr int kRing = 3;  // dense rows in flight on the copy stream
   void* buf[kSlots] = {nullptr};
   size_t cap[kSlots] = {0};
+  void* hbuf[kHostSlots] = {nullptr};
+  size_t hcap[kHostSlots] = {0};
   int device = -1;
   cudaStream_t copy = nullptr, comp = nullptr;
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  cudaEvent_t ring[kRing] = {nullptr};
+  Pool pool;
+  // settings and accounting of the packed transfer (ml_host_set_packing and friends)
+  int pack_mode = 1, pack_threads = 0;
+  double last_packed_fraction = 0.0;
+  std::atomic<uint64_t> h2d_bytes{0};
   void release() {
     for (int i = 0; i < kSlots; ++i) {
       if (buf[i]) cudaFree(buf[i]);
       buf[i] = nullptr;
       cap[i] = 0;
     }
+    for (int i = 0; i < kHostSlots; ++i) {
+      if (hbuf[i]) cudaFreeHost(hbuf[i]);
+      hbuf[i] = nullptr;
+      hcap[i] = 0;
+    }
     for (int i = 0; i < 2; ++i) {
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (freed[i]) cudaEventDestroy(freed[i]);
       copied[i] = freed[i] = nullptr;
+    }
+    for (int i = 0; i < kRing; ++i) {
+      if (ring[i]) cudaEventDestroy(ring[i]);
+      ring[i] = nullptr;
     }
     if (copy) cudaStreamDestroy(copy);
     if (comp) cudaStreamDestroy(comp);
@@ -53,6 +143,8 @@ struct Resources {
       if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
+    for (int i = 0; i < kRing; ++i)
+      if (!ring[i] && (e = cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     return cudaSuccess;
   }
   // slot i grows to at least `bytes`
@@ -68,11 +160,314 @@ struct Resources {
     *p = buf[i];
     return cudaSuccess;
   }
+  // pinned host slot i grows to at least `bytes`
+  cudaError_t halloc(int i, void** p, size_t bytes) {
+    if (hcap[i] < bytes) {
+      if (hbuf[i]) cudaFreeHost(hbuf[i]);
+      hbuf[i] = nullptr;
+      hcap[i] = 0;
+      cudaError_t e = cudaHostAlloc(&hbuf[i], bytes, cudaHostAllocDefault);
+      if (e != cudaSuccess) return e;
+      hcap[i] = bytes;
+    }
+    *p = hbuf[i];
+    return cudaSuccess;
+  }
 };
 
 Resources& resources() {
   static thread_local Resources r;
   return r;
+}
+
+int default_threads() {
+  cpu_set_t set;
+  int n = 0;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
+  if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  return std::max(1, std::min(n - 1, 64));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Packed transfer.  A window is nt_w * nz level rows of T and of S.  The reference never uses either
+// field where the reference volcello is missing (steric.py:151-153, 163; derived.py:435-438), so a row
+// may cross PCIe as its present cells only.  Compressing a row costs host memory bandwidth, moving it
+// as it is costs PCIe time, and which of the two runs out first depends on the machine and on what
+// else it is doing; so the rows of a window are put in order of how much of them is present and the
+// two sides work towards each other: the calling thread queues the fullest rows as plain copies from
+// the caller's buffer (at most kRing rows ahead of the copy engine), the workers compress the emptiest
+// rows into pinned staging, segment by segment, and queue each one as soon as it is whole.  The
+// window is done when they meet.  On the device k_unpack_rows spreads the compressed rows back into
+// the dense window (NaN where the volume is missing) and the steric kernels run on it unchanged.
+// ---------------------------------------------------------------------------------------------------
+struct PackPlan {
+  bool on = false;
+  int mode = 0, threads = 0, nseg = 1;
+  int64_t nz = 0, ncol = 0, ngrp = 0;
+  uint64_t nwet = 0;            // present cells of one step
+  uint32_t *words = nullptr, *before = nullptr;  // pinned host [nz][ngrp]
+  uint64_t *lvloff = nullptr;   // pinned host [nz + 1]: present cells in the levels above
+  std::vector<int> order;       // levels, fullest first
+  int first_packable = 0;       // position in `order` of the first level worth compressing
+  uint32_t *d_words = nullptr, *d_before = nullptr;
+  uint64_t* d_lvloff = nullptr;
+  float *stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // pinned [window parity][T,S]: [t][nwet]
+  float *d_packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  uint8_t *flags[2] = {nullptr, nullptr}, *d_flags[2] = {nullptr, nullptr};  // [t][z]: 1 = row crossed packed
+  int64_t rows_total = 0, rows_packed = 0;
+};
+
+constexpr double kPackableBelow = 0.9;  // a level with more of its cells present than this is never compressed
+
+__global__ void __launch_bounds__(256) k_unpack_rows(const float* __restrict__ pT, const float* __restrict__ pS,
+                                                      float* __restrict__ T, float* __restrict__ S,
+                                                      const uint32_t* __restrict__ words,
+                                                      const uint32_t* __restrict__ before,
+                                                      const uint64_t* __restrict__ lvloff,
+                                                      const uint8_t* __restrict__ flags, int nz, int64_t ncol,
+                                                      int64_t ngrp, uint64_t nwet, int xblocks) {
+  const int row = blockIdx.x / xblocks;  // (t, z)
+  if (!flags[row]) return;
+  const int t = row / nz, z = row % nz;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t src0 = (uint64_t)t * nwet + lvloff[z];
+  const size_t dst0 = (size_t)row * (size_t)ncol;
+  const float nanf32 = __int_as_float(0x7fc00000);
+  const int64_t gfirst = ((int64_t)(blockIdx.x % xblocks) * 8 + warp) * 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int64_t g = gfirst + k;
+    if (g >= ngrp) break;
+    const uint32_t m = words[(size_t)z * ngrp + g];
+    const uint64_t src = src0 + before[(size_t)z * ngrp + g] + __popc(m & ((1u << lane) - 1u));
+    const bool here = (m >> lane) & 1u;
+    const float a = here ? pT[src] : nanf32;
+    const float b = here ? pS[src] : nanf32;
+    const int64_t col = g * 32 + lane;
+    if (col < ncol) {
+      T[dst0 + col] = a;
+      S[dst0 + col] = b;
+    }
+  }
+}
+
+// Presence words of the reference volcello, the device copies of them and the staging buffers.
+// Leaves plan.on false (every row crosses as it is) when packing is off, cannot help or cannot get
+// its pinned memory.
+int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_t nz, int64_t ncol, int64_t spw,
+                 bool allowed) {
+  using namespace ml;
+  plan.on = false;
+  plan.mode = r.pack_mode;
+  if (!allowed || plan.mode == 0 || dtype != ML_F32) return ML_OK;
+  plan.nz = nz;
+  plan.ncol = ncol;
+  plan.ngrp = (ncol + 31) / 32;
+  plan.threads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
+  plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / 2048));
+  const size_t nw = (size_t)nz * (size_t)plan.ngrp;
+  void *hw, *hb, *hl;
+  if (r.halloc(0, &hw, nw * 4) != cudaSuccess || r.halloc(1, &hb, nw * 4) != cudaSuccess ||
+      r.halloc(2, &hl, (size_t)(nz + 1) * 8) != cudaSuccess) {
+    cudaGetLastError();
+    return ML_OK;
+  }
+  plan.words = (uint32_t*)hw;
+  plan.before = (uint32_t*)hb;
+  plan.lvloff = (uint64_t*)hl;
+  r.pool.ensure(plan.threads);
+  std::vector<uint64_t> cnt((size_t)nz);
+  {
+    std::atomic<int64_t> next{0};
+    const float* v = (const float*)v0;
+    r.pool.start(plan.threads, [&](int) {
+      for (;;) {
+        const int64_t z = next.fetch_add(1);
+        if (z >= nz) break;
+        ml_pack_index_rows(v + z * ncol, 1, ncol, plan.words + z * plan.ngrp, plan.before + z * plan.ngrp, &cnt[z]);
+      }
+    });
+    r.pool.wait();
+  }
+  plan.lvloff[0] = 0;
+  for (int64_t z = 0; z < nz; ++z) plan.lvloff[z + 1] = plan.lvloff[z] + cnt[z];
+  plan.nwet = plan.lvloff[nz];
+  plan.order.resize((size_t)nz);
+  for (int64_t z = 0; z < nz; ++z) plan.order[z] = (int)z;
+  std::stable_sort(plan.order.begin(), plan.order.end(), [&](int a, int b) { return cnt[a] > cnt[b]; });
+  plan.first_packable = (int)nz;
+  for (int64_t i = 0; i < nz; ++i)
+    if ((double)cnt[plan.order[i]] < kPackableBelow * (double)ncol) {
+      plan.first_packable = (int)i;
+      break;
+    }
+  if (plan.first_packable == (int)nz || plan.nwet == 0) return ML_OK;  // nothing worth compressing
+  const size_t stage_bytes = (size_t)spw * plan.nwet * 4;
+  const size_t flag_bytes = (size_t)spw * (size_t)nz;
+  for (int b = 0; b < 2; ++b) {
+    for (int f = 0; f < 2; ++f) {
+      void *h, *d;
+      if (r.halloc(3 + 2 * b + f, &h, stage_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return ML_OK;
+      }
+      ML_CUDA(r.alloc(16 + 2 * b + f, &d, stage_bytes));
+      plan.stage[b][f] = (float*)h;
+      plan.d_packed[b][f] = (float*)d;
+    }
+    void *hf, *df;
+    if (r.halloc(7, &hf, 2 * flag_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      return ML_OK;
+    }
+    ML_CUDA(r.alloc(23 + b, &df, flag_bytes));
+    plan.flags[b] = (uint8_t*)hf + (size_t)b * flag_bytes;
+    plan.d_flags[b] = (uint8_t*)df;
+  }
+  void *dw, *db, *dl;
+  ML_CUDA(r.alloc(20, &dw, nw * 4));
+  ML_CUDA(r.alloc(21, &db, nw * 4));
+  ML_CUDA(r.alloc(22, &dl, (size_t)(nz + 1) * 8));
+  plan.d_words = (uint32_t*)dw;
+  plan.d_before = (uint32_t*)db;
+  plan.d_lvloff = (uint64_t*)dl;
+  ML_CUDA(cudaMemcpyAsync(dw, plan.words, nw * 4, cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(db, plan.before, nw * 4, cudaMemcpyHostToDevice, r.copy));
+  ML_CUDA(cudaMemcpyAsync(dl, plan.lvloff, (size_t)(nz + 1) * 8, cudaMemcpyHostToDevice, r.copy));
+  r.h2d_bytes += 2 * nw * 4 + (size_t)(nz + 1) * 8;
+  plan.on = true;
+  return ML_OK;
+}
+
+// One window of T and S to the device buffers dT / dS of parity b: on return every copy is queued on the
+// copy stream, copied[b] is recorded behind them and the compute stream waits for it (and has expanded
+// the rows that crossed packed).  T_w / S_w point at the window's first step in the caller's buffers.
+int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w, const void* S_w, int64_t nt_w,
+                 size_t es, int64_t nz, int64_t ncol, void* dT, void* dS) {
+  using namespace ml;
+  const size_t bytes = (size_t)nt_w * (size_t)nz * (size_t)ncol * es;
+  if (w >= 2) ML_CUDA(cudaStreamWaitEvent(r.copy, r.freed[b], 0));
+  if (!plan.on) {
+    ML_CUDA(cudaMemcpyAsync(dT, T_w, bytes, cudaMemcpyHostToDevice, r.copy));
+    ML_CUDA(cudaMemcpyAsync(dS, S_w, bytes, cudaMemcpyHostToDevice, r.copy));
+    r.h2d_bytes += 2 * bytes;
+    ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
+    ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
+    return ML_OK;
+  }
+  // the staging of this parity was last read by the copies of window w - 2
+  if (w >= 2) ML_CUDA(cudaEventSynchronize(r.copied[b]));
+
+  const float* Th = (const float*)T_w;
+  const float* Sh = (const float*)S_w;
+  const int nrows = (int)(nt_w * nz);
+  const size_t row_bytes = (size_t)ncol * 4;
+  uint8_t* flags = plan.flags[b];
+  memset(flags, 0, (size_t)nrows);
+  // position i of the window's row order = step i % nt_w of level order[i / nt_w]
+  auto row_of = [&](int i, int& t, int& z) {
+    z = plan.order[i / (int)nt_w];
+    t = i % (int)nt_w;
+  };
+  struct Shared {
+    std::mutex m;
+    int lo = 0, hi = 0, hi_min = 0, lo_end = 0;
+    int cur = -1, next_seg = 0;
+    int packed = 0;
+    cudaError_t err = cudaSuccess;
+  } sh;
+  sh.hi = nrows - 1;
+  sh.hi_min = plan.first_packable * (int)nt_w;
+  sh.lo_end = plan.mode == 2 ? sh.hi_min : nrows;
+  sh.next_seg = plan.nseg;  // no row open yet
+  std::vector<std::atomic<int>> done((size_t)nrows);
+  for (auto& d : done) d.store(0, std::memory_order_relaxed);
+  const int dev = r.device;
+  float *stT = plan.stage[b][0], *stS = plan.stage[b][1];
+  float *dpT = plan.d_packed[b][0], *dpS = plan.d_packed[b][1];
+
+  r.pool.start(plan.threads, [&, dev](int) {
+    cudaSetDevice(dev);
+    for (;;) {
+      int pos, seg;
+      {
+        std::lock_guard<std::mutex> l(sh.m);
+        if (sh.next_seg >= plan.nseg) {
+          if (sh.hi < sh.lo || sh.hi < sh.hi_min || sh.err != cudaSuccess) break;
+          sh.cur = sh.hi--;
+          sh.next_seg = 0;
+          sh.packed++;
+        }
+        pos = sh.cur;
+        seg = sh.next_seg++;
+      }
+      int t, z;
+      row_of(pos, t, z);
+      const size_t src = ((size_t)t * (size_t)nz + (size_t)z) * (size_t)ncol;
+      const size_t dst = (size_t)t * plan.nwet + plan.lvloff[z];
+      const int64_t g0 = plan.ngrp * seg / plan.nseg, g1 = plan.ngrp * (seg + 1) / plan.nseg;
+      ml_pack_rows(Th + src, Sh + src, plan.words + (size_t)z * plan.ngrp, plan.before + (size_t)z * plan.ngrp, g0, g1,
+                   ncol, stT + dst, stS + dst);
+      const int row = t * (int)nz + z;
+      if (done[row].fetch_add(1, std::memory_order_acq_rel) + 1 == plan.nseg) {  // the row is whole: queue it
+        const size_t nb = (size_t)(plan.lvloff[z + 1] - plan.lvloff[z]) * 4;
+        flags[row] = 1;
+        cudaError_t e = cudaSuccess;
+        if (nb) {
+          e = cudaMemcpyAsync(dpT + dst, stT + dst, nb, cudaMemcpyHostToDevice, r.copy);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(dpS + dst, stS + dst, nb, cudaMemcpyHostToDevice, r.copy);
+          r.h2d_bytes += 2 * nb;
+        }
+        if (e != cudaSuccess) {
+          std::lock_guard<std::mutex> l(sh.m);
+          sh.err = e;
+        }
+      }
+    }
+  });
+
+  // this thread: the fullest rows as they are, straight from the caller's buffer
+  cudaError_t err = cudaSuccess;
+  for (int issued = 0;; ++issued) {
+    int pos;
+    {
+      std::lock_guard<std::mutex> l(sh.m);
+      if (sh.lo > sh.hi || sh.lo >= sh.lo_end) break;
+      pos = sh.lo++;
+    }
+    int t, z;
+    row_of(pos, t, z);
+    const size_t off = ((size_t)t * (size_t)nz + (size_t)z) * (size_t)ncol;
+    cudaEvent_t ev = r.ring[issued % Resources::kRing];
+    if (issued >= Resources::kRing && (err = cudaEventSynchronize(ev)) != cudaSuccess) break;
+    if ((err = cudaMemcpyAsync((float*)dT + off, Th + off, row_bytes, cudaMemcpyHostToDevice, r.copy)) != cudaSuccess) break;
+    if ((err = cudaMemcpyAsync((float*)dS + off, Sh + off, row_bytes, cudaMemcpyHostToDevice, r.copy)) != cudaSuccess) break;
+    r.h2d_bytes += 2 * row_bytes;
+    if ((err = cudaEventRecord(ev, r.copy)) != cudaSuccess) break;
+  }
+  if (err != cudaSuccess) {  // stop the workers before the error leaves with their captured locals
+    std::lock_guard<std::mutex> l(sh.m);
+    sh.err = err;
+  }
+  r.pool.wait();
+  if (sh.err != cudaSuccess) return cuda_fail(sh.err, "packed transfer");
+  plan.rows_total += nrows;
+  plan.rows_packed += sh.packed;
+
+  if (sh.packed) {
+    ML_CUDA(cudaMemcpyAsync(plan.d_flags[b], flags, (size_t)nrows, cudaMemcpyHostToDevice, r.copy));
+    r.h2d_bytes += (size_t)nrows;
+  }
+  ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
+  ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
+  if (sh.packed) {
+    const int xblocks = (int)((plan.ngrp + 31) / 32);
+    k_unpack_rows<<<(unsigned)((int64_t)nrows * xblocks), 256, 0, r.comp>>>(
+        dpT, dpS, (float*)dT, (float*)dS, plan.d_words, plan.d_before, plan.d_lvloff, plan.d_flags[b], (int)nz, ncol,
+        plan.ngrp, plan.nwet, xblocks);
+    if (int rc = launched("k_unpack_rows")) return rc;
+  }
+  return ML_OK;
 }
 
 }  // namespace
@@ -81,6 +476,18 @@ extern "C" int ml_host_release(void) {
   resources().release();
   return ML_OK;
 }
+
+extern "C" int ml_host_set_packing(int mode, int threads) {
+  if (mode < 0 || mode > 2) return ml::fail(ML_ERR_MODE, "packing mode %d is not 0, 1 or 2", mode);
+  Resources& r = resources();
+  r.pack_mode = mode;
+  r.pack_threads = threads > 0 ? threads : 0;
+  return ML_OK;
+}
+
+extern "C" double ml_host_last_packed_fraction(void) { return resources().last_packed_fraction; }
+
+extern "C" uint64_t ml_host_last_h2d_bytes(void) { return resources().h2d_bytes.load(); }
 
 // eta_thermo / eta_halo: optional extra heights from the same transfer (NULL = steric only)
 static int steric_local_host_impl(int eos, int dtype, const void* T, const void* S, const void* v0, const double* z_i,
@@ -133,10 +540,17 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
     if (eta_halo) ML_CUDA(r.alloc(15, &dEtaH, (size_t)nt * ncol * sizeof(double)));
   }
 
+  r.h2d_bytes = 0;
+  r.last_packed_fraction = 0.0;
   ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dV, v0, lvl * es, cudaMemcpyHostToDevice, r.copy));
+  r.h2d_bytes += (size_t)(2 * nz + 1 + ncol) * sizeof(double) + lvl * es;
+  // rho_ref is defined where the volume is missing too (reference.py:71), so a call that wants it back
+  // moves every row as it is
+  PackPlan plan;
+  if (int rc = plan_packing(r, plan, dtype, v0, nz, ncol, spw, rho_ref_out == nullptr)) return rc;
 
   const int64_t nwin = (nt + spw - 1) / spw;
   for (int64_t w = 0; w < nwin; ++w) {
@@ -144,14 +558,8 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
     const int64_t t_first = w * spw;
     const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
     const size_t off = (size_t)t_first * lvl * es;
-    const size_t bytes = (size_t)nt_w * lvl * es;
-    if (w >= 2) ML_CUDA(cudaStreamWaitEvent(r.copy, r.freed[b], 0));
-    ML_CUDA(cudaMemcpyAsync(dT[b], (const char*)T + off, bytes, cudaMemcpyHostToDevice, r.copy));
-    ML_CUDA(cudaMemcpyAsync(dS[b], (const char*)S + off, bytes, cudaMemcpyHostToDevice, r.copy));
-    ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
-
-    ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
-    int rc;
+    int rc = stage_window(r, plan, b, w, (const char*)T + off, (const char*)S + off, nt_w, es, nz, ncol, dT[b], dS[b]);
+    if (rc) return rc;
     if (w == 0)  // the window that starts at the reference step (reference.py:60-80): fused pass
       rc = ml_steric_local_selfref(eos, dtype, dT[0], dS[0], 0, 0, dV, dtype, (const double*)dZi,
                                    (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
@@ -193,6 +601,7 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
   if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   ML_CUDA(cudaStreamSynchronize(r.comp));
   ML_CUDA(cudaStreamSynchronize(r.copy));
+  r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
   return ML_OK;
 }
 
@@ -247,8 +656,14 @@ extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const vo
   ML_CUDA(r.alloc(6, &dM, (size_t)nt * sizeof(double)));
   ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
   ML_CUDA(r.alloc(11, &dWs, ws_bytes));
+  r.h2d_bytes = 0;
+  r.last_packed_fraction = 0.0;
   ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dV, v_ref, lvl * es, cudaMemcpyHostToDevice, r.copy));
+  r.h2d_bytes += (size_t)nz * sizeof(double) + lvl * es;
+  // rho * volcello is skipped where the reference volume is missing (derived.py:435-438)
+  PackPlan plan;
+  if (int rc = plan_packing(r, plan, dtype, v_ref, nz, ncol, spw, true)) return rc;
 
   const int64_t nwin = (nt + spw - 1) / spw;
   for (int64_t w = 0; w < nwin; ++w) {
@@ -256,13 +671,9 @@ extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const vo
     const int64_t t_first = w * spw;
     const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
     const size_t off = (size_t)t_first * lvl * es;
-    const size_t bytes = (size_t)nt_w * lvl * es;
-    if (w >= 2) ML_CUDA(cudaStreamWaitEvent(r.copy, r.freed[b], 0));
-    ML_CUDA(cudaMemcpyAsync(dT[b], (const char*)T + off, bytes, cudaMemcpyHostToDevice, r.copy));
-    ML_CUDA(cudaMemcpyAsync(dS[b], (const char*)S + off, bytes, cudaMemcpyHostToDevice, r.copy));
-    ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
-    ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
-    int rc = ml_steric_global(eos, dtype, dT[b], dS[b], 0, 0, dV, dtype, (const double*)dP, nt_w, nz, ncol,
+    int rc = stage_window(r, plan, b, w, (const char*)T + off, (const char*)S + off, nt_w, es, nz, ncol, dT[b], dS[b]);
+    if (rc) return rc;
+    rc = ml_steric_global(eos, dtype, dT[b], dS[b], 0, 0, dV, dtype, (const double*)dP, nt_w, nz, ncol,
                               (double*)dM + t_first, dWs, ws_bytes, r.comp);
     if (rc) return rc;
     ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
@@ -270,5 +681,6 @@ extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const vo
   ML_CUDA(cudaMemcpyAsync(masso, dM, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   ML_CUDA(cudaStreamSynchronize(r.comp));
   ML_CUDA(cudaStreamSynchronize(r.copy));
+  r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
   return ML_OK;
 }

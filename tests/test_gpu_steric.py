@@ -702,6 +702,107 @@ def test_host_entry_all_variants_from_one_transfer(ml):
         assert masso == pytest.approx(float(ref["masso"]), rel=1e-14)
 
 
+def _disagreeing_masks(ds, seed):
+    """Host fields whose volcello mask, bathymetry and data holes disagree (as in test_nan_semantics_tma_family)."""
+    T, S = ds["thetao"].data.clone(), ds["so"].data.clone()
+    V = ds["volcello"].data[0].clone()
+    depth = ds["deptho"].data.clone()
+    shape = tuple(T.shape)
+    g = torch.Generator().manual_seed(seed)
+    for k in range(40):
+        t, z, y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in shape)
+        (T if k % 2 else S)[t, z, y, x] = float("nan")
+    for _ in range(30):
+        z, y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in shape[1:])
+        V[z, y, x] = float("nan") if torch.isfinite(V[z, y, x]) else 1.0e9
+    for _ in range(12):
+        y, x = (int(torch.randint(0, n, (1,), generator=g)) for n in shape[2:])
+        depth[y, x] = float("nan") if torch.isfinite(depth[y, x]) else 3000.0
+    # data where the reference volume is missing: the reference never reads it, the packed rows never carry it
+    junk = torch.isnan(V).unsqueeze(0) & (torch.rand(shape, generator=g) < 0.3)
+    T[junk] = 25.0
+    S[junk] = 31.0
+    return T, S, V, depth
+
+
+@pytest.mark.parametrize("shape", [(5, 12, 20, 32), (4, 7, 5, 7), (3, 8, 256, 520)])
+def test_host_packed_transfer_is_bit_identical(ml, shape):
+    """Level rows that cross PCIe as their present cells give the heights of rows that cross as they are,
+    bit for bit, and both agree with the oracle -- whatever the masks, the window width or the split."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(*shape, seed=11, device="cpu", dtype=torch.float32)
+    T, S, V, depth = _disagreeing_masks(ds, 3)
+    z_l, z_i = ds["z_l"].values, ds["z_i"].values
+    pres = z_l * 1e4 + 101325.0
+    T64, S64, V64 = T.double().numpy(), S.double().numpy(), V.double().numpy()
+    oref = osteric.reference_state(T64, S64, np.broadcast_to(V64, T64.shape), ds["areacello"].values, z_l)
+    want, _ = osteric.steric_local(T64, S64, z_l, z_i, depth.numpy(), oref, variant="steric")
+    dense_bytes = 2 * T.numel() * 4
+    try:
+        core.host_packing(0)
+        eta0, _, sums0 = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, steps_per_window=2)
+        bytes0, frac0 = core.host_last_transfer()
+        assert frac0 == 0.0 and bytes0 >= dense_bytes
+        _close_nan(eta0.numpy(), want, atol=ETA_ATOL)
+        assert sums0[1] == pytest.approx(oref["masso"], rel=1e-12) and sums0[0] == pytest.approx(oref["volo"], rel=1e-12)
+        for mode, threads, spw in ((2, 0, 1), (2, 3, 2), (2, 1, shape[0]), (1, 0, 1), (1, 2, 3)):
+            core.host_packing(mode, threads)
+            eta, rho, sums = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, steps_per_window=spw)
+            nbytes, frac = core.host_last_transfer()
+            assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64)), (mode, threads, spw)
+            assert sums == sums0
+            if mode == 2:
+                assert frac > 0.0 and nbytes < bytes0
+        # a call that wants rho_ref back moves every row as it is (rho_ref is defined on absent cells too)
+        core.host_packing(2)
+        eta, rho, _ = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, want_rho_ref=True)
+        assert core.host_last_transfer()[1] == 0.0
+        assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64))
+        _close_nan(rho.numpy(), oref["rho"], rtol=RHO_RTOL)
+        # all three heights from one packed transfer
+        core.host_packing(0)
+        etas0, _, _ = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, variants=True)
+        core.host_packing(2)
+        etas2, _, _ = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, variants=True)
+        assert core.host_last_transfer()[1] > 0.0
+        for variant in ("steric", "thermosteric", "halosteric"):
+            assert torch.equal(etas2[variant].view(torch.int64), etas0[variant].view(torch.int64)), variant
+            o, _ = osteric.steric_local(T64, S64, z_l, z_i, depth.numpy(), oref, variant=variant)
+            _close_nan(etas2[variant].numpy(), o, atol=ETA_ATOL)
+        # the global masses through the same transfer
+        core.host_packing(0)
+        m0 = core.steric_global_host(T, S, V, pres, steps_per_window=2)
+        for mode in (2, 1):
+            core.host_packing(mode)
+            m = core.steric_global_host(T, S, V, pres, steps_per_window=1)
+            assert torch.allclose(m, m0, rtol=1e-14, atol=0)
+        _, _, omass = osteric.steric_global(T64, S64, z_l, oref, variant="steric")
+        assert np.allclose(m.numpy(), omass, rtol=1e-12, atol=0)
+    finally:
+        core.host_packing(1)
+
+
+def test_host_packed_transfer_of_a_dense_field_sends_it_as_it_is(ml):
+    """No absent cells (the reference's own 5x5x5 test dataset): nothing is worth compressing."""
+    from momlevel_b200 import core
+
+    ds = ml.test_data.generate_test_data()
+    T = torch.from_numpy(ds["thetao"].values).float()
+    S = torch.from_numpy(ds["so"].values).float()
+    V = torch.from_numpy(ds["volcello"].values[0]).float()
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    try:
+        core.host_packing(2)
+        eta, _, _ = core.steric_local_host(T, S, V, ds["z_i"].values, ds["deptho"].values, pres)
+        assert core.host_last_transfer()[1] == 0.0
+        core.host_packing(0)
+        eta0, _, _ = core.steric_local_host(T, S, V, ds["z_i"].values, ds["deptho"].values, pres)
+        assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64))
+    finally:
+        core.host_packing(1)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_random_shapes_tma_against_direct(ml, seed):
     """Shapes drawn at random around the TMA family's edges -- a last tile with a few columns, one or two

@@ -1,0 +1,81 @@
+"""CPU checks of the host-side packing loops of the ``*_host`` entry points (csrc/ml_pack.cpp).
+
+``ml_pack_index_rows`` / ``ml_pack_rows`` compress a level row to the cells where the reference volcello
+is present -- the only cells the reference reads (src/momlevel/steric.py:151-153, 163).  They are plain
+host code, so they are checked here against numpy boolean indexing; the transfer built on them is checked
+on the GPU (tests/test_gpu_steric.py::test_host_packed_transfer_*).
+"""
+
+import ctypes
+
+import numpy as np
+import pytest
+
+
+@pytest.fixture(scope="module")
+def L():
+    from momlevel_b200 import _lib
+
+    return _lib.lib()
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _index(L, V):
+    nrows, ncol = V.shape
+    ngrp = (ncol + 31) // 32
+    words = np.zeros((nrows, ngrp), dtype=np.uint32)
+    before = np.zeros((nrows, ngrp), dtype=np.uint32)
+    count = np.zeros(nrows, dtype=np.uint64)
+    total = L.ml_pack_index_rows(_ptr(V), nrows, ncol, _ptr(words), _ptr(before), _ptr(count))
+    return words, before, count, total
+
+
+@pytest.mark.parametrize("ncol", [1, 25, 31, 32, 33, 64, 1000, 4099])
+@pytest.mark.parametrize("wet", [0.0, 0.07, 0.5, 0.93, 1.0])
+def test_index_and_pack_match_numpy(L, ncol, wet):
+    rng = np.random.default_rng(ncol * 7 + int(wet * 100))
+    nrows = 3
+    V = rng.uniform(1.0, 2.0, (nrows, ncol)).astype(np.float32)
+    V[rng.uniform(size=V.shape) >= wet] = np.nan
+    if wet == 0.5:  # other NaN payloads and infinities: only "is NaN" decides
+        V.view(np.uint32)[0, 0] = 0xFFC00001
+        V[1, 0] = np.inf
+    T = rng.normal(10, 5, (nrows, ncol)).astype(np.float32)
+    S = rng.normal(35, 1, (nrows, ncol)).astype(np.float32)
+    T[rng.uniform(size=T.shape) < 0.1] = np.nan  # holes in the fields travel as they are
+    words, before, count, total = _index(L, V)
+    present = ~np.isnan(V)
+    assert total == present.sum()
+    assert np.array_equal(count, present.sum(axis=1).astype(np.uint64))
+    ngrp = (ncol + 31) // 32
+    padded = np.zeros((nrows, ngrp * 32), dtype=bool)
+    padded[:, :ncol] = present
+    bits = padded.reshape(nrows, ngrp, 32)
+    assert np.array_equal(words, (bits.astype(np.uint64) << np.arange(32, dtype=np.uint64)).sum(axis=2).astype(np.uint32))
+    assert np.array_equal(before, np.cumsum(bits.sum(axis=2), axis=1) - bits.sum(axis=2))
+    for r in range(nrows):
+        n = int(count[r])
+        for cuts in ([0, ngrp], [0, ngrp // 2, ngrp], list(range(ngrp + 1))[:: max(1, ngrp // 5)] + [ngrp]):
+            guard = np.float32(-777.0)
+            t_out = np.full(n + 40, guard, dtype=np.float32)
+            s_out = np.full(n + 40, guard, dtype=np.float32)
+            for g0, g1 in zip(cuts[:-1], cuts[1:]):
+                L.ml_pack_rows(_ptr(T[r]), _ptr(S[r]), _ptr(words[r]), _ptr(before[r]), g0, g1, ncol, _ptr(t_out), _ptr(s_out))
+            assert np.array_equal(t_out[:n].view(np.uint32), T[r][present[r]].view(np.uint32))
+            assert np.array_equal(s_out[:n].view(np.uint32), S[r][present[r]].view(np.uint32))
+            assert np.all(t_out[n:] == guard) and np.all(s_out[n:] == guard), "wrote past the row's share"
+
+
+def test_simd_body_is_reported(L):
+    assert L.ml_pack_simd() in (0, 512)
+
+
+def test_packing_mode_argument(L):
+    assert L.ml_host_set_packing(3, 0) == -5 and b"packing mode" in L.ml_last_error()
+    assert L.ml_host_set_packing(-1, 0) == -5
+    for mode in (0, 2, 1):
+        assert L.ml_host_set_packing(mode, 0) == 0
+    assert L.ml_host_last_packed_fraction() == 0.0
