@@ -239,6 +239,14 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
     n_e2e = max(1, min(args.steps, 3))
 
+    # Level rows cross PCIe as they are or packed to the cells the reference reads (ml_host_set_packing).  Packing
+    # trades host memory bandwidth for PCIe bytes: it pays while PCIe is what a rank waits for (one or two
+    # GPUs on this host); from four ranks up the host's memory system is the bound and every row goes as it is.
+    cores = len(os.sched_getaffinity(0))
+    pack_mode = 1 if world <= 2 else 0
+    pack_threads = max(1, cores // (2 * world))
+    core.host_packing(pack_mode, pack_threads)
+
     def e2e_step():
         return core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, eta_out=eta_h)
 
@@ -255,17 +263,21 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     # what the library copied: level rows cross PCIe either as they are or as the cells the reference reads
     # (volcello present, steric.py:151-153), whichever side has time left -- the share differs from run to run
     h2d, packed_rows = core.host_last_transfer()
+    host_ms = core.host_last_timings()
     d2h = eta_h.numel() * 8 + 16
     line["e2e"] = {"value": world * points / float(dt[0]), "unit": UNIT, "h2d_bytes_per_step": h2d,
                    "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
                    "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)",
                    "host_input_bytes_per_step": dense, "level_rows_sent_packed": packed_rows,
-                   "host_pack_threads": max(1, min(len(os.sched_getaffinity(0)) - 1, 64)), "host_pack_simd": core.host_pack_simd()}
+                   "host_pack_mode": pack_mode, "host_pack_threads": pack_threads, "host_pack_simd": core.host_pack_simd(),
+                   "last_call_host_ms": host_ms}
     # the device-resident and the host-streamed paths must agree
     err = (eta_h.to(dev) - eta).abs()
     line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
-    # A/B: every row as it is (the PCIe-bound transfer of the whole fields)
-    core.host_packing(0)
+    # A/B: the other way of moving the rows (every row as it is when the timed setting packs, and the reverse)
+    alt_mode = 0 if pack_mode else 1
+    alt_key = "every_row_dense" if pack_mode else "rows_packed_where_cores_allow"
+    core.host_packing(alt_mode, pack_threads)
     try:
         e2e_step()
         barrier()
@@ -276,12 +288,13 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
         dt0 = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(dt0, op=dist.ReduceOp.MAX)
-        line["e2e"]["every_row_dense"] = {"value": world * points / float(dt0[0]), "unit": UNIT,
-                                          "ms_per_step": float(dt0[0]) * 1e3,
-                                          "h2d_bytes_per_step": core.host_last_transfer()[0],
-                                          "max_abs_diff_vs_resident_m": float(torch.nan_to_num((eta_h.to(dev) - eta).abs()).max())}
+        line["e2e"][alt_key] = {"value": world * points / float(dt0[0]), "unit": UNIT,
+                                "ms_per_step": float(dt0[0]) * 1e3,
+                                "h2d_bytes_per_step": core.host_last_transfer()[0],
+                                "level_rows_sent_packed": core.host_last_transfer()[1],
+                                "max_abs_diff_vs_resident_m": float(torch.nan_to_num((eta_h.to(dev) - eta).abs()).max())}
     finally:
-        core.host_packing(1)
+        core.host_packing(pack_mode, pack_threads)
     # BASELINE config 2 names all three variants: the same transfer feeding three integrations per window
     # (grid points counted once; three heights come back)
     try:

@@ -279,10 +279,12 @@ int ml_host_release(void);
  * rho_ref_out moves every row as it is (rho_ref is defined on absent cells too).
  *   ml_host_set_packing(mode, threads)  mode 0 = never pack, 1 = balance dynamically (default),
  *                                       2 = pack every row that has absent cells; threads <= 0 keeps
- *                                       the default (the calling thread's CPU affinity count - 1).
+ *                                       the default (half the calling thread's CPU affinity count).
  *                                       Applies to the calling host thread.
  *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed
  *   ml_host_last_h2d_bytes()            bytes the last host call of this thread copied host -> device
+ *   ml_host_last_timings(ms4)           host wall time of the last ml_steric_local*_host call, milliseconds:
+ *                                       presence index, windows, drain (kernels of the last window + read-back), whole call
  * The two loops underneath are exported for testing (csrc/ml_pack.cpp, no CUDA inside):
  *   ml_pack_index_rows  v [nrows][ncol] fp32 -> words / before [nrows][ceil(ncol/32)]: bit i of a word
  *                       = column 32 g + i is not NaN; before = present cells of the row in front of the
@@ -294,6 +296,7 @@ int ml_host_release(void);
 int ml_host_set_packing(int mode, int threads);
 double ml_host_last_packed_fraction(void);
 uint64_t ml_host_last_h2d_bytes(void);
+int ml_host_last_timings(double* ms4);
 uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t ncol, uint32_t* words,
                             uint32_t* before, uint64_t* row_count);
 void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,

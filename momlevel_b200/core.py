@@ -7,6 +7,8 @@ every number is computed by libmomlevel_b200's kernels.  Field layout is MOM6 or
 Each function names the reference code it stands in for; see include/momlevel_b200.h.
 """
 
+import ctypes
+
 import numpy as np
 import torch
 
@@ -26,6 +28,7 @@ __all__ = [
     "host_packing",
     "host_last_transfer",
     "host_pack_simd",
+    "host_last_timings",
     "last_path",
     "launch_count",
     "force_direct",
@@ -518,6 +521,13 @@ def host_last_transfer():
     """``(host->device bytes, share of level rows that crossed packed)`` of this thread's last ``*_host`` call."""
     L = _lib.lib()
     return int(L.ml_host_last_h2d_bytes()), float(L.ml_host_last_packed_fraction())
+
+
+def host_last_timings():
+    """Host wall time of this thread's last ``steric_local_host`` call in ms: presence index, windows, drain, whole call."""
+    out = (ctypes.c_double * 4)()
+    _lib.check(_lib.lib().ml_host_last_timings(ctypes.cast(out, ctypes.c_void_p)))
+    return {"presence_index_ms": out[0], "windows_ms": out[1], "drain_ms": out[2], "call_ms": out[3]}
 
 
 def host_pack_simd():

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -95,13 +96,14 @@ struct Resources {
   void* hbuf[kHostSlots] = {nullptr};
   size_t hcap[kHostSlots] = {0};
   int device = -1;
-  cudaStream_t copy = nullptr, comp = nullptr;
+  cudaStream_t copy = nullptr, comp = nullptr, back = nullptr;  // host->device, kernels, device->host
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
   cudaEvent_t ring[kRing] = {nullptr};
   Pool pool;
   // settings and accounting of the packed transfer (ml_host_set_packing and friends)
   int pack_mode = 1, pack_threads = 0;
   double last_packed_fraction = 0.0;
+  double last_ms[4] = {0.0, 0.0, 0.0, 0.0};  // presence index, windows (host side), drain, whole call
   std::atomic<uint64_t> h2d_bytes{0};
   void release() {
     for (int i = 0; i < kSlots; ++i) {
@@ -125,7 +127,8 @@ struct Resources {
     }
     if (copy) cudaStreamDestroy(copy);
     if (comp) cudaStreamDestroy(comp);
-    copy = comp = nullptr;
+    if (back) cudaStreamDestroy(back);
+    copy = comp = back = nullptr;
     device = -1;
   }
   ~Resources() { release(); }
@@ -139,6 +142,7 @@ struct Resources {
     }
     if (!copy && (e = cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if (!comp && (e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if (!back && (e = cudaStreamCreateWithFlags(&back, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (int b = 0; b < 2; ++b) {
       if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -180,12 +184,19 @@ Resources& resources() {
   return r;
 }
 
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int default_threads() {
   cpu_set_t set;
   int n = 0;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
   if (n <= 0) n = (int)std::thread::hardware_concurrency();
-  return std::max(1, std::min(n - 1, 64));
+  // half the cores: the packers and the DMA engine share the host's memory bandwidth, and past that point
+  // every extra thread slows the copies by as much as it saves (tools/e2e_sweep.py: 4 / 6 / 8 / 10 / 12 / 15
+  // threads on a 16-core host gave 156 / 148 / 145 / 148 / 152 / 157 ms for an OM4p25 year)
+  return std::max(1, std::min(n / 2, 64));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -489,6 +500,12 @@ extern "C" double ml_host_last_packed_fraction(void) { return resources().last_p
 
 extern "C" uint64_t ml_host_last_h2d_bytes(void) { return resources().h2d_bytes.load(); }
 
+extern "C" int ml_host_last_timings(double* ms4) {
+  ML_REQUIRE_PTR(ms4);
+  for (int i = 0; i < 4; ++i) ms4[i] = resources().last_ms[i];
+  return ML_OK;
+}
+
 // eta_thermo / eta_halo: optional extra heights from the same transfer (NULL = steric only)
 static int steric_local_host_impl(int eos, int dtype, const void* T, const void* S, const void* v0, const double* z_i,
                                   const double* deptho, const double* p_level, double neg_inv_rhozero, int64_t nt,
@@ -542,6 +559,7 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
 
   r.h2d_bytes = 0;
   r.last_packed_fraction = 0.0;
+  const double t_call = now_ms();
   ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
@@ -551,6 +569,7 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
   // moves every row as it is
   PackPlan plan;
   if (int rc = plan_packing(r, plan, dtype, v0, nz, ncol, spw, rho_ref_out == nullptr)) return rc;
+  const double t_plan = now_ms();
 
   const int64_t nwin = (nt + spw - 1) / spw;
   for (int64_t w = 0; w < nwin; ++w) {
@@ -593,15 +612,25 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
       }
     }
     ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
+    // the heights of this window go home while the next windows come in (PCIe carries both directions)
+    const size_t eoff = (size_t)t_first * ncol, ebytes = (size_t)nt_w * ncol * sizeof(double);
+    ML_CUDA(cudaStreamWaitEvent(r.back, r.freed[b], 0));
+    ML_CUDA(cudaMemcpyAsync(eta + eoff, (double*)dEta + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
+    if (eta_thermo) ML_CUDA(cudaMemcpyAsync(eta_thermo + eoff, (double*)dEtaT + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
+    if (eta_halo) ML_CUDA(cudaMemcpyAsync(eta_halo + eoff, (double*)dEtaH + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
   }
-  ML_CUDA(cudaMemcpyAsync(eta, dEta, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
-  if (eta_thermo) ML_CUDA(cudaMemcpyAsync(eta_thermo, dEtaT, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
-  if (eta_halo) ML_CUDA(cudaMemcpyAsync(eta_halo, dEtaH, (size_t)nt * ncol * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
+  const double t_windows = now_ms();
   if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
   ML_CUDA(cudaStreamSynchronize(r.comp));
+  ML_CUDA(cudaStreamSynchronize(r.back));
   ML_CUDA(cudaStreamSynchronize(r.copy));
   r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
+  const double t_end = now_ms();
+  r.last_ms[0] = t_plan - t_call;
+  r.last_ms[1] = t_windows - t_plan;
+  r.last_ms[2] = t_end - t_windows;
+  r.last_ms[3] = t_end - t_call;
   return ML_OK;
 }
 

@@ -11,8 +11,8 @@
 //                        running count of present cells in front of each group
 //   ml_pack_rows         compress one segment of a T row and an S row through those words
 //
-// Both have an AVX-512 body (VCOMPRESSPS in registers + a masked store) chosen at run time and a
-// scalar body for anything else.  Threading lives with the caller (ml_hostpath.cu).
+// Both have an AVX-512 body (VCOMPRESSPS in registers, whole lines written with non-temporal stores)
+// chosen at run time and a scalar body for anything else.  Threading lives with the caller (ml_hostpath.cu).
 #include <stddef.h>
 #include <stdint.h>
 #include <string.h>
@@ -93,6 +93,7 @@ void pack_scalar(const float* t, const float* s, const uint32_t* words, int64_t 
   }
 }
 
+#ifdef ML_PACK_PLAIN_STORES  // A/B: masked stores straight into the staging memory (tools/packbench.cpp)
 __attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx512(const float* t, const float* s,
                                                                                  const uint32_t* words, int64_t g0,
                                                                                  int64_t g1, int64_t ncol,
@@ -129,6 +130,79 @@ __attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx51
   }
   if (gfull < g1) pack_scalar(t, s, words, gfull, g1, t_out, s_out);
 }
+
+#else
+// Compressed vectors are appended to a small cache-resident buffer and leave it as whole, aligned
+// 64-byte lines written with non-temporal stores: the staging memory is only ever read by the DMA
+// engine, so pulling its lines into the cache first (what an ordinary store does) is wasted traffic,
+// and a masked store that straddles two lines costs several cycles more than a full one.  The
+// first and the last line of a segment are shared with its neighbours and are written with masks.
+struct LineWriter {
+  static constexpr int kLines = 16;
+  alignas(64) float buf[(kLines + 2) * 16];
+  float* line;  // 64-byte aligned destination of buf[0]
+  int n;        // floats in buf (the first `head` of them are not ours)
+  int head;
+  __attribute__((target("avx512f,avx512bw,avx512vl"))) explicit LineWriter(float* dst) {
+    head = (int)(((uintptr_t)dst & 63u) >> 2);
+    line = dst - head;
+    n = head;
+  }
+  __attribute__((target("avx512f,avx512bw,avx512vl"))) inline void put(__m512 v, int count) {
+    _mm512_storeu_ps(buf + n, v);
+    n += count;
+    if (n >= kLines * 16) flush_full();
+  }
+  __attribute__((target("avx512f,avx512bw,avx512vl"))) inline void flush_full() {
+    const int nl = n >> 4;
+    int l = 0;
+    if (head) {  // the line we share with the segment in front
+      _mm512_mask_storeu_ps(line, (__mmask16)(0xffffu << head), _mm512_load_ps(buf));
+      head = 0;
+      l = 1;
+    }
+    for (; l < nl; ++l) _mm512_stream_ps(line + l * 16, _mm512_load_ps(buf + l * 16));
+    _mm512_store_ps(buf, _mm512_load_ps(buf + nl * 16));
+    line += nl * 16;
+    n &= 15;
+  }
+  __attribute__((target("avx512f,avx512bw,avx512vl"))) inline void finish() {
+    if (n >= 16) flush_full();
+    if (n > head) {
+      const __mmask16 m = (__mmask16)(((1u << n) - 1u) & (0xffffu << head));
+      _mm512_mask_storeu_ps(line, m, _mm512_load_ps(buf));
+    }
+    _mm_sfence();
+  }
+};
+
+__attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx512(const float* t, const float* s,
+                                                                                 const uint32_t* words, int64_t g0,
+                                                                                 int64_t g1, int64_t ncol,
+                                                                                 float* t_out, float* s_out) {
+  // a ragged last group is left to the scalar body (a 16-lane load would run past the row)
+  const int64_t gfull = (g1 * 32 <= ncol) ? g1 : g1 - 1;
+  LineWriter wt(t_out), ws(s_out);
+  int64_t written = 0;
+  for (int64_t g = g0; g < gfull; ++g) {
+    const uint32_t m = words[g];
+    if (m == 0) continue;
+    const float* tp = t + g * 32;
+    const float* sp = s + g * 32;
+    const __mmask16 lo = (__mmask16)(m & 0xffffu), hi = (__mmask16)(m >> 16);
+    const int nlo = _mm_popcnt_u32(m & 0xffffu), nhi = _mm_popcnt_u32(m >> 16);
+    wt.put(_mm512_maskz_compress_ps(lo, _mm512_loadu_ps(tp)), nlo);
+    ws.put(_mm512_maskz_compress_ps(lo, _mm512_loadu_ps(sp)), nlo);
+    wt.put(_mm512_maskz_compress_ps(hi, _mm512_loadu_ps(tp + 16)), nhi);
+    ws.put(_mm512_maskz_compress_ps(hi, _mm512_loadu_ps(sp + 16)), nhi);
+    written += nlo + nhi;
+  }
+  wt.finish();
+  ws.finish();
+  if (gfull < g1) pack_scalar(t, s, words, gfull, g1, t_out + written, s_out + written);
+}
+
+#endif
 
 }  // namespace
 
