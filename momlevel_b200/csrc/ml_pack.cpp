@@ -15,6 +15,7 @@
 // chosen at run time and a scalar body for anything else.  Threading lives with the caller (ml_hostpath.cu).
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <immintrin.h>
@@ -23,9 +24,11 @@
 
 namespace {
 
+// ML_PACK_FORCE_SCALAR=1 in the environment selects the scalar bodies on any CPU (tests/test_pack.py)
 bool has_avx512() {
   static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
-                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("popcnt");
+                         __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("popcnt") &&
+                         !(getenv("ML_PACK_FORCE_SCALAR") && getenv("ML_PACK_FORCE_SCALAR")[0] == '1');
   return ok;
 }
 

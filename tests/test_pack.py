@@ -73,6 +73,38 @@ def test_simd_body_is_reported(L):
     assert L.ml_pack_simd() in (0, 512)
 
 
+def test_scalar_bodies_give_the_same_rows():
+    """A CPU without AVX-512 runs the scalar loops; force them in a fresh process and repeat one case."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import ctypes, numpy as np\n"
+        "from momlevel_b200 import _lib\n"
+        "L = _lib.lib()\n"
+        "assert L.ml_pack_simd() == 0\n"
+        "p = lambda a: a.ctypes.data_as(ctypes.c_void_p)\n"
+        "rng = np.random.default_rng(4)\n"
+        "ncol = 1003; ngrp = (ncol + 31) // 32\n"
+        "V = rng.uniform(1, 2, (2, ncol)).astype(np.float32); V[rng.uniform(size=V.shape) < 0.6] = np.nan\n"
+        "T = rng.normal(size=(2, ncol)).astype(np.float32); S = rng.normal(size=(2, ncol)).astype(np.float32)\n"
+        "w = np.zeros((2, ngrp), np.uint32); b = np.zeros((2, ngrp), np.uint32); c = np.zeros(2, np.uint64)\n"
+        "assert L.ml_pack_index_rows(p(V), 2, ncol, p(w), p(b), p(c)) == (~np.isnan(V)).sum()\n"
+        "for r in range(2):\n"
+        "    n = int(c[r]); to = np.zeros(n + 8, np.float32); so = np.zeros(n + 8, np.float32)\n"
+        "    L.ml_pack_rows(p(T[r]), p(S[r]), p(w[r]), p(b[r]), 0, ngrp // 2, ncol, p(to), p(so))\n"
+        "    L.ml_pack_rows(p(T[r]), p(S[r]), p(w[r]), p(b[r]), ngrp // 2, ngrp, ncol, p(to), p(so))\n"
+        "    m = ~np.isnan(V[r])\n"
+        "    assert np.array_equal(to[:n], T[r][m]) and np.array_equal(so[:n], S[r][m]) and not to[n:].any()\n"
+        "print('scalar ok')\n"
+    )
+    env = dict(os.environ, ML_PACK_FORCE_SCALAR="1")
+    root = str(__import__("pathlib").Path(__file__).resolve().parent.parent)
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "scalar ok" in out.stdout, out.stderr[-2000:]
+
+
 def test_packing_mode_argument(L):
     assert L.ml_host_set_packing(3, 0) == -5 and b"packing mode" in L.ml_last_error()
     assert L.ml_host_set_packing(-1, 0) == -5
