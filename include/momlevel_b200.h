@@ -276,7 +276,9 @@ int ml_host_release(void);
  * caller's buffer) or as its present cells only (compressed by host threads into pinned staging,
  * expanded on the device with NaN in the absent cells), whichever side -- PCIe or the host cores --
  * has time left; the heights are bit-identical either way.  fp32 fields only; a call that asks for
- * rho_ref_out moves every row as it is (rho_ref is defined on absent cells too).
+ * rho_ref_out moves every row as it is (rho_ref is defined on absent cells too).  Fields in PAGEABLE memory
+ * (plain malloc / numpy; a DMA from it is a slow synchronous bounce through the driver) send every row through the
+ * packers and the pinned staging, full rows included, unless mode is 0.
  *   ml_host_set_packing(mode, threads)  mode 0 = never pack, 1 = balance dynamically (default),
  *                                       2 = pack every row that has absent cells; threads <= 0 keeps
  *                                       the default (half the calling thread's CPU affinity count).

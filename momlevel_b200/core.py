@@ -477,7 +477,8 @@ def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
     from time step 0; copies are pipelined against the kernels inside the library.
     Returns ``(eta [nt,...], rho_ref or None, (volo, masso))``.  With ``variants=True`` ``eta`` is a dict
     ``{"steric", "thermosteric", "halosteric"}``: the fields cross PCIe once and every window is
-    integrated three times on the device (``ml_steric_local_variants_host``).  ``eta_out`` may hand in
+    integrated three times on the device (``ml_steric_local_variants_host``); a tuple of names asks for steric
+    plus those.  ``eta_out`` may hand in
     the output tensor (or, with ``variants``, a dict of them) -- pinned memory keeps the read-back asynchronous.
     """
     L = _lib.lib()
@@ -503,11 +504,14 @@ def steric_local_host(T, S, V0, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
     if not variants:
         _lib.check(L.ml_steric_local_host(*head, eta.data_ptr(), *tail))
         return eta, rho, (float(sums[0]), float(sums[1]))
-    eta_t, eta_h = outs.get("thermosteric"), outs.get("halosteric")
-    eta_t = torch.empty_like(eta) if eta_t is None else eta_t
-    eta_h = torch.empty_like(eta) if eta_h is None else eta_h
-    _lib.check(L.ml_steric_local_variants_host(*head, eta.data_ptr(), eta_t.data_ptr(), eta_h.data_ptr(), *tail))
-    return {"steric": eta, "thermosteric": eta_t, "halosteric": eta_h}, rho, (float(sums[0]), float(sums[1]))
+    wanted = ("thermosteric", "halosteric") if variants is True else tuple(v for v in variants if v != "steric")
+    extra = {}
+    for name in ("thermosteric", "halosteric"):
+        if name in wanted:
+            extra[name] = outs.get(name) if outs.get(name) is not None else torch.empty_like(eta)
+    ptr = lambda name: extra[name].data_ptr() if name in extra else None  # noqa: E731
+    _lib.check(L.ml_steric_local_variants_host(*head, eta.data_ptr(), ptr("thermosteric"), ptr("halosteric"), *tail))
+    return {"steric": eta, **extra}, rho, (float(sums[0]), float(sums[1]))
 
 
 def host_packing(mode=1, threads=0):

@@ -179,6 +179,16 @@ struct Resources {
   }
 };
 
+// true for memory the driver does not know (malloc / numpy): copies from it are staged by the driver
+bool is_pageable(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return true;
+  }
+  return a.type == cudaMemoryTypeUnregistered;
+}
+
 Resources& resources() {
   static thread_local Resources r;
   return r;
@@ -226,6 +236,7 @@ struct PackPlan {
   float *d_packed[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   uint8_t *flags[2] = {nullptr, nullptr}, *d_flags[2] = {nullptr, nullptr};  // [t][z]: 1 = row crossed packed
   int64_t rows_total = 0, rows_packed = 0;
+  bool all_staged = false;  // pageable source: no row is copied straight from the caller's buffer
 };
 
 constexpr double kPackableBelow = 0.9;  // a level with more of its cells present than this is never compressed
@@ -266,10 +277,11 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const float* __restrict__ p
 // Leaves plan.on false (every row crosses as it is) when packing is off, cannot help or cannot get
 // its pinned memory.
 int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_t nz, int64_t ncol, int64_t spw,
-                 bool allowed) {
+                 bool allowed, bool pageable) {
   using namespace ml;
   plan.on = false;
   plan.mode = r.pack_mode;
+  plan.all_staged = false;
   if (!allowed || plan.mode == 0 || dtype != ML_F32) return ML_OK;
   plan.nz = nz;
   plan.ncol = ncol;
@@ -312,6 +324,13 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
       plan.first_packable = (int)i;
       break;
     }
+  if (pageable && plan.nwet != 0) {
+    // Pageable source (a plain numpy array): a DMA from it is a synchronous, single-threaded bounce through the
+    // driver at a fraction of the PCIe rate, so every row goes through the packers and the pinned staging,
+    // full rows included.
+    plan.all_staged = true;
+    plan.first_packable = 0;
+  }
   if (plan.first_packable == (int)nz || plan.nwet == 0) return ML_OK;  // nothing worth compressing
   const size_t stage_bytes = (size_t)spw * plan.nwet * 4;
   const size_t flag_bytes = (size_t)spw * (size_t)nz;
@@ -389,7 +408,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   } sh;
   sh.hi = nrows - 1;
   sh.hi_min = plan.first_packable * (int)nt_w;
-  sh.lo_end = plan.mode == 2 ? sh.hi_min : nrows;
+  sh.lo_end = (plan.mode == 2 || plan.all_staged) ? sh.hi_min : nrows;
   sh.next_seg = plan.nseg;  // no row open yet
   std::vector<std::atomic<int>> done((size_t)nrows);
   for (auto& d : done) d.store(0, std::memory_order_relaxed);
@@ -568,7 +587,8 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
   // rho_ref is defined where the volume is missing too (reference.py:71), so a call that wants it back
   // moves every row as it is
   PackPlan plan;
-  if (int rc = plan_packing(r, plan, dtype, v0, nz, ncol, spw, rho_ref_out == nullptr)) return rc;
+  if (int rc = plan_packing(r, plan, dtype, v0, nz, ncol, spw, rho_ref_out == nullptr,
+                            is_pageable(T) || is_pageable(S))) return rc;
   const double t_plan = now_ms();
 
   const int64_t nwin = (nt + spw - 1) / spw;
@@ -692,7 +712,7 @@ extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const vo
   r.h2d_bytes += (size_t)nz * sizeof(double) + lvl * es;
   // rho * volcello is skipped where the reference volume is missing (derived.py:435-438)
   PackPlan plan;
-  if (int rc = plan_packing(r, plan, dtype, v_ref, nz, ncol, spw, true)) return rc;
+  if (int rc = plan_packing(r, plan, dtype, v_ref, nz, ncol, spw, true, is_pageable(T) || is_pageable(S))) return rc;
 
   const int64_t nwin = (nt + spw - 1) / spw;
   for (int64_t w = 0; w < nwin; ++w) {

@@ -75,7 +75,12 @@ def steric(
         if verbose:
             print("Using supplied reference state")
     else:
-        if domain != "global" and variant in ("steric", "thermosteric", "halosteric"):
+        if domain != "global" and variant in VARIANTS and _host_resident(dset, tcoord, zcoord, zbounds):
+            # fields in host memory (numpy, what xarray hands over): streamed through device windows by the
+            # library, level rows packed to their present cells on the way (ml_steric_local_host)
+            reference, fused_eta = _selfref_host(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord,
+                                                 zbounds)
+        elif domain != "global" and variant in ("steric", "thermosteric", "halosteric"):
             # reference state and column integral in one pass over T, S (ml_steric_local_selfref)
             reference, fused_eta, area_total = _selfref(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord,
                                                         zbounds, deferred, strict, additional_vars)
@@ -216,6 +221,56 @@ def _reference_from_pass(dset, tcoord, eos, rho, sums, pres=None):
         "long_name": "Global Average Sea Water Density", "units": "kg m-3"})
     reference["areacello"] = dset["areacello"]
     return reference
+
+
+HOST_ROUTE_MIN_BYTES = 1 << 26  # fields smaller than this are simply copied to the device
+
+
+def _host_resident(dset, tcoord, zcoord, zbounds):
+    """Whether ``steric()`` should take the host route: every input lives in host memory (numpy or CPU tensors),
+    the fields are laid out ``(time, z, y, x)`` in one piece, and there is enough of them for the streaming to pay."""
+    try:
+        arrs = [dset[n].data for n in ("thetao", "so", "volcello", "deptho", zcoord, zbounds)]
+        if any(isinstance(a, torch.Tensor) and a.is_cuda for a in arrs):
+            return False
+        T, S, V = (dset[n] for n in ("thetao", "so", "volcello"))
+        if not (T.dims == S.dims == V.dims and T.ndim == 4 and T.dims[0] == tcoord and T.dims[1] == zcoord):
+            return False
+        if not (T.shape == S.shape == V.shape and dset["deptho"].shape == T.shape[2:]):
+            return False
+        for a in arrs[:2]:
+            if not (a.is_contiguous() if isinstance(a, torch.Tensor) else a.flags["C_CONTIGUOUS"]):
+                return False
+        nbytes = 2 * int(np.prod(T.shape)) * (4 if str(arrs[0].dtype).endswith("float32") else 8)
+        return nbytes >= HOST_ROUTE_MIN_BYTES
+    except (KeyError, AttributeError, TypeError):
+        return False
+
+
+def _selfref_host(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
+    """``setup_reference_state(dset)`` + the local column integral for fields that live in HOST memory.
+
+    The library streams the time steps through device windows (``ml_steric_local_host`` /
+    ``ml_steric_local_variants_host``); the heights come back as host arrays.  Returns ``(reference, eta)``.
+    """
+    from .util import eos_func_from_str
+
+    eos_func_from_str(eos)
+    _check_depths(dset, zcoord, zbounds)
+    T, S = dset["thetao"].data, dset["so"].data
+    V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
+    step_bytes = 2 * int(np.prod(dset["thetao"].shape[1:])) * 4
+    spw = int(min(max(1, -(-(1 << 28) // step_bytes)), dset["thetao"].shape[0]))  # windows of >= 256 MB
+    etas, _, (volo, masso) = core.steric_local_host(
+        T, S, V0, _host_numpy(dset[zbounds].data), _host_numpy(dset["deptho"].data), _host_numpy(pres),
+        rhozero=rhozero, eos=eos, steps_per_window=spw, variants=False if variant == "steric" else (variant,))
+    eta = etas if variant == "steric" else etas[variant]
+    sums = torch.tensor([volo, masso], dtype=torch.float64)
+    return _reference_from_pass(dset, tcoord, eos, None, sums, pres), eta
+
+
+def _host_numpy(x):
+    return x.detach().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
 
 
 def _on_one_cuda_device(dset, names):

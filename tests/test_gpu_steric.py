@@ -783,8 +783,9 @@ def test_host_packed_transfer_is_bit_identical(ml, shape):
         core.host_packing(1)
 
 
-def test_host_packed_transfer_of_a_dense_field_sends_it_as_it_is(ml):
-    """No absent cells (the reference's own 5x5x5 test dataset): nothing is worth compressing."""
+def test_host_packed_transfer_of_a_dense_field(ml):
+    """No absent cells (the reference's own 5x5x5 test dataset): from pinned memory nothing is worth compressing
+    and every row is copied as it is; from pageable memory every row goes through the pinned staging."""
     from momlevel_b200 import core
 
     ds = ml.test_data.generate_test_data()
@@ -792,15 +793,102 @@ def test_host_packed_transfer_of_a_dense_field_sends_it_as_it_is(ml):
     S = torch.from_numpy(ds["so"].values).float()
     V = torch.from_numpy(ds["volcello"].values[0]).float()
     pres = ds["z_l"].values * 1e4 + 101325.0
+    args = (ds["z_i"].values, ds["deptho"].values, pres)
     try:
-        core.host_packing(2)
-        eta, _, _ = core.steric_local_host(T, S, V, ds["z_i"].values, ds["deptho"].values, pres)
-        assert core.host_last_transfer()[1] == 0.0
         core.host_packing(0)
-        eta0, _, _ = core.steric_local_host(T, S, V, ds["z_i"].values, ds["deptho"].values, pres)
-        assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64))
+        eta0, _, _ = core.steric_local_host(T, S, V, *args)
+        for mode in (1, 2):
+            core.host_packing(mode)
+            eta, _, _ = core.steric_local_host(T.pin_memory(), S.pin_memory(), V.pin_memory(), *args)
+            assert core.host_last_transfer()[1] == 0.0
+            assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64))
+            eta, _, _ = core.steric_local_host(T, S, V, *args)  # pageable
+            assert core.host_last_transfer()[1] == 1.0
+            assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64))
     finally:
         core.host_packing(1)
+
+
+def test_host_packed_transfer_from_pinned_memory(ml):
+    """Pinned fields: the fullest rows are copied straight from the caller's buffer, the emptiest ones are packed,
+    and the split (which depends on timing) does not change a bit of the result."""
+    from momlevel_b200 import core, synth
+
+    ds = synth.make_dataset(4, 10, 128, 520, seed=12, device="cpu", dtype=torch.float32)
+    T, S, V, depth = _disagreeing_masks(ds, 5)
+    V[:3] = 1.0e9  # three levels with every volume present: rows that are never worth packing
+    pres = ds["z_l"].values * 1e4 + 101325.0
+    args = (ds["z_i"].values, depth.numpy(), pres)
+    Tp, Sp, Vp = T.pin_memory(), S.pin_memory(), V.pin_memory()
+    try:
+        core.host_packing(0)
+        eta0, _, sums0 = core.steric_local_host(Tp, Sp, Vp, *args)
+        seen = set()
+        for mode, threads in ((1, 0), (1, 1), (2, 0), (1, 4), (2, 2)):
+            core.host_packing(mode, threads)
+            for spw in (1, 3):
+                eta, _, sums = core.steric_local_host(Tp, Sp, Vp, *args, steps_per_window=spw)
+                frac = core.host_last_transfer()[1]
+                seen.add(round(frac, 3))
+                assert 0.0 <= frac <= 0.7  # three of the ten levels are fully present: never packed
+                assert torch.equal(eta.view(torch.int64), eta0.view(torch.int64)) and sums == sums0
+                if mode == 2:
+                    assert frac == pytest.approx(0.7)
+        assert max(seen) > 0.0
+    finally:
+        core.host_packing(1)
+
+
+def test_steric_takes_the_host_route_for_host_resident_fields(ml, monkeypatch):
+    """``steric(dset)`` on numpy-backed fields (what xarray hands over) streams them through the host entry
+    point; the heights agree with the device-resident call and the oracle for every variant."""
+    from momlevel_b200 import core, steric as steric_mod, synth
+
+    shape = (6, 20, 256, 520)  # 128 MB of T and S: above HOST_ROUTE_MIN_BYTES
+    ds = synth.make_dataset(*shape, seed=21, device="cpu", dtype=torch.float32)
+    dims = ("time", "z_l", "yh", "xh")
+    host = ml.Dataset()
+    dev = ml.Dataset()
+    for k in ds.variables:
+        host[k] = ds[k]
+        dev[k] = ds[k]
+    for k in ("thetao", "so"):
+        host[k] = ml.DataArray(ds[k].data.numpy(), dims)  # plain numpy: pageable memory
+        dev[k] = ml.DataArray(ds[k].data.cuda(), dims)
+    host["volcello"] = ml.DataArray(np.ascontiguousarray(ds["volcello"].values), dims)
+    dev["volcello"] = ml.DataArray(ds["volcello"].data.cuda(), dims)
+    for k in ("deptho", "areacello", "z_l", "z_i"):
+        dev[k] = ml.DataArray(torch.as_tensor(ds[k].values).cuda(), ds[k].dims)
+    assert steric_mod._host_resident(host, "time", "z_l", "z_i") and not steric_mod._host_resident(dev, "time", "z_l", "z_i")
+    T64, S64 = ds["thetao"].values.astype(np.float64), ds["so"].values.astype(np.float64)
+    V64 = ds["volcello"].values.astype(np.float64)
+    z_l, z_i = ds["z_l"].values, ds["z_i"].values
+    oref = osteric.reference_state(T64, S64, V64, ds["areacello"].values, z_l)
+    for variant in ("steric", "thermosteric", "halosteric"):
+        core.host_packing(1)
+        got, ref = ml.steric(host, variant=variant)
+        nbytes, frac = core.host_last_transfer()
+        assert frac == 1.0 and nbytes < 2 * T64.size * 4, "expected the packed host route"
+        assert not got[variant].data.is_cuda
+        want, wref = ml.steric(dev, variant=variant)
+        _close_nan(got[variant].values, want[variant].values, atol=1e-12)
+        assert float(ref["masso"]) == pytest.approx(float(wref["masso"]), rel=1e-14)
+        assert float(ref["volo"]) == pytest.approx(float(wref["volo"]), rel=1e-14)
+        o, _ = osteric.steric_local(T64, S64, z_l, z_i, ds["deptho"].values, oref, variant=variant)
+        _close_nan(got[variant].values, o, atol=ETA_ATOL)
+        if variant == "steric":  # the lazy members still work from host fields
+            _close_nan(ref["rho"].values, oref["rho"], rtol=RHO_RTOL)
+            assert got["delta_rho"].shape == shape
+    # small datasets are simply copied to the device; forcing the route shows the same numbers
+    small = synth.make_dataset(5, 12, 20, 32, seed=5, device="cpu", dtype=torch.float32)
+    assert not steric_mod._host_resident(small, "time", "z_l", "z_i")
+    want, _ = ml.steric(small)
+    monkeypatch.setattr(steric_mod, "HOST_ROUTE_MIN_BYTES", 0)
+    assert steric_mod._host_resident(small, "time", "z_l", "z_i")
+    got, _ = ml.steric(small)
+    _close_nan(got["steric"].values, want["steric"].values, atol=1e-13)
+    res, _ = ml.steric(small, annual=False, domain="global")  # the global branch is untouched by the route
+    assert res["steric"].shape == (5,)
 
 
 @pytest.mark.parametrize("seed", range(12))
