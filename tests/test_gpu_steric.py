@@ -842,8 +842,11 @@ def test_host_packed_transfer_from_pinned_memory(ml):
 def test_steric_takes_the_host_route_for_host_resident_fields(ml, monkeypatch):
     """``steric(dset)`` on numpy-backed fields (what xarray hands over) streams them through the host entry
     point; the heights agree with the device-resident call and the oracle for every variant."""
-    from momlevel_b200 import core, steric as steric_mod, synth
+    import importlib
 
+    from momlevel_b200 import core, synth
+
+    steric_mod = importlib.import_module("momlevel_b200.steric")  # the package attribute is the function
     shape = (6, 20, 256, 520)  # 128 MB of T and S: above HOST_ROUTE_MIN_BYTES
     ds = synth.make_dataset(*shape, seed=21, device="cpu", dtype=torch.float32)
     dims = ("time", "z_l", "yh", "xh")

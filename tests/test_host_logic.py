@@ -193,3 +193,48 @@ def test_bind_host_to_device_is_harmless_without_a_gpu():
     assert n == 0 or n == len(os.sched_getaffinity(0))
     if n == 0:
         assert os.sched_getaffinity(0) == before
+
+
+def test_steric_routes_host_resident_fields_to_the_host_entry(monkeypatch):
+    """steric() hands numpy / CPU-tensor fields to ``core.steric_local_host`` (the streaming entry point) with
+    host arrays for the grid, asks for the one extra height a variant needs, and assembles the same result and
+    reference Datasets around what comes back.  The library call itself is replaced: no device here."""
+    import importlib
+
+    import torch
+
+    import momlevel_b200 as ml
+    from momlevel_b200 import core, synth
+
+    steric_mod = importlib.import_module("momlevel_b200.steric")
+    small = synth.make_dataset(5, 12, 20, 32, seed=5, device="cpu", dtype=torch.float32)
+    assert not steric_mod._host_resident(small, "time", "z_l", "z_i")  # too small to be worth streaming
+    monkeypatch.setattr(steric_mod, "HOST_ROUTE_MIN_BYTES", 0)
+    assert steric_mod._host_resident(small, "time", "z_l", "z_i")
+    calls = []
+
+    def fake(T, S, V0, z_i, depth, pres, rhozero=1035.0, eos="Wright", steps_per_window=1, want_rho_ref=False,
+             eta_out=None, variants=False):
+        calls.append((tuple(V0.shape), type(z_i).__name__, type(depth).__name__, type(pres).__name__,
+                      steps_per_window, variants, eos, rhozero))
+        eta = torch.zeros((T.shape[0],) + tuple(T.shape[2:]), dtype=torch.float64)
+        if not variants:
+            return eta, None, (2.0, 2070.0)
+        return {"steric": eta, **{v: eta + 1.0 for v in variants}}, None, (2.0, 2070.0)
+
+    monkeypatch.setattr(core, "steric_local_host", fake)
+    for variant, level in (("steric", 0.0), ("thermosteric", 1.0), ("halosteric", 1.0)):
+        res, ref = ml.steric(small, variant=variant, rhozero=1030.0)
+        assert res[variant].shape == (5, 20, 32) and float(res[variant].values.max()) == level
+        assert res[variant].attrs["long_name"] == f"{variant.capitalize()} height adjustment"
+        assert res["delta_rho"].shape == (5, 12, 20, 32)  # lazy: not evaluated here
+        assert float(ref["volo"]) == 2.0 and float(ref["masso"]) == 2070.0 and float(ref["rhoga"]) == 1035.0
+        assert set(ref.variables) >= {"thetao", "so", "volcello", "rho", "volo", "masso", "rhoga", "areacello"}
+    assert [c[5] for c in calls] == [False, ("thermosteric",), ("halosteric",)]
+    assert all(c[0] == (12, 20, 32) and c[1:4] == ("ndarray",) * 3 and c[4] == 5 and c[6] == "Wright"
+               and c[7] == 1030.0 for c in calls)
+    # a supplied reference, the global domain and device-resident fields keep their own routes
+    calls.clear()
+    with pytest.raises(ml._lib.MLError):  # reaches the device check of the ordinary route
+        ml.steric(small, domain="global")
+    assert calls == []
