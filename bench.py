@@ -314,6 +314,30 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
                                              "api": "core.steric_local_host(variants=True) -> ml_steric_local_variants_host"}
     except (RuntimeError, MemoryError) as exc:  # the two extra pageable height fields are a few hundred MB
         line["e2e"]["all_three_variants"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+    # the call a user of the reference makes: steric(dset) on a Dataset backed by plain (pageable) numpy arrays,
+    # validation, reference Dataset and result assembly included
+    if world == 1 and not args.no_extras:
+        try:
+            import momlevel_b200 as ml
+            from momlevel_b200 import synth
+
+            cpu_grid = {k: v.cpu() for k, v in grid.items()}
+            ds = synth.dataset_from_fields(cpu_grid, torch.from_numpy(Th.numpy().copy()),
+                                           torch.from_numpy(Sh.numpy().copy()), torch.from_numpy(Vh.numpy().copy()))
+            res, _ = ml.steric(ds)
+            t0 = time.perf_counter()
+            for _ in range(2):
+                res, _ = ml.steric(ds)
+                got = res["steric"].data
+            dtp = (time.perf_counter() - t0) / 2
+            nb, frac = core.host_last_transfer()
+            line["e2e"]["public_api_numpy_dataset"] = {
+                "value": points / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "h2d_bytes_per_step": nb,
+                "level_rows_sent_packed": frac, "api": "momlevel_b200.steric(dset), fields in pageable host memory",
+                "max_abs_diff_vs_resident_m": float(torch.nan_to_num((got.to(dev) - eta).abs()).max())}
+            del ds, res, got
+        except Exception as exc:  # noqa: BLE001 -- an optional leg must not take the bench line down with it
+            line["e2e"]["public_api_numpy_dataset"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
     return (Th.numpy(), Sh.numpy(), Vh.numpy(), grid["areacello"].cpu().numpy(), d_h, grid["z_l"].cpu().numpy(), z_h)
 
 
