@@ -278,7 +278,8 @@ int ml_host_release(void);
  * has time left; the heights are bit-identical either way.  fp32 fields only; a call that asks for
  * rho_ref_out moves every row as it is (rho_ref is defined on absent cells too).  Fields in PAGEABLE memory
  * (plain malloc / numpy; a DMA from it is a slow synchronous bounce through the driver) send every row through the
- * packers and the pinned staging, full rows included, unless mode is 0.
+ * packers and the pinned staging, full rows included, and volcello and the heights cross through pinned
+ * buffers of the library's own, unless mode is 0.
  *   ml_host_set_packing(mode, threads)  mode 0 = never pack, 1 = balance dynamically (default),
  *                                       2 = pack every row that has absent cells; threads <= 0 keeps
  *                                       the default (half the calling thread's CPU affinity count).

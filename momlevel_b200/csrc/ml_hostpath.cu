@@ -89,7 +89,7 @@ class Pool {
 // milliseconds per call) and released by ml_host_release() or at thread exit.
 struct Resources {
   static constexpr int kSlots = 28;
-  static constexpr int kHostSlots = 8;
+  static constexpr int kHostSlots = 12;
   static constexpr int kRing = 3;  // dense rows in flight on the copy stream
   void* buf[kSlots] = {nullptr};
   size_t cap[kSlots] = {0};
@@ -207,6 +207,22 @@ int default_threads() {
   // every extra thread slows the copies by as much as it saves (tools/e2e_sweep.py: 4 / 6 / 8 / 10 / 12 / 15
   // threads on a 16-core host gave 156 / 148 / 145 / 148 / 152 / 157 ms for an OM4p25 year)
   return std::max(1, std::min(n / 2, 64));
+}
+
+// memcpy by the worker threads (one thread moves ~10 GB/s, the memory system many times that)
+void parallel_copy(Resources& r, void* dst, const void* src, size_t bytes, int threads) {
+  threads = std::max(1, threads);
+  if (bytes < (size_t)(8u << 20) || threads == 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  r.pool.ensure(threads);
+  const size_t chunk = ((bytes + (size_t)threads - 1) / (size_t)threads + 63) & ~(size_t)63;
+  r.pool.start(threads, [=](int id) {
+    const size_t a = (size_t)id * chunk;
+    if (a < bytes) memcpy((char*)dst + a, (const char*)src + a, std::min(chunk, bytes - a));
+  });
+  r.pool.wait();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -582,8 +598,33 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
   ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
   ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(dV, v0, lvl * es, cudaMemcpyHostToDevice, r.copy));
+  // Pageable memory (plain numpy) on either end of a copy makes it a synchronous bounce through the driver that
+  // holds this thread -- and with it the pipeline -- for the length of the copy.  Unless packing is off such
+  // operands go through pinned buffers of our own, filled / emptied by the worker threads.
+  const int nthreads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
+  const void* v0_src = v0;
+  if (r.pack_mode != 0 && is_pageable(v0)) {
+    void* hv;
+    if (r.halloc(11, &hv, lvl * es) == cudaSuccess) {
+      parallel_copy(r, hv, v0, lvl * es, nthreads);
+      v0_src = hv;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  ML_CUDA(cudaMemcpyAsync(dV, v0_src, lvl * es, cudaMemcpyHostToDevice, r.copy));
   r.h2d_bytes += (size_t)(2 * nz + 1 + ncol) * sizeof(double) + lvl * es;
+  double* user_eta[3] = {eta, eta_thermo, eta_halo};
+  double* host_eta[3] = {eta, eta_thermo, eta_halo};  // where the device->host copies land
+  const size_t eta_bytes = (size_t)nt * ncol * sizeof(double);
+  for (int v = 0; v < 3; ++v) {
+    void* hb;
+    if (user_eta[v] == nullptr || r.pack_mode == 0 || !is_pageable(user_eta[v])) continue;
+    if (r.halloc(8 + v, &hb, eta_bytes) == cudaSuccess)
+      host_eta[v] = (double*)hb;
+    else
+      cudaGetLastError();
+  }
   // rho_ref is defined where the volume is missing too (reference.py:71), so a call that wants it back
   // moves every row as it is
   PackPlan plan;
@@ -635,9 +676,9 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
     // the heights of this window go home while the next windows come in (PCIe carries both directions)
     const size_t eoff = (size_t)t_first * ncol, ebytes = (size_t)nt_w * ncol * sizeof(double);
     ML_CUDA(cudaStreamWaitEvent(r.back, r.freed[b], 0));
-    ML_CUDA(cudaMemcpyAsync(eta + eoff, (double*)dEta + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
-    if (eta_thermo) ML_CUDA(cudaMemcpyAsync(eta_thermo + eoff, (double*)dEtaT + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
-    if (eta_halo) ML_CUDA(cudaMemcpyAsync(eta_halo + eoff, (double*)dEtaH + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
+    ML_CUDA(cudaMemcpyAsync(host_eta[0] + eoff, (double*)dEta + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
+    if (eta_thermo) ML_CUDA(cudaMemcpyAsync(host_eta[1] + eoff, (double*)dEtaT + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
+    if (eta_halo) ML_CUDA(cudaMemcpyAsync(host_eta[2] + eoff, (double*)dEtaH + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
   }
   const double t_windows = now_ms();
   if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
@@ -645,6 +686,8 @@ static int steric_local_host_impl(int eos, int dtype, const void* T, const void*
   ML_CUDA(cudaStreamSynchronize(r.comp));
   ML_CUDA(cudaStreamSynchronize(r.back));
   ML_CUDA(cudaStreamSynchronize(r.copy));
+  for (int v = 0; v < 3; ++v)
+    if (user_eta[v] != nullptr && host_eta[v] != user_eta[v]) parallel_copy(r, user_eta[v], host_eta[v], eta_bytes, nthreads);
   r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
   const double t_end = now_ms();
   r.last_ms[0] = t_plan - t_call;
