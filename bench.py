@@ -11,7 +11,9 @@ Inputs (11.2 GB) are far larger than L2 (126 MB), so no flush is needed between 
 
 Prints ONE JSON line (rank 0).  ``value`` = points of all ranks / max-over-ranks device time;
 ``e2e`` = the same metric through the host-buffer C-ABI entry (``ml_steric_local_host``:
-pinned host -> device copies and the eta read-back inside the timed region);
+pinned host -> device copies and the eta read-back inside the timed region; level rows cross
+PCIe as they are or packed to the cells the reference reads, ``e2e.every_row_dense`` is the A/B,
+``e2e.public_api_numpy_dataset`` the public ``steric(dset)`` call on pageable numpy fields);
 ``roofline`` is for the dominant kernel, timed with CUDA events on its stream;
 ``cpu_baseline`` = the numpy oracle (a port of the reference's path) on a bounded sample.
 ``--impl reference`` times only that CPU path, threaded over all host cores.
