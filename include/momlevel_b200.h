@@ -281,7 +281,10 @@ int ml_host_release(void);
  * packers and the pinned staging, full rows included, and volcello and the heights cross through pinned
  * buffers of the library's own, unless mode is 0.
  *   ml_host_set_packing(mode, threads)  mode 0 = never pack, 1 = balance dynamically (default),
- *                                       2 = pack every row that has absent cells; threads <= 0 keeps
+ *                                       2 = pack every row that has absent cells, 3 = as 1 but the packed
+ *                                       rows wait for the copy engine in a six-row ring of pinned memory
+ *                                       written with ordinary stores (meant to stay in the last-level cache,
+ *                                       so that the packed bytes never touch DRAM); threads <= 0 keeps
  *                                       the default (half the calling thread's CPU affinity count).
  *                                       Applies to the calling host thread.
  *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed
@@ -294,6 +297,7 @@ int ml_host_release(void);
  *                       group; row_count [nrows]; returns the total
  *   ml_pack_rows        present cells of groups [g0, g1) of one T row and one S row, written to
  *                       t_out / s_out (the row's packed base) at offset before[g0]
+ *   ml_pack_rows_cached the same with ordinary instead of non-temporal stores (mode 3)
  *   ml_pack_simd        512 when the AVX-512 bodies are in use, 0 for the scalar ones
  * ------------------------------------------------------------------------------------- */
 int ml_host_set_packing(int mode, int threads);
@@ -304,6 +308,8 @@ uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t ncol, uint32_
                             uint32_t* before, uint64_t* row_count);
 void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,
                   int64_t g0, int64_t g1, int64_t ncol, float* t_out, float* s_out);
+void ml_pack_rows_cached(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,
+                         int64_t g0, int64_t g1, int64_t ncol, float* t_out, float* s_out);
 int ml_pack_simd(void);
 
 /* =======================================================================================

@@ -48,6 +48,7 @@ EXPORTS = {
     "ml_host_last_timings": (_i, [_vp]),
     "ml_pack_index_rows": (ctypes.c_uint64, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ml_pack_rows": (None, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
+    "ml_pack_rows_cached": (None, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ml_pack_simd": (_i, []),
     "ml_calc_n2": (_i, [_i, _i, _vp, _vp, _vp, _d, _d, _i, _i, _i64, _i64, _i64, _vp, _vp]),
     "ml_adjust_negative_n2": (_i, [_vp, _i, _i64, _i64, _i64, _vp, _vp]),

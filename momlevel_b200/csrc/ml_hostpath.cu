@@ -91,6 +91,7 @@ struct Resources {
   static constexpr int kSlots = 28;
   static constexpr int kHostSlots = 12;
   static constexpr int kRing = 3;  // dense rows in flight on the copy stream
+  static constexpr int kStageRing = 6;  // packed rows between the packers and the copy engine (packing mode 3)
   void* buf[kSlots] = {nullptr};
   size_t cap[kSlots] = {0};
   void* hbuf[kHostSlots] = {nullptr};
@@ -99,6 +100,7 @@ struct Resources {
   cudaStream_t copy = nullptr, comp = nullptr, back = nullptr;  // host->device, kernels, device->host
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
   cudaEvent_t ring[kRing] = {nullptr};
+  cudaEvent_t slot_done[kStageRing] = {nullptr};  // the copies out of a slot of the staging ring have finished
   Pool pool;
   // settings and accounting of the packed transfer (ml_host_set_packing and friends)
   int pack_mode = 1, pack_threads = 0;
@@ -125,6 +127,10 @@ struct Resources {
       if (ring[i]) cudaEventDestroy(ring[i]);
       ring[i] = nullptr;
     }
+    for (int i = 0; i < kStageRing; ++i) {
+      if (slot_done[i]) cudaEventDestroy(slot_done[i]);
+      slot_done[i] = nullptr;
+    }
     if (copy) cudaStreamDestroy(copy);
     if (comp) cudaStreamDestroy(comp);
     if (back) cudaStreamDestroy(back);
@@ -149,6 +155,9 @@ struct Resources {
     }
     for (int i = 0; i < kRing; ++i)
       if (!ring[i] && (e = cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    for (int i = 0; i < kStageRing; ++i)
+      if (!slot_done[i] && (e = cudaEventCreateWithFlags(&slot_done[i], cudaEventDisableTiming)) != cudaSuccess)
+        return e;
     return cudaSuccess;
   }
   // slot i grows to at least `bytes`
@@ -253,6 +262,12 @@ struct PackPlan {
   uint8_t *flags[2] = {nullptr, nullptr}, *d_flags[2] = {nullptr, nullptr};  // [t][z]: 1 = row crossed packed
   int64_t rows_total = 0, rows_packed = 0;
   bool all_staged = false;  // pageable source: no row is copied straight from the caller's buffer
+  // mode 3: packed rows wait for the copy engine in a ring of kStageRing row slots (T half, S half) that is
+  // small enough to stay in the last-level cache, instead of in staging the size of the window
+  bool ring = false;
+  float* ring_buf = nullptr;
+  int64_t ring_next = 0;                                    // rows that have taken a slot so far (under the lock)
+  std::atomic<int64_t> slot_queued[Resources::kStageRing];  // rows whose copies out of the slot have been queued
 };
 
 constexpr double kPackableBelow = 0.9;  // a level with more of its cells present than this is never compressed
@@ -350,10 +365,21 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   if (plan.first_packable == (int)nz || plan.nwet == 0) return ML_OK;  // nothing worth compressing
   const size_t stage_bytes = (size_t)spw * plan.nwet * 4;
   const size_t flag_bytes = (size_t)spw * (size_t)nz;
+  plan.ring = plan.mode == 3;
+  plan.ring_next = 0;
+  for (auto& q : plan.slot_queued) q.store(0, std::memory_order_relaxed);
+  if (plan.ring) {
+    void* h;
+    if (r.halloc(3, &h, (size_t)Resources::kStageRing * 2 * (size_t)ncol * 4) != cudaSuccess) {
+      cudaGetLastError();
+      return ML_OK;
+    }
+    plan.ring_buf = (float*)h;
+  }
   for (int b = 0; b < 2; ++b) {
     for (int f = 0; f < 2; ++f) {
-      void *h, *d;
-      if (r.halloc(3 + 2 * b + f, &h, stage_bytes) != cudaSuccess) {
+      void *h = nullptr, *d;
+      if (!plan.ring && r.halloc(3 + 2 * b + f, &h, stage_bytes) != cudaSuccess) {
         cudaGetLastError();
         return ML_OK;
       }
@@ -418,9 +444,9 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   struct Shared {
     std::mutex m;
     int lo = 0, hi = 0, hi_min = 0, lo_end = 0;
-    int cur = -1, next_seg = 0;
+    int cur = -1, next_seg = 0, cur_slot = 0;
     int packed = 0;
-    cudaError_t err = cudaSuccess;
+    std::atomic<int> err{(int)cudaSuccess};  // first CUDA error of any thread; set without the lock
   } sh;
   sh.hi = nrows - 1;
   sh.hi_min = plan.first_packable * (int)nt_w;
@@ -435,39 +461,61 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   r.pool.start(plan.threads, [&, dev](int) {
     cudaSetDevice(dev);
     for (;;) {
-      int pos, seg;
+      int pos, seg, slot;
       {
         std::lock_guard<std::mutex> l(sh.m);
         if (sh.next_seg >= plan.nseg) {
-          if (sh.hi < sh.lo || sh.hi < sh.hi_min || sh.err != cudaSuccess) break;
+          if (sh.hi < sh.lo || sh.hi < sh.hi_min || sh.err.load() != (int)cudaSuccess) break;
           sh.cur = sh.hi--;
           sh.next_seg = 0;
           sh.packed++;
+          if (plan.ring) {
+            // the next slot of the ring, once the copy engine has emptied it.  Waiting here, with the lock held,
+            // keeps every packer (they all want this row) no more than kStageRing rows ahead of the copies.
+            const int64_t turn = plan.ring_next++;
+            sh.cur_slot = (int)(turn % Resources::kStageRing);
+            // the slot's previous row must have been queued (its last segment may still be with a thread that
+            // lost its core) before the event below speaks for it
+            while (plan.slot_queued[sh.cur_slot].load(std::memory_order_acquire) < turn / Resources::kStageRing &&
+                   sh.err.load() == (int)cudaSuccess)
+              std::this_thread::yield();
+            const cudaError_t e = cudaEventSynchronize(r.slot_done[sh.cur_slot]);
+            if (e != cudaSuccess) {
+              sh.err.store((int)e);
+              break;
+            }
+          }
         }
         pos = sh.cur;
         seg = sh.next_seg++;
+        slot = sh.cur_slot;
       }
       int t, z;
       row_of(pos, t, z);
       const size_t src = ((size_t)t * (size_t)nz + (size_t)z) * (size_t)ncol;
       const size_t dst = (size_t)t * plan.nwet + plan.lvloff[z];
       const int64_t g0 = plan.ngrp * seg / plan.nseg, g1 = plan.ngrp * (seg + 1) / plan.nseg;
-      ml_pack_rows(Th + src, Sh + src, plan.words + (size_t)z * plan.ngrp, plan.before + (size_t)z * plan.ngrp, g0, g1,
-                   ncol, stT + dst, stS + dst);
+      float* rowT = plan.ring ? plan.ring_buf + (size_t)slot * 2 * (size_t)ncol : stT + dst;
+      float* rowS = plan.ring ? rowT + (size_t)ncol : stS + dst;
+      if (plan.ring)
+        ml_pack_rows_cached(Th + src, Sh + src, plan.words + (size_t)z * plan.ngrp,
+                            plan.before + (size_t)z * plan.ngrp, g0, g1, ncol, rowT, rowS);
+      else
+        ml_pack_rows(Th + src, Sh + src, plan.words + (size_t)z * plan.ngrp, plan.before + (size_t)z * plan.ngrp, g0,
+                     g1, ncol, rowT, rowS);
       const int row = t * (int)nz + z;
       if (done[row].fetch_add(1, std::memory_order_acq_rel) + 1 == plan.nseg) {  // the row is whole: queue it
         const size_t nb = (size_t)(plan.lvloff[z + 1] - plan.lvloff[z]) * 4;
         flags[row] = 1;
         cudaError_t e = cudaSuccess;
         if (nb) {
-          e = cudaMemcpyAsync(dpT + dst, stT + dst, nb, cudaMemcpyHostToDevice, r.copy);
-          if (e == cudaSuccess) e = cudaMemcpyAsync(dpS + dst, stS + dst, nb, cudaMemcpyHostToDevice, r.copy);
+          e = cudaMemcpyAsync(dpT + dst, rowT, nb, cudaMemcpyHostToDevice, r.copy);
+          if (e == cudaSuccess) e = cudaMemcpyAsync(dpS + dst, rowS, nb, cudaMemcpyHostToDevice, r.copy);
           r.h2d_bytes += 2 * nb;
         }
-        if (e != cudaSuccess) {
-          std::lock_guard<std::mutex> l(sh.m);
-          sh.err = e;
-        }
+        if (plan.ring && e == cudaSuccess) e = cudaEventRecord(r.slot_done[slot], r.copy);
+        if (e != cudaSuccess) sh.err.store((int)e);
+        if (plan.ring) plan.slot_queued[slot].fetch_add(1, std::memory_order_release);
       }
     }
   });
@@ -491,12 +539,9 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
     r.h2d_bytes += 2 * row_bytes;
     if ((err = cudaEventRecord(ev, r.copy)) != cudaSuccess) break;
   }
-  if (err != cudaSuccess) {  // stop the workers before the error leaves with their captured locals
-    std::lock_guard<std::mutex> l(sh.m);
-    sh.err = err;
-  }
+  if (err != cudaSuccess) sh.err.store((int)err);  // stops the workers; wait for them before the locals they captured go
   r.pool.wait();
-  if (sh.err != cudaSuccess) return cuda_fail(sh.err, "packed transfer");
+  if (sh.err.load() != (int)cudaSuccess) return cuda_fail((cudaError_t)sh.err.load(), "packed transfer");
   plan.rows_total += nrows;
   plan.rows_packed += sh.packed;
 
@@ -524,7 +569,7 @@ extern "C" int ml_host_release(void) {
 }
 
 extern "C" int ml_host_set_packing(int mode, int threads) {
-  if (mode < 0 || mode > 2) return ml::fail(ML_ERR_MODE, "packing mode %d is not 0, 1 or 2", mode);
+  if (mode < 0 || mode > 3) return ml::fail(ML_ERR_MODE, "packing mode %d is not 0, 1, 2 or 3", mode);
   Resources& r = resources();
   r.pack_mode = mode;
   r.pack_threads = threads > 0 ? threads : 0;

@@ -100,7 +100,7 @@ void pack_scalar(const float* t, const float* s, const uint32_t* words, int64_t 
 __attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx512(const float* t, const float* s,
                                                                                  const uint32_t* words, int64_t g0,
                                                                                  int64_t g1, int64_t ncol,
-                                                                                 float* t_out, float* s_out) {
+                                                                                 float* t_out, float* s_out, bool) {
   // a ragged last group is left to the scalar body (a 16-lane load would run past the row)
   const int64_t gfull = (g1 * 32 <= ncol) ? g1 : g1 - 1;
   for (int64_t g = g0; g < gfull; ++g) {
@@ -146,7 +146,9 @@ struct LineWriter {
   float* line;  // 64-byte aligned destination of buf[0]
   int n;        // floats in buf (the first `head` of them are not ours)
   int head;
-  __attribute__((target("avx512f,avx512bw,avx512vl"))) explicit LineWriter(float* dst) {
+  bool cached;  // ordinary stores: the destination is a small ring meant to stay in the last-level cache
+  __attribute__((target("avx512f,avx512bw,avx512vl"))) LineWriter(float* dst, bool keep_in_cache) {
+    cached = keep_in_cache;
     head = (int)(((uintptr_t)dst & 63u) >> 2);
     line = dst - head;
     n = head;
@@ -164,7 +166,10 @@ struct LineWriter {
       head = 0;
       l = 1;
     }
-    for (; l < nl; ++l) _mm512_stream_ps(line + l * 16, _mm512_load_ps(buf + l * 16));
+    if (cached)
+      for (; l < nl; ++l) _mm512_store_ps(line + l * 16, _mm512_load_ps(buf + l * 16));
+    else
+      for (; l < nl; ++l) _mm512_stream_ps(line + l * 16, _mm512_load_ps(buf + l * 16));
     _mm512_store_ps(buf, _mm512_load_ps(buf + nl * 16));
     line += nl * 16;
     n &= 15;
@@ -182,10 +187,11 @@ struct LineWriter {
 __attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx512(const float* t, const float* s,
                                                                                  const uint32_t* words, int64_t g0,
                                                                                  int64_t g1, int64_t ncol,
-                                                                                 float* t_out, float* s_out) {
+                                                                                 float* t_out, float* s_out,
+                                                                                 bool cached) {
   // a ragged last group is left to the scalar body (a 16-lane load would run past the row)
   const int64_t gfull = (g1 * 32 <= ncol) ? g1 : g1 - 1;
-  LineWriter wt(t_out), ws(s_out);
+  LineWriter wt(t_out, cached), ws(s_out, cached);
   int64_t written = 0;
   for (int64_t g = g0; g < gfull; ++g) {
     const uint32_t m = words[g];
@@ -222,15 +228,26 @@ extern "C" uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t nc
   return total;
 }
 
-extern "C" void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,
-                             int64_t g0, int64_t g1, int64_t ncol, float* t_out, float* s_out) {
+static void pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before, int64_t g0,
+                      int64_t g1, int64_t ncol, float* t_out, float* s_out, bool cached) {
   if (g0 >= g1) return;
   t_out += before[g0];
   s_out += before[g0];
   if (has_avx512())
-    pack_avx512(t_row, s_row, words, g0, g1, ncol, t_out, s_out);
+    pack_avx512(t_row, s_row, words, g0, g1, ncol, t_out, s_out, cached);
   else
     pack_scalar(t_row, s_row, words, g0, g1, t_out, s_out);
+}
+
+extern "C" void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,
+                             int64_t g0, int64_t g1, int64_t ncol, float* t_out, float* s_out) {
+  pack_rows(t_row, s_row, words, before, g0, g1, ncol, t_out, s_out, false);
+}
+
+extern "C" void ml_pack_rows_cached(const float* t_row, const float* s_row, const uint32_t* words,
+                                    const uint32_t* before, int64_t g0, int64_t g1, int64_t ncol, float* t_out,
+                                    float* s_out) {
+  pack_rows(t_row, s_row, words, before, g0, g1, ncol, t_out, s_out, true);
 }
 
 extern "C" int ml_pack_simd(void) { return has_avx512() ? 512 : 0; }

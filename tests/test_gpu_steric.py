@@ -746,7 +746,7 @@ def test_host_packed_transfer_is_bit_identical(ml, shape):
         assert frac0 == 0.0 and bytes0 >= dense_bytes
         _close_nan(eta0.numpy(), want, atol=ETA_ATOL)
         assert sums0[1] == pytest.approx(oref["masso"], rel=1e-12) and sums0[0] == pytest.approx(oref["volo"], rel=1e-12)
-        for mode, threads, spw in ((2, 0, 1), (2, 3, 2), (2, 1, shape[0]), (1, 0, 1), (1, 2, 3)):
+        for mode, threads, spw in ((2, 0, 1), (2, 3, 2), (2, 1, shape[0]), (1, 0, 1), (1, 2, 3), (3, 0, 1), (3, 3, 2)):
             core.host_packing(mode, threads)
             eta, rho, sums = core.steric_local_host(T, S, V, z_i, depth.numpy(), pres, steps_per_window=spw)
             nbytes, frac = core.host_last_transfer()
@@ -773,7 +773,7 @@ def test_host_packed_transfer_is_bit_identical(ml, shape):
         # the global masses through the same transfer
         core.host_packing(0)
         m0 = core.steric_global_host(T, S, V, pres, steps_per_window=2)
-        for mode in (2, 1):
+        for mode in (2, 3, 1):
             core.host_packing(mode)
             m = core.steric_global_host(T, S, V, pres, steps_per_window=1)
             assert torch.allclose(m, m0, rtol=1e-14, atol=0)
@@ -824,7 +824,7 @@ def test_host_packed_transfer_from_pinned_memory(ml):
         core.host_packing(0)
         eta0, _, sums0 = core.steric_local_host(Tp, Sp, Vp, *args)
         seen = set()
-        for mode, threads in ((1, 0), (1, 1), (2, 0), (1, 4), (2, 2)):
+        for mode, threads in ((1, 0), (1, 1), (2, 0), (1, 4), (2, 2), (3, 0), (3, 5)):
             core.host_packing(mode, threads)
             for spw in (1, 3):
                 eta, _, sums = core.steric_local_host(Tp, Sp, Vp, *args, steps_per_window=spw)

@@ -1,7 +1,7 @@
 """A/B of the host path on an OM4p25 year: how level rows cross PCIe (as they are / packed / balanced), how many
 host threads pack, how many steps a window holds.  One JSON line per setting.
 
-    python tools/e2e_sweep.py [reps]
+    python tools/e2e_sweep.py [reps] [ring]
 """
 
 import json
@@ -18,6 +18,7 @@ from momlevel_b200 import core, synth  # noqa: E402
 
 def main():
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+    quick = len(sys.argv) > 2 and sys.argv[2] == "ring"  # only the staging-ring A/B
     nt, nz, ny, nx = synth.CONFIGS["om4p25"]
     dev = torch.device("cuda", 0)
     grid = synth.make_grid(nz, ny, nx, seed=123, device=dev)
@@ -32,6 +33,8 @@ def main():
     first = None
     settings = [(0, 0, 1), (1, 0, 1), (2, 0, 1), (1, 4, 1), (1, 6, 1), (1, 8, 1), (1, 10, 1), (1, 12, 1), (2, 8, 1),
                 (2, 12, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4), (1, 0, 6), (1, 0, 12), (1, 8, 3), (1, 0, 1)]
+    if quick:
+        settings = [(1, 8, 1), (3, 8, 1), (3, 0, 1), (3, 12, 1), (3, 6, 1), (1, 0, 1), (3, 15, 1)]
     for mode, threads, spw in settings:
         core.host_packing(mode, threads)
         run = lambda: core.steric_local_host(Th, Sh, Vh, z_i, depth, pres, steps_per_window=spw, eta_out=eta_h)  # noqa: E731
