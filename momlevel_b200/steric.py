@@ -108,8 +108,18 @@ def steric(
 
     if domain == "global":
         # steric.py:134-147
-        masso = core.steric_global(thetao.data, so.data, reference["volcello"].data, pres, eos=equation_of_state,
-                                   t_bcast=t_bcast, s_bcast=s_bcast).cpu().numpy()
+        v_ref = reference["volcello"].data
+        if (variant == "steric" and _host_resident(dset, tcoord, zcoord, zbounds, need_depth=False)
+                and not (isinstance(v_ref, torch.Tensor) and v_ref.is_cuda)):
+            # fields in host memory (a daily series does not fit in HBM): streamed through device windows,
+            # level rows packed to the cells of the reference volume on the way (ml_steric_global_host)
+            step_bytes = 2 * int(np.prod(full.shape[1:])) * 4
+            spw = int(min(max(1, -(-(1 << 28) // step_bytes)), full.shape[0]))
+            masso = core.steric_global_host(thetao.data, so.data, v_ref, _host_numpy(pres), eos=equation_of_state,
+                                            steps_per_window=spw).numpy()
+        else:
+            masso = core.steric_global(thetao.data, so.data, v_ref, pres, eos=equation_of_state,
+                                       t_bcast=t_bcast, s_bcast=s_bcast).cpu().numpy()
         volo, rhoga = float(reference["volo"]), float(reference["rhoga"])
         expansion_coeff = np.log(rhoga / (masso / volo))
         reference_height = volo / float(reference["areacello"].sum())
@@ -226,17 +236,18 @@ def _reference_from_pass(dset, tcoord, eos, rho, sums, pres=None):
 HOST_ROUTE_MIN_BYTES = 1 << 26  # fields smaller than this are simply copied to the device
 
 
-def _host_resident(dset, tcoord, zcoord, zbounds):
+def _host_resident(dset, tcoord, zcoord, zbounds, need_depth=True):
     """Whether ``steric()`` should take the host route: every input lives in host memory (numpy or CPU tensors),
     the fields are laid out ``(time, z, y, x)`` in one piece, and there is enough of them for the streaming to pay."""
     try:
-        arrs = [dset[n].data for n in ("thetao", "so", "volcello", "deptho", zcoord, zbounds)]
+        names = ("thetao", "so", "volcello", zcoord) + (("deptho", zbounds) if need_depth else ())
+        arrs = [dset[n].data for n in names]
         if any(isinstance(a, torch.Tensor) and a.is_cuda for a in arrs):
             return False
         T, S, V = (dset[n] for n in ("thetao", "so", "volcello"))
         if not (T.dims == S.dims == V.dims and T.ndim == 4 and T.dims[0] == tcoord and T.dims[1] == zcoord):
             return False
-        if not (T.shape == S.shape == V.shape and dset["deptho"].shape == T.shape[2:]):
+        if not (T.shape == S.shape == V.shape and (not need_depth or dset["deptho"].shape == T.shape[2:])):
             return False
         for a in arrs[:2]:
             if not (a.is_contiguous() if isinstance(a, torch.Tensor) else a.flags["C_CONTIGUOUS"]):
@@ -355,8 +366,18 @@ def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rh
         if verbose:
             print("Generating reference state from first timestep")
         V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
-        etas, rho, sums = core.steric_local_variants(*args, V0, *tail, **kw)
-        reference = _reference_from_pass(dset, tcoord, equation_of_state, rho, sums)
+        if _host_resident(dset, tcoord, zcoord, zbounds):
+            # fields in host memory: one pass over PCIe feeds the three integrations (ml_steric_local_variants_host)
+            step_bytes = 2 * int(np.prod(full.shape[1:])) * 4
+            spw = int(min(max(1, -(-(1 << 28) // step_bytes)), full.shape[0]))
+            etas, _, (volo, masso) = core.steric_local_host(
+                *args, V0, _host_numpy(dset[zbounds].data), _host_numpy(dset["deptho"].data), _host_numpy(pres),
+                steps_per_window=spw, variants=True, **kw)
+            reference = _reference_from_pass(dset, tcoord, equation_of_state, None,
+                                             torch.tensor([volo, masso], dtype=torch.float64), pres)
+        else:
+            etas, rho, sums = core.steric_local_variants(*args, V0, *tail, **kw)
+            reference = _reference_from_pass(dset, tcoord, equation_of_state, rho, sums)
         validate_dataset(reference, reference=True, strict=strict)
     result = Dataset()
     for variant in VARIANTS:

@@ -220,7 +220,8 @@ def test_steric_routes_host_resident_fields_to_the_host_entry(monkeypatch):
         eta = torch.zeros((T.shape[0],) + tuple(T.shape[2:]), dtype=torch.float64)
         if not variants:
             return eta, None, (2.0, 2070.0)
-        return {"steric": eta, **{v: eta + 1.0 for v in variants}}, None, (2.0, 2070.0)
+        names = ("thermosteric", "halosteric") if variants is True else variants
+        return {"steric": eta, **{v: eta + 1.0 for v in names}}, None, (2.0, 2070.0)
 
     monkeypatch.setattr(core, "steric_local_host", fake)
     for variant, level in (("steric", 0.0), ("thermosteric", 1.0), ("halosteric", 1.0)):
@@ -233,8 +234,36 @@ def test_steric_routes_host_resident_fields_to_the_host_entry(monkeypatch):
     assert [c[5] for c in calls] == [False, ("thermosteric",), ("halosteric",)]
     assert all(c[0] == (12, 20, 32) and c[1:4] == ("ndarray",) * 3 and c[4] == 5 and c[6] == "Wright"
                and c[7] == 1030.0 for c in calls)
-    # a supplied reference, the global domain and device-resident fields keep their own routes
+    # steric_variants: one host call for the three heights
     calls.clear()
-    with pytest.raises(ml._lib.MLError):  # reaches the device check of the ordinary route
-        ml.steric(small, domain="global")
-    assert calls == []
+    res, ref = ml.steric_variants(small)
+    assert [c[5] for c in calls] == [True] and calls[0][4] == 5
+    assert float(res["steric"].values.max()) == 0.0 and float(res["halosteric"].values.min()) == 1.0
+    assert float(ref["rhoga"]) == 1035.0
+    # the global domain: the masses of host-resident fields come from the streaming entry point as well
+    from oracle import steric as osteric
+
+    f64 = lambda k: small[k].values.astype(np.float64)  # noqa: E731
+    o = osteric.reference_state(f64("thetao"), f64("so"), f64("volcello"), f64("areacello"), f64("z_l"))
+    ref_in = ml.Dataset()
+    for k in ("thetao", "so", "volcello", "rho"):
+        ref_in[k] = ml.DataArray(o[k], ("z_l", "yh", "xh"))
+    for k in ("volo", "masso", "rhoga"):
+        ref_in[k] = ml.DataArray(np.float64(o[k]), ())
+    ref_in["areacello"] = small["areacello"]
+    gcalls = []
+
+    def fake_global(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
+        gcalls.append((tuple(T.shape), tuple(v_ref.shape), type(p_level).__name__, steps_per_window, eos))
+        return torch.full((T.shape[0],), float(o["masso"]), dtype=torch.float64)
+
+    monkeypatch.setattr(core, "steric_global_host", fake_global)
+    calls.clear()
+    res, _ = ml.steric(small, domain="global", reference=ref_in)
+    assert gcalls == [((5, 12, 20, 32), (12, 20, 32), "ndarray", 5, "Wright")] and calls == []
+    assert res["steric"].shape == (5,) and np.allclose(res["steric"].values, 0.0, atol=1e-12)  # M(t) = M_ref
+    assert float(res["reference_height"]) == pytest.approx(o["volo"] / small["areacello"].values.sum())
+    # thermosteric / halosteric in the global domain hold one field at its reference slab: the ordinary route
+    with pytest.raises(ml._lib.MLError):  # reaches its device check
+        ml.steric(small, domain="global", reference=ref_in, variant="thermosteric")
+    assert len(gcalls) == 1
