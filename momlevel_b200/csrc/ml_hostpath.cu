@@ -271,7 +271,16 @@ struct PackPlan {
 };
 
 constexpr double kPackableBelow = 0.9;  // a level with more of its cells present than this is never compressed
+#ifdef ML_HOSTPATH_TEST_HOOKS
+constexpr int64_t kSegmentGroups = 8;  // small rows are cut into several segments too
+#else
+constexpr int64_t kSegmentGroups = 2048;  // 32-column groups per segment of a row (64 K columns, 256 KB per field)
+#endif
 
+// tests/sim/hostpath_sim.cpp compiles this file with g++ against a simulated CUDA runtime (streams that run
+// behind the host, events, pinned / pageable bookkeeping) to put the threads and the buffer recycling below under
+// ThreadSanitizer on a box without a GPU; it brings its own launch_unpack().
+#ifndef ML_HOSTPATH_TEST_HOOKS
 __global__ void __launch_bounds__(256) k_unpack_rows(const float* __restrict__ pT, const float* __restrict__ pS,
                                                       float* __restrict__ T, float* __restrict__ S,
                                                       const uint32_t* __restrict__ words,
@@ -304,6 +313,15 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const float* __restrict__ p
   }
 }
 
+int launch_unpack(cudaStream_t stream, int nrows, int xblocks, const float* pT, const float* pS, float* T, float* S,
+                  const uint32_t* words, const uint32_t* before, const uint64_t* lvloff, const uint8_t* flags, int nz,
+                  int64_t ncol, int64_t ngrp, uint64_t nwet) {
+  k_unpack_rows<<<(unsigned)((int64_t)nrows * xblocks), 256, 0, stream>>>(pT, pS, T, S, words, before, lvloff, flags, nz,
+                                                                          ncol, ngrp, nwet, xblocks);
+  return ml::launched("k_unpack_rows");
+}
+#endif
+
 // Presence words of the reference volcello, the device copies of them and the staging buffers.
 // Leaves plan.on false (every row crosses as it is) when packing is off, cannot help or cannot get
 // its pinned memory.
@@ -318,7 +336,7 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   plan.ncol = ncol;
   plan.ngrp = (ncol + 31) / 32;
   plan.threads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
-  plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / 2048));
+  plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / kSegmentGroups));
   const size_t nw = (size_t)nz * (size_t)plan.ngrp;
   void *hw, *hb, *hl;
   if (r.halloc(0, &hw, nw * 4) != cudaSuccess || r.halloc(1, &hb, nw * 4) != cudaSuccess ||
@@ -553,10 +571,9 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
   if (sh.packed) {
     const int xblocks = (int)((plan.ngrp + 31) / 32);
-    k_unpack_rows<<<(unsigned)((int64_t)nrows * xblocks), 256, 0, r.comp>>>(
-        dpT, dpS, (float*)dT, (float*)dS, plan.d_words, plan.d_before, plan.d_lvloff, plan.d_flags[b], (int)nz, ncol,
-        plan.ngrp, plan.nwet, xblocks);
-    if (int rc = launched("k_unpack_rows")) return rc;
+    if (int rc = launch_unpack(r.comp, nrows, xblocks, dpT, dpS, (float*)dT, (float*)dS, plan.d_words, plan.d_before,
+                               plan.d_lvloff, plan.d_flags[b], (int)nz, ncol, plan.ngrp, plan.nwet))
+      return rc;
   }
   return ML_OK;
 }

@@ -1,0 +1,239 @@
+// hostpath_sim.cpp -- the host entry points of libmomlevel_b200 (csrc/ml_hostpath.cu + csrc/ml_pack.cpp) run on a
+// box without a GPU, against the simulated runtime of tests/sim/cuda_runtime.h and under ThreadSanitizer.
+//
+// What is under test is everything the *_host entry points do on the host: the windows, the double buffers and
+// their events, the presence index, the packers and the calling thread working towards each other, the staging
+// ring, the pinned bounce buffers of pageable operands.  The device kernels are replaced by toy ones with the
+// same data dependences (a "density" T + 2 S, used only where the reference volume is present); the real kernels
+// are tested on the GPU.  Every combination must give, bit for bit, what the toy kernels give on the caller's
+// whole arrays -- whichever rows crossed packed -- and ThreadSanitizer must stay silent.
+//
+//   g++ -std=c++17 -O1 -g -fsanitize=thread -pthread -I tests/sim -x c++ tests/sim/hostpath_sim.cpp -o hostpath_sim
+#define ML_HOSTPATH_TEST_HOOKS
+#include <cuda_runtime.h>  // tests/sim/cuda_runtime.h
+
+#include <math.h>
+#include <stdio.h>
+
+#include <random>
+#include <vector>
+
+#include "../../momlevel_b200/csrc/ml_host.cuh"
+
+namespace ml {
+ThreadState& tls() {
+  static thread_local ThreadState s = {{0}, 0, 0, 0};
+  return s;
+}
+}  // namespace ml
+
+// ---- toy kernels: run on the stream they are given, like the real ones -----------------------------------------
+
+static inline double toy_rho(float t, float s) { return (double)t + 2.0 * (double)s; }
+static inline bool present(float v) { return !std::isnan(v); }
+
+static void toy_local(const float* T, const float* S, int tb, int sb, const double* rho_ref, const float* V, int64_t nt,
+                      int64_t nz, int64_t ncol, double* eta) {
+  for (int64_t t = 0; t < nt; ++t)
+    for (int64_t c = 0; c < ncol; ++c) {
+      double acc = 0.0;
+      for (int64_t z = 0; z < nz; ++z) {
+        const size_t i = (size_t)z * ncol + c;
+        if (!present(V[i])) continue;
+        const double d = toy_rho(T[(tb ? 0 : (size_t)t * nz * ncol) + i], S[(sb ? 0 : (size_t)t * nz * ncol) + i]) - rho_ref[i];
+        if (!std::isnan(d)) acc += d;
+      }
+      eta[(size_t)t * ncol + c] = acc;
+    }
+}
+
+static void toy_reference(const float* T, const float* S, const float* V, int64_t nz, int64_t ncol, double* rho_ref,
+                          double* sums) {
+  double volo = 0.0, masso = 0.0;
+  for (size_t i = 0; i < (size_t)nz * ncol; ++i) {
+    rho_ref[i] = toy_rho(T[i], S[i]);
+    if (!present(V[i])) continue;
+    volo += V[i];
+    if (!std::isnan(rho_ref[i])) masso += rho_ref[i] * V[i];
+  }
+  sums[0] = volo;
+  sums[1] = masso;
+}
+
+static void toy_global(const float* T, const float* S, const float* V, int64_t nt, int64_t nz, int64_t ncol,
+                       double* masso) {
+  for (int64_t t = 0; t < nt; ++t) {
+    double m = 0.0;
+    for (size_t i = 0; i < (size_t)nz * ncol; ++i) {
+      if (!present(V[i])) continue;
+      const double x = toy_rho(T[(size_t)t * nz * ncol + i], S[(size_t)t * nz * ncol + i]) * V[i];
+      if (!std::isnan(x)) m += x;
+    }
+    masso[t] = m;
+  }
+}
+
+extern "C" size_t ml_workspace_bytes(int64_t, int64_t, int64_t) { return 64; }
+
+extern "C" int ml_steric_local(int, int, const void* T, const void* S, int tb, int sb, const double* rho_ref,
+                               const void* v_ref, int, const double*, const double*, const double*, double, int64_t nt,
+                               int64_t nz, int64_t ncol, double* eta, double*, void* stream) {
+  ((cudaStream_t)stream)->enqueue([=] {
+    toy_local((const float*)T, (const float*)S, tb, sb, rho_ref, (const float*)v_ref, nt, nz, ncol, eta);
+  });
+  return 0;
+}
+
+extern "C" int ml_steric_local_selfref(int, int, const void* T, const void* S, int tb, int sb, const void* v_ref, int,
+                                       const double*, const double*, const double*, double, int64_t nt, int64_t nz,
+                                       int64_t ncol, double* eta, double* rho_ref, double* sums, void*, size_t,
+                                       void* stream) {
+  ((cudaStream_t)stream)->enqueue([=] {
+    // the reference state is step 0 of whichever operand varies in time (the other one IS the reference slab)
+    toy_reference((const float*)T, (const float*)S, (const float*)v_ref, nz, ncol, rho_ref, sums);
+    toy_local((const float*)T, (const float*)S, tb, sb, rho_ref, (const float*)v_ref, nt, nz, ncol, eta);
+  });
+  return 0;
+}
+
+extern "C" int ml_steric_global(int, int, const void* T, const void* S, int, int, const void* v_ref, int, const double*,
+                                int64_t nt, int64_t nz, int64_t ncol, double* masso, void*, size_t, void* stream) {
+  ((cudaStream_t)stream)->enqueue([=] { toy_global((const float*)T, (const float*)S, (const float*)v_ref, nt, nz, ncol, masso); });
+  return 0;
+}
+
+// the expansion kernel, as a loop (k_unpack_rows itself is tested on the GPU)
+static int launch_unpack(cudaStream_t stream, int nrows, int, const float* pT, const float* pS, float* T, float* S,
+                         const uint32_t* words, const uint32_t* before, const uint64_t* lvloff, const uint8_t* flags,
+                         int nz, int64_t ncol, int64_t ngrp, uint64_t nwet) {
+  stream->enqueue([=] {
+    for (int row = 0; row < nrows; ++row) {
+      if (!flags[row]) continue;
+      const int t = row / nz, z = row % nz;
+      for (int64_t g = 0; g < ngrp; ++g) {
+        const uint32_t m = words[(size_t)z * ngrp + g];
+        uint64_t src = (uint64_t)t * nwet + lvloff[z] + before[(size_t)z * ngrp + g];
+        for (int lane = 0; lane < 32; ++lane) {
+          const int64_t col = g * 32 + lane;
+          if (col >= ncol) break;
+          const bool here = (m >> lane) & 1u;
+          T[(size_t)row * ncol + col] = here ? pT[src] : NAN;
+          S[(size_t)row * ncol + col] = here ? pS[src] : NAN;
+          src += here;
+        }
+      }
+    }
+  });
+  ml::tls().launches++;
+  return 0;
+}
+
+#include "../../momlevel_b200/csrc/ml_hostpath.cu"
+#include "../../momlevel_b200/csrc/ml_pack.cpp"
+
+// ---- the harness ------------------------------------------------------------------------------------------------
+
+template <class T>
+static T* alloc(size_t n, bool pinned) {
+  void* p = nullptr;
+  if (pinned)
+    cudaHostAlloc(&p, n * sizeof(T), 0);
+  else
+    p = malloc(n * sizeof(T));
+  return (T*)p;
+}
+template <class T>
+static void release(T* p, bool pinned) {
+  if (pinned)
+    cudaFreeHost(p);
+  else
+    free(p);
+}
+
+static bool same(const double* a, const double* b, size_t n) { return memcmp(a, b, n * sizeof(double)) == 0; }
+
+int main() {
+  struct Shape {
+    int64_t nt, nz, ncol;
+  } shapes[] = {{5, 7, 1000}, {4, 3, 33}, {3, 12, 4111}};  // 32, 2 and 129 groups per row: 4, 1 and 16 segments
+  int runs = 0, bad = 0;
+  for (const Shape& sh : shapes) {
+    const int64_t nt = sh.nt, nz = sh.nz, ncol = sh.ncol;
+    const size_t lvl = (size_t)nz * ncol, all = (size_t)nt * lvl;
+    for (int pinned = 0; pinned < 2; ++pinned) {
+      float* T = alloc<float>(all, pinned);
+      float* S = alloc<float>(all, pinned);
+      float* V = alloc<float>(lvl, pinned);
+      double* eta[3];
+      for (auto& e : eta) e = alloc<double>((size_t)nt * ncol, pinned);
+      std::mt19937 rng(17 + (unsigned)ncol);
+      std::uniform_real_distribution<float> u(0.f, 1.f);
+      for (int64_t z = 0; z < nz; ++z) {
+        const float wet = z == 0 ? 0.97f : 1.0f - (float)z / (float)nz;  // level 0 is never worth packing
+        for (int64_t c = 0; c < ncol; ++c) V[(size_t)z * ncol + c] = u(rng) < wet ? 1.0f + u(rng) : NAN;
+      }
+      for (size_t i = 0; i < all; ++i) {
+        const bool here = present(V[i % lvl]);
+        const float r = u(rng);
+        // present cells: data with a few holes; absent cells: NaN or junk the reference never reads
+        T[i] = here ? (r < 0.01f ? NAN : 10.f + 5.f * u(rng)) : (r < 0.5f ? NAN : 99.f);
+        S[i] = here ? (r > 0.99f ? NAN : 35.f + u(rng)) : (r < 0.5f ? NAN : -7.f);
+      }
+      // what the toy kernels give on the caller's whole arrays
+      std::vector<double> rho_ref(lvl), want[3], want_m(nt);
+      double want_sums[2];
+      toy_reference(T, S, V, nz, ncol, rho_ref.data(), want_sums);
+      for (auto& w : want) w.resize((size_t)nt * ncol);
+      toy_local(T, S, 0, 0, rho_ref.data(), V, nt, nz, ncol, want[0].data());
+      toy_local(T, S, 0, 1, rho_ref.data(), V, nt, nz, ncol, want[1].data());  // thermosteric: S held at step 0
+      toy_local(T, S, 1, 0, rho_ref.data(), V, nt, nz, ncol, want[2].data());  // halosteric: T held at step 0
+      toy_global(T, S, V, nt, nz, ncol, want_m.data());
+      std::vector<double> z_i(nz + 1, 0.0), depth(ncol, 1.0), p(nz, 0.0), masso(nt), rho_out(lvl);
+      int packable = 0;  // levels with less than 90 % of their cells present: what mode 2 packs from pinned memory
+      for (int64_t z = 0; z < nz; ++z) {
+        int64_t n = 0;
+        for (int64_t c = 0; c < ncol; ++c) n += present(V[(size_t)z * ncol + c]);
+        packable += (double)n < 0.9 * (double)ncol;
+      }
+      const int spws[] = {1, 2, (int)nt};
+      for (int mode = 0; mode <= 3; ++mode)
+        for (int threads : {1, 3, 7})
+          for (int spw : spws)
+            for (int slow = 0; slow < 2; ++slow) {
+              if (mode == 0 && threads != 1) continue;
+              simcuda::copy_ns_per_kib() = slow ? 300 : 0;
+              ml_host_set_packing(mode, threads);
+              double sums[2] = {0, 0};
+              for (auto& e : eta) memset(e, 0, (size_t)nt * ncol * sizeof(double));
+              int rc = ml_steric_local_variants_host(0, ML_F32, T, S, V, z_i.data(), depth.data(), p.data(), -1.0, nt, nz,
+                                                     ncol, spw, eta[0], eta[1], eta[2], nullptr, sums);
+              const double frac = ml_host_last_packed_fraction();
+              bool ok = rc == 0 && sums[0] == want_sums[0] && sums[1] == want_sums[1];
+              for (int v = 0; v < 3; ++v) ok = ok && same(eta[v], want[v].data(), (size_t)nt * ncol);
+              ok = ok && (mode != 0 || frac == 0.0) && (mode == 0 || pinned || frac == 1.0) &&
+                   (mode != 2 || !pinned || fabs(frac - (double)packable / (double)nz) < 1e-9) &&
+                   (mode == 0 || !pinned || frac <= (double)packable / (double)nz + 1e-9);
+              rc = ml_steric_global_host(0, ML_F32, T, S, V, p.data(), nt, nz, ncol, spw, masso.data());
+              ok = ok && rc == 0 && same(masso.data(), want_m.data(), (size_t)nt);
+              // a call that wants rho_ref back sends every row as it is
+              rc = ml_steric_local_host(0, ML_F32, T, S, V, z_i.data(), depth.data(), p.data(), -1.0, nt, nz, ncol, spw,
+                                        eta[0], rho_out.data(), sums);
+              ok = ok && rc == 0 && ml_host_last_packed_fraction() == 0.0 && same(eta[0], want[0].data(), (size_t)nt * ncol) &&
+                   same(rho_out.data(), rho_ref.data(), lvl);
+              ++runs;
+              if (!ok) {
+                ++bad;
+                printf("MISMATCH nt=%lld nz=%lld ncol=%lld pinned=%d mode=%d threads=%d spw=%d slow=%d frac=%.3f\n",
+                       (long long)nt, (long long)nz, (long long)ncol, pinned, mode, threads, spw, slow, frac);
+              }
+            }
+      release(T, pinned);
+      release(S, pinned);
+      release(V, pinned);
+      for (auto& e : eta) release(e, pinned);
+    }
+  }
+  ml_host_release();
+  printf("hostpath_sim: %d runs, %d mismatches\n", runs, bad);
+  return bad ? 1 : 0;
+}
