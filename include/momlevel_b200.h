@@ -284,7 +284,9 @@ int ml_host_release(void);
  *                                       2 = pack every row that has absent cells, 3 = as 1 but the packed
  *                                       rows wait for the copy engine in a six-row ring of pinned memory
  *                                       written with ordinary stores (meant to stay in the last-level cache,
- *                                       so that the packed bytes never touch DRAM); threads <= 0 keeps
+ *                                       so that the packed bytes never touch DRAM), 4 = as 3 but a row goes
+ *                                       as it is only while no packed row is waiting for the copy stream
+ *                                       (checked on the simulated runtime only; not yet measured); threads <= 0 keeps
  *                                       the default (half the calling thread's CPU affinity count).
  *                                       Applies to the calling host thread.
  *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed

@@ -268,6 +268,9 @@ struct PackPlan {
   float* ring_buf = nullptr;
   int64_t ring_next = 0;                                    // rows that have taken a slot so far (under the lock)
   std::atomic<int64_t> slot_queued[Resources::kStageRing];  // rows whose copies out of the slot have been queued
+  // mode 4: a row goes as it is only while no packed row is waiting for the copy stream
+  bool packed_first = false;
+  std::atomic<int> last_slot{-1};  // slot of the packed row queued last
 };
 
 constexpr double kPackableBelow = 0.9;  // a level with more of its cells present than this is never compressed
@@ -383,7 +386,9 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   if (plan.first_packable == (int)nz || plan.nwet == 0) return ML_OK;  // nothing worth compressing
   const size_t stage_bytes = (size_t)spw * plan.nwet * 4;
   const size_t flag_bytes = (size_t)spw * (size_t)nz;
-  plan.ring = plan.mode == 3;
+  plan.ring = plan.mode >= 3;
+  plan.packed_first = plan.mode == 4;
+  plan.last_slot.store(-1);
   plan.ring_next = 0;
   for (auto& q : plan.slot_queued) q.store(0, std::memory_order_relaxed);
   if (plan.ring) {
@@ -533,15 +538,40 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
         }
         if (plan.ring && e == cudaSuccess) e = cudaEventRecord(r.slot_done[slot], r.copy);
         if (e != cudaSuccess) sh.err.store((int)e);
-        if (plan.ring) plan.slot_queued[slot].fetch_add(1, std::memory_order_release);
+        if (plan.ring) {
+          plan.last_slot.store(slot, std::memory_order_release);
+          plan.slot_queued[slot].fetch_add(1, std::memory_order_release);
+        }
       }
     }
   });
 
   // this thread: the fullest rows as they are, straight from the caller's buffer
   cudaError_t err = cudaSuccess;
+  const int in_flight = plan.packed_first ? 1 : Resources::kRing;
   for (int issued = 0;; ++issued) {
     int pos;
+    if (plan.packed_first) {
+      // the copy stream belongs to the packed rows: wait until the one queued last has crossed (the stream is
+      // in order, so then none is waiting) or until the rows have run out
+      for (;;) {
+        const int last = plan.last_slot.load(std::memory_order_acquire);
+        if (last < 0) break;
+        const cudaError_t q = cudaEventQuery(r.slot_done[last]);
+        if (q == cudaSuccess) break;
+        cudaGetLastError();  // cudaErrorNotReady is an answer, not a failure
+        if (q != cudaErrorNotReady) {
+          err = q;
+          break;
+        }
+        {
+          std::lock_guard<std::mutex> l(sh.m);
+          if (sh.lo > sh.hi || sh.lo >= sh.lo_end) break;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+      }
+      if (err != cudaSuccess) break;
+    }
     {
       std::lock_guard<std::mutex> l(sh.m);
       if (sh.lo > sh.hi || sh.lo >= sh.lo_end) break;
@@ -550,8 +580,8 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
     int t, z;
     row_of(pos, t, z);
     const size_t off = ((size_t)t * (size_t)nz + (size_t)z) * (size_t)ncol;
-    cudaEvent_t ev = r.ring[issued % Resources::kRing];
-    if (issued >= Resources::kRing && (err = cudaEventSynchronize(ev)) != cudaSuccess) break;
+    cudaEvent_t ev = r.ring[issued % in_flight];
+    if (issued >= in_flight && (err = cudaEventSynchronize(ev)) != cudaSuccess) break;
     if ((err = cudaMemcpyAsync((float*)dT + off, Th + off, row_bytes, cudaMemcpyHostToDevice, r.copy)) != cudaSuccess) break;
     if ((err = cudaMemcpyAsync((float*)dS + off, Sh + off, row_bytes, cudaMemcpyHostToDevice, r.copy)) != cudaSuccess) break;
     r.h2d_bytes += 2 * row_bytes;
@@ -586,7 +616,7 @@ extern "C" int ml_host_release(void) {
 }
 
 extern "C" int ml_host_set_packing(int mode, int threads) {
-  if (mode < 0 || mode > 3) return ml::fail(ML_ERR_MODE, "packing mode %d is not 0, 1, 2 or 3", mode);
+  if (mode < 0 || mode > 4) return ml::fail(ML_ERR_MODE, "packing mode %d is not 0 ... 4", mode);
   Resources& r = resources();
   r.pack_mode = mode;
   r.pack_threads = threads > 0 ? threads : 0;

@@ -21,7 +21,7 @@
 #include <thread>
 
 typedef int cudaError_t;
-enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1 };
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorNotReady = 600 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaMemoryType { cudaMemoryTypeUnregistered = 0, cudaMemoryTypeHost = 1, cudaMemoryTypeDevice = 2 };
@@ -181,6 +181,10 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
   }
   e->wait_for(n);
   return cudaSuccess;
+}
+inline cudaError_t cudaEventQuery(cudaEvent_t e) {
+  std::lock_guard<std::mutex> l(e->m);
+  return e->completed >= e->recorded ? cudaSuccess : cudaErrorNotReady;
 }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t s, cudaEvent_t e, unsigned) {
   uint64_t n;

@@ -157,6 +157,8 @@ int main() {
     int64_t nt, nz, ncol;
   } shapes[] = {{5, 7, 1000}, {4, 3, 33}, {3, 12, 4111}};  // 32, 2 and 129 groups per row: 4, 1 and 16 segments
   int runs = 0, bad = 0;
+  double frac_sum[5][2] = {{0}}, frac_max[5][2] = {{0}};  // pinned sources: share of rows packed by mode, fast / slow copies
+  int frac_n[5][2] = {{0}};
   for (const Shape& sh : shapes) {
     const int64_t nt = sh.nt, nz = sh.nz, ncol = sh.ncol;
     const size_t lvl = (size_t)nz * ncol, all = (size_t)nt * lvl;
@@ -196,7 +198,7 @@ int main() {
         packable += (double)n < 0.9 * (double)ncol;
       }
       const int spws[] = {1, 2, (int)nt};
-      for (int mode = 0; mode <= 3; ++mode)
+      for (int mode = 0; mode <= 4; ++mode)
         for (int threads : {1, 3, 7})
           for (int spw : spws)
             for (int slow = 0; slow < 2; ++slow) {
@@ -213,6 +215,11 @@ int main() {
               ok = ok && (mode != 0 || frac == 0.0) && (mode == 0 || pinned || frac == 1.0) &&
                    (mode != 2 || !pinned || fabs(frac - (double)packable / (double)nz) < 1e-9) &&
                    (mode == 0 || !pinned || frac <= (double)packable / (double)nz + 1e-9);
+              if (pinned) {
+                frac_sum[mode][slow] += frac;
+                frac_max[mode][slow] += (double)packable / (double)nz;
+                frac_n[mode][slow]++;
+              }
               rc = ml_steric_global_host(0, ML_F32, T, S, V, p.data(), nt, nz, ncol, spw, masso.data());
               ok = ok && rc == 0 && same(masso.data(), want_m.data(), (size_t)nt);
               // a call that wants rho_ref back sends every row as it is
@@ -234,6 +241,10 @@ int main() {
     }
   }
   ml_host_release();
+  for (int mode = 1; mode <= 4; ++mode)
+    for (int slow = 0; slow < 2; ++slow)
+      printf("mode %d, %s copies: %.2f of the rows packed on average (%.2f packable)\n", mode, slow ? "slow" : "fast",
+             frac_sum[mode][slow] / frac_n[mode][slow], frac_max[mode][slow] / frac_n[mode][slow]);
   printf("hostpath_sim: %d runs, %d mismatches\n", runs, bad);
   return bad ? 1 : 0;
 }

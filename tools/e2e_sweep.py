@@ -34,7 +34,7 @@ def main():
     settings = [(0, 0, 1), (1, 0, 1), (2, 0, 1), (1, 4, 1), (1, 6, 1), (1, 8, 1), (1, 10, 1), (1, 12, 1), (2, 8, 1),
                 (2, 12, 1), (1, 0, 2), (1, 0, 3), (1, 0, 4), (1, 0, 6), (1, 0, 12), (1, 8, 3), (1, 0, 1)]
     if quick:
-        settings = [(1, 8, 1), (3, 8, 1), (3, 0, 1), (3, 12, 1), (3, 6, 1), (1, 0, 1), (3, 15, 1)]
+        settings = [(1, 8, 1), (3, 8, 1), (4, 8, 1), (4, 0, 1), (4, 12, 1), (4, 6, 1), (1, 0, 1), (4, 15, 1), (2, 12, 1)]
     for mode, threads, spw in settings:
         core.host_packing(mode, threads)
         run = lambda: core.steric_local_host(Th, Sh, Vh, z_i, depth, pres, steps_per_window=spw, eta_out=eta_h)  # noqa: E731
