@@ -33,6 +33,14 @@ for s in $STAGES; do
       timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_steric_tma -s 14 -c 1 \
           -o gpurun_out/prof_kglobal python tools/k3_bench.py ncu > gpurun_out/ncu_k3b.log 2>&1
       echo "[ncuk3] exit $?"; cat gpurun_out/k3_plain.log | tail -1 ;;
+    e2esweep)
+      # the host path by packing mode / threads / window width; "ring" = only the staging-ring modes against the default
+      timeout 300 python tools/e2e_sweep.py 2 ${E2E_SWEEP_ARGS:-} > gpurun_out/e2e_sweep.log 2> gpurun_out/e2e_sweep.err
+      echo "[e2esweep] exit $?"; cut -c1-260 gpurun_out/e2e_sweep.log; tail -3 gpurun_out/e2e_sweep.err ;;
+    packbench)
+      (cd tools && g++ -O3 -std=c++17 -pthread -o /tmp/packbench packbench.cpp ../momlevel_b200/csrc/ml_pack.cpp &&
+        for n in 1 4 8 15; do /tmp/packbench $n; done) > gpurun_out/packbench.log 2>&1
+      echo "[packbench] exit $?"; grep -E "pack step|memcpy" gpurun_out/packbench.log | tail -20 ;;
     benchref)
       timeout 900 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2> gpurun_out/bench_ref.err
       echo "[benchref] exit $?"; tail -3 gpurun_out/bench_ref.log ;;
