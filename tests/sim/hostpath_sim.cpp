@@ -155,7 +155,9 @@ static bool same(const double* a, const double* b, size_t n) { return memcmp(a, 
 int main() {
   struct Shape {
     int64_t nt, nz, ncol;
-  } shapes[] = {{5, 7, 1000}, {4, 3, 33}, {3, 12, 4111}};  // 32, 2 and 129 groups per row: 4, 1 and 16 segments
+    int pattern;  // 0 = levels thin out with depth, 1 = every volume present, 2 = none
+  } shapes[] = {{5, 7, 1000, 0}, {4, 3, 33, 0}, {3, 12, 4111, 0},  // 32, 2 and 129 groups per row: 4, 1 and 16 segments
+                {1, 1, 5, 0},    {2, 3, 64, 1}, {2, 3, 70, 2}};
   int runs = 0, bad = 0;
   double frac_sum[5][2] = {{0}}, frac_max[5][2] = {{0}};  // pinned sources: share of rows packed by mode, fast / slow copies
   int frac_n[5][2] = {{0}};
@@ -171,7 +173,8 @@ int main() {
       std::mt19937 rng(17 + (unsigned)ncol);
       std::uniform_real_distribution<float> u(0.f, 1.f);
       for (int64_t z = 0; z < nz; ++z) {
-        const float wet = z == 0 ? 0.97f : 1.0f - (float)z / (float)nz;  // level 0 is never worth packing
+        float wet = z == 0 ? 0.97f : 1.0f - (float)z / (float)nz;  // level 0 is never worth packing
+        if (sh.pattern) wet = sh.pattern == 1 ? 2.0f : -1.0f;
         for (int64_t c = 0; c < ncol; ++c) V[(size_t)z * ncol + c] = u(rng) < wet ? 1.0f + u(rng) : NAN;
       }
       for (size_t i = 0; i < all; ++i) {
@@ -197,6 +200,7 @@ int main() {
         for (int64_t c = 0; c < ncol; ++c) n += present(V[(size_t)z * ncol + c]);
         packable += (double)n < 0.9 * (double)ncol;
       }
+      if (sh.pattern == 2) packable = 0;  // nothing present at all: the library does not bother (every row as it is)
       const int spws[] = {1, 2, (int)nt};
       for (int mode = 0; mode <= 4; ++mode)
         for (int threads : {1, 3, 7})
@@ -212,7 +216,7 @@ int main() {
               const double frac = ml_host_last_packed_fraction();
               bool ok = rc == 0 && sums[0] == want_sums[0] && sums[1] == want_sums[1];
               for (int v = 0; v < 3; ++v) ok = ok && same(eta[v], want[v].data(), (size_t)nt * ncol);
-              ok = ok && (mode != 0 || frac == 0.0) && (mode == 0 || pinned || frac == 1.0) &&
+              ok = ok && (mode != 0 || frac == 0.0) && (mode == 0 || pinned || frac == (sh.pattern == 2 ? 0.0 : 1.0)) &&
                    (mode != 2 || !pinned || fabs(frac - (double)packable / (double)nz) < 1e-9) &&
                    (mode == 0 || !pinned || frac <= (double)packable / (double)nz + 1e-9);
               if (pinned) {
