@@ -271,8 +271,8 @@ int ml_host_release(void);
 /* ---------------------------------------------------------------------------------------
  * Wet-cell packing of the host path.  The reference never uses T or S where the reference
  * volcello is missing: delta_rho is NaN there (src/momlevel/steric.py:151-153), the column sum
- * skips it (:163) and so do volo / masso (derived.py:435-438, 787-789).  ml_steric_local_host and
- * ml_steric_local_variants_host therefore move a level row either as it is (DMA straight from the
+ * skips it (:163) and so do volo / masso (derived.py:435-438, 787-789).  ml_steric_local_host,
+ * ml_steric_local_variants_host and ml_steric_global_host therefore move a level row either as it is (DMA straight from the
  * caller's buffer) or as its present cells only (compressed by host threads into pinned staging,
  * expanded on the device with NaN in the absent cells), whichever side -- PCIe or the host cores --
  * has time left; the heights are bit-identical either way.  fp32 fields only; a call that asks for
