@@ -54,6 +54,9 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--force-direct", action="store_true", help="use the direct kernel family (A/B against TMA)")
+    ap.add_argument("--configs", default=os.environ.get("ML_BENCH_CONFIGS", "3,4,5"),
+                    help="BASELINE configs timed beside the headline (extras.configs); '' or --no-configs for none")
+    ap.add_argument("--no-configs", action="store_true")
     return ap.parse_args()
 
 
@@ -145,6 +148,20 @@ class ClockSampler:
 # ------------------------------------------------------------------------- CPU baseline
 
 
+def reference_kernels():
+    """Put the reference's own numpy EOS modules under the oracle's driver when an install of the reference is on
+    the box (``pip install --no-deps --target baseline/_ref``); returns ``(kind, files)``.
+
+    The reference PACKAGE cannot be imported (xarray, xgcm, cftime are not installable here), so its driver
+    (steric.py / reference.py / derived.py) stays the oracle's restatement either way.
+    """
+    from oracle import eos as oeos
+
+    used = oeos.use_reference_modules(ROOT / "baseline" / "_ref")
+    used = [str(pathlib.Path(u).relative_to(ROOT)) for u in used]
+    return ("reference-numpy+port-driver" if used else "port"), used
+
+
 def _oracle_slab(args_tuple):
     """One y-slab of the whole path on the host: reference state + local steric (numpy oracle)."""
     from oracle import steric as osteric
@@ -185,6 +202,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    kind, ref_files = reference_kernels()
     nt, nz, ny, nx = WORKLOADS[args.workload]
     cores = os.cpu_count() or 1
     workers = min(cores, 64)
@@ -209,11 +227,14 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample,
-                         "host_cpu_count": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": workers, "kind": kind, "sample": sample,
+                         "host_cpu_count": cores, "reference_files_used": ref_files},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-        "note": "numpy port of momlevel's steric path (oracle/), y-slabs on a thread pool; xarray is not installable here",
+        "note": "momlevel's steric path on the host: the reference's own eos/wright.py under the oracle's restatement of "
+                "steric.py / reference.py / derived.py when baseline/_ref holds an install (kind says which), y-slabs on a "
+                "thread pool; the package itself needs xarray, which is not installable here.  A RATE measured on a "
+                "sample of the grid, not the whole grid",
     }
     print(json.dumps(line), flush=True)
 
@@ -241,13 +262,32 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
     n_e2e = max(1, min(args.steps, 3))
 
-    # Level rows cross PCIe as they are or packed to the cells the reference reads (ml_host_set_packing).  Packing
-    # trades host memory bandwidth for PCIe bytes: it pays while PCIe is what a rank waits for (one or two
-    # GPUs on this host); from four ranks up the host's memory system is the bound and every row goes as it is.
+    # the ceiling the host-fed leg can be judged against: plain pinned cudaMemcpyAsync of 2 GB, all ranks at once
+    n_probe = min(Th.numel(), 1 << 29)
+    probe_dst = torch.empty(n_probe, dtype=Th.dtype, device=dev)
+    probe_src = Th.view(-1)[:n_probe]
+    probe_dst.copy_(probe_src, non_blocking=True)
+    barrier()
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(3):
+        probe_dst.copy_(probe_src, non_blocking=True)
+    pb.record()
+    torch.cuda.synchronize()
+    probe = torch.tensor([pa.elapsed_time(pb) / 3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(probe, op=dist.ReduceOp.MAX)
+    h2d_peak_gbs = n_probe * Th.element_size() / (float(probe[0]) * 1e-3) / 1e9  # per rank, slowest rank
+    del probe_dst
+
+    # Level rows cross PCIe as they are or packed to the cells the reference reads.  The choice is the LIBRARY's
+    # (ml_host_set_packing's default: rows taken from both ends until the packers and the copy engine meet, with
+    # half the host's cores divided by the ranks that share them, LOCAL_WORLD_SIZE) -- what a caller of
+    # momlevel_b200.steric(dset) gets; the A/B leg below sends every row as it is.
     cores = len(os.sched_getaffinity(0))
-    pack_mode = 1 if world <= 2 else 0
-    pack_threads = max(1, cores // (2 * world))
+    pack_mode, pack_threads = 1, 0  # 0 = the library's own thread count
     core.host_packing(pack_mode, pack_threads)
+    lib_threads = max(1, min(cores // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1))), 64))
 
     def e2e_step():
         return core.steric_local_host(Th, Sh, Vh, z_h, d_h, p_h, steps_per_window=1, eta_out=eta_h)
@@ -271,8 +311,17 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
                    "d2h_bytes_per_step": d2h, "steps": n_e2e, "ms_per_step": float(dt[0]) * 1e3,
                    "api": "momlevel_b200.core.steric_local_host -> ml_steric_local_host (pinned host buffers)",
                    "host_input_bytes_per_step": dense, "level_rows_sent_packed": packed_rows,
-                   "host_pack_mode": pack_mode, "host_pack_threads": pack_threads, "host_pack_simd": core.host_pack_simd(),
+                   "host_pack_mode": pack_mode, "host_pack_threads": lib_threads, "host_pack_policy": "library default", "host_pack_simd": core.host_pack_simd(),
                    "last_call_host_ms": host_ms}
+    line["e2e"]["roofline"] = {
+        "bound": "pcie_h2d", "h2d_bytes": h2d, "achieved_gbs": h2d / float(dt[0]) / 1e9,
+        "peak_concurrent_h2d_gbs": h2d_peak_gbs, "frac": h2d / float(dt[0]) / 1e9 / h2d_peak_gbs,
+        "dense_equivalent_gbs": dense / float(dt[0]) / 1e9,
+        "dense_equivalent_frac": dense / float(dt[0]) / 1e9 / h2d_peak_gbs,
+        "peak_source": f"plain pinned cudaMemcpyAsync of {n_probe * Th.element_size() >> 20} MiB on all {world} ranks at "
+                       "once, slowest rank, measured in this run",
+        "note": "frac counts the bytes that crossed PCIe per rank; dense_equivalent counts the caller's bytes (rows that "
+                "travel packed to their present cells make it exceed the link rate)"}
     # the device-resident and the host-streamed paths must agree
     err = (eta_h.to(dev) - eta).abs()
     line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
@@ -367,6 +416,11 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     if args.force_direct:
         core.force_direct(True)
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_configs", str(ROOT / "tools" / "bench_configs.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
 
     nt, nz, ny, nx = WORKLOADS[args.workload]
     ncol = ny * nx
@@ -471,6 +525,20 @@ def run_ours(args):
     }
     if world > 1:
         line["host_cpus_bound_per_rank"] = bound_cpus
+    if rank == 0 and not args.no_cpu:
+        # the headline's heights against the oracle on columns from every part of the grid (first / last / edge tiles
+        # and a stride across the rest); the cpu_baseline leg below also compares the contiguous slab it times
+        line["parity"] = bc.oracle_local_parity(T, S, V, None, grid, eta)
+        line["parity"]["tolerance_m"] = 1e-9
+    # the timed region above is tens of milliseconds; the same step 200 times under one event pair as a self-check
+    e2, e3 = ev(), ev()
+    e2.record()
+    for _ in range(200):
+        step()
+    e3.record()
+    torch.cuda.synchronize()
+    line["selfcheck_200_steps"] = {"ms_per_step": e2.elapsed_time(e3) / 200,
+                                   "value_this_rank": points / (e2.elapsed_time(e3) / 200 * 1e-3), "unit": UNIT}
 
     # ---- extras: the other variants / domains of the same dataset, a few steps each
     if not args.no_extras:
@@ -546,6 +614,7 @@ def run_ours(args):
                            depth.cpu().numpy(), grid["z_l"].cpu().numpy(), z_i.cpu().numpy())
         rows, nslabs = 8, 3
         row0 = max(0, ny // 2 - rows * nslabs // 2)
+        kind, ref_files = reference_kernels()
         cpu_path(host_fields, rows, 1, 1, row0)  # warm-up
         sec, pts, etas = cpu_path(host_fields, rows, nslabs, 1, row0)
         got = eta[:, row0: row0 + rows * nslabs].cpu().numpy()
@@ -555,12 +624,29 @@ def run_ours(args):
         m[0, 0, 0] = m.any() or True  # never reduce over an empty set
         got, want = np.nan_to_num(got), np.nan_to_num(want)
         line["cpu_baseline"] = {
-            "value": pts / sec, "unit": UNIT, "cores": 1, "kind": "port",
+            "value": pts / sec, "unit": UNIT, "cores": 1, "kind": kind, "reference_files_used": ref_files,
             "sample": f"rows {row0}..{row0 + rows * nslabs} of {ny}: {rows * nslabs}x{nx} columns x {nz} levels x {nt} steps"
                       f" = {pts} points, numpy oracle on fp64-upcast inputs, single thread",
             "seconds": sec, "host_cpu_count": os.cpu_count(),
             "parity_max_abs_err_m": float(np.max(np.abs(got[m] - want[m]))), "parity_nan_pattern_equal": same_nan,
         }
+
+    # ---- the other BASELINE configs (3: ensemble sharded by member x time block, 4: time-sharded global series with
+    # its gather inside the timed region, 5: linear EOS + spice), each with its own roofline and oracle check
+    which = [c for c in (args.configs or "").replace(" ", "").split(",") if c in ("3", "4", "5")]
+    if which and not args.no_configs and args.workload == "om4p25":
+        host_fields = eta = rho_ref = sums = V = None  # noqa: F841 -- release the headline's buffers first
+        try:
+            del T, S
+        except NameError:  # the e2e leg has released them already
+            pass
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        launches1 = core.launch_count()
+        line.setdefault("extras", {})["configs"] = bc.run_configs(which, rank, world, dev)
+        line["extras"]["configs_gpu_launches_rank0"] = core.launch_count() - launches1
 
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -258,10 +258,11 @@ def _workspace(nt, nz, ncol, device):
     return torch.empty((n + 7) // 8, dtype=torch.float64, device=device), n
 
 
-def reference_state(T0, S0, V0, p_level, eos="Wright"):
+def reference_state(T0, S0, V0, p_level, eos="Wright", out=None):
     """``reference.setup_reference_state`` arithmetic (reference.py:71-80).
 
-    Returns ``(rho_ref [nz,...] fp64, sums fp64[2] = {volo, masso})`` on the device.
+    Returns ``(rho_ref [nz,...] fp64, sums fp64[2] = {volo, masso})`` on the device; ``out`` may hand
+    in those two tensors when the caller manages streams.
     """
     L = _lib.lib()
     T0, S0, V0 = to_device(T0), to_device(S0), to_device(V0)
@@ -271,8 +272,13 @@ def reference_state(T0, S0, V0, p_level, eos="Wright"):
     nz = T0.shape[0]
     ncol = T0.numel() // nz
     p = _f64(p_level)
-    rho = torch.empty(T0.shape, dtype=torch.float64, device=T0.device)
-    sums = torch.empty(2, dtype=torch.float64, device=T0.device)
+    if out is not None:
+        rho, sums = out
+        assert rho.dtype == sums.dtype == torch.float64 and rho.is_contiguous() and rho.numel() == T0.numel()
+        assert sums.numel() == 2
+    else:
+        rho = torch.empty(T0.shape, dtype=torch.float64, device=T0.device)
+        sums = torch.empty(2, dtype=torch.float64, device=T0.device)
     ws, nbytes = _workspace(2, nz, ncol, T0.device)
     _lib.check(
         L.ml_reference_state(_eos_id(eos), _dt_id(T0), T0.data_ptr(), S0.data_ptr(), V0.data_ptr(), p.data_ptr(), nz,
@@ -299,10 +305,11 @@ def _steric_operands(T, S, t_bcast, s_bcast):
 
 
 def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", t_bcast=False,
-                 s_bcast=False, want_delta_rho=False):
+                 s_bcast=False, want_delta_rho=False, eta_out=None):
     """Local branch of ``steric.steric`` (steric.py:128,150-166).
 
-    Returns ``(eta [nt,...], delta_rho [nt,nz,...] or None)`` fp64 on the device.
+    Returns ``(eta [nt,...], delta_rho [nt,nz,...] or None)`` fp64 on the device; ``eta_out`` may hand in
+    the height tensor when the caller manages streams.
     """
     L = _lib.lib()
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
@@ -311,7 +318,11 @@ def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos
     z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
     assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and depth.numel() == ncol
     assert z_i.numel() == nz + 1 and p.numel() == nz
-    eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
+    if eta_out is not None:
+        eta = eta_out
+        assert eta.dtype == torch.float64 and eta.is_contiguous() and eta.numel() == nt * ncol
+    else:
+        eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
     drho = torch.empty((nt, nz) + hshape, dtype=torch.float64, device=T.device) if want_delta_rho else None
     _lib.check(
         L.ml_steric_local(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),

@@ -7,6 +7,7 @@
 // window k run on the compute stream.  Pinned (page-locked) host buffers make the copies
 // truly asynchronous; pageable buffers work but serialise inside the driver.
 #include <sched.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -207,6 +208,15 @@ double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Ranks that share this host's cores and memory system: one process per GPU under torchrun exports
+// LOCAL_WORLD_SIZE; a lone process counts as one.
+int local_ranks() {
+  const char* v = getenv("LOCAL_WORLD_SIZE");
+  if (v == nullptr || *v == 0) return 1;
+  const long n = strtol(v, nullptr, 10);
+  return (n >= 1 && n <= 1024) ? (int)n : 1;
+}
+
 int default_threads() {
   cpu_set_t set;
   int n = 0;
@@ -214,8 +224,11 @@ int default_threads() {
   if (n <= 0) n = (int)std::thread::hardware_concurrency();
   // half the cores: the packers and the DMA engine share the host's memory bandwidth, and past that point
   // every extra thread slows the copies by as much as it saves (tools/e2e_sweep.py: 4 / 6 / 8 / 10 / 12 / 15
-  // threads on a 16-core host gave 156 / 148 / 145 / 148 / 152 / 157 ms for an OM4p25 year)
-  return std::max(1, std::min(n / 2, 64));
+  // threads on a 16-core host gave 156 / 148 / 145 / 148 / 152 / 157 ms for an OM4p25 year).  That half is
+  // shared by the ranks of the host: with every rank taking half the affinity mask, four ranks oversubscribed
+  // the cores and eight lost to plain copies (SCALE_r01: packed 366 ms against 409 ms dense at four ranks with
+  // cores / (2 ranks) threads each, a tie at eight).
+  return std::max(1, std::min(n / (2 * local_ranks()), 64));
 }
 
 // memcpy by the worker threads (one thread moves ~10 GB/s, the memory system many times that)

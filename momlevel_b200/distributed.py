@@ -13,8 +13,9 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_sizes", "assign_members", "gather_series", "global_sea_level",
-           "steric_global_sharded", "steric_local_members", "bind_host_to_device"]
+__all__ = ["shard_range", "shard_sizes", "assign_members", "assign_member_blocks", "gather_series",
+           "global_sea_level", "steric_global_sharded", "steric_local_members", "steric_local_pieces",
+           "bind_host_to_device", "local_world_size"]
 
 
 def bind_host_to_device(device_index):
@@ -64,26 +65,54 @@ def assign_members(n_members, world, rank):
     return list(range(start, stop))
 
 
-def gather_series(local, n_total, group=None):
+def assign_member_blocks(n_members, nt, world, rank, block=12):
+    """This rank's share of an ensemble cut along member AND time: ``[(member, t_start, t_stop), ...]``.
+
+    Whole members per rank leave 30 members on 8 ranks at 4,4,4,4,4,4,3,3 -- the two light ranks idle for a
+    quarter of the job.  A member's time axis shards as freely as the members do once the rank has that
+    member's reference state (its step 0, one extra step to load: steric.py:105-107 takes it from
+    ``dset.isel(time=0)``), so the flattened list of (member, ``block``-step block) pairs is cut into
+    contiguous shares instead: 30 x 120 months on 8 ranks -> 38,38,38,38,37,37,37,37 blocks of 12 steps.
+    Consecutive blocks of one member are merged into one piece.
+    """
+    per = -(-int(nt) // int(block))
+    lo, hi = shard_range(int(n_members) * per, world, rank)
+    pieces = []
+    i = lo
+    while i < hi:
+        m, b = divmod(i, per)
+        b_hi = min(per, b + (hi - i))
+        pieces.append((m, b * block, min(int(nt), b_hi * block)))
+        i += b_hi - b
+    return pieces
+
+
+def gather_series(local, n_total, group=None, extra=None):
     """All-gather the ranks' contiguous shards of a 1-D series into the full series on every rank.
 
     ``local`` is this rank's block (length ``shard_sizes(n_total, world)[rank]``), a tensor on
     the device the process group communicates with.  Blocks are padded to a common length so
-    a single ``all_gather_into_tensor`` moves them.
+    a single ``all_gather_into_tensor`` moves them.  ``extra`` (a small 1-D tensor of the same
+    length on every rank, or ``None`` everywhere) rides in the same message: the scalars of the
+    reference state, which only the rank that owns step 0 has; returns ``(series, extras[world, k])`` then.
     """
     if not dist.is_available() or not dist.is_initialized():
         assert local.numel() == n_total
-        return local.clone()
+        return local.clone() if extra is None else (local.clone(), extra.clone().view(1, -1))
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     sizes = shard_sizes(n_total, world)
     assert local.numel() == sizes[rank], f"rank {rank} holds {local.numel()} values, expected {sizes[rank]}"
     width = max(sizes)
-    send = torch.zeros(width, dtype=local.dtype, device=local.device)
+    k = 0 if extra is None else int(extra.numel())
+    send = torch.zeros(width + k, dtype=local.dtype, device=local.device)
     send[: local.numel()] = local
-    recv = torch.empty(world * width, dtype=local.dtype, device=local.device)
+    if k:
+        send[width:] = extra.to(send.dtype)
+    recv = torch.empty(world * (width + k), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(recv, send, group=group)
-    recv = recv.view(world, width)
-    return torch.cat([recv[r, : sizes[r]] for r in range(world)])
+    recv = recv.view(world, width + k)
+    series = torch.cat([recv[r, : sizes[r]] for r in range(world)])
+    return series if extra is None else (series, recv[:, width:].clone())
 
 
 def global_sea_level(masso, volo, rhoga, area_sum):
@@ -93,18 +122,34 @@ def global_sea_level(masso, volo, rhoga, area_sum):
     return reference_height * np.log(np.float64(rhoga) / (masso / np.float64(volo))), reference_height
 
 
-def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_sum, n_total, eos="Wright", group=None):
+def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_sum, n_total, eos="Wright", group=None,
+                          masso_local=None, ref_sums=None):
     """Global steric series with the time axis sharded over ranks.
 
     Each rank passes its own contiguous block of time steps ``T_local, S_local`` (resident on
-    its GPU) plus the shared reference volume; returns ``(eta[n_total], reference_height)`` on
-    every rank.
+    its GPU) plus the shared reference volume -- or, when its block was streamed through windows,
+    the per-step masses ``masso_local`` it has already computed; returns
+    ``(eta[n_total], reference_height)`` on every rank.
+
+    ``volo, rhoga`` are the scalars of the reference state (reference.py:74-80).  Only the rank whose
+    block holds step 0 can compute them without loading that step again; it passes
+    ``ref_sums = tensor([volo, masso_ref])`` (what ``core.reference_state`` returns) and every other rank
+    ``volo = rhoga = None``: the two numbers then travel in the one all-gather of the series.
     """
     from . import core
 
-    masso_local = core.steric_global(T_local, S_local, v_ref, p_level, eos=eos)
-    masso = gather_series(masso_local, n_total, group=group)
-    return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
+    if masso_local is None:
+        masso_local = core.steric_global(T_local, S_local, v_ref, p_level, eos=eos)
+    if volo is not None and rhoga is not None:
+        masso = gather_series(masso_local, n_total, group=group)
+        return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
+    mine = ref_sums if ref_sums is not None else torch.zeros(2, dtype=masso_local.dtype, device=masso_local.device)
+    masso, extras = gather_series(masso_local, n_total, group=group, extra=mine.to(masso_local.device))
+    host = torch.cat([masso, extras.reshape(-1)]).cpu().numpy()  # one read-back
+    masso_h, extras_h = host[:n_total], host[n_total:].reshape(-1, 2)
+    owner = int(np.argmax(extras_h[:, 0] != 0.0))  # the rank that holds step 0 (volo > 0)
+    volo, masso_ref = float(extras_h[owner, 0]), float(extras_h[owner, 1])
+    return global_sea_level(masso_h, volo, masso_ref / volo, area_sum)
 
 
 _STREAMS = {}  # device index -> side streams, kept so that the allocator's per-stream pools stay warm
@@ -150,3 +195,53 @@ def steric_local_members(members, z_i, deptho, p_level, rhozero=1035.0, eos="Wri
         join.record(st)
         caller.wait_event(join)
     return outs
+
+
+def steric_local_pieces(pieces, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", n_streams=4):
+    """Local steric height of this rank's share of an ensemble cut by :func:`assign_member_blocks`.
+
+    ``pieces`` is a sequence of ``(T, S, v_ref, ref)``: the time block of one member resident on this GPU,
+    the member's reference volume, and ``ref = None`` when the block starts at the member's step 0 (the
+    fused self-reference pass) or ``ref = (T0, S0)``, the member's step-0 slabs, when it does not: the
+    reference density is then evaluated from them first (reference.py:60-71) and the block integrated
+    against it.  Issued round-robin on ``n_streams`` streams like :func:`steric_local_members`.
+    Returns a list of ``(eta, rho_ref, sums)``.
+    """
+    from . import core
+
+    pieces = list(pieces)
+    if not pieces:
+        return []
+    dev = pieces[0][0].device
+    caller = torch.cuda.current_stream(dev)
+    streams = _member_streams(dev, max(1, min(int(n_streams), len(pieces))))
+    outs = [core.selfref_outputs(T, S) for T, S, _, _ in pieces]  # on the caller's stream, before the fork
+    fork = torch.cuda.Event()
+    fork.record(caller)
+    for i, (T, S, V, ref) in enumerate(pieces):
+        st = streams[i % len(streams)]
+        if i < len(streams):
+            st.wait_event(fork)
+        with torch.cuda.stream(st):
+            if ref is None:
+                core.steric_local_selfref(T, S, V, z_i, deptho, p_level, rhozero=rhozero, eos=eos, out=outs[i])
+            else:
+                eta, rho, sums = outs[i]
+                core.reference_state(ref[0], ref[1], V, p_level, eos=eos, out=(rho, sums))
+                core.steric_local(T, S, rho, V, z_i, deptho, p_level, rhozero=rhozero, eos=eos, eta_out=eta)
+    for st in streams:
+        join = torch.cuda.Event()
+        join.record(st)
+        caller.wait_event(join)
+    return outs
+
+
+def local_world_size():
+    """Ranks sharing this host (``LOCAL_WORLD_SIZE`` under torchrun; the world size of a one-node job otherwise)."""
+    import os
+
+    for key in ("LOCAL_WORLD_SIZE", "WORLD_SIZE"):
+        v = os.environ.get(key)
+        if v and v.isdigit() and int(v) > 0:
+            return int(v)
+    return 1

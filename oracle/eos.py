@@ -131,3 +131,32 @@ def density(eos, T, S, p):
     if key not in _DENSITY:
         raise ValueError(f"Unknown equation of state: {key}")
     return _DENSITY[key](T, S, p)
+
+
+def use_reference_modules(root):
+    """Swap the reference's OWN numpy kernels in under the oracle's driver, when an install of it is at hand.
+
+    ``root`` is a directory that holds the reference package (``<root>/momlevel/eos/wright.py`` after
+    ``pip install --target baseline/_ref``, or ``<root>/src/momlevel/...`` for a source tree).  The
+    package itself cannot be imported without xarray, but ``eos/wright.py`` and ``eos/linear.py`` depend on
+    numpy alone and load by file path.  Returns the list of files now in use (empty: nothing found, the
+    restatement above stays).  Used by ``bench.py --impl reference`` and its ``cpu_baseline`` leg.
+    """
+    import importlib.util
+    import pathlib
+
+    used = []
+    for base in (pathlib.Path(root) / "momlevel", pathlib.Path(root) / "src" / "momlevel"):
+        for name in ("wright", "linear"):
+            path = base / "eos" / f"{name}.py"
+            if not path.exists() or name in [pathlib.Path(u).stem for u in used]:
+                continue
+            try:
+                spec = importlib.util.spec_from_file_location(f"_momlevel_ref_{name}", str(path))
+                mod = importlib.util.module_from_spec(spec)
+                spec.loader.exec_module(mod)
+                _DENSITY[name] = mod.density
+                used.append(str(path))
+            except Exception:  # noqa: BLE001 -- a broken install leaves the restatement in place
+                continue
+    return used
