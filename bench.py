@@ -645,7 +645,12 @@ def run_ours(args):
         gc.collect()
         torch.cuda.empty_cache()
         launches1 = core.launch_count()
-        line.setdefault("extras", {})["configs"] = bc.run_configs(which, rank, world, dev)
+        try:
+            line.setdefault("extras", {})["configs"] = bc.run_configs(which, rank, world, dev)
+        except Exception as exc:  # noqa: BLE001 -- the headline line must still be printed
+            if world > 1:
+                raise
+            line.setdefault("extras", {})["configs"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         line["extras"]["configs_gpu_launches_rank0"] = core.launch_count() - launches1
 
     if rank == 0:

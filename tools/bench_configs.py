@@ -351,7 +351,7 @@ def config5(rank, world, dev, parity=True, reps=3):
     spice, ms_sp = timed(lambda: core.flament_spice(T, S))
     chk_sp = None
     if parity and rank == 0:
-        idx = torch.linspace(0, pts - 1, 1 << 20, device=dev).long()
+        idx = torch.arange(0, pts, max(1, pts // (1 << 20)), device=dev)  # exact integer stride
         Tc, Sc = (x.flatten()[idx].cpu().numpy().astype(np.float64) for x in (T, S))
         m = ~(np.isnan(Tc) | np.isnan(Sc))
         want = ospice.flament_spice(Tc[m], Sc[m])
@@ -392,7 +392,11 @@ def run_configs(which, rank, world, dev):
             if world > 1:
                 raise  # the other ranks would wait forever in the next collective
             res[key] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
-        torch.cuda.empty_cache()
+        try:
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 -- a sticky device error: report what there is
+            res.setdefault(key, {})["error_after"] = f"{type(exc).__name__}: {exc}"[:200]
+            break
     return res
 
 
