@@ -531,14 +531,17 @@ def run_ours(args):
         line["parity"] = bc.oracle_local_parity(T, S, V, None, grid, eta)
         line["parity"]["tolerance_m"] = 1e-9
     # the timed region above is tens of milliseconds; the same step 200 times under one event pair as a self-check
-    e2, e3 = ev(), ev()
-    e2.record()
-    for _ in range(200):
-        step()
-    e3.record()
-    torch.cuda.synchronize()
+    clk2 = ClockSampler(local_rank)
+    with clk2:
+        e2, e3 = ev(), ev()
+        e2.record()
+        for _ in range(200):
+            step()
+        e3.record()
+        torch.cuda.synchronize()
     line["selfcheck_200_steps"] = {"ms_per_step": e2.elapsed_time(e3) / 200,
-                                   "value_this_rank": points / (e2.elapsed_time(e3) / 200 * 1e-3), "unit": UNIT}
+                                   "value_this_rank": points / (e2.elapsed_time(e3) / 200 * 1e-3), "unit": UNIT,
+                                   "clocks": clk2.summary()}
 
     # ---- extras: the other variants / domains of the same dataset, a few steps each
     if not args.no_extras:

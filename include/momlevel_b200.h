@@ -75,8 +75,12 @@ const char* ml_last_error(void);
 int ml_last_path(void);
 /* number of kernels this library has launched from the calling thread (monotonic) */
 int64_t ml_launch_count(void);
-/* force ML_PATH_DIRECT (1) / allow ML_PATH_TMA (0) for this thread; returns previous */
+/* force ML_PATH_DIRECT (1) / allow ML_PATH_TMA (0) for this thread; 2 = TMA family without the one-pass
+ * three-height kernel of ml_steric_local_variants (A/B); returns previous */
 int ml_set_force_direct(int on);
+/* time steps per register chunk of the one-pass three-height kernel (4, 6, 8 or 12; 0 = default) for this
+ * thread; a tuning knob for experiments and tests -- the results do not depend on it; returns previous */
+int ml_set_variants_chunk(int tc);
 
 /* ---------------------------------------------------------------------------------------
  * ml_eos_eval -- elementwise equation of state, fp64 out.
@@ -194,15 +198,19 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
  * steric.py:115-121 selects per call which operand of the EOS is held at its reference value;
  * BASELINE config 2 asks for all three:
  *   rho(T,S) - rho_ref,  rho(T,S_ref) - rho_ref,  rho(T_ref,S) - rho_ref        (steric.py:128,151-153)
- * One launch per requested height over device-resident fields (a fused three-variant kernel was
- * measured and dropped: the evaluation, not HBM, bounds these kernels); the host entry point
- * ml_steric_local_variants_host is where sharing pays, one PCIe transfer feeding all three.
+ * Fields that suit the TMA family (fp32, 16-byte aligned, ncol % 4 == 0, ncol >= 256) take ONE pass for
+ * all the heights asked for (csrc/ml_tma3.cu: T and S cross HBM once, a point's three densities come from
+ * the same two shared-memory words; bit-identical to the single-height kernels); anything else, or a call
+ * that asks for one height only, runs one single-height launch per height.  ml_set_force_direct(2) keeps
+ * the TMA family but turns the one-pass kernel off (A/B).
  *   T, S          [nt][nz][ncol] of `dtype`
  *   T_ref, S_ref  [nz][ncol] of `dtype`: reference["thetao"], reference["so"]; when they are step 0
  *                 of T, S themselves (the same pointers) the heights of step 0 are exactly zero
  *   rho_ref       [nz][ncol] fp64 in, or NULL: evaluate it from T_ref, S_ref (reference.py:71-80),
  *                 store it in rho_ref_out [nz][ncol] and put {volo, masso} into sums (workspace as
- *                 for ml_reference_state)
+ *                 for ml_reference_state).  rho_ref_out may be NULL when the one-pass kernel serves a
+ *                 self-reference call (it needs only the sums); any other call with both NULL returns
+ *                 ML_ERR_NULL
  *   eta_*         [nt][ncol] fp64 out each; a NULL pointer skips that variant's store
  * ------------------------------------------------------------------------------------- */
 int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, const void* T_ref,

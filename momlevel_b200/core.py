@@ -32,6 +32,7 @@ __all__ = [
     "last_path",
     "launch_count",
     "force_direct",
+    "variants_chunk",
 ]
 
 
@@ -92,7 +93,13 @@ def launch_count():
 
 
 def force_direct(on):
-    return _lib.lib().ml_set_force_direct(1 if on else 0)
+    """``True`` / 1: direct kernel family only; 2: TMA family without the one-pass three-height kernel; 0: default."""
+    return _lib.lib().ml_set_force_direct(2 if on == 2 else (1 if on else 0))
+
+
+def variants_chunk(tc=0):
+    """Time steps per register chunk of the one-pass three-height kernel (4, 6, 8, 12; 0 = default); returns previous."""
+    return _lib.lib().ml_set_variants_chunk(int(tc))
 
 
 # --------------------------------------------------------------------------- elementwise
@@ -420,12 +427,14 @@ def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos=
 
 
 def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=None, rho_ref=None, rhozero=1035.0,
-                          eos="Wright"):
+                          eos="Wright", want_rho_ref=True):
     """Steric, thermosteric and halosteric height in one call (steric.py:115-121, :150-166).
 
     ``T_ref, S_ref`` default to step 0 of ``T, S`` (what ``steric()`` does without ``reference=``); with
     ``rho_ref=None`` the reference density is evaluated on the way.  Returns
     ``({"steric": eta, "thermosteric": eta, "halosteric": eta}, rho_ref, sums or None)`` on the device.
+    ``want_rho_ref=False`` (self-reference calls only) asks the library not to store the reference density when
+    the one-pass kernel does not need the field; ``rho_ref`` is then ``None`` unless the layout needs it.
     """
     L = _lib.lib()
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, False, False)
@@ -438,7 +447,8 @@ def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=N
     eta = torch.empty((3, nt) + hshape, dtype=torch.float64, device=T.device)
     sums, ws, nbytes = None, None, 0
     if rho_ref is None:
-        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+        store = want_rho_ref or T_ref is not None or S_ref is not None
+        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device) if store else None
         sums = torch.empty(2, dtype=torch.float64, device=T.device)
         ws, nbytes = _workspace(2, nz, ncol, T.device)
         rho_in = None
@@ -446,14 +456,20 @@ def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=N
         rho = _f64(rho_ref)
         assert rho.numel() == nz * ncol
         rho_in = rho.data_ptr()
-    _lib.check(
-        L.ml_steric_local_variants(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), Tr.data_ptr(), Sr.data_ptr(),
-                                   rho_in, v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(),
-                                   p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, eta[0].data_ptr(), eta[1].data_ptr(),
-                                   eta[2].data_ptr(), rho.data_ptr() if rho_ref is None else None,
-                                   sums.data_ptr() if sums is not None else None,
-                                   ws.data_ptr() if ws is not None else None, nbytes, _stream())
-    )
+
+    def call(rho_t):
+        return L.ml_steric_local_variants(
+            _eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), Tr.data_ptr(), Sr.data_ptr(), rho_in, v_ref.data_ptr(),
+            _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(), p.data_ptr(), -1.0 / rhozero, nt, nz, ncol,
+            eta[0].data_ptr(), eta[1].data_ptr(), eta[2].data_ptr(),
+            rho_t.data_ptr() if (rho_ref is None and rho_t is not None) else None,
+            sums.data_ptr() if sums is not None else None, ws.data_ptr() if ws is not None else None, nbytes, _stream())
+
+    rc = call(rho)
+    if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
+        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+        rc = call(rho)
+    _lib.check(rc)
     return {"steric": eta[0], "thermosteric": eta[1], "halosteric": eta[2]}, rho, sums
 
 

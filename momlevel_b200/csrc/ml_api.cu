@@ -506,7 +506,13 @@ int ml_last_path(void) { return tls().last_path; }
 int64_t ml_launch_count(void) { return tls().launches; }
 int ml_set_force_direct(int on) {
   const int prev = tls().force_direct;
-  tls().force_direct = on ? 1 : 0;
+  tls().force_direct = on == 2 ? 2 : (on ? 1 : 0);
+  return prev;
+}
+
+int ml_set_variants_chunk(int tc) {
+  const int prev = tls().variants_chunk;
+  tls().variants_chunk = (tc == 4 || tc == 6 || tc == 8 || tc == 12) ? tc : 0;
   return prev;
 }
 
@@ -683,7 +689,7 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tma_ok = !tls().force_direct && tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref,
+  const bool tma_ok = tls().force_direct != 1 && tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref,
                                                                  vref_dtype, nt, nz, ncol, eta, nullptr);
   // rho_ref is an output the caller may not want (8 bytes per reference point, 7 % of the traffic of a
   // 12-step call).  It can be left out when one fused chunk serves the whole call; longer series and the
@@ -730,7 +736,7 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
   cudaStream_t st = (cudaStream_t)stream;
   const int v_f32 = vref_dtype == ML_F32;
 
-  if (!tls().force_direct &&
+  if (tls().force_direct != 1 &&
       tma::local_eligible(dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, nt, nz, ncol, eta, delta_rho)) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_local(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
@@ -829,8 +835,7 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
   ML_REQUIRE_PTR(z_i);
   ML_REQUIRE_PTR(deptho);
   ML_REQUIRE_PTR(p_level);
-  if (rho_ref == nullptr) {  // the reference density is evaluated here and handed back
-    ML_REQUIRE_PTR(rho_ref_out);
+  if (rho_ref == nullptr) {  // the reference density is evaluated here (and handed back if rho_ref_out is given)
     ML_REQUIRE_PTR(sums);
     if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
       return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
@@ -842,11 +847,20 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
   ML_REQUIRE_ALIGNED(T_ref, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S_ref, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
-  // steric.py:115-121: thermosteric holds S at the reference slab, halosteric holds T.  Three launches that
-  // share nothing but the reference state: a fused three-variant kernel was measured and dropped (a density
-  // evaluation is bound by instruction issue, not by HBM, so sharing the loads gained nothing:
-  // profiles/r01_experiments.md), and the single-variant kernels fold the pinned operand into the coefficients.
+  // steric.py:115-121: thermosteric holds S at the reference slab, halosteric holds T.
   const bool self_reference = rho_ref == nullptr && T_ref == T && S_ref == S;  // the reference state is step 0
+  // One pass over T and S for all the heights asked for (csrc/ml_tma3.cu): a point's three densities come from the
+  // same two shared-memory words.  Taken when the fields suit the TMA family and more than one height is wanted.
+  const int wanted = (eta_steric != nullptr) + (eta_thermosteric != nullptr) + (eta_halosteric != nullptr);
+  const bool fused_ok = tls().force_direct == 0 && wanted >= 2 &&
+                        tma::variants_eligible(dtype, T, S, T_ref, S_ref, vref_dtype, nt, nz, ncol);
+  if (fused_ok && (self_reference || rho_ref != nullptr)) {
+    tls().last_path = ML_PATH_TMA;
+    return tma::launch_variants(eos, T, S, T_ref, S_ref, rho_ref, v_ref, z_i, deptho, p_level, neg_inv_rhozero, (int)nt,
+                                (int)nz, ncol, eta_steric, eta_thermosteric, eta_halosteric, rho_ref_out, sums,
+                                static_cast<double*>(workspace), (cudaStream_t)stream);
+  }
+  if (rho_ref == nullptr) ML_REQUIRE_PTR(rho_ref_out);  // the launches below read the reference density from memory
   bool steric_done = false;
   if (rho_ref == nullptr) {
     if (self_reference && eta_steric) {  // reference state and steric height in one fused pass
@@ -859,6 +873,12 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
     }
     if (rc) return rc;
     rho_ref = rho_ref_out;
+    if (fused_ok && !steric_done) {
+      tls().last_path = ML_PATH_TMA;
+      return tma::launch_variants(eos, T, S, T_ref, S_ref, rho_ref, v_ref, z_i, deptho, p_level, neg_inv_rhozero,
+                                  (int)nt, (int)nz, ncol, eta_steric, eta_thermosteric, eta_halosteric, nullptr, nullptr,
+                                  nullptr, (cudaStream_t)stream);
+    }
   }
   // one single-variant launch per remaining height; with a self-reference the TMA family is told that step 0 is
   // the reference state itself, so that height is exactly zero there as in the reference (rho - rho_ref == 0)
@@ -872,7 +892,7 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
                            {eta_halosteric, T_ref, S, 1, 0}};
   for (const Variant& v : todo) {
     if (v.eta == nullptr) continue;
-    if (!tls().force_direct && tma::local_eligible(dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, nt,
+    if (tls().force_direct != 1 && tma::local_eligible(dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, nt,
                                                    nz, ncol, v.eta, nullptr)) {
       tls().last_path = ML_PATH_TMA;
       rc = tma::launch_local(eos, dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho,
@@ -913,7 +933,7 @@ int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bca
   const int v_f32 = vref_dtype == ML_F32;
   double* partials = (double*)workspace;
 
-  if (!tls().force_direct && tma::global_eligible(dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, nt, nz, ncol)) {
+  if (tls().force_direct != 1 && tma::global_eligible(dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, nt, nz, ncol)) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_global(eos, dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, p_level, (int)nt, (int)nz, ncol,
                               masso, partials, st);

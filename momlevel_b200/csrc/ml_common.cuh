@@ -128,6 +128,17 @@ struct Eos<0> {
     const double pp = fma(S, q.b1, q.b0);
     return div_lean(pp, fma(fma(K.a2, S, q.a), pp, fma(S, q.c1, q.c0)));
   }
+  // numerator and denominator on their own (same expressions as above), for callers that share one
+  // reciprocal seed between several densities of a point
+  __device__ __forceinline__ void terms_of(double T, double S, double& pp, double& den) const { terms(T, S, b0p, pp, den); }
+  __device__ __forceinline__ void terms_pinned_s(const Pinned& q, double T, double& pp, double& den) const {
+    pp = fma(T, fma(T, fma(K.b3, T, K.b2), q.b1), q.b0);
+    den = fma(fma(K.a1, T, q.a), pp, fma(T, fma(T, fma(K.c3, T, K.c2), q.c1), q.c0));
+  }
+  __device__ __forceinline__ void terms_pinned_t(const Pinned& q, double S, double& pp, double& den) const {
+    pp = fma(S, q.b1, q.b0);
+    den = fma(fma(K.a2, S, q.a), pp, fma(S, q.c1, q.c0));
+  }
 };
 
 // linear.py:55-58 -- pressure is ignored by design

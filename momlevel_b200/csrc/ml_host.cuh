@@ -16,6 +16,7 @@ struct ThreadState {
   int last_path;
   int force_direct;
   int64_t launches;
+  int variants_chunk;  // main chunk width of the one-pass three-height kernel (0 = built-in default)
 };
 ThreadState& tls();
 

@@ -21,18 +21,12 @@
 // Eligibility: fp32 fields, 16-byte aligned bases, ncol % 4 == 0 (TMA global strides are
 // multiples of 16 bytes), ncol >= kTile, no delta_rho output.  Everything else takes the
 // direct family in ml_api.cu.
-#include <cuda.h>
-
-#include "ml_common.cuh"
-#include "ml_host.cuh"
+#include "ml_tma_dev.cuh"
 #include "ml_tma.cuh"
 
 namespace ml {
 namespace tma {
 
-constexpr int kTile = 256;                    // columns per CTA = threads per CTA
-constexpr int kConsumerWarps = kTile / 32;    // 8
-constexpr int kThreads = kTile;               // no dedicated producer warp, see refill_stage()
 // Ring depth (levels in flight per CTA) and resident CTAs per SM, by mode.  The local modes run two
 // CTAs per SM with a 4-level ring and ~120 registers per thread.  The global kernel carries no
 // rho_ref / dz operands and fits 64 registers, so it runs four CTAs per SM with a 2-level ring (the
@@ -56,110 +50,6 @@ __host__ __device__ constexpr int ctas_per_sm_of(int mode) { return mode == 1 /*
 #define ML_TMA_EXPERIMENT 0
 #endif
 
-// ------------------------------------------------------------------------- PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE_%=;\n\t"
-      "bra WAIT_%=;\n\t"
-      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-// acc += w * d unless d is NaN (xarray's skipna sum).  d comes out of fp64 arithmetic, so a
-// NaN is quiet and the test is one integer compare on the high word.
-__device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
-  asm("{\n\t.reg .pred p;\n\t.reg .b32 lo, hi;\n\t"
-      "mov.b64 {lo, hi}, %1;\n\t"
-      "add.u32 hi, hi, hi;\n\t"
-      "setp.le.u32 p, hi, 0xffe00000;\n\t"
-      "@p fma.rn.f64 %0, %2, %1, %0;\n\t}"
-      : "+d"(acc)
-      : "d"(d), "d"(w));
-}
-
-// v_ref (fp32 in this family) is prefetched one level ahead as a raw bit pattern: converting,
-// testing or even MOVing the value at load time makes the warp wait for the very load it is
-// trying to hide (25-30 % of all stall samples in two profiles).
-__device__ __forceinline__ unsigned ld_vraw(const float* v, i64 i) { return __ldg(reinterpret_cast<const unsigned*>(v) + i); }
-__device__ __forceinline__ bool vraw_isnan(unsigned w) { return (w & 0x7fffffffu) > 0x7f800000u; }
-__device__ __forceinline__ double vraw_value(unsigned w) { return (double)__uint_as_float(w); }
-
-// partial-cell thickness, derived.py:308-318 for top = 0 / bottom = None, written with plain
-// compares: depth and z_i are never NaN here (deptho is NaN-filled with 0 on entry, derived.py:295)
-__device__ __forceinline__ double level_dz(double depth, double ztop, double zbot) {
-  const double part = depth - ztop, full = zbot - ztop;
-  const double p0 = part < 0.0 ? 0.0 : part;
-  return p0 < full ? p0 : full;
-}
-__device__ __forceinline__ bool nonzero(double x) {  // x != 0 without touching the fp64 pipe
-  return ((((unsigned)__double2hiint(x)) << 1) | (unsigned)__double2loint(x)) != 0u;
-}
-
-// number of levels whose upper interface lies above the sea floor (those with dz > 0); NaN depth = land = 0
-__device__ __forceinline__ int wet_levels(double depth, const double* s_zi, int nz) {
-  int lo = 0, hi = nz;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (s_zi[mid] < depth) lo = mid + 1; else hi = mid;
-  }
-  return lo;
-}
-
-// Column of the tile that thread `tid` integrates, given every thread's key (wet levels of column
-// `tid`): a bitonic sort of the 256 (key, column) words, deepest first -- unique words, so one fixed
-// order -- in registers (shuffles) and one shared-memory array.  Sorted position p goes to warp slot
-// 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the two warps an SM sub-partition hosts (w and
-// w + 4) carry a deep and a shallow band.  Every thread of the CTA must call it.
-__device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_col) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  unsigned v = ((unsigned)key << 8) | (unsigned)(kTile - 1 - tid);
-  for (int k = 2; k <= kTile; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      unsigned o;
-      if (j >= 32) {
-        __syncthreads();
-        s_key[tid] = v;
-        __syncthreads();
-        o = s_key[tid ^ j];
-      } else {
-        o = __shfl_xor_sync(0xffffffffu, v, j);
-      }
-      const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = 256): descending
-      v = (lower == desc) ? max(v, o) : min(v, o);
-    }
-  }
-  const int band = tid >> 5;
-  s_col[(band < 4 ? band : 11 - band) * 32 + lane] = kTile - 1 - (int)(v & 255u);
-  __syncthreads();
-  return s_col[tid];
-}
 
 struct Params {
   const float* T;         // the fields themselves (the streaming path goes through the tensor maps;
@@ -449,36 +339,6 @@ __global__ void ML_TMA_KERNEL_ATTR
 }
 
 // ----------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn query_encode_fn() {
-  void* p = nullptr;
-  cudaDriverEntryPointQueryResult q;
-  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-      q == cudaDriverEntryPointSuccess)
-    return reinterpret_cast<EncodeTiledFn>(p);
-  return nullptr;
-}
-
-static EncodeTiledFn encode_fn() {
-  static const EncodeTiledFn fn = query_encode_fn();  // initialised once, thread-safe
-  return fn;
-}
-
-// fp32 field [nt][nz][ncol] (rank 3) or [nz][ncol] (rank 2); box = {kTile, 1, tc}
-static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc) {
-  EncodeTiledFn fn = encode_fn();
-  if (!fn) return false;
-  cuuint64_t dims[3] = {(cuuint64_t)ncol, (cuuint64_t)nz, (cuuint64_t)nt};
-  cuuint64_t strides[2] = {(cuuint64_t)ncol * 4, (cuuint64_t)ncol * (cuuint64_t)nz * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTile, 1, (cuuint32_t)tc};
-  cuuint32_t estr[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
 
 static bool common_eligible(int dtype, int vref_dtype, const void* T, const void* S, int64_t nt, int64_t nz,
                             int64_t ncol) {

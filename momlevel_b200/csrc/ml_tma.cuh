@@ -25,6 +25,16 @@ int launch_global(int eos, int dtype, const void* T, const void* S, int t_bcast,
                   int vref_dtype, const double* p_level, int nt, int nz, int64_t ncol, double* masso, double* partials,
                   cudaStream_t st);
 
+// steric, thermosteric and halosteric height from one pass (ml_tma3.cu).  rho_ref != NULL: the reference is
+// supplied (T_ref, S_ref, rho_ref); rho_ref == NULL: T_ref / S_ref are the step-0 slabs of T / S and the reference
+// density, volo and masso are evaluated on the way (rho_ref_out optional).  Any eta may be NULL.
+bool variants_eligible(int dtype, const void* T, const void* S, const void* T_ref, const void* S_ref, int vref_dtype,
+                       int64_t nt, int64_t nz, int64_t ncol);
+int launch_variants(int eos, const void* T, const void* S, const void* T_ref, const void* S_ref, const double* rho_ref,
+                    const void* v_ref, const double* z_i, const double* deptho, const double* p_level, double coef, int nt,
+                    int nz, int64_t ncol, double* eta_steric, double* eta_thermo, double* eta_halo, double* rho_ref_out,
+                    double* sums, double* partials, cudaStream_t st);
+
 // fixed-order second reduction stage (defined in ml_api.cu): out[r] = sum_b partials[r][b]
 int reduce_rows(const double* partials, int64_t nblk, double* out, int nrows, cudaStream_t st);
 

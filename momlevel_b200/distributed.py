@@ -197,7 +197,7 @@ def steric_local_members(members, z_i, deptho, p_level, rhozero=1035.0, eos="Wri
     return outs
 
 
-def steric_local_pieces(pieces, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", n_streams=4):
+def steric_local_pieces(pieces, z_i, deptho, p_level, rhozero=1035.0, eos="Wright", n_streams=4, outs=None):
     """Local steric height of this rank's share of an ensemble cut by :func:`assign_member_blocks`.
 
     ``pieces`` is a sequence of ``(T, S, v_ref, ref)``: the time block of one member resident on this GPU,
@@ -205,7 +205,7 @@ def steric_local_pieces(pieces, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
     fused self-reference pass) or ``ref = (T0, S0)``, the member's step-0 slabs, when it does not: the
     reference density is then evaluated from them first (reference.py:60-71) and the block integrated
     against it.  Issued round-robin on ``n_streams`` streams like :func:`steric_local_members`.
-    Returns a list of ``(eta, rho_ref, sums)``.
+    Returns a list of ``(eta, rho_ref, sums)``; ``outs`` may hand those tensors in (``core.selfref_outputs``).
     """
     from . import core
 
@@ -215,7 +215,8 @@ def steric_local_pieces(pieces, z_i, deptho, p_level, rhozero=1035.0, eos="Wrigh
     dev = pieces[0][0].device
     caller = torch.cuda.current_stream(dev)
     streams = _member_streams(dev, max(1, min(int(n_streams), len(pieces))))
-    outs = [core.selfref_outputs(T, S) for T, S, _, _ in pieces]  # on the caller's stream, before the fork
+    if outs is None:
+        outs = [core.selfref_outputs(T, S) for T, S, _, _ in pieces]  # on the caller's stream, before the fork
     fork = torch.cuda.Event()
     fork.record(caller)
     for i, (T, S, V, ref) in enumerate(pieces):

@@ -413,6 +413,60 @@ def test_all_variants_in_one_pass(ml, shape, dtype, eos):
         _close_nan(again[variant].values, res[variant].values, atol=1e-12)
 
 
+@pytest.mark.parametrize("nt", [1, 4, 5, 7, 9, 12, 13, 25])
+@pytest.mark.parametrize("tc", [0, 4, 6, 8, 12])
+def test_one_pass_variants_equal_single_launches_bit_for_bit(ml, nt, tc):
+    """csrc/ml_tma3.cu: the one-pass kernel evaluates each height with the single-height kernel's instructions, so
+    the three fields, the reference density and volo / masso are bit-identical to separate launches -- for every
+    chunk width, with remainder chunks, holes at wet cells (repair pass) and masks that disagree with the bathymetry."""
+    from momlevel_b200 import core, synth
+
+    shape = (nt, 20, 8, 160)  # 1280 columns: five tiles
+    grid = synth.make_grid(*shape[1:], seed=17, device="cuda")
+    pres = (grid["z_l"] * 1.0e4 + 101325.0).contiguous()
+    T, S, V = synth.make_fields(grid, nt, seed=17, dtype=torch.float32)
+    z_i, depth = grid["z_i"], grid["deptho"]
+    if nt > 1:
+        T[nt // 2, 2, 3, 7] = float("nan")      # a hole at a wet cell of one step
+        S[nt - 1, 1, 5, 100] = float("nan")
+    V[3, 2, 40:60] = float("nan")               # volume missing where the bathymetry says water
+    T_ref = (T[0] + 0.25).contiguous()          # a supplied reference that is not step 0
+    S_ref = (S[0] - 0.05).contiguous()
+    rho_given, _ = core.reference_state(T_ref, S_ref, V, pres)
+
+    def run(mode, **kw):
+        prev, prev_tc = core.force_direct(mode), core.variants_chunk(tc)
+        try:
+            out = core.steric_local_variants(T, S, V, z_i, depth, pres, **kw)
+            return out, core.last_path()
+        finally:
+            core.force_direct(prev)
+            core.variants_chunk(prev_tc)
+
+    same = lambda a, b: torch.equal(torch.nan_to_num(a, nan=-7.0), torch.nan_to_num(b, nan=-7.0))  # noqa: E731
+    for kw in ({}, {"T_ref": T_ref, "S_ref": S_ref, "rho_ref": rho_given}, {"T_ref": T_ref, "S_ref": S_ref}):
+        (eta1, rho1, sums1), path1 = run(0, **kw)
+        (eta3, rho3, sums3), path3 = run(2, **kw)
+        assert path1 == 2 and path3 == 2
+        for v in ("steric", "thermosteric", "halosteric"):
+            assert same(eta1[v], eta3[v]), (v, kw.keys(), float(torch.nan_to_num(eta1[v] - eta3[v]).abs().max()))
+        assert same(rho1, rho3)
+        if sums1 is not None:
+            assert torch.equal(sums1, sums3)
+    # the reference density is optional for a self-reference call; the heights do not depend on it
+    prev_tc = core.variants_chunk(tc)
+    try:
+        eta_n, rho_n, sums_n = core.steric_local_variants(T, S, V, z_i, depth, pres, want_rho_ref=False)
+    finally:
+        core.variants_chunk(prev_tc)
+    (eta1, _, sums1), _ = run(0)
+    assert rho_n is None and torch.equal(sums_n, sums1)
+    for v in ("steric", "thermosteric", "halosteric"):
+        assert same(eta_n[v], eta1[v])
+        wet = ~torch.isnan(V[0])
+        assert torch.all(eta_n[v][0][wet] == 0.0)  # the reference step: exactly zero, as in the reference
+
+
 # ------------------------------------------------------- size-independent properties
 
 
