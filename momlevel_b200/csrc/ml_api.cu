@@ -11,6 +11,7 @@
 // (level, column) and reused for TC steps, and the column sum never leaves registers.
 #include "ml_common.cuh"
 #include "ml_host.cuh"
+#include "ml_stream.cuh"
 #include "ml_tma.cuh"
 
 namespace ml {
@@ -429,6 +430,11 @@ int launch_eos(int dtype, const void* T, const void* S, i64 ts, i64 ss, const do
                i64 ncol, double* out, cudaStream_t st) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(out) |
                          (pmode == ML_P_FULL ? reinterpret_cast<uintptr_t>(p) : 0);
+  // fp32 fields, density, a pressure per row: the ring-staged streaming kernel (ml_stream.cu)
+  if (FUNC == 0 && dtype == ML_F32 && pmode != ML_P_FULL && tls().force_direct != 1 && stream::eligible(T, S, nullptr, out, ncol) &&
+      ts % 4 == 0 && ss % 4 == 0 && nz > 0)
+    return stream::launch_density(EOS == 0 ? ML_EOS_WRIGHT : ML_EOS_LINEAR, (const float*)T, (const float*)S, ts, ss, p,
+                                  pmode, nrows, nz, ncol, out, st);
   if (ncol % 4 == 0 && (bits & 15u) == 0) {
     // ~16 resident blocks per SM; each block walks its share of the rows
     const i64 gx = cdiv(ncol / 4, kBlock);
@@ -564,6 +570,8 @@ int ml_flament_spice(int dtype, const void* T, const void* S, int64_t n, double*
   const int es = elem_size(dtype);
   i64 done = 0;
   const bool aligned = ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+  if (aligned && dtype == ML_F32 && n >= 4 && n % 4 == 0 && tls().force_direct != 1)  // ring-staged streaming kernel (ml_stream.cu)
+    return stream::launch_spice((const float*)T, (const float*)S, n, out, st);
   if (aligned && n >= 4) {
     const i64 n4 = n / 4;
     const unsigned grid = (unsigned)(cdiv(n4, kBlock) < 148 * 8 ? cdiv(n4, kBlock) : 148 * 8);
@@ -620,6 +628,15 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
   const int v_f32 = v_dtype == ML_F32;
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T0) | reinterpret_cast<uintptr_t>(S0) |
                          reinterpret_cast<uintptr_t>(V0) | reinterpret_cast<uintptr_t>(rho_ref);
+  if (dtype == ML_F32 && v_dtype == ML_F32 && tls().force_direct != 1 && stream::eligible(T0, S0, V0, rho_ref, ncol) &&
+      (size_t)stream::refstate_blocks(nz, ncol) * 2 * sizeof(double) <= workspace_bytes) {
+    // ring-staged streaming kernel (ml_stream.cu): persistent CTAs, block partials [2][blocks]
+    if ((rc = stream::launch_refstate(eos, (const float*)T0, (const float*)S0, (const float*)V0, p_level, nz, ncol,
+                                      rho_ref, partials, st)))
+      return rc;
+    k_reduce_rows<<<2, kBlock, 0, st>>>(partials, stream::refstate_blocks(nz, ncol), sums);
+    return launched("k_reduce_rows");
+  }
   if (v_dtype == dtype && ncol % 4 == 0 && (bits & 15u) == 0 && nz <= 65535) {
     // ~12 resident blocks per SM over all levels; each thread walks its level in 2-quad trips
     i64 gx = cdiv(148 * 12, nz);

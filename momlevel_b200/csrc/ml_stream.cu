@@ -1,0 +1,294 @@
+// ml_stream.cu -- the elementwise operators as streaming kernels over a shared-memory ring (sm_100a).
+//
+// eos.wright.density / eos.linear.density applied over a field (src/momlevel/derived.py:624-630),
+// spice.flament.spice (src/momlevel/spice/flament.py:78-90) and the reference-state pass
+// (src/momlevel/reference.py:71-80) read 8-12 bytes and write 8 bytes per point around 18-30 fp64
+// instructions.  With plain loads a thread holds its operands in registers while they are in flight, and
+// the ~50-60 registers of the evaluation leave room for ~1000 threads per SM: too few bytes in flight to
+// cover HBM latency at 6.5 TB/s, so those kernels sat at 0.66-0.82 of the copy bandwidth.  Here a
+// persistent CTA streams its tiles through a 4-stage ring filled by 1-D bulk copies
+// (cp.async.bulk.shared::cluster.global, one mbarrier per stage): loads cost no registers and no issue
+// slots, ~128 KB per SM are in flight whatever the occupancy, the math reads 128-bit words from shared
+// memory and results leave as 128-bit streaming stores.
+//
+// Layout: the operands are rows of `ncol` points (a level of one time step; a flat array is one row); a tile
+// is kTile consecutive points of one row.  Rows must start 16-byte aligned in every operand
+// (ncol % 4 == 0 and aligned bases); anything else takes the plain kernels in ml_api.cu.
+#include "ml_tma_dev.cuh"
+
+#include "ml_stream.cuh"
+
+namespace ml {
+namespace stream {
+
+constexpr int kTile = 2048;     // points per tile: 8 KB per fp32 operand
+constexpr int kStages = 4;
+constexpr int kThreads = 256;   // two quads of a tile per thread
+constexpr int kWarps = kThreads / 32;
+
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   tma::smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(tma::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void st2(double* p, double a, double b) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+struct Geom {
+  i64 ncol;           // points per row
+  i64 ntiles;         // rows * tiles_per_row
+  int tiles_per_row;
+  int nz;             // rows per outer (time) index: row = t * nz + z
+};
+
+// Ring of kStages stages of NIN fp32 operand tiles.  Thread 0 issues the copies; everybody waits on the
+// stage's mbarrier; a stage is refilled after the CTA-wide barrier that follows its last read.
+template <int NIN>
+struct Ring {
+  float* base;
+  uint64_t* full;
+  __device__ __forceinline__ float* stage(int s, int k) const { return base + ((size_t)s * NIN + k) * kTile; }
+  __device__ __forceinline__ void init(unsigned char* smem) {
+    base = reinterpret_cast<float*>(smem);
+    full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * NIN * kTile * sizeof(float));
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) tma::mbar_init(full + s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+  }
+};
+template <int NIN>
+constexpr size_t ring_bytes() {
+  return (size_t)kStages * NIN * kTile * sizeof(float) + kStages * sizeof(uint64_t) + 64;
+}
+
+// ------------------------------------------------------------------------------ spice / density
+// OP 0: Flament spiciness (T, S).  OP 1: density of EOS (T, S, p per row: scalar or per level).
+template <int OP, int EOS>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_stream_map(const float* __restrict__ T, const float* __restrict__ S, i64 t_stride, i64 s_stride,
+                 const double* __restrict__ p, int pmode, Geom g, double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring<2> ring;
+  ring.init(smem_raw);
+  const int tid = threadIdx.x;
+  auto issue = [&](i64 tile, int s) {
+    const i64 row = tile / g.tiles_per_row;
+    const i64 col0 = (tile - row * g.tiles_per_row) * kTile;
+    const i64 t = row / g.nz, z = row - t * g.nz;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    const uint32_t bytes = (uint32_t)len * 4u;
+    tma::mbar_expect_tx(ring.full + s, 2 * bytes);
+    bulk_load(ring.stage(s, 0), T + t * t_stride + z * g.ncol + col0, bytes, ring.full + s);
+    bulk_load(ring.stage(s, 1), S + t * s_stride + z * g.ncol + col0, bytes, ring.full + s);
+  };
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) {
+      const i64 tile = (i64)blockIdx.x + (i64)s * gridDim.x;
+      if (tile < g.ntiles) issue(tile, s);
+    }
+  Eos<EOS> eos;
+  int it = 0;
+  for (i64 tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const i64 row = tile / g.tiles_per_row;
+    const i64 col0 = (tile - row * g.tiles_per_row) * kTile;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    if (OP == 1) {
+      const i64 z = row % g.nz;
+      eos.set_level(pmode == ML_P_SCALAR ? __ldg(p) : (pmode == ML_P_PER_LEVEL ? __ldg(p + z) : 0.0));
+    }
+    double* o = out + row * g.ncol + col0;
+    tma::mbar_wait(ring.full + s, (uint32_t)(it / kStages) & 1u);
+    const float4* sT = reinterpret_cast<const float4*>(ring.stage(s, 0));
+    const float4* sS = reinterpret_cast<const float4*>(ring.stage(s, 1));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = tid + h * kThreads;
+      if (4 * q < len) {
+        const float4 a = sT[q], b = sS[q];
+        double r0, r1, r2, r3;
+        if (OP == 0) {
+          r0 = flament_spice((double)a.x, (double)b.x);
+          r1 = flament_spice((double)a.y, (double)b.y);
+          r2 = flament_spice((double)a.z, (double)b.z);
+          r3 = flament_spice((double)a.w, (double)b.w);
+        } else {
+          r0 = eos.rho_checked((double)a.x, (double)b.x);
+          r1 = eos.rho_checked((double)a.y, (double)b.y);
+          r2 = eos.rho_checked((double)a.z, (double)b.z);
+          r3 = eos.rho_checked((double)a.w, (double)b.w);
+        }
+        st2(o + 4 * q, r0, r1);
+        st2(o + 4 * q + 2, r2, r3);
+      }
+    }
+    __syncthreads();  // every thread has read the stage
+    if (tid == 0) {
+      const i64 next = tile + (i64)kStages * gridDim.x;
+      if (next < g.ntiles) issue(next, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ reference state
+// rho_ref = rho(T0, S0, p_z) everywhere, volo = nansum(V0), masso = nansum(rho_ref * V0)
+// (reference.py:71-80, derived.py:787-789, :435-438).  Block partials: [2][gridDim.x], fixed order.
+template <int EOS>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_stream_refstate(const float* __restrict__ T0, const float* __restrict__ S0, const float* __restrict__ V0,
+                      const double* __restrict__ p_level, Geom g, double* __restrict__ rho_ref,
+                      double* __restrict__ partials) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double sm[kWarps];
+  Ring<3> ring;
+  ring.init(smem_raw);
+  const int tid = threadIdx.x;
+  auto issue = [&](i64 tile, int s) {
+    const i64 row = tile / g.tiles_per_row;
+    const i64 col0 = (tile - row * g.tiles_per_row) * kTile;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    const uint32_t bytes = (uint32_t)len * 4u;
+    const i64 off = row * g.ncol + col0;
+    tma::mbar_expect_tx(ring.full + s, 3 * bytes);
+    bulk_load(ring.stage(s, 0), T0 + off, bytes, ring.full + s);
+    bulk_load(ring.stage(s, 1), S0 + off, bytes, ring.full + s);
+    bulk_load(ring.stage(s, 2), V0 + off, bytes, ring.full + s);
+  };
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < kStages; ++s) {
+      const i64 tile = (i64)blockIdx.x + (i64)s * gridDim.x;
+      if (tile < g.ntiles) issue(tile, s);
+    }
+  Eos<EOS> eos;
+  double vol = 0.0, mass = 0.0;
+  int it = 0;
+  for (i64 tile = blockIdx.x; tile < g.ntiles; tile += gridDim.x, ++it) {
+    const int s = it % kStages;
+    const i64 row = tile / g.tiles_per_row;
+    const i64 col0 = (tile - row * g.tiles_per_row) * kTile;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    eos.set_level(__ldg(p_level + row));
+    double* o = rho_ref + row * g.ncol + col0;
+    tma::mbar_wait(ring.full + s, (uint32_t)(it / kStages) & 1u);
+    const float4* sT = reinterpret_cast<const float4*>(ring.stage(s, 0));
+    const float4* sS = reinterpret_cast<const float4*>(ring.stage(s, 1));
+    const float4* sV = reinterpret_cast<const float4*>(ring.stage(s, 2));
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int q = tid + h * kThreads;
+      if (4 * q < len) {
+        const float4 a = sT[q], b = sS[q], v = sV[q];
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+        double r[4];
+        r[0] = eos.rho((double)a.x, (double)b.x);
+        r[1] = eos.rho((double)a.y, (double)b.y);
+        r[2] = eos.rho((double)a.z, (double)b.z);
+        r[3] = eos.rho((double)a.w, (double)b.w);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (!isnan(vv[j])) {
+            vol += (double)vv[j];
+            const double m = r[j] * (double)vv[j];
+            if (!is_nan_q(m)) mass += m;
+          }
+        st2(o + 4 * q, r[0], r[1]);
+        st2(o + 4 * q + 2, r[2], r[3]);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      const i64 next = tile + (i64)kStages * gridDim.x;
+      if (next < g.ntiles) issue(next, s);
+    }
+  }
+  vol = block_sum<kWarps>(vol, sm);
+  mass = block_sum<kWarps>(mass, sm);
+  if (tid == 0) {
+    partials[blockIdx.x] = vol;
+    partials[(i64)gridDim.x + blockIdx.x] = mass;
+  }
+}
+
+// ----------------------------------------------------------------------- host side
+static Geom geometry(i64 nrows, int nz, i64 ncol) {
+  Geom g;
+  g.ncol = ncol;
+  g.tiles_per_row = (int)((ncol + kTile - 1) / kTile);
+  g.ntiles = nrows * g.tiles_per_row;
+  g.nz = nz;
+  return g;
+}
+
+static unsigned persistent_grid(i64 ntiles) {
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const i64 want = 2 * (i64)sms;  // two CTAs per SM
+  return (unsigned)(ntiles < want ? ntiles : want);
+}
+
+bool eligible(const void* a, const void* b, const void* c, const void* out, i64 ncol) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
+                         reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(out);
+  return (bits & 15u) == 0 && ncol % 4 == 0 && ncol >= 4 && ncol / kTile < 0x7fffffff;
+}
+
+template <typename K>
+static int opt_in(K kern, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  return e == cudaSuccess ? ML_OK : cuda_fail(e, "cudaFuncSetAttribute(k_stream)");
+}
+
+int launch_spice(const float* T, const float* S, i64 n, double* out, cudaStream_t st) {
+  const Geom g = geometry(1, 1, n);
+  auto kern = k_stream_map<0, 0>;
+  if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
+  kern<<<persistent_grid(g.ntiles), kThreads, ring_bytes<2>(), st>>>(T, S, 0, 0, nullptr, 0, g, out);
+  return launched("k_stream_map(spice)");
+}
+
+int launch_density(int eos, const float* T, const float* S, i64 t_stride, i64 s_stride, const double* p, int pmode,
+                   i64 nrows, int nz, i64 ncol, double* out, cudaStream_t st) {
+  const Geom g = geometry(nrows, nz, ncol);
+  const unsigned grid = persistent_grid(g.ntiles);
+  if (eos == ML_EOS_WRIGHT) {
+    auto kern = k_stream_map<1, 0>;
+    if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
+    kern<<<grid, kThreads, ring_bytes<2>(), st>>>(T, S, t_stride, s_stride, p, pmode, g, out);
+  } else {
+    auto kern = k_stream_map<1, 1>;
+    if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
+    kern<<<grid, kThreads, ring_bytes<2>(), st>>>(T, S, t_stride, s_stride, p, pmode, g, out);
+  }
+  return launched("k_stream_map(density)");
+}
+
+int refstate_blocks(i64 nz, i64 ncol) {
+  const Geom g = geometry(nz, (int)nz, ncol);
+  return (int)persistent_grid(g.ntiles);
+}
+
+int launch_refstate(int eos, const float* T0, const float* S0, const float* V0, const double* p_level, i64 nz, i64 ncol,
+                    double* rho_ref, double* partials, cudaStream_t st) {
+  const Geom g = geometry(nz, (int)nz, ncol);
+  const unsigned grid = persistent_grid(g.ntiles);
+  if (eos == ML_EOS_WRIGHT) {
+    auto kern = k_stream_refstate<0>;
+    if (int rc = opt_in(kern, ring_bytes<3>())) return rc;
+    kern<<<grid, kThreads, ring_bytes<3>(), st>>>(T0, S0, V0, p_level, g, rho_ref, partials);
+  } else {
+    auto kern = k_stream_refstate<1>;
+    if (int rc = opt_in(kern, ring_bytes<3>())) return rc;
+    kern<<<grid, kThreads, ring_bytes<3>(), st>>>(T0, S0, V0, p_level, g, rho_ref, partials);
+  }
+  return launched("k_stream_refstate");
+}
+
+}  // namespace stream
+}  // namespace ml

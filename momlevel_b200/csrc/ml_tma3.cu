@@ -234,16 +234,15 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
       eos.set_level(s_p[z]);
       const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
       const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
-      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
-      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
 #pragma unroll
       for (int k = 0; k < TC; ++k) {
         if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
         const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
         const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
+        // (the single-height kernels repair with the unpinned evaluation; the same here keeps the fields identical)
         fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
-        fma_skipnan(acc[1][k], w, eos.rho_pinned_s(qs, Tv) - sub);
-        fma_skipnan(acc[2][k], w, eos.rho_pinned_t(qt, Sv) - sub);
+        fma_skipnan(acc[1][k], w, eos.rho(Tv, Sr) - sub);
+        fma_skipnan(acc[2][k], w, eos.rho(Tr, Sv) - sub);
       }
     }
   }

@@ -230,3 +230,108 @@ def test_inverse_barometer_kat(ml):
     result = ml.inverse_barometer(d["thetao"], d["so"], 101325.0)
     assert result.attrs == {"long_name": "Inverse Barometer Height", "units": "m"}
     assert float(result.sum()) == pytest.approx(-1259.79345168, abs=5e-9)
+
+
+# ------------------------------------------------------ ring-staged streaming kernels (csrc/ml_stream.cu)
+
+
+@pytest.mark.parametrize("n", [4, 2044, 2048, 2052, 5 * 2048 + 8, 148 * 2 * 4 * 2048 + 4 * 377])
+def test_stream_spice_against_oracle_and_plain_kernel(ml, n):
+    """fp32, n % 4 == 0: the ring-staged kernel -- whole tiles, a short last tile, fewer tiles than CTAs, and more
+    tiles than one pass of the ring -- against the oracle and bit for bit against the plain kernel."""
+    from momlevel_b200 import core
+
+    rng = np.random.default_rng(n)
+    T = rng.uniform(-2, 32, n).astype(np.float32)
+    S = rng.uniform(30, 40, n).astype(np.float32)
+    T[n // 2] = np.nan
+    S[n - 1] = np.nan
+    Td, Sd = torch.from_numpy(T).cuda(), torch.from_numpy(S).cuda()
+    before = core.launch_count()
+    got = core.flament_spice(Td, Sd)
+    assert core.launch_count() == before + 1
+    prev = core.force_direct(1)
+    try:
+        plain = core.flament_spice(Td, Sd)
+    finally:
+        core.force_direct(prev)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(plain, nan=-7.0))
+    m = slice(None) if n <= 1 << 20 else slice(0, None, 97)
+    want = ospice.flament_spice(T[m].astype(np.float64), S[m].astype(np.float64))
+    g = got.cpu().numpy()[m]
+    assert np.array_equal(np.isnan(g), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(g[ok] - want[ok])) < 1e-12
+
+
+@pytest.mark.parametrize("eos", ["Wright", "linear"])
+@pytest.mark.parametrize("shape,bcast", [((3, 7, 4, 516), None), ((2, 5, 8, 1024), "t"), ((2, 5, 8, 1024), "s"),
+                                         ((1, 75, 16, 160), None), ((4, 3, 1, 8), None)])
+def test_stream_density_rows_pressure_and_broadcast(ml, eos, shape, bcast):
+    """eos.<name>.density over [t][z][y][x] with one pressure per level: rows that are not a whole number of tiles,
+    a broadcast operand (steric.py:115-121), against the oracle (1e-10 relative) and the plain kernel (bit for bit)."""
+    from momlevel_b200 import core
+    from oracle import eos as oeos
+
+    nt, nz, ny, nx = shape
+    rng = np.random.default_rng(nt * 1000 + nz)
+    T = rng.uniform(-2, 32, shape).astype(np.float32)
+    S = rng.uniform(30, 40, shape).astype(np.float32)
+    T[0, 0, 0, 1] = np.nan
+    p = np.linspace(1e5, 6e7, nz)
+    Td, Sd = torch.from_numpy(T).cuda(), torch.from_numpy(S).cuda()
+    Tin = Td[0].contiguous() if bcast == "t" else Td
+    Sin = Sd[0].contiguous() if bcast == "s" else Sd
+    kw = dict(z_axis=1, t_bcast=bcast == "t", s_bcast=bcast == "s")
+    got = core.eos_eval(eos, "density", Tin, Sin, p, **kw)
+    prev = core.force_direct(1)
+    try:
+        plain = core.eos_eval(eos, "density", Tin, Sin, p, **kw)
+    finally:
+        core.force_direct(prev)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(plain, nan=-7.0))
+    T64 = (T[0:1] if bcast == "t" else T).astype(np.float64)
+    S64 = (S[0:1] if bcast == "s" else S).astype(np.float64)
+    want = np.broadcast_to(oeos.density(eos, T64, S64, p[None, :, None, None]), shape)
+    g = got.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(g[ok] - want[ok]) / np.abs(want[ok])) < RHO_RTOL
+    # a scalar pressure takes the same kernel
+    got_s = core.eos_eval(eos, "density", Td, Sd, 2.0e5)
+    want_s = oeos.density(eos, T.astype(np.float64), S.astype(np.float64), 2.0e5)
+    ok = ~np.isnan(want_s)
+    assert np.max(np.abs(got_s.cpu().numpy()[ok] - want_s[ok]) / np.abs(want_s[ok])) < RHO_RTOL
+
+
+@pytest.mark.parametrize("eos", ["Wright", "linear"])
+@pytest.mark.parametrize("shape", [(7, 4, 516), (75, 16, 160), (3, 1, 8), (12, 60, 1024)])
+def test_stream_reference_state(ml, eos, shape):
+    """reference.py:71-80 through the ring-staged kernel: rho_ref bit for bit with the plain kernel and within
+    1e-10 of the oracle, volo / masso (another summation order) to 1e-13."""
+    from momlevel_b200 import core
+    from oracle import eos as oeos
+
+    nz, ny, nx = shape
+    rng = np.random.default_rng(nz * 31 + nx)
+    T = rng.uniform(-2, 32, shape).astype(np.float32)
+    S = rng.uniform(30, 40, shape).astype(np.float32)
+    V = rng.uniform(1e6, 1e9, shape).astype(np.float32)
+    V[:, 0, :3] = np.nan
+    T[0, 0, 5] = np.nan  # a hole where the volume is present: skipped by masso, kept by volo
+    p = np.linspace(1e5, 6e7, nz)
+    args = [torch.from_numpy(x).cuda() for x in (T, S, V)]
+    rho, sums = core.reference_state(*args, p, eos=eos)
+    prev = core.force_direct(1)
+    try:
+        rho_p, sums_p = core.reference_state(*args, p, eos=eos)
+    finally:
+        core.force_direct(prev)
+    assert torch.equal(torch.nan_to_num(rho, nan=-7.0), torch.nan_to_num(rho_p, nan=-7.0))
+    assert torch.allclose(sums, sums_p, rtol=1e-13, atol=0)
+    want = oeos.density(eos, T.astype(np.float64), S.astype(np.float64), p[:, None, None])
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(rho.cpu().numpy()[ok] - want[ok]) / np.abs(want[ok])) < RHO_RTOL
+    V64 = V.astype(np.float64)
+    assert float(sums[0]) == pytest.approx(np.nansum(V64), rel=1e-13)
+    assert float(sums[1]) == pytest.approx(np.nansum(want * V64), rel=1e-13)
