@@ -9,7 +9,7 @@
 // persistent CTA streams its tiles through a 4-stage ring filled by 1-D bulk copies
 // (cp.async.bulk.shared::cluster.global, one mbarrier per stage): loads cost no registers and no issue
 // slots, ~128 KB per SM are in flight whatever the occupancy, the math reads 128-bit words from shared
-// memory and results leave as 128-bit streaming stores.
+// memory and results leave as 256-bit streaming stores.
 //
 // Layout: the operands are rows of `ncol` points (a level of one time step; a flat array is one row); a tile
 // is kTile consecutive points of one row.  Rows must start 16-byte aligned in every operand
@@ -32,8 +32,19 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
                "l"(src), "r"(bytes), "r"(tma::smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void st2(double* p, double a, double b) {
-  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+// four results of a quad leave as ONE 256-bit store (sm_100: STG.256): a lane writes a whole 32-byte sector and a
+// warp 1 KB in a row; two 128-bit stores per lane would each write half of every sector they touch
+__device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
+               : "memory");
+}
+// A warp is done with a stage: returns true in lane 0 of the warp that is the LAST of the CTA to leave it (that
+// lane refills the stage).  acq_rel on the counter orders every warp's shared-memory reads of the stage -- made
+// visible to lane 0 by the __syncwarp() -- before the refill that the last lane issues.
+__device__ __forceinline__ bool last_to_leave(int* counter) {
+  __syncwarp();
+  if ((threadIdx.x & 31) != 0) return false;
+  return (tma::stage_released(counter) & (kWarps - 1)) == kWarps - 1;
 }
 
 struct Geom {
@@ -43,19 +54,24 @@ struct Geom {
   int nz;             // rows per outer (time) index: row = t * nz + z
 };
 
-// Ring of kStages stages of NIN fp32 operand tiles.  Thread 0 issues the copies; everybody waits on the
-// stage's mbarrier; a stage is refilled after the CTA-wide barrier that follows its last read.
+// Ring of kStages stages of NIN fp32 operand tiles.  Everybody waits on the stage's mbarrier; the warp that is the
+// last to leave a stage refills it (no producer warp, no CTA-wide barrier in the loop).
 template <int NIN>
 struct Ring {
   float* base;
   uint64_t* full;
+  int* released;  // [kStages] warps that have left the stage (mod kWarps)
   __device__ __forceinline__ float* stage(int s, int k) const { return base + ((size_t)s * NIN + k) * kTile; }
   __device__ __forceinline__ void init(unsigned char* smem) {
     base = reinterpret_cast<float*>(smem);
     full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * NIN * kTile * sizeof(float));
+    released = reinterpret_cast<int*>(full + kStages);
     if (threadIdx.x == 0) {
 #pragma unroll
-      for (int s = 0; s < kStages; ++s) tma::mbar_init(full + s, 1);
+      for (int s = 0; s < kStages; ++s) {
+        tma::mbar_init(full + s, 1);
+        released[s] = 0;
+      }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -63,13 +79,13 @@ struct Ring {
 };
 template <int NIN>
 constexpr size_t ring_bytes() {
-  return (size_t)kStages * NIN * kTile * sizeof(float) + kStages * sizeof(uint64_t) + 64;
+  return (size_t)kStages * NIN * kTile * sizeof(float) + kStages * (sizeof(uint64_t) + sizeof(int)) + 64;
 }
 
 // ------------------------------------------------------------------------------ spice / density
 // OP 0: Flament spiciness (T, S).  OP 1: density of EOS (T, S, p per row: scalar or per level).
 template <int OP, int EOS>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 3)
     k_stream_map(const float* __restrict__ T, const float* __restrict__ S, i64 t_stride, i64 s_stride,
                  const double* __restrict__ p, int pmode, Geom g, double* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -124,12 +140,10 @@ __global__ void __launch_bounds__(kThreads, 2)
           r2 = eos.rho_checked((double)a.z, (double)b.z);
           r3 = eos.rho_checked((double)a.w, (double)b.w);
         }
-        st2(o + 4 * q, r0, r1);
-        st2(o + 4 * q + 2, r2, r3);
+        st4(o + 4 * q, r0, r1, r2, r3);
       }
     }
-    __syncthreads();  // every thread has read the stage
-    if (tid == 0) {
+    if (last_to_leave(ring.released + s)) {
       const i64 next = tile + (i64)kStages * gridDim.x;
       if (next < g.ntiles) issue(next, s);
     }
@@ -198,12 +212,10 @@ __global__ void __launch_bounds__(kThreads, 2)
             const double m = r[j] * (double)vv[j];
             if (!is_nan_q(m)) mass += m;
           }
-        st2(o + 4 * q, r[0], r[1]);
-        st2(o + 4 * q + 2, r[2], r[3]);
+        st4(o + 4 * q, r[0], r[1], r[2], r[3]);
       }
     }
-    __syncthreads();
-    if (tid == 0) {
+    if (last_to_leave(ring.released + s)) {
       const i64 next = tile + (i64)kStages * gridDim.x;
       if (next < g.ntiles) issue(next, s);
     }
@@ -226,17 +238,18 @@ static Geom geometry(i64 nrows, int nz, i64 ncol) {
   return g;
 }
 
-static unsigned persistent_grid(i64 ntiles) {
+static unsigned persistent_grid(i64 ntiles, int ctas_per_sm) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const i64 want = 2 * (i64)sms;  // two CTAs per SM
+  const i64 want = (i64)ctas_per_sm * sms;
   return (unsigned)(ntiles < want ? ntiles : want);
 }
 
 bool eligible(const void* a, const void* b, const void* c, const void* out, i64 ncol) {
-  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) |
-                         reinterpret_cast<uintptr_t>(c) | reinterpret_cast<uintptr_t>(out);
-  return (bits & 15u) == 0 && ncol % 4 == 0 && ncol >= 4 && ncol / kTile < 0x7fffffff;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c);
+  // fp32 rows start on 16 bytes (bulk copies), fp64 result rows on 32 (256-bit stores)
+  return (bits & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 31u) == 0 && ncol % 4 == 0 && ncol >= 4 &&
+         ncol / kTile < 0x7fffffff;
 }
 
 template <typename K>
@@ -249,14 +262,14 @@ int launch_spice(const float* T, const float* S, i64 n, double* out, cudaStream_
   const Geom g = geometry(1, 1, n);
   auto kern = k_stream_map<0, 0>;
   if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
-  kern<<<persistent_grid(g.ntiles), kThreads, ring_bytes<2>(), st>>>(T, S, 0, 0, nullptr, 0, g, out);
+  kern<<<persistent_grid(g.ntiles, 3), kThreads, ring_bytes<2>(), st>>>(T, S, 0, 0, nullptr, 0, g, out);
   return launched("k_stream_map(spice)");
 }
 
 int launch_density(int eos, const float* T, const float* S, i64 t_stride, i64 s_stride, const double* p, int pmode,
                    i64 nrows, int nz, i64 ncol, double* out, cudaStream_t st) {
   const Geom g = geometry(nrows, nz, ncol);
-  const unsigned grid = persistent_grid(g.ntiles);
+  const unsigned grid = persistent_grid(g.ntiles, 3);
   if (eos == ML_EOS_WRIGHT) {
     auto kern = k_stream_map<1, 0>;
     if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
@@ -271,13 +284,13 @@ int launch_density(int eos, const float* T, const float* S, i64 t_stride, i64 s_
 
 int refstate_blocks(i64 nz, i64 ncol) {
   const Geom g = geometry(nz, (int)nz, ncol);
-  return (int)persistent_grid(g.ntiles);
+  return (int)persistent_grid(g.ntiles, 2);
 }
 
 int launch_refstate(int eos, const float* T0, const float* S0, const float* V0, const double* p_level, i64 nz, i64 ncol,
                     double* rho_ref, double* partials, cudaStream_t st) {
   const Geom g = geometry(nz, (int)nz, ncol);
-  const unsigned grid = persistent_grid(g.ntiles);
+  const unsigned grid = persistent_grid(g.ntiles, 2);
   if (eos == ML_EOS_WRIGHT) {
     auto kern = k_stream_refstate<0>;
     if (int rc = opt_in(kern, ring_bytes<3>())) return rc;

@@ -266,7 +266,7 @@ __global__ void ML_TMA_KERNEL_ATTR
       __syncwarp();
       if (lane == 0) {
         // the 8th warp to leave the stage refills it with the level kStages further on
-        const int before = atomicAdd(released + s, 1);
+        const int before = stage_released(released + s);
         if (ML_TMA_EXPERIMENT != 1 && (before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz)
           refill_stage(z + kStages);
       }

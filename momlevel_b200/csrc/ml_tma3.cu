@@ -208,23 +208,26 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
     }
     __syncwarp();
     if (lane == 0) {
-      const int before = atomicAdd(released + s, 1);
+      const int before = stage_released(released + s);
       if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz) refill_stage(z + kStages);
     }
   }
 
   // Repair pass (rare): a hole at a wet cell turned the column's sums into NaN; xarray's sum skips the
   // missing term (steric.py:163), so the column is integrated again from global memory with that rule.
-  bool poisoned = false;
+  // Each height is repaired on its own, as its single-height kernel would (a hole in T does not touch the
+  // halosteric sums, which hold T at the reference slab).
+  bool poisoned[3] = {false, false, false};
 #pragma unroll
   for (int v = 0; v < 3; ++v)
 #pragma unroll
-    for (int k = 0; k < TC; ++k) poisoned |= is_nan_q(acc[v][k]);
-  if (poisoned && in) {
+    for (int k = 0; k < TC; ++k) poisoned[v] |= is_nan_q(acc[v][k]);
+  if ((poisoned[0] || poisoned[1] || poisoned[2]) && in) {
 #pragma unroll
     for (int v = 0; v < 3; ++v)
 #pragma unroll
-      for (int k = 0; k < TC; ++k) acc[v][k] = 0.0;
+      for (int k = 0; k < TC; ++k)
+        if (poisoned[v]) acc[v][k] = 0.0;
     const i64 lvl = (i64)nz * P.ncol;
     for (int z = 0; z < nz; ++z) {
       const i64 j = (i64)z * P.ncol + c;
@@ -240,9 +243,9 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
         const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
         const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
         // (the single-height kernels repair with the unpinned evaluation; the same here keeps the fields identical)
-        fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
-        fma_skipnan(acc[1][k], w, eos.rho(Tv, Sr) - sub);
-        fma_skipnan(acc[2][k], w, eos.rho(Tr, Sv) - sub);
+        if (poisoned[0]) fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
+        if (poisoned[1]) fma_skipnan(acc[1][k], w, eos.rho(Tv, Sr) - sub);
+        if (poisoned[2]) fma_skipnan(acc[2][k], w, eos.rho(Tr, Sv) - sub);
       }
     }
   }

@@ -49,6 +49,20 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// One more warp has finished reading a ring stage; returns how many had before it.  The warp whose count completes
+// the CTA issues the TMA refill, an async-proxy write into memory the other warps have just read through the
+// generic proxy: acq_rel (CTA scope) on the counter puts every warp's reads -- gathered by the __syncwarp() in front
+// of the call -- before that write.  ML_TMA_RELAXED_RELEASE restores the relaxed atomicAdd for an A/B.
+__device__ __forceinline__ int stage_released(int* counter) {
+#ifdef ML_TMA_RELAXED_RELEASE
+  return atomicAdd(counter, 1);
+#else
+  int before;
+  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(before) : "r"(smem_u32(counter)) : "memory");
+  return before;
+#endif
+}
+
 // acc += w * d unless d is NaN (xarray's skipna sum).  d comes out of fp64 arithmetic, so a
 // NaN is quiet and the test is one integer compare on the high word.
 __device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
