@@ -518,7 +518,8 @@ int ml_set_force_direct(int on) {
 
 int ml_set_variants_chunk(int tc) {
   const int prev = tls().variants_chunk;
-  tls().variants_chunk = (tc == 4 || tc == 6 || tc == 8 || tc == 12) ? tc : 0;
+  const int w = tc % 100;  // + 100: 128-column tiles, + 200: 256-column tiles (experiments)
+  tls().variants_chunk = (tc >= 0 && tc < 300 && (w == 0 || w == 4 || w == 6 || w == 8 || w == 12)) ? tc : 0;
   return prev;
 }
 

@@ -38,13 +38,12 @@ __device__ __forceinline__ void st4(double* p, double a, double b, double c, dou
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
                : "memory");
 }
-// A warp is done with a stage: returns true in lane 0 of the warp that is the LAST of the CTA to leave it (that
-// lane refills the stage).  acq_rel on the counter orders every warp's shared-memory reads of the stage -- made
-// visible to lane 0 by the __syncwarp() -- before the refill that the last lane issues.
-__device__ __forceinline__ bool last_to_leave(int* counter) {
+// A warp is done with a stage: true in lane 0 of the warp that is the LAST of the CTA to leave it (that lane
+// refills the stage); tma::stage_done orders every warp's reads of the stage before the refill.
+__device__ __forceinline__ bool last_to_leave(uint64_t* empty_bar, int* counter, uint32_t parity) {
   __syncwarp();
   if ((threadIdx.x & 31) != 0) return false;
-  return (tma::stage_released(counter) & (kWarps - 1)) == kWarps - 1;
+  return tma::stage_done(empty_bar, counter, kWarps, parity);
 }
 
 struct Geom {
@@ -59,17 +58,19 @@ struct Geom {
 template <int NIN>
 struct Ring {
   float* base;
-  uint64_t* full;
+  uint64_t *full, *empty;
   int* released;  // [kStages] warps that have left the stage (mod kWarps)
   __device__ __forceinline__ float* stage(int s, int k) const { return base + ((size_t)s * NIN + k) * kTile; }
   __device__ __forceinline__ void init(unsigned char* smem) {
     base = reinterpret_cast<float*>(smem);
     full = reinterpret_cast<uint64_t*>(smem + (size_t)kStages * NIN * kTile * sizeof(float));
-    released = reinterpret_cast<int*>(full + kStages);
+    empty = full + kStages;
+    released = reinterpret_cast<int*>(full + 2 * kStages);
     if (threadIdx.x == 0) {
 #pragma unroll
       for (int s = 0; s < kStages; ++s) {
         tma::mbar_init(full + s, 1);
+        tma::mbar_init(empty + s, kWarps);
         released[s] = 0;
       }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -79,7 +80,7 @@ struct Ring {
 };
 template <int NIN>
 constexpr size_t ring_bytes() {
-  return (size_t)kStages * NIN * kTile * sizeof(float) + kStages * (sizeof(uint64_t) + sizeof(int)) + 64;
+  return (size_t)kStages * NIN * kTile * sizeof(float) + kStages * (2 * sizeof(uint64_t) + sizeof(int)) + 64;
 }
 
 // ------------------------------------------------------------------------------ spice / density
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         st4(o + 4 * q, r0, r1, r2, r3);
       }
     }
-    if (last_to_leave(ring.released + s)) {
+    if (last_to_leave(ring.empty + s, ring.released + s, (uint32_t)(it / kStages) & 1u)) {
       const i64 next = tile + (i64)kStages * gridDim.x;
       if (next < g.ntiles) issue(next, s);
     }
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         st4(o + 4 * q, r[0], r[1], r[2], r[3]);
       }
     }
-    if (last_to_leave(ring.released + s)) {
+    if (last_to_leave(ring.empty + s, ring.released + s, (uint32_t)(it / kStages) & 1u)) {
       const i64 next = tile + (i64)kStages * gridDim.x;
       if (next < g.ntiles) issue(next, s);
     }

@@ -103,8 +103,9 @@ __global__ void ML_TMA_KERNEL_ATTR
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
-  int* released = reinterpret_cast<int*>(full + kStages);     // [kStages] warps that are done with the stage
-  double* red = reinterpret_cast<double*>(full + 2 * kStages);  // [kConsumerWarps][TC]
+  uint64_t* empty = full + kStages;                            // [kStages] "every warp has left the stage"
+  int* released = reinterpret_cast<int*>(full + 2 * kStages);  // [kStages] warps that are done with the stage
+  double* red = reinterpret_cast<double*>(full + 3 * kStages);  // [kConsumerWarps][TC]
   double* s_p = red + kConsumerWarps * TC;                   // [nz]   pressure per level
   double* s_zi = s_p + P.nz;                                 // [nz+1] interfaces (local modes)
   int* s_key = reinterpret_cast<int*>(s_zi + P.nz + 1);      // [kTile] wet levels per column (SORT)
@@ -136,6 +137,7 @@ __global__ void ML_TMA_KERNEL_ATTR
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full + s, 1);
+      mbar_init(empty + s, kConsumerWarps);
       released[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -266,8 +268,8 @@ __global__ void ML_TMA_KERNEL_ATTR
       __syncwarp();
       if (lane == 0) {
         // the 8th warp to leave the stage refills it with the level kStages further on
-        const int before = stage_released(released + s);
-        if (ML_TMA_EXPERIMENT != 1 && (before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz)
+        if (stage_done(empty + s, released + s, kConsumerWarps, (uint32_t)(z / kStages) & 1u) && ML_TMA_EXPERIMENT != 1 &&
+            z + kStages < nz)
           refill_stage(z + kStages);
       }
     }
@@ -295,12 +297,18 @@ __global__ void ML_TMA_KERNEL_ATTR
         eos.set_level(s_p[z]);
         if (SELFREF)  // the reference density again, from step 0 of this column (same arithmetic as in the sweep)
           sub = eos.rho((double)__ldg(P.T + j), (double)__ldg(P.S + j));
+        // the same evaluation as the sweep (a pinned operand folded into the coefficients), so that a repaired
+        // column does not depend on how the time axis was cut into chunks
+        typename Eos<EOS>::Pinned pin = {};
+        if (BC == 1) pin = eos.pin_t((double)__ldg(P.T + j));
+        if (BC == 2) pin = eos.pin_s((double)__ldg(P.S + j));
 #pragma unroll
         for (int k = SELFREF ? 1 : 0; k < TC; ++k) {
           if (t0 + k >= P.nt || (k == 0 && zero_first)) continue;
           const double Tv = (double)__ldg(P.T + (BC == 1 ? 0 : (i64)(t0 + k) * lvl) + j);
           const double Sv = (double)__ldg(P.S + (BC == 2 ? 0 : (i64)(t0 + k) * lvl) + j);
-          fma_skipnan(acc[k], w, GLOBAL ? eos.rho(Tv, Sv) : eos.rho(Tv, Sv) - sub);
+          const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
+          fma_skipnan(acc[k], w, GLOBAL ? rho : rho - sub);
         }
       }
     }
@@ -366,7 +374,7 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
 template <int TC>
 inline size_t smem_bytes(int bc, int nz, int mode) {
   const int kStages = stages_of(mode);
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 2 * kStages * sizeof(uint64_t) +
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 3 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 

@@ -55,33 +55,38 @@ struct Params3 {
 
 // Registers: 3 x TC running sums.  TC = 12 needs ~216 registers (one CTA of 8 warps per SM, a 6-level ring);
 // TC <= 8 fits the 128 of two CTAs per SM (4-level rings).
-__host__ __device__ constexpr int ctas_per_sm3(int tc) { return tc > 8 ? 1 : 2; }
+// TILE = 128 halves the CTA (one warp per SM sub-partition) and doubles the CTAs per SM: the four warps that share
+// a sub-partition then come from four CTAs at unrelated depths of their sweeps, instead of a fixed deep / shallow
+// pair of one CTA whose partner idles whenever its own band is dry.
+__host__ __device__ constexpr int ctas_per_sm3(int tc, int tile = 256) { return (tc > 8 ? 1 : 2) * (256 / tile); }
 __host__ __device__ constexpr int stages3(int tc) { return tc > 8 ? 6 : 4; }
 
-template <int EOS, int TC, int MODE>
-__global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
+template <int EOS, int TC, int MODE, int TILE>
+__global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
     k_steric_tma3(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS,
                   const __grid_constant__ CUtensorMap mapTr, const __grid_constant__ CUtensorMap mapSr, const Params3 P) {
   constexpr bool SELFREF = MODE == kSelfRef3;
+  constexpr int kWarpsT = TILE / 32;
   constexpr int kStages = stages3(TC);
   constexpr int kRows = 2 * TC + 2;
-  constexpr uint32_t kStageBytes = (uint32_t)kRows * kTile * sizeof(float);
-  constexpr int kStageFloats = kRows * kTile;
-  constexpr int kOffS = TC * kTile, kOffTr = 2 * TC * kTile, kOffSr = (2 * TC + 1) * kTile;
+  constexpr uint32_t kStageBytes = (uint32_t)kRows * TILE * sizeof(float);
+  constexpr int kStageFloats = kRows * TILE;
+  constexpr int kOffS = TC * TILE, kOffTr = 2 * TC * TILE, kOffSr = (2 * TC + 1) * TILE;
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* stage_base = reinterpret_cast<float*>(smem_raw);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
-  int* released = reinterpret_cast<int*>(full + kStages);
-  double* red = reinterpret_cast<double*>(full + 2 * kStages);  // [kConsumerWarps][2]
-  double* s_p = red + kConsumerWarps * 2;
+  uint64_t* empty = full + kStages;
+  int* released = reinterpret_cast<int*>(full + 2 * kStages);
+  double* red = reinterpret_cast<double*>(full + 3 * kStages);  // [kWarpsT][2]
+  double* s_p = red + kWarpsT * 2;
   double* s_zi = s_p + P.nz;
   int* s_key = reinterpret_cast<int*>(s_zi + P.nz + 1);
-  int* s_col = s_key + kTile;
+  int* s_col = s_key + TILE;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned tile = blockIdx.x / P.nchunks;
-  const int c0 = (int)tile * kTile;
+  const int c0 = (int)tile * TILE;
   const int t0 = P.t_start + (int)(blockIdx.x - tile * P.nchunks) * TC;
   const int nz = P.nz;
   const bool chunk0 = SELFREF && t0 == 0;  // this CTA's chunk starts at the reference step
@@ -100,14 +105,15 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full + s, 1);
+      mbar_init(empty + s, kWarpsT);
       released[s] = 0;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     for (int z = 0; z < kStages && z < nz; ++z) refill_stage(z);
   }
-  for (int i = threadIdx.x; i < nz; i += kThreads) s_p[i] = __ldg(P.p_level + i);
-  for (int i = threadIdx.x; i <= nz; i += kThreads) s_zi[i] = __ldg(P.z_i + i);
+  for (int i = threadIdx.x; i < nz; i += TILE) s_p[i] = __ldg(P.p_level + i);
+  for (int i = threadIdx.x; i <= nz; i += TILE) s_zi[i] = __ldg(P.z_i + i);
   __syncthreads();
 
   // columns of the tile ranked by wet depth (see ml_tma.cu): thread i integrates the i-th deepest column
@@ -115,7 +121,7 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
   {
     const i64 cg = (i64)c0 + tid;
     const int key = wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
-    col = sorted_column(key, reinterpret_cast<unsigned*>(s_key), s_col);
+    col = sorted_column_t<TILE>(key, reinterpret_cast<unsigned*>(s_key), s_col);
   }
 
   const i64 c = (i64)c0 + col;
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
 #pragma unroll
       for (int kk = 0; kk < TC; ++kk) {
         if (SELFREF && kk == 0 && chunk0) continue;  // step 0 is the reference itself: exactly zero
-        const double Tv = (double)st[kk * kTile + src];
-        const double Sv = (double)st[kOffS + kk * kTile + src];
+        const double Tv = (double)st[kk * TILE + src];
+        const double Sv = (double)st[kOffS + kk * TILE + src];
         if constexpr (ML_TMA3_MONTGOMERY != 0 && EOS == 0) {
           double p1, d1, p2, d2, p3, d3;
           eos.terms_of(Tv, Sv, p1, d1);
@@ -207,10 +213,8 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
       if (P.rho_ref_out) P.rho_ref_out[(i64)z * P.ncol + c] = sub;
     }
     __syncwarp();
-    if (lane == 0) {
-      const int before = stage_released(released + s);
-      if ((before & (kConsumerWarps - 1)) == kConsumerWarps - 1 && z + kStages < nz) refill_stage(z + kStages);
-    }
+    if (lane == 0 && stage_done(empty + s, released + s, kWarpsT, (uint32_t)(z / kStages) & 1u) && z + kStages < nz)
+      refill_stage(z + kStages);
   }
 
   // Repair pass (rare): a hole at a wet cell turned the column's sums into NaN; xarray's sum skips the
@@ -237,15 +241,17 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
       eos.set_level(s_p[z]);
       const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
       const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
+      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
+      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
 #pragma unroll
       for (int k = 0; k < TC; ++k) {
         if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
         const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
         const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
-        // (the single-height kernels repair with the unpinned evaluation; the same here keeps the fields identical)
+        // the sweep's evaluation (as in the single-height kernels): a repaired column does not depend on the chunking
         if (poisoned[0]) fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
-        if (poisoned[1]) fma_skipnan(acc[1][k], w, eos.rho(Tv, Sr) - sub);
-        if (poisoned[2]) fma_skipnan(acc[2][k], w, eos.rho(Tr, Sv) - sub);
+        if (poisoned[1]) fma_skipnan(acc[1][k], w, eos.rho_pinned_s(qs, Tv) - sub);
+        if (poisoned[2]) fma_skipnan(acc[2][k], w, eos.rho_pinned_t(qt, Sv) - sub);
       }
     }
   }
@@ -269,29 +275,29 @@ __global__ void __launch_bounds__(kThreads, ctas_per_sm3(TC))
     if (tid < 2) {
       double sacc = 0.0;
 #pragma unroll
-      for (int w8 = 0; w8 < kConsumerWarps; ++w8) sacc += red[w8 * 2 + tid];
+      for (int w8 = 0; w8 < kWarpsT; ++w8) sacc += red[w8 * 2 + tid];
       P.partials[(i64)tid * P.tiles + tile] = sacc;
     }
   }
 }
 
 // ----------------------------------------------------------------------- host side
-template <int TC>
+template <int TC, int TILE>
 static size_t smem_bytes3(int nz) {
-  return (size_t)stages3(TC) * (size_t)((2 * TC + 2) * kTile * 4) + 2 * stages3(TC) * sizeof(uint64_t) +
-         (size_t)kConsumerWarps * 2 * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
+  return (size_t)stages3(TC) * (size_t)((2 * TC + 2) * TILE * 4) + 3 * stages3(TC) * sizeof(uint64_t) +
+         (size_t)(TILE / 32) * 2 * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * TILE * sizeof(int) + 128;
 }
 
-template <int EOS, int TC, int MODE>
+template <int EOS, int TC, int MODE, int TILE>
 static int launch_one3(const CUtensorMap maps[4], const Params3& P, unsigned tiles, unsigned chunks, cudaStream_t st) {
-  auto kern = k_steric_tma3<EOS, TC, MODE>;
-  const size_t smem = smem_bytes3<TC>(P.nz);
+  auto kern = k_steric_tma3<EOS, TC, MODE, TILE>;
+  const size_t smem = smem_bytes3<TC, TILE>(P.nz);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(k_steric_tma3)");
   Params3 Q = P;
   Q.tiles = tiles;
   Q.nchunks = chunks;
-  kern<<<tiles * chunks, kThreads, smem, st>>>(maps[0], maps[1], maps[2], maps[3], Q);
+  kern<<<tiles * chunks, TILE, smem, st>>>(maps[0], maps[1], maps[2], maps[3], Q);
   return launched("k_steric_tma3");
 }
 
@@ -301,28 +307,43 @@ static int launch_one3(const CUtensorMap maps[4], const Params3& P, unsigned til
 #ifndef ML_TMA3_TC
 #define ML_TMA3_TC 6
 #endif
+// columns per CTA: 256 or 128 (ML_TMA3_TILE in the environment, or 100 added to the value given to
+// ml_set_variants_chunk, e.g. 106 = 128-column tiles with 6-step chunks)
+#ifndef ML_TMA3_TILE
+#define ML_TMA3_TILE 256
+#endif
+static int tile3() {
+  static const int from_env = [] {
+    const char* v = getenv("ML_TMA3_TILE");
+    const int n = v ? atoi(v) : ML_TMA3_TILE;
+    return n == 128 ? 128 : (n == 256 ? 256 : ML_TMA3_TILE);
+  }();
+  const int t = tls().variants_chunk;
+  if (t >= 200) return 256;
+  return t >= 100 ? 128 : from_env;
+}
 static int main_tc3() {
   static const int from_env = [] {
     const char* v = getenv("ML_TMA3_TC");
     const int n = v ? atoi(v) : ML_TMA3_TC;
     return (n == 4 || n == 6 || n == 8 || n == 12) ? n : ML_TMA3_TC;
   }();
-  const int t = tls().variants_chunk;  // ml_set_variants_chunk
+  const int t = tls().variants_chunk % 100;  // ml_set_variants_chunk
   return (t == 4 || t == 6 || t == 8 || t == 12) ? t : from_env;
 }
 
-template <int MODE>
+template <int MODE, int TILE>
 static int launch_span3(int eos, const void* T, const void* S, const void* Tr, const void* Sr, Params3 P, int t_begin,
                         int t_end, int tc, cudaStream_t st) {
   // one launch: chunks of `tc` steps covering [t_begin, t_end)
   CUtensorMap maps[4];
-  const bool ok = make_map(&maps[0], T, 3, P.ncol, P.nz, P.nt, tc) && make_map(&maps[1], S, 3, P.ncol, P.nz, P.nt, tc) &&
-                  make_map(&maps[2], Tr, 2, P.ncol, P.nz, 1, 1) && make_map(&maps[3], Sr, 2, P.ncol, P.nz, 1, 1);
+  const bool ok = make_map(&maps[0], T, 3, P.ncol, P.nz, P.nt, tc, TILE) && make_map(&maps[1], S, 3, P.ncol, P.nz, P.nt, tc, TILE) &&
+                  make_map(&maps[2], Tr, 2, P.ncol, P.nz, 1, 1, TILE) && make_map(&maps[3], Sr, 2, P.ncol, P.nz, 1, 1, TILE);
   if (!ok) return fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
   P.t_start = t_begin;
-  const unsigned tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
+  const unsigned tiles = (unsigned)((P.ncol + TILE - 1) / TILE);
   const unsigned chunks = (unsigned)((t_end - t_begin + tc - 1) / tc);
-#define ML_TMA3_GO(E, TCV) return launch_one3<E, TCV, MODE>(maps, P, tiles, chunks, st)
+#define ML_TMA3_GO(E, TCV) return launch_one3<E, TCV, MODE, TILE>(maps, P, tiles, chunks, st)
   if (eos == ML_EOS_WRIGHT) {
     if (tc == 12) ML_TMA3_GO(0, 12);
     if (tc == 8) ML_TMA3_GO(0, 8);
@@ -336,16 +357,16 @@ static int launch_span3(int eos, const void* T, const void* S, const void* Tr, c
 #undef ML_TMA3_GO
 }
 
-template <int MODE>
+template <int MODE, int TILE>
 static int launch_all3(int eos, const void* T, const void* S, const void* Tr, const void* Sr, const Params3& P,
                        cudaStream_t st) {
   const int main_tc = main_tc3();
   const int full = P.nt / main_tc, rest = P.nt % main_tc;
   int rc = ML_OK;
-  if (full > 0) rc = launch_span3<MODE>(eos, T, S, Tr, Sr, P, 0, full * main_tc, main_tc, st);
+  if (full > 0) rc = launch_span3<MODE, TILE>(eos, T, S, Tr, Sr, P, 0, full * main_tc, main_tc, st);
   if (rc == ML_OK && rest > 0) {
     const int tc = rest <= 4 ? 4 : (rest <= 6 ? 6 : (rest <= 8 ? 8 : 12));
-    rc = launch_span3<MODE>(eos, T, S, Tr, Sr, P, full * main_tc, P.nt, tc, st);
+    rc = launch_span3<MODE, TILE>(eos, T, S, Tr, Sr, P, full * main_tc, P.nt, tc, st);
   }
   return rc;
 }
@@ -382,11 +403,15 @@ int launch_variants(int eos, const void* T, const void* S, const void* T_ref, co
   P.eta[1] = eta_thermo;
   P.eta[2] = eta_halo;
   P.partials = partials;
-  if (rho_ref != nullptr) return launch_all3<kLocal3>(eos, T, S, T_ref, S_ref, P, st);
+  const int tile = tile3();
+  if (rho_ref != nullptr)
+    return tile == 128 ? launch_all3<kLocal3, 128>(eos, T, S, T_ref, S_ref, P, st)
+                       : launch_all3<kLocal3, 256>(eos, T, S, T_ref, S_ref, P, st);
   // reference = step 0 of the fields: T_ref / S_ref are the step-0 slabs
-  int rc = launch_all3<kSelfRef3>(eos, T, S, T_ref, S_ref, P, st);
+  int rc = tile == 128 ? launch_all3<kSelfRef3, 128>(eos, T, S, T_ref, S_ref, P, st)
+                       : launch_all3<kSelfRef3, 256>(eos, T, S, T_ref, S_ref, P, st);
   if (rc) return rc;
-  return reduce_rows(partials, (ncol + kTile - 1) / kTile, sums, 2, st);
+  return reduce_rows(partials, (ncol + tile - 1) / tile, sums, 2, st);
 }
 
 }  // namespace tma

@@ -49,18 +49,24 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
-// One more warp has finished reading a ring stage; returns how many had before it.  The warp whose count completes
-// the CTA issues the TMA refill, an async-proxy write into memory the other warps have just read through the
-// generic proxy: acq_rel (CTA scope) on the counter puts every warp's reads -- gathered by the __syncwarp() in front
-// of the call -- before that write.  ML_TMA_RELAXED_RELEASE restores the relaxed atomicAdd for an A/B.
-__device__ __forceinline__ int stage_released(int* counter) {
-#ifdef ML_TMA_RELAXED_RELEASE
-  return atomicAdd(counter, 1);
-#else
-  int before;
-  asm volatile("atom.acq_rel.cta.shared::cta.add.s32 %0, [%1], 1;" : "=r"(before) : "r"(smem_u32(counter)) : "memory");
-  return before;
+// A warp has finished reading a ring stage (call from lane 0, after a __syncwarp() that gathers the warp's reads).
+// Returns true in the lane whose warp is the LAST of the CTA to leave the stage: that lane issues the TMA refill,
+// an async-proxy write into memory the other warps have just read through the generic proxy.  Ordering: every warp
+// ARRIVES (release) on the stage's "empty" mbarrier before it bumps the election counter, and the elected lane
+// WAITS (acquire) for that phase before it returns -- all arrivals precede its own bump, so the wait falls
+// through -- which puts every warp's reads before the refill without a MEMBAR in the loop (an acq_rel atomic on
+// the counter compiles to MEMBAR.ALL.CTA + ATOMS and cost the thermo- / halosteric kernels 5-11 %).
+// ML_TMA_RELAXED_RELEASE keeps only the relaxed counter (round 1's scheme) for an A/B.
+__device__ __forceinline__ bool stage_done(uint64_t* empty_bar, int* counter, int nwarps, uint32_t parity) {
+#ifndef ML_TMA_RELAXED_RELEASE
+  mbar_arrive(empty_bar);
 #endif
+  const int before = atomicAdd(counter, 1);
+  if ((before & (nwarps - 1)) != nwarps - 1) return false;
+#ifndef ML_TMA_RELAXED_RELEASE
+  mbar_wait(empty_bar, parity);
+#endif
+  return true;
 }
 
 // acc += w * d unless d is NaN (xarray's skipna sum).  d comes out of fp64 arithmetic, so a
@@ -108,10 +114,11 @@ __device__ __forceinline__ int wet_levels(double depth, const double* s_zi, int 
 // order -- in registers (shuffles) and one shared-memory array.  Sorted position p goes to warp slot
 // 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the two warps an SM sub-partition hosts (w and
 // w + 4) carry a deep and a shallow band.  Every thread of the CTA must call it.
-__device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_col) {
+template <int TILE>
+__device__ __forceinline__ int sorted_column_t(int key, unsigned* s_key, int* s_col) {
   const int tid = threadIdx.x, lane = tid & 31;
-  unsigned v = ((unsigned)key << 8) | (unsigned)(kTile - 1 - tid);
-  for (int k = 2; k <= kTile; k <<= 1) {
+  unsigned v = ((unsigned)key << 8) | (unsigned)(TILE - 1 - tid);
+  for (int k = 2; k <= TILE; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       unsigned o;
       if (j >= 32) {
@@ -122,14 +129,20 @@ __device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_co
       } else {
         o = __shfl_xor_sync(0xffffffffu, v, j);
       }
-      const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = 256): descending
+      const bool lower = (tid & j) == 0, desc = (tid & k) == 0;  // final merge (k = TILE): descending
       v = (lower == desc) ? max(v, o) : min(v, o);
     }
   }
   const int band = tid >> 5;
-  s_col[(band < 4 ? band : 11 - band) * 32 + lane] = kTile - 1 - (int)(v & 255u);
+  // 256 columns: bands to warp slots 0 1 2 3 7 6 5 4 (a deep and a shallow band per SM sub-partition);
+  // 128 columns: one warp per sub-partition, bands in order
+  const int slot = TILE == 256 ? (band < 4 ? band : 11 - band) : band;
+  s_col[slot * 32 + lane] = TILE - 1 - (int)(v & 255u);
   __syncthreads();
   return s_col[tid];
+}
+__device__ __forceinline__ int sorted_column(int key, unsigned* s_key, int* s_col) {
+  return sorted_column_t<kTile>(key, s_key, s_col);
 }
 
 // ----------------------------------------------------------------------- host side
@@ -152,12 +165,12 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 field [nt][nz][ncol] (rank 3) or [nz][ncol] (rank 2); box = {kTile, 1, tc}
-static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc) {
+static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc, int tile = kTile) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
   cuuint64_t dims[3] = {(cuuint64_t)ncol, (cuuint64_t)nz, (cuuint64_t)nt};
   cuuint64_t strides[2] = {(cuuint64_t)ncol * 4, (cuuint64_t)ncol * (cuuint64_t)nz * 4};
-  cuuint32_t box[3] = {(cuuint32_t)kTile, 1, (cuuint32_t)tc};
+  cuuint32_t box[3] = {(cuuint32_t)tile, 1, (cuuint32_t)tc};
   cuuint32_t estr[3] = {1, 1, 1};
   return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

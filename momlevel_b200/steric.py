@@ -13,7 +13,7 @@ import torch
 from . import core
 from .labeled import DataArray, Dataset
 from .reference import _pressure, setup_reference_state
-from .util import annual_average, default_coords, validate_dataset
+from .util import annual_average, calendar_axis, default_coords, validate_dataset, whole_years_in_order
 
 __all__ = ["halosteric", "steric", "steric_variants", "thermosteric"]
 
@@ -38,7 +38,8 @@ def steric(
 
     Arguments as ``momlevel.steric`` (steric.py:17-82).  ``days_in_month`` is the one
     addition: the annual-mean weights when ``annual=True`` and the time axis carries no
-    calendar (the reference reads them from cftime).
+    calendar.  With a calendar time axis (cftime objects, as MOM6 output decodes to) the years
+    and weights are read from it, as the reference does (util.py:79-87).
 
     Returns ``(result, reference)``.
     """
@@ -143,10 +144,19 @@ def steric(
                                   eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
 
         drho_shape = full.shape
-        if annual and days_in_month is not None:
+        if annual and days_in_month is None and tcoord in dset.variables:
+            # util.py:79-87: year and days-in-month of every step come from the calendar objects of the time axis
+            cal = calendar_axis(dset[tcoord].values)
+            if cal is not None and whole_years_in_order(cal[0]):
+                fused_weights = cal[1]
+            else:
+                fused_weights = None
+        else:
+            fused_weights = days_in_month
+        if annual and fused_weights is not None:
             # steric.py:181-182 averages every result variable, the 4-D anomaly included: its annual means
             # come out of one fused pass instead of averaging a materialised monthly field
-            weights = np.asarray(days_in_month, dtype=np.float64)
+            weights = np.asarray(fused_weights, dtype=np.float64)
             assert weights.size == full.shape[0] and weights.size % 12 == 0, \
                 "annual averaging needs whole years of monthly data"
 

@@ -3,8 +3,10 @@
 Mirrors ``momlevel.test_data.generate_test_data`` / ``generate_test_data_dz``
 (src/momlevel/test_data/__init__.py:16-140): the same ``numpy.random.default_rng(seed)``
 draws, so every known-answer value of the reference's tests applies unchanged.  The
-calendar time axis of the ``nyears >= 1`` variant needs cftime and is replaced by a month
-index plus ``days_in_month``.
+``nyears >= 1`` variant carries the reference's monthly calendar time axis
+(test_data/time.py:44-99: the mid-points of consecutive month starts) as ``cftime`` objects
+when cftime is importable and as ``cftime_lite.Datetime`` otherwise, plus a ``days_in_month``
+variable (not in the reference) for callers that want the weights as numbers.
 """
 
 import numpy as np
@@ -16,13 +18,29 @@ __all__ = ["generate_test_data", "generate_test_data_dz"]
 _NOLEAP = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31])
 
 
+def _monthly_time_axis(start_year, ntimes, calendar):
+    """Mid-points of ``ntimes`` consecutive months (test_data/time.py:66-89), an object array of calendar dates."""
+    try:
+        import cftime
+
+        bounds = [cftime.datetime(start_year + k // 12, k % 12 + 1, 1, calendar=calendar) for k in range(ntimes + 1)]
+    except ImportError:
+        from .cftime_lite import month_starts
+
+        bounds = month_starts(start_year, ntimes + 1, calendar)
+    out = np.empty(ntimes, dtype=object)
+    for k in range(ntimes):
+        out[k] = bounds[k] + (bounds[k + 1] - bounds[k]) / 2
+    return out
+
+
 def generate_test_data(start_year=1981, nyears=0, calendar="noleap", seed=123):
     """ntimes x 5 x 5 x 5 dataset for unit testing (test_data/__init__.py:16-105)."""
     dset = Dataset()
     if nyears >= 1:
         ntimes = 12 * nyears
-        dset["time"] = DataArray(np.arange(ntimes, dtype=np.float64), ("time",), attrs={
-            "long_name": "time", "cartesian_axis": "T", "calendar_type": calendar})
+        dset["time"] = DataArray(_monthly_time_axis(start_year, ntimes, calendar), ("time",), attrs={
+            "long_name": "time", "cartesian_axis": "T", "calendar_type": calendar, "bounds": "time_bnds"})
         dim = _NOLEAP.copy()
         years = start_year + np.arange(nyears)
         leap = np.zeros(nyears, dtype=bool)

@@ -11,7 +11,8 @@ import warnings
 
 import numpy as np
 
-__all__ = ["default_coords", "eos_func_from_str", "validate_areacello", "validate_dataset", "annual_average"]
+__all__ = ["default_coords", "eos_func_from_str", "validate_areacello", "validate_dataset", "annual_average",
+           "calendar_axis", "whole_years_in_order"]
 
 
 def default_coords(coord_names=None):
@@ -112,22 +113,81 @@ def validate_dataset(dset, reference=False, strict=True, additional_vars=None, a
         raise ValueError("Errors found in dataset.")
 
 
+def calendar_axis(tvals):
+    """``(years, days_in_month)`` per step of a calendar time axis, or ``None`` when the axis carries no calendar.
+
+    What ``util.py:79-87`` reads through ``time.dt.year`` / ``time.dt.days_in_month``: cftime objects (and
+    ``cftime_lite.Datetime``) have ``.year`` and ``.daysinmonth``; numpy ``datetime64`` is handled arithmetically.
+    """
+    vals = np.asarray(tvals)
+    if vals.ndim != 1 or vals.size == 0:
+        return None
+    if vals.dtype.kind == "M":
+        months = vals.astype("datetime64[M]")
+        dim = ((months + 1).astype("datetime64[D]") - months.astype("datetime64[D]")).astype(np.int64)
+        years = vals.astype("datetime64[Y]").astype(np.int64) + 1970
+        return years, dim.astype(np.float64)
+    if vals.dtype == object and all(hasattr(v, "year") and hasattr(v, "daysinmonth") for v in vals):
+        return (np.array([int(v.year) for v in vals], dtype=np.int64),
+                np.array([float(v.daysinmonth) for v in vals], dtype=np.float64))
+    return None
+
+
+def _mid_year(sample, year):
+    """Mid-point of ``year`` in the calendar of ``sample`` (util.py:96-102: ``bounds[0] + (bounds[1] - bounds[0]) / 2``)."""
+    if isinstance(sample, np.datetime64):
+        b0, b1 = np.datetime64(f"{int(year):04d}-01-01", "s"), np.datetime64(f"{int(year) + 1:04d}-01-01", "s")
+        return b0 + (b1 - b0) // 2
+    b0 = sample.replace(year=int(year), month=1, day=1, hour=0, minute=0, second=0, microsecond=0)
+    b1 = b0.replace(year=int(year) + 1)
+    return b0 + (b1 - b0) / 2
+
+
+def whole_years_in_order(years):
+    """True when the steps come as consecutive blocks of twelve, one calendar year each, in ascending order."""
+    years = np.asarray(years)
+    if years.size % 12:
+        return False
+    blocks = years.reshape(-1, 12)
+    return bool(np.all(blocks == blocks[:, :1]) and np.all(np.diff(blocks[:, 0]) > 0))
+
+
 def annual_average(xobj, tcoord="time", days_in_month=None):
     """Days-in-month weighted annual means (util.py:49-119), for labelled Datasets.
 
-    The reference derives the weights from a cftime calendar; cftime is not a dependency
-    here, so ``days_in_month`` (length nt, a multiple of 12) must be supplied -- or, for a
-    real ``xarray`` object with a cftime axis, they are read from ``time.dt.days_in_month``.
+    As in the reference the steps are grouped by calendar year (``groupby("time.year")``, every group must hold
+    twelve steps), weighted by the days in their month (``time.dt.days_in_month``) with NaNs skipped and the
+    weights renormalised per cell, and each mean is labelled with the mid-point of its year.  Year and weights are
+    read from the time axis when it holds calendar objects (cftime, ``cftime_lite.Datetime``, ``datetime64``).
+    ``days_in_month`` (length nt, a multiple of 12; not in the reference) supplies the weights for a time axis
+    without a calendar: the steps are then taken as consecutive years of twelve.
     """
     from .labeled import DataArray, Dataset
 
+    if isinstance(xobj, DataArray):
+        tvals = np.asarray(xobj.coords[tcoord].values) if tcoord in xobj.coords else None
+    else:
+        tvals = np.asarray(xobj[tcoord].values) if tcoord in xobj.variables else None
+    cal = calendar_axis(tvals) if tvals is not None else None
+    order = None
+    year_labels = None
     if days_in_month is None:
-        t = xobj[tcoord]
-        if hasattr(t, "dt"):
-            days_in_month = np.asarray(t.dt.days_in_month)
-        else:
-            raise ValueError("annual_average needs `days_in_month` when the time axis is not a cftime index")
+        if cal is None:
+            raise ValueError("annual_average needs `days_in_month` when the time axis carries no calendar")
+        years, days_in_month = cal
+    elif cal is not None:
+        years = cal[0]
+    else:
+        years = None
     w = np.asarray(days_in_month, dtype=np.float64)
+    if years is not None:
+        assert years.size == w.size, "one weight per time step"
+        uniq, counts = np.unique(years, return_counts=True)
+        assert np.all(counts == 12), "annual averaging needs twelve steps in every year"  # util.py:82
+        if not whole_years_in_order(years):
+            order = np.argsort(years, kind="stable")  # groupby gathers a year's steps wherever they are
+            w = w[order]
+        year_labels = uniq
     assert w.size % 12 == 0, "annual averaging needs whole years of monthly data"
     nyears = w.size // 12
     w = w.reshape(nyears, 12)
@@ -138,9 +198,13 @@ def annual_average(xobj, tcoord="time", days_in_month=None):
         import torch
 
         d = da.data
+        if not isinstance(d, torch.Tensor) and np.asarray(d).dtype.kind not in "fiu":
+            return None  # util.py:72-73: non-numeric variables are skipped
         ax = da.dims.index(tcoord)
         lib = torch if isinstance(d, torch.Tensor) else np
         d = lib.movedim(d, ax, 0) if ax else d
+        if order is not None:
+            d = d[torch.as_tensor(order, device=d.device)] if lib is torch else d[order]
         d = d.reshape((nyears, 12) + tuple(d.shape[1:]))
         ww = w.reshape((nyears, 12) + (1,) * (d.ndim - 2))
         if lib is torch:
@@ -159,13 +223,21 @@ def annual_average(xobj, tcoord="time", days_in_month=None):
         return _one(xobj)
     out = Dataset(attrs=xobj.attrs)
     for k, v in xobj.data_vars.items():
-        out[k] = _one(v)
+        r = _one(v)
+        if r is not None:
+            out[k] = r
     for k, v in xobj.coords.items():
         if k != tcoord:
             out[k] = v
-    # the reference labels each mean with the mid-point of its year (util.py:96-107); without a
-    # calendar the label is the mean of the twelve original time values
-    if tcoord in xobj.variables and np.issubdtype(np.asarray(xobj[tcoord].values).dtype, np.number):
-        tv = np.asarray(xobj[tcoord].values, dtype=np.float64).reshape(nyears, 12).mean(1)
-        out[tcoord] = DataArray(tv, (tcoord,), attrs=xobj[tcoord].attrs)
+    # each mean is labelled with the mid-point of its year (util.py:96-107); a time axis without a calendar keeps
+    # the mean of the twelve original time values
+    if tvals is not None:
+        if year_labels is not None:
+            mids = np.empty(nyears, dtype=object if tvals.dtype == object else tvals.dtype)
+            for i, y in enumerate(year_labels):
+                mids[i] = _mid_year(tvals[0], y)
+            out[tcoord] = DataArray(mids, (tcoord,), attrs=xobj[tcoord].attrs)
+        elif np.issubdtype(tvals.dtype, np.number):
+            tv = np.asarray(tvals, dtype=np.float64).reshape(nyears, 12).mean(1)
+            out[tcoord] = DataArray(tv, (tcoord,), attrs=xobj[tcoord].attrs)
     return out

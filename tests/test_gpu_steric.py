@@ -151,13 +151,23 @@ def test_encoding(ml, dset):
 
 
 def test_steric_annual_average(ml):
-    # tests/test_steric.py:158-163 (julian calendar, 1983-1984; weights from the calendar)
+    # tests/test_steric.py:158-163, called as the reference calls it: julian calendar, 1983-1984, the weights and the
+    # year groups are read from the calendar objects on the time axis (util.py:79-87)
     dset3 = ml.test_data.generate_test_data(start_year=1983, nyears=2, calendar="julian")
-    result, _ = ml.steric(dset3, annual=True, days_in_month=dset3["days_in_month"].values)
-    assert len(result["time"]) == 2 if "time" in result.variables else result["steric"].shape[0] == 2
+    result, _ = ml.steric(dset3, annual=True)
+    assert len(result["time"]) == 2
+    assert [(t.year, t.month, t.day) for t in result["time"].values] == [(1983, 7, 2), (1984, 7, 2)]  # util.py:96-102
+    assert result["delta_rho"].shape == (2, 5, 5, 5) and result["steric"].shape == (2, 5, 5)
     summed = result.sum()
     assert float(summed["steric"]) == pytest.approx(1.07892738, abs=5e-9)
     assert float(summed["delta_rho"]) == pytest.approx(-4.15906613, abs=5e-9)
+    # explicit weights (the extension for time axes without a calendar) give the same numbers
+    again, _ = ml.steric(dset3, annual=True, days_in_month=dset3["days_in_month"].values)
+    assert np.array_equal(again["steric"].values, result["steric"].values, equal_nan=True)
+    assert np.array_equal(again["delta_rho"].values, result["delta_rho"].values, equal_nan=True)
+    # the global series is averaged the same way (steric.py:181-182)
+    g, _ = ml.steric(dset3, annual=True, domain="global")
+    assert g["steric"].shape == (2,) and len(g["time"]) == 2
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
@@ -414,7 +424,7 @@ def test_all_variants_in_one_pass(ml, shape, dtype, eos):
 
 
 @pytest.mark.parametrize("nt", [1, 4, 5, 7, 9, 12, 13, 25])
-@pytest.mark.parametrize("tc", [0, 4, 6, 8, 12])
+@pytest.mark.parametrize("tc", [0, 4, 6, 8, 12, 104, 106, 108, 112])
 def test_one_pass_variants_equal_single_launches_bit_for_bit(ml, nt, tc):
     """csrc/ml_tma3.cu: the one-pass kernel evaluates each height with the single-height kernel's instructions, so
     the three fields, the reference density and volo / masso are bit-identical to separate launches -- for every

@@ -51,3 +51,20 @@ def test_xarray_dataset_in_and_out(xr):
     assert np.array_equal(np.asarray(again["time"].values), np.asarray(ds["time"].values))
     with pytest.raises(AssertionError):
         ml.steric(ds, reference=wref)  # a non-xarray reference next to an xarray dataset (steric.py:99-101)
+
+
+def test_xarray_annual_average_with_a_calendar_axis(xr):
+    """steric(xr_dset, annual=True) without extra arguments (tests/test_steric.py:158-163): the calendar objects of the
+    time axis cross the adapter and supply years and weights."""
+    import momlevel_b200 as ml
+
+    lab = ml.test_data.generate_test_data(start_year=1983, nyears=2, calendar="julian")
+    ds = xr.Dataset()
+    for name, var in lab.variables.items():
+        if name != "days_in_month":
+            ds[name] = xr.DataArray(np.asarray(var.values), dims=var.dims, attrs=dict(var.attrs))
+    result, _ = ml.steric(ds, annual=True)
+    assert type(result).__module__.startswith("xarray")
+    assert np.asarray(result["time"].values).shape == (2,)
+    assert float(np.nansum(result["steric"].values)) == pytest.approx(1.07892738, abs=5e-9)
+    assert float(np.nansum(result["delta_rho"].values)) == pytest.approx(-4.15906613, abs=5e-9)

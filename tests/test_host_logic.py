@@ -267,3 +267,60 @@ def test_steric_routes_host_resident_fields_to_the_host_entry(monkeypatch):
     with pytest.raises(ml._lib.MLError):  # reaches its device check
         ml.steric(small, domain="global", reference=ref_in, variant="thermosteric")
     assert len(gcalls) == 1
+
+
+def test_annual_average_reads_a_calendar_time_axis():
+    """util.py:49-119 as the reference calls it (tests/test_steric.py:158-163): no weights argument -- year and
+    days-in-month of every step come from the calendar objects on the time axis, each mean is labelled with the
+    mid-point of its year, non-numeric variables are dropped."""
+    import datetime
+
+    from momlevel_b200 import test_data
+    from momlevel_b200.cftime_lite import Datetime
+
+    d3 = test_data.generate_test_data(start_year=1983, nyears=2, calendar="julian")
+    t = d3["time"].values
+    assert t.dtype == object and t[0].year == 1983 and t[0].month == 1 and t[13].daysinmonth == 29
+    years, dim = util.calendar_axis(t)
+    assert years.tolist() == [1983] * 12 + [1984] * 12 and util.whole_years_in_order(years)
+    assert np.array_equal(dim, d3["days_in_month"].values)
+    d = Dataset()
+    d["time"] = d3["time"]
+    vals = np.arange(24, dtype=np.float64)
+    d["x"] = DataArray(vals.reshape(24, 1) * np.ones((1, 3)), ("time", "p"))
+    d["label"] = DataArray(np.array(["m%d" % i for i in range(24)], dtype=object), ("time",))
+    out = util.annual_average(d)
+    expect = [(vals[:12] * dim[:12]).sum() / dim[:12].sum(), (vals[12:] * dim[12:]).sum() / dim[12:].sum()]
+    assert np.allclose(out["x"].values[:, 0], expect, rtol=1e-15)
+    assert "label" not in out.variables  # util.py:72-73
+    mids = out["time"].values
+    assert len(mids) == 2 and (mids[0].year, mids[0].month, mids[0].day, mids[0].hour) == (1983, 7, 2, 12)
+    assert (mids[1].year, mids[1].month, mids[1].day, mids[1].hour) == (1984, 7, 2, 0)  # 366 days: mid-point at midnight
+    # the reference groups by year wherever the steps are: a shuffled axis gives the same means
+    perm = np.random.default_rng(0).permutation(24)
+    ds = Dataset()
+    ds["time"] = DataArray(t[perm], ("time",))
+    ds["x"] = DataArray(d["x"].values[perm], ("time", "p"))
+    assert np.allclose(util.annual_average(ds)["x"].values[:, 0], expect, rtol=1e-15)
+    # a year with fewer than twelve steps is an error, as in the reference (util.py:82)
+    short = Dataset()
+    short["time"] = DataArray(t[:23], ("time",))
+    short["x"] = DataArray(np.zeros((23, 1)), ("time", "p"))
+    with pytest.raises(AssertionError):
+        util.annual_average(short)
+    # no calendar and no weights: nothing to weight with
+    bare = Dataset()
+    bare["time"] = DataArray(np.arange(24.0), ("time",))
+    bare["x"] = DataArray(np.zeros((24, 1)), ("time", "p"))
+    with pytest.raises(ValueError):
+        util.annual_average(bare)
+    # numpy datetime64 axes carry a (proleptic Gregorian) calendar too
+    t64 = np.array([f"{y}-{m:02d}-15" for y in (2023, 2024) for m in range(1, 13)], dtype="datetime64[D]")
+    y64, d64 = util.calendar_axis(t64)
+    assert y64[0] == 2023 and d64[1] == 28 and d64[13] == 29
+    # calendar arithmetic of the stand-in class
+    a = Datetime(1900, 2, 28, calendar="gregorian") + datetime.timedelta(days=1)
+    assert (a.month, a.day) == (3, 1)
+    b = Datetime(1900, 2, 28, calendar="julian") + datetime.timedelta(days=1)
+    assert (b.month, b.day) == (2, 29)
+    assert Datetime(2001, 1, 1, calendar="360_day") - Datetime(2000, 1, 1, calendar="360_day") == datetime.timedelta(days=360)

@@ -53,13 +53,14 @@ def main():
     base = call(True)[0]
     out["three_launches_ms"] = best_ms(lambda: call(True))
     core.force_direct(0)
-    for tc in (4, 6, 8, 12):
-        core.variants_chunk(tc)
-        got = call(False)[0]
-        err = max(float(torch.nan_to_num(got[v] - base[v]).abs().max()) for v in got)
-        out[f"one_pass_tc{tc}"] = {"ms": best_ms(lambda: call(False)), "ms_rho_ref_stored": best_ms(lambda: call(True)),
-                                   "max_abs_diff_vs_three_launches_m": err,
-                                   "gpts": pts / best_ms(lambda: call(False)) / 1e6}
+    for tile in (256, 128):
+        for tc in (4, 6, 8, 12):
+            core.variants_chunk(tc + (100 if tile == 128 else 200))
+            got = call(False)[0]
+            err = max(float(torch.nan_to_num(got[v] - base[v]).abs().max()) for v in got)
+            ms = best_ms(lambda: call(False))
+            out[f"one_pass_tile{tile}_tc{tc}"] = {"ms": ms, "ms_rho_ref_stored": best_ms(lambda: call(True)),
+                                                  "max_abs_diff_vs_three_launches_m": err, "gpts": pts / ms / 1e6}
     core.variants_chunk(0)
     print(json.dumps(out), flush=True)
 
