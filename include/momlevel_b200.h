@@ -78,6 +78,13 @@ int64_t ml_launch_count(void);
 /* force ML_PATH_DIRECT (1) / allow ML_PATH_TMA (0) for this thread; 2 = TMA family without the one-pass
  * three-height kernel of ml_steric_local_variants (A/B); returns previous */
 int ml_set_force_direct(int on);
+/* Per-column pressure offset for this thread's next calls, until cleared with (NULL, 0): `patm` given as a 2-D
+ * field instead of a scalar (src/momlevel/steric.py:96 and reference.py:54 broadcast `z_l * 1e4 + patm` by
+ * dimension name).  p_col is a DEVICE array [ncol] of fp64; while it is set, ml_reference_state,
+ * ml_steric_local(_selfref / _variants), ml_steric_global and ml_delta_rho(_annual) evaluate the EOS at
+ * p_level[z] + p_col[col] and take the plain-load kernel family (ML_PATH_DIRECT); a call whose ncol differs
+ * returns ML_ERR_SHAPE.  The *_host entry points do not read it. */
+int ml_set_column_pressure(const double* p_col, int64_t ncol);
 /* time steps per register chunk of the one-pass three-height kernel (4, 6, 8 or 12; 0 = default) for this
  * thread; a tuning knob for experiments and tests -- the results do not depend on it; returns previous */
 int ml_set_variants_chunk(int tc);

@@ -29,6 +29,7 @@ EXPORTS = {
     "ml_launch_count": (_i64, []),
     "ml_set_force_direct": (_i, [_i]),
     "ml_set_variants_chunk": (_i, [_i]),
+    "ml_set_column_pressure": (_i, [_vp, _i64]),
     "ml_eos_eval": (_i, [_i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _i64, _i64, _i64, _vp, _vp]),
     "ml_flament_spice": (_i, [_i, _vp, _vp, _i64, _vp, _vp]),
     "ml_calc_dz": (_i, [_vp, _vp, _d, _d, _i, _i, _i64, _i64, _vp, _vp]),

@@ -84,6 +84,40 @@ def _f64(x):
     return to_device(x, torch.float64)
 
 
+class Pressure:
+    """``z_l * 1e4 + patm`` (steric.py:96, reference.py:54) when ``patm`` is a 2-D field: the per-level part
+    ``[nz]`` and the per-column part ``[ny, nx]``; the kernels evaluate the EOS at ``level[z] + column[y, x]``.
+    Every function of this module that takes ``p_level`` takes one of these instead of a plain vector."""
+
+    def __init__(self, level, column):
+        self.level = level
+        self.column = column
+
+
+class _ColumnPressure:
+    """Context manager: hand the per-column pressure offset to the library for the calls inside (this thread)."""
+
+    def __init__(self, column):
+        self.column = None if column is None else _f64(column).contiguous()
+
+    def __enter__(self):
+        if self.column is not None:
+            _lib.check(_lib.lib().ml_set_column_pressure(self.column.data_ptr(), self.column.numel()))
+        return self
+
+    def __exit__(self, *exc):
+        if self.column is not None:
+            _lib.lib().ml_set_column_pressure(None, 0)
+        return False
+
+
+def _pressure_parts(p):
+    """``(p_level, context manager)`` for a plain per-level vector or a :class:`Pressure`."""
+    if isinstance(p, Pressure):
+        return p.level, _ColumnPressure(p.column)
+    return p, _ColumnPressure(None)
+
+
 def last_path():
     return _lib.lib().ml_last_path()
 
@@ -272,6 +306,7 @@ def reference_state(T0, S0, V0, p_level, eos="Wright", out=None):
     in those two tensors when the caller manages streams.
     """
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T0, S0, V0 = to_device(T0), to_device(S0), to_device(V0)
     dt = _field_dtype(T0, S0, V0)
     T0, S0, V0 = T0.to(dt), S0.to(dt), V0.to(dt)
@@ -287,10 +322,11 @@ def reference_state(T0, S0, V0, p_level, eos="Wright", out=None):
         rho = torch.empty(T0.shape, dtype=torch.float64, device=T0.device)
         sums = torch.empty(2, dtype=torch.float64, device=T0.device)
     ws, nbytes = _workspace(2, nz, ncol, T0.device)
-    _lib.check(
-        L.ml_reference_state(_eos_id(eos), _dt_id(T0), T0.data_ptr(), S0.data_ptr(), V0.data_ptr(), p.data_ptr(), nz,
-                             ncol, rho.data_ptr(), sums.data_ptr(), ws.data_ptr(), nbytes, _stream())
-    )
+    with _pcol:
+        _lib.check(
+            L.ml_reference_state(_eos_id(eos), _dt_id(T0), T0.data_ptr(), S0.data_ptr(), V0.data_ptr(), p.data_ptr(), nz,
+                                 ncol, rho.data_ptr(), sums.data_ptr(), ws.data_ptr(), nbytes, _stream())
+        )
     return rho, sums
 
 
@@ -319,6 +355,7 @@ def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos
     the height tensor when the caller manages streams.
     """
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     rho_ref = _f64(rho_ref)
     v_ref = to_device(v_ref)
@@ -331,27 +368,30 @@ def steric_local(T, S, rho_ref, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos
     else:
         eta = torch.empty((nt,) + hshape, dtype=torch.float64, device=T.device)
     drho = torch.empty((nt, nz) + hshape, dtype=torch.float64, device=T.device) if want_delta_rho else None
-    _lib.check(
-        L.ml_steric_local(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
-                          rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(),
-                          p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(),
-                          drho.data_ptr() if drho is not None else None, _stream())
-    )
+    with _pcol:
+        _lib.check(
+            L.ml_steric_local(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                              rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), z_i.data_ptr(), depth.data_ptr(),
+                              p.data_ptr(), -1.0 / rhozero, nt, nz, ncol, eta.data_ptr(),
+                              drho.data_ptr() if drho is not None else None, _stream())
+        )
     return eta, drho
 
 
 def delta_rho(T, S, rho_ref, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):
     """``where(v_ref.notnull(), rho - rho_ref, nan)`` time-first (steric.py:151-158), fp64 on the device."""
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     rho_ref, v_ref, p = _f64(rho_ref), to_device(v_ref), _f64(p_level)
     assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and p.numel() == nz
     out = torch.empty((nt, nz) + hshape, dtype=torch.float64, device=T.device)
-    _lib.check(
-        L.ml_delta_rho(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
-                       rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol,
-                       out.data_ptr(), _stream())
-    )
+    with _pcol:
+        _lib.check(
+            L.ml_delta_rho(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                           rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol,
+                           out.data_ptr(), _stream())
+        )
     return out
 
 
@@ -361,16 +401,18 @@ def delta_rho_annual(T, S, rho_ref, v_ref, p_level, days_in_month, eos="Wright",
     ``[nt/12, nz, ...]`` fp64 on the device; the monthly 4-D anomaly is never materialised.
     """
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     rho_ref, v_ref, p, w = _f64(rho_ref), to_device(v_ref), _f64(p_level), _f64(days_in_month)
     assert rho_ref.numel() == nz * ncol and v_ref.numel() == nz * ncol and p.numel() == nz
     assert w.numel() == nt and nt % 12 == 0, "annual averaging needs whole years of monthly data"
     out = torch.empty((nt // 12, nz) + hshape, dtype=torch.float64, device=T.device)
-    _lib.check(
-        L.ml_delta_rho_annual(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
-                              rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), w.data_ptr(), nt, nz,
-                              ncol, out.data_ptr(), _stream())
-    )
+    with _pcol:
+        _lib.check(
+            L.ml_delta_rho_annual(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                                  rho_ref.data_ptr(), v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), w.data_ptr(), nt, nz,
+                                  ncol, out.data_ptr(), _stream())
+        )
     return out
 
 
@@ -396,6 +438,7 @@ def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos=
     fields the TMA family does not take), in which case it is produced anyway.
     """
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, t_bcast, s_bcast)
     v_ref = to_device(v_ref)
     z_i, depth, p = _f64(z_i), _f64(deptho), _f64(p_level)
@@ -418,11 +461,12 @@ def steric_local_selfref(T, S, v_ref, z_i, deptho, p_level, rhozero=1035.0, eos=
                                          rho_t.data_ptr() if rho_t is not None else None, sums.data_ptr(),
                                          ws.data_ptr(), nbytes, _stream())
 
-    rc = call(rho)
-    if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
-        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+    with _pcol:
         rc = call(rho)
-    _lib.check(rc)
+        if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
+            rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+            rc = call(rho)
+        _lib.check(rc)
     return eta, rho, sums
 
 
@@ -437,6 +481,7 @@ def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=N
     the one-pass kernel does not need the field; ``rho_ref`` is then ``None`` unless the layout needs it.
     """
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, hshape = _steric_operands(T, S, False, False)
     Tr = T[0] if T_ref is None else to_device(T_ref).to(T.dtype)
     Sr = S[0] if S_ref is None else to_device(S_ref).to(S.dtype)
@@ -465,28 +510,31 @@ def steric_local_variants(T, S, v_ref, z_i, deptho, p_level, T_ref=None, S_ref=N
             rho_t.data_ptr() if (rho_ref is None and rho_t is not None) else None,
             sums.data_ptr() if sums is not None else None, ws.data_ptr() if ws is not None else None, nbytes, _stream())
 
-    rc = call(rho)
-    if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
-        rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+    with _pcol:
         rc = call(rho)
-    _lib.check(rc)
+        if rc == -1 and rho is None:  # ML_ERR_NULL: this layout needs the field itself
+            rho = torch.empty((nz,) + hshape, dtype=torch.float64, device=T.device)
+            rc = call(rho)
+        _lib.check(rc)
     return {"steric": eta[0], "thermosteric": eta[1], "halosteric": eta[2]}, rho, sums
 
 
 def steric_global(T, S, v_ref, p_level, eos="Wright", t_bcast=False, s_bcast=False):
     """``calc_masso(rho, reference.volcello)`` of the global branch (steric.py:135) -> ``masso[nt]``."""
     L = _lib.lib()
+    p_level, _pcol = _pressure_parts(p_level)
     T, S, nt, nz, ncol, _ = _steric_operands(T, S, t_bcast, s_bcast)
     v_ref = to_device(v_ref)
     p = _f64(p_level)
     assert v_ref.numel() == nz * ncol and p.numel() == nz
     masso = torch.empty(nt, dtype=torch.float64, device=T.device)
     ws, nbytes = _workspace(nt, nz, ncol, T.device)
-    _lib.check(
-        L.ml_steric_global(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
-                           v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol, masso.data_ptr(),
-                           ws.data_ptr(), nbytes, _stream())
-    )
+    with _pcol:
+        _lib.check(
+            L.ml_steric_global(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), int(t_bcast), int(s_bcast),
+                               v_ref.data_ptr(), _dt_id(v_ref), p.data_ptr(), nt, nz, ncol, masso.data_ptr(),
+                               ws.data_ptr(), nbytes, _stream())
+        )
     return masso
 
 

@@ -114,14 +114,16 @@ __global__ void __launch_bounds__(kBlock) k_delta_rho(const TIn* __restrict__ T,
                                                       const double* __restrict__ rho_ref,
                                                       const void* __restrict__ v_ref, int v_f32,
                                                       const double* __restrict__ p_level,
+                                                      const double* __restrict__ p_col,
                                                       const double* __restrict__ weights, int nt, int nz, i64 ncol,
                                                       double* __restrict__ out) {
   const i64 c = VEC * ((i64)blockIdx.x * kBlock + threadIdx.x);
   if (c >= ncol) return;
   Eos<EOS> eos;
+  const double pc = (VEC == 1 && p_col != nullptr) ? __ldg(p_col + c) : 0.0;  // a 2-D patm (steric.py:96); VEC = 1 then
   for (int z = blockIdx.y; z < nz; z += gridDim.y) {
     const i64 i = (i64)z * ncol + c;
-    eos.set_level(__ldg(p_level + z));
+    eos.set_level(__ldg(p_level + z) + pc);
     double ref[VEC];
     if (VEC == 4) {
       ld4(rho_ref + i, ref);
@@ -234,6 +236,7 @@ template <typename TIn, int EOS>
 __global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restrict__ T0, const TIn* __restrict__ S0,
                                                             const void* __restrict__ V0, int v_f32,
                                                             const double* __restrict__ p_level,
+                                                            const double* __restrict__ p_col,
                                                             int nz, i64 ncol, double* __restrict__ rho_ref,
                                                             double* __restrict__ partials /* [2][gridDim.x] */) {
   __shared__ double sm[kWarps];
@@ -241,9 +244,10 @@ __global__ void __launch_bounds__(kBlock) k_reference_state(const TIn* __restric
   double vol = 0.0, mass = 0.0;
   Eos<EOS> eos;
   if (c < ncol) {
+    const double pc = p_col != nullptr ? __ldg(p_col + c) : 0.0;  // a 2-D patm: pres = z_l * 1e4 + patm (reference.py:54)
     for (int z = 0; z < nz; ++z) {
       const i64 i = (i64)z * ncol + c;
-      eos.set_level(__ldg(p_level + z));
+      eos.set_level(__ldg(p_level + z) + pc);
       const double rho = eos.rho(ldf(T0 + i), ldf(S0 + i));
       const double v = vref_val(V0, v_f32, i);
       rho_ref[i] = rho;
@@ -321,8 +325,8 @@ __global__ void __launch_bounds__(kBlock)
     k_steric_local_direct(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 t_stride, i64 s_stride,
                           const double* __restrict__ rho_ref, const void* __restrict__ v_ref, int v_f32,
                           const double* __restrict__ z_i, const double* __restrict__ deptho,
-                          const double* __restrict__ p_level, double coef, int nt, int nz, i64 ncol,
-                          double* __restrict__ eta, double* __restrict__ drho) {
+                          const double* __restrict__ p_level, const double* __restrict__ p_col, double coef, int nt,
+                          int nz, i64 ncol, double* __restrict__ eta, double* __restrict__ drho) {
   const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
   if (c >= ncol) return;
   const int t0 = blockIdx.y * kTC;
@@ -336,13 +340,14 @@ __global__ void __launch_bounds__(kBlock)
 #pragma unroll
   for (int k = 0; k < kTC; ++k) acc[k] = 0.0;
   Eos<EOS> eos;
+  const double pc = p_col != nullptr ? __ldg(p_col + c) : 0.0;  // a 2-D patm (steric.py:96)
 
   for (int z = 0; z < nz; ++z) {
     const i64 i = (i64)z * lvl + c;
     const double dz = clipped_dz(depth, __ldg(z_i + z), __ldg(z_i + z + 1));
     // steric.py:151-153: delta_rho is NaN wherever the reference volume is missing
     const double rref = vref_wet(v_ref, v_f32, i) ? __ldg(rho_ref + i) : nan("");
-    eos.set_level(__ldg(p_level + z));
+    eos.set_level(__ldg(p_level + z) + pc);
     // all loads of the chunk first (time index clamped: a short last chunk re-reads the
     // final step instead of branching), then the arithmetic
     TIn tv[kTC], sv[kTC];
@@ -372,8 +377,9 @@ __global__ void __launch_bounds__(kBlock)
 template <typename TIn, int EOS>
 __global__ void __launch_bounds__(kBlock)
     k_steric_global_direct(const TIn* __restrict__ T, const TIn* __restrict__ S, i64 t_stride, i64 s_stride,
-                           const void* __restrict__ v_ref, int v_f32, const double* __restrict__ p_level, int nt,
-                           int nz, i64 ncol, double* __restrict__ partials /* [nt][gridDim.x] */) {
+                           const void* __restrict__ v_ref, int v_f32, const double* __restrict__ p_level,
+                           const double* __restrict__ p_col, int nt, int nz, i64 ncol,
+                           double* __restrict__ partials /* [nt][gridDim.x] */) {
   __shared__ double sm[kWarps];
   const i64 c = (i64)blockIdx.x * kBlock + threadIdx.x;
   const int t0 = blockIdx.y * kTC;
@@ -382,11 +388,12 @@ __global__ void __launch_bounds__(kBlock)
   for (int k = 0; k < kTC; ++k) acc[k] = 0.0;
   Eos<EOS> eos;
   if (c < ncol) {
+    const double pc = p_col != nullptr ? __ldg(p_col + c) : 0.0;  // a 2-D patm (steric.py:96)
     for (int z = 0; z < nz; ++z) {
       const i64 i = (i64)z * ncol + c;
       const double v = vref_val(v_ref, v_f32, i);
       if (isnan(v)) continue;  // rho*NaN is dropped by the skipna sum (derived.py:435-438)
-      eos.set_level(__ldg(p_level + z));
+      eos.set_level(__ldg(p_level + z) + pc);
       TIn tv[kTC], sv[kTC];
 #pragma unroll
       for (int k = 0; k < kTC; ++k) {
@@ -414,6 +421,17 @@ __global__ void __launch_bounds__(kBlock)
 // --------------------------------------------------------------------------- dispatch
 inline i64 cdiv(i64 a, i64 b) { return (a + b - 1) / b; }
 
+// the plain-load kernels only: asked for (ml_set_force_direct(1)) or needed because a per-column pressure offset
+// is set (ml_set_column_pressure), which the ring-staged families do not carry
+inline bool direct_only() { return tls().force_direct == 1 || tls().p_col != nullptr; }
+
+// every entry point that evaluates the EOS per column checks the offset's length against its own ncol
+inline int check_column_pressure(int64_t ncol) {
+  if (tls().p_col != nullptr && tls().p_col_n != ncol)
+    return fail(ML_ERR_SHAPE, "column pressure set for %lld columns, call has %lld", (long long)tls().p_col_n, (long long)ncol);
+  return ML_OK;
+}
+
 inline int check_common(int eos, int dtype) {
   if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
   if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
@@ -431,7 +449,7 @@ int launch_eos(int dtype, const void* T, const void* S, i64 ts, i64 ss, const do
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) | reinterpret_cast<uintptr_t>(out) |
                          (pmode == ML_P_FULL ? reinterpret_cast<uintptr_t>(p) : 0);
   // fp32 fields, density, a pressure per row: the ring-staged streaming kernel (ml_stream.cu)
-  if (FUNC == 0 && dtype == ML_F32 && pmode != ML_P_FULL && tls().force_direct != 1 && stream::eligible(T, S, nullptr, out, ncol) &&
+  if (FUNC == 0 && dtype == ML_F32 && pmode != ML_P_FULL && direct_only() == false && stream::eligible(T, S, nullptr, out, ncol) &&
       ts % 4 == 0 && ss % 4 == 0 && nz > 0)
     return stream::launch_density(EOS == 0 ? ML_EOS_WRIGHT : ML_EOS_LINEAR, (const float*)T, (const float*)S, ts, ss, p,
                                   pmode, nrows, nz, ncol, out, st);
@@ -474,9 +492,9 @@ int launch_local_direct(const void* T, const void* S, i64 ts, i64 ss, const doub
                         int nz, i64 ncol, double* eta, double* drho, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)cdiv(nt, kTC));
   if (drho)
-    k_steric_local_direct<TIn, EOS, true><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, coef, nt, nz, ncol, eta, drho);
+    k_steric_local_direct<TIn, EOS, true><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, tls().p_col, coef, nt, nz, ncol, eta, drho);
   else
-    k_steric_local_direct<TIn, EOS, false><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, coef, nt, nz, ncol, eta, drho);
+    k_steric_local_direct<TIn, EOS, false><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, rho_ref, v_ref, v_f32, z_i, deptho, p_level, tls().p_col, coef, nt, nz, ncol, eta, drho);
   return launched("k_steric_local_direct");
 }
 
@@ -486,7 +504,7 @@ int launch_global_direct(const void* T, const void* S, i64 ts, i64 ss, const voi
                          cudaStream_t st) {
   const i64 nblk = cdiv(ncol, kBlock);
   dim3 grid((unsigned)nblk, (unsigned)cdiv(nt, kTC));
-  k_steric_global_direct<TIn, EOS><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, v_ref, v_f32, p_level, nt, nz, ncol, partials);
+  k_steric_global_direct<TIn, EOS><<<grid, kBlock, 0, st>>>((const TIn*)T, (const TIn*)S, ts, ss, v_ref, v_f32, p_level, tls().p_col, nt, nz, ncol, partials);
   int rc = launched("k_steric_global_direct");
   if (rc) return rc;
   k_reduce_rows<<<nt, kBlock, 0, st>>>(partials, nblk, masso);
@@ -514,6 +532,13 @@ int ml_set_force_direct(int on) {
   const int prev = tls().force_direct;
   tls().force_direct = on == 2 ? 2 : (on ? 1 : 0);
   return prev;
+}
+
+int ml_set_column_pressure(const double* p_col, int64_t ncol) {
+  if (p_col != nullptr && ncol <= 0) return fail(ML_ERR_SHAPE, "column pressure needs ncol > 0, got %lld", (long long)ncol);
+  tls().p_col = p_col;
+  tls().p_col_n = p_col ? ncol : 0;
+  return ML_OK;
 }
 
 int ml_set_variants_chunk(int tc) {
@@ -602,6 +627,7 @@ int ml_calc_dz(const double* z_i, const double* deptho, double top, double botto
   ML_REQUIRE_PTR(deptho);
   ML_REQUIRE_PTR(out);
   if (nz <= 0 || ncol < 0 || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nz=%lld ncol=%lld", (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   if (ncol == 0) return ML_OK;
   dim3 grid((unsigned)cdiv(ncol, kBlock), (unsigned)(nz < 65535 ? nz : 65535));
   k_calc_dz<<<grid, kBlock, 0, (cudaStream_t)stream>>>(z_i, deptho, top, bottom, has_bottom, fraction, (int)nz, ncol, out);
@@ -621,6 +647,7 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
   ML_REQUIRE_PTR(rho_ref);
   ML_REQUIRE_PTR(sums);
   if (nz <= 0 || ncol <= 0 || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nz=%lld ncol=%lld", (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
     return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
   ML_REQUIRE_ALIGNED(workspace, 8);
@@ -629,7 +656,7 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
   const int v_f32 = v_dtype == ML_F32;
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T0) | reinterpret_cast<uintptr_t>(S0) |
                          reinterpret_cast<uintptr_t>(V0) | reinterpret_cast<uintptr_t>(rho_ref);
-  if (dtype == ML_F32 && v_dtype == ML_F32 && tls().force_direct != 1 && stream::eligible(T0, S0, V0, rho_ref, ncol) &&
+  if (dtype == ML_F32 && v_dtype == ML_F32 && direct_only() == false && stream::eligible(T0, S0, V0, rho_ref, ncol) &&
       (size_t)stream::refstate_blocks(nz, ncol) * 2 * sizeof(double) <= workspace_bytes) {
     // ring-staged streaming kernel (ml_stream.cu): persistent CTAs, block partials [2][blocks]
     if ((rc = stream::launch_refstate(eos, (const float*)T0, (const float*)S0, (const float*)V0, p_level, nz, ncol,
@@ -638,7 +665,7 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
     k_reduce_rows<<<2, kBlock, 0, st>>>(partials, stream::refstate_blocks(nz, ncol), sums);
     return launched("k_reduce_rows");
   }
-  if (v_dtype == dtype && ncol % 4 == 0 && (bits & 15u) == 0 && nz <= 65535) {
+  if (v_dtype == dtype && ncol % 4 == 0 && (bits & 15u) == 0 && nz <= 65535 && tls().p_col == nullptr) {
     // ~12 resident blocks per SM over all levels; each thread walks its level in 2-quad trips
     i64 gx = cdiv(148 * 12, nz);
     const i64 need = cdiv(cdiv(ncol / 4, kBlock), 2);
@@ -663,7 +690,7 @@ static int reference_state_impl(int eos, int dtype, const void* T0, const void* 
   }
   const i64 nblk = cdiv(ncol, kBlock);
 #define ML_LAUNCH_REF(TIN, E) \
-  k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, V0, v_f32, p_level, (int)nz, ncol, rho_ref, partials)
+  k_reference_state<TIN, E><<<(unsigned)nblk, kBlock, 0, st>>>((const TIN*)T0, (const TIN*)S0, V0, v_f32, p_level, tls().p_col, (int)nz, ncol, rho_ref, partials)
   if (dtype == ML_F32) {
     if (eos == ML_EOS_WRIGHT) ML_LAUNCH_REF(float, 0); else ML_LAUNCH_REF(float, 1);
   } else {
@@ -700,6 +727,7 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   ML_REQUIRE_PTR(eta);
   ML_REQUIRE_PTR(sums);
   if (nt <= 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(2, nz, ncol))
     return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(2, nz, ncol), workspace_bytes);
   ML_REQUIRE_ALIGNED(workspace, 8);
@@ -707,7 +735,7 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tma_ok = tls().force_direct != 1 && tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref,
+  const bool tma_ok = !direct_only() && tma::local_eligible(dtype, T, S, t_bcast, s_bcast, nullptr, v_ref,
                                                                  vref_dtype, nt, nz, ncol, eta, nullptr);
   // rho_ref is an output the caller may not want (8 bytes per reference point, 7 % of the traffic of a
   // 12-step call).  It can be left out when one fused chunk serves the whole call; longer series and the
@@ -745,6 +773,7 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
   ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(eta);
   if (nt < 0 || nz <= 0 || ncol < 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   ML_REQUIRE_ALIGNED(T, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(v_ref, elem_size(vref_dtype));
@@ -754,7 +783,7 @@ int ml_steric_local(int eos, int dtype, const void* T, const void* S, int t_bcas
   cudaStream_t st = (cudaStream_t)stream;
   const int v_f32 = vref_dtype == ML_F32;
 
-  if (tls().force_direct != 1 &&
+  if (direct_only() == false &&
       tma::local_eligible(dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, nt, nz, ncol, eta, delta_rho)) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_local(eos, dtype, T, S, t_bcast, s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho, p_level,
@@ -783,6 +812,7 @@ static int delta_rho_impl(int eos, int dtype, const void* T, const void* S, int 
   ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(delta_rho);
   if (nt < 0 || nz <= 0 || ncol < 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   if (weights && nt % 12 != 0) return fail(ML_ERR_SHAPE, "annual averaging needs whole years of monthly data, got nt=%lld", (long long)nt);
   ML_REQUIRE_ALIGNED(T, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
@@ -795,7 +825,7 @@ static int delta_rho_impl(int eos, int dtype, const void* T, const void* S, int 
   const int v_f32 = vref_dtype == ML_F32;
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) |
                          reinterpret_cast<uintptr_t>(rho_ref) | reinterpret_cast<uintptr_t>(delta_rho);
-  const bool vec = ncol % 4 == 0 && (bits & 15u) == 0;
+  const bool vec = ncol % 4 == 0 && (bits & 15u) == 0 && tls().p_col == nullptr;
   const i64 gx = cdiv(vec ? ncol / 4 : ncol, kBlock);
   i64 gy = cdiv(148 * 16, gx);
   gy = gy < 1 ? 1 : (gy > nz ? nz : gy);
@@ -804,10 +834,10 @@ static int delta_rho_impl(int eos, int dtype, const void* T, const void* S, int 
   do {                                                                                                                 \
     if (weights)                                                                                                       \
       k_delta_rho<TIN, E, V, true><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref, v_f32, \
-                                                            p_level, weights, (int)nt, (int)nz, ncol, delta_rho);     \
+                                                            p_level, tls().p_col, weights, (int)nt, (int)nz, ncol, delta_rho);     \
     else                                                                                                               \
       k_delta_rho<TIN, E, V, false><<<grid, kBlock, 0, st>>>((const TIN*)T, (const TIN*)S, ts, ss, rho_ref, v_ref,     \
-                                                             v_f32, p_level, nullptr, (int)nt, (int)nz, ncol, delta_rho); \
+                                                             v_f32, p_level, tls().p_col, nullptr, (int)nt, (int)nz, ncol, delta_rho); \
   } while (0)
   if (dtype == ML_F32) {
     if (eos == ML_EOS_WRIGHT) { if (vec) ML_LAUNCH_DRHO(float, 0, 4); else ML_LAUNCH_DRHO(float, 0, 1); }
@@ -860,6 +890,7 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
     ML_REQUIRE_ALIGNED(workspace, 8);
   }
   if (nt <= 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   ML_REQUIRE_ALIGNED(T, elem_size(dtype));
   ML_REQUIRE_ALIGNED(S, elem_size(dtype));
   ML_REQUIRE_ALIGNED(T_ref, elem_size(dtype));
@@ -870,7 +901,7 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
   // One pass over T and S for all the heights asked for (csrc/ml_tma3.cu): a point's three densities come from the
   // same two shared-memory words.  Taken when the fields suit the TMA family and more than one height is wanted.
   const int wanted = (eta_steric != nullptr) + (eta_thermosteric != nullptr) + (eta_halosteric != nullptr);
-  const bool fused_ok = tls().force_direct == 0 && wanted >= 2 &&
+  const bool fused_ok = tls().force_direct == 0 && !direct_only() && wanted >= 2 &&
                         tma::variants_eligible(dtype, T, S, T_ref, S_ref, vref_dtype, nt, nz, ncol);
   if (fused_ok && (self_reference || rho_ref != nullptr)) {
     tls().last_path = ML_PATH_TMA;
@@ -910,7 +941,7 @@ int ml_steric_local_variants(int eos, int dtype, const void* T, const void* S, c
                            {eta_halosteric, T_ref, S, 1, 0}};
   for (const Variant& v : todo) {
     if (v.eta == nullptr) continue;
-    if (tls().force_direct != 1 && tma::local_eligible(dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, nt,
+    if (direct_only() == false && tma::local_eligible(dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, nt,
                                                    nz, ncol, v.eta, nullptr)) {
       tls().last_path = ML_PATH_TMA;
       rc = tma::launch_local(eos, dtype, v.T, v.S, v.t_bcast, v.s_bcast, rho_ref, v_ref, vref_dtype, z_i, deptho,
@@ -938,6 +969,7 @@ int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bca
   ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(masso);
   if (nt < 0 || nz <= 0 || ncol <= 0 || nt > INT32_MAX || nz > INT32_MAX) return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld", (long long)nt, (long long)nz, (long long)ncol);
+  if (int rcp = check_column_pressure(ncol)) return rcp;
   if (nt == 0) return ML_OK;
   if (workspace == nullptr || workspace_bytes < ml_workspace_bytes(nt, nz, ncol))
     return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", ml_workspace_bytes(nt, nz, ncol), workspace_bytes);
@@ -951,7 +983,7 @@ int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bca
   const int v_f32 = vref_dtype == ML_F32;
   double* partials = (double*)workspace;
 
-  if (tls().force_direct != 1 && tma::global_eligible(dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, nt, nz, ncol)) {
+  if (direct_only() == false && tma::global_eligible(dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, nt, nz, ncol)) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_global(eos, dtype, T, S, t_bcast, s_bcast, v_ref, vref_dtype, p_level, (int)nt, (int)nz, ncol,
                               masso, partials, st);

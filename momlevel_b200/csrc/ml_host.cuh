@@ -17,6 +17,8 @@ struct ThreadState {
   int force_direct;
   int64_t launches;
   int variants_chunk;  // main chunk width of the one-pass three-height kernel (0 = built-in default)
+  const double* p_col;  // ml_set_column_pressure: per-column pressure offset (device, [ncol]) or NULL
+  int64_t p_col_n;
 };
 ThreadState& tls();
 

@@ -14,13 +14,37 @@ __all__ = ["setup_reference_state"]
 
 
 def _pressure(dset, zcoord, patm):
-    """steric.py:96 / reference.py:54: 1 m ~ 1 dbar = 1e4 Pa, plus the surface pressure."""
-    if not isinstance(patm, (int, float, np.floating, np.integer)):
-        if getattr(patm, "ndim", np.ndim(patm)) != 0:
-            raise NotImplementedError("momlevel_b200 supports a scalar `patm` only")
-        patm = float(patm)
+    """steric.py:96 / reference.py:54: 1 m ~ 1 dbar = 1e4 Pa, plus the surface pressure.
+
+    ``patm`` is a scalar (a per-level pressure vector comes back) or a 2-D field over the horizontal dims of the
+    dataset -- sea-level pressure from a reanalysis, say -- which the reference broadcasts by dimension name into
+    ``pres[z, y, x]``; a :class:`core.Pressure` (per-level part + per-column part) comes back then.
+    """
     z = dset[zcoord].data
-    if isinstance(z, torch.Tensor) and z.is_cuda:  # stays on the device: no read-back in front of the launch
+    on_device = isinstance(z, torch.Tensor) and z.is_cuda
+    if not isinstance(patm, (int, float, np.floating, np.integer)):
+        nd = getattr(patm, "ndim", np.ndim(patm))
+        if nd == 0:
+            patm = float(patm)
+        elif nd == 2:
+            hdims = tuple(d for d in dset["thetao"].dims if d not in (zcoord,))[-2:]
+            pdims = getattr(patm, "dims", None)
+            if isinstance(patm, (DataArray, torch.Tensor)):
+                col = patm.data
+            else:  # numpy, or an xarray.DataArray (its .values)
+                col = np.asarray(patm.values if hasattr(patm, "values") else patm)
+            if pdims is not None and tuple(pdims) != hdims:
+                if set(pdims) != set(hdims):
+                    raise ValueError(f"`patm` has dims {tuple(pdims)}, expecting the horizontal dims {hdims}")
+                col = col.T  # name-based broadcasting: the order of the dims does not matter to the reference
+            hshape = tuple(dset["thetao"].shape[-2:])
+            if tuple(np.shape(col)) != hshape:
+                raise ValueError(f"`patm` has shape {tuple(np.shape(col))}, expecting {hshape}")
+            level = (z.to(torch.float64) * 1.0e4) if on_device else np.asarray(dset[zcoord].values, dtype=np.float64) * 1.0e4
+            return core.Pressure(level, col)
+        else:
+            raise NotImplementedError("momlevel_b200 takes `patm` as a scalar or as a 2-D (y, x) field")
+    if on_device:  # stays on the device: no read-back in front of the launch
         return (z.to(torch.float64) * 1.0e4) + float(patm)
     return (np.asarray(dset[zcoord].values, dtype=np.float64) * 1.0e4) + float(patm)
 

@@ -76,7 +76,8 @@ def steric(
         if verbose:
             print("Using supplied reference state")
     else:
-        if domain != "global" and variant in VARIANTS and _host_resident(dset, tcoord, zcoord, zbounds):
+        array_patm = isinstance(pres, core.Pressure)  # a 2-D patm: device kernels only (ml_set_column_pressure)
+        if domain != "global" and variant in VARIANTS and not array_patm and _host_resident(dset, tcoord, zcoord, zbounds):
             # fields in host memory (numpy, what xarray hands over): streamed through device windows by the
             # library, level rows packed to their present cells on the way (ml_steric_local_host)
             reference, fused_eta = _selfref_host(dset, pres, equation_of_state, variant, rhozero, tcoord, zcoord,
@@ -110,7 +111,8 @@ def steric(
     if domain == "global":
         # steric.py:134-147
         v_ref = reference["volcello"].data
-        if (variant == "steric" and _host_resident(dset, tcoord, zcoord, zbounds, need_depth=False)
+        if (variant == "steric" and not isinstance(pres, core.Pressure)
+                and _host_resident(dset, tcoord, zcoord, zbounds, need_depth=False)
                 and not (isinstance(v_ref, torch.Tensor) and v_ref.is_cuda)):
             # fields in host memory (a daily series does not fit in HBM): streamed through device windows,
             # level rows packed to the cells of the reference volume on the way (ml_steric_global_host)
@@ -376,7 +378,7 @@ def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rh
         if verbose:
             print("Generating reference state from first timestep")
         V0 = dset["volcello"].isel({tcoord: 0}).squeeze().data
-        if _host_resident(dset, tcoord, zcoord, zbounds):
+        if not isinstance(pres, core.Pressure) and _host_resident(dset, tcoord, zcoord, zbounds):
             # fields in host memory: one pass over PCIe feeds the three integrations (ml_steric_local_variants_host)
             step_bytes = 2 * int(np.prod(full.shape[1:])) * 4
             spw = int(min(max(1, -(-(1 << 28) // step_bytes)), full.shape[0]))

@@ -39,6 +39,14 @@ def pressure_from_depth(z_l, patm=101325.0):
     return (np.asarray(z_l, dtype=np.float64) * 1.0e4) + patm
 
 
+def _pres3(z_l, patm):
+    """``(z_l * 1e4) + patm`` broadcast by dimension name to ``[z][y][x]``: ``patm`` a scalar or a ``[y][x]`` field."""
+    z = np.asarray(z_l, dtype=np.float64) * 1.0e4
+    if np.ndim(patm) == 0:
+        return (z + patm)[:, None, None]
+    return z[:, None, None] + np.asarray(patm, dtype=np.float64)[None, :, :]
+
+
 def calc_dz(z_l, z_i, deptho, top=0.0, bottom=None, fraction=False):
     """Partial-bottom-cell thickness, shape ``[z][y][x]`` (derived.py:249-325).
 
@@ -78,7 +86,7 @@ def calc_dz(z_l, z_i, deptho, top=0.0, bottom=None, fraction=False):
 
 def reference_state(thetao, so, volcello, areacello, z_l, patm=101325.0, eos="Wright", time_index=0):
     """reference.py:15-85 -- returns a dict with the 8 reference variables."""
-    pres = pressure_from_depth(z_l, patm)[:, None, None]
+    pres = _pres3(z_l, patm)
     T0 = np.asarray(thetao)[time_index]
     S0 = np.asarray(so)[time_index]
     V0 = np.asarray(volcello)[time_index]
@@ -110,7 +118,7 @@ def _select(variant, thetao, so, reference):
 
 def _rho(variant, thetao, so, reference, z_l, patm, eos):
     T, S = _select(variant, thetao, so, reference)
-    pres = pressure_from_depth(z_l, patm)[None, :, None, None]
+    pres = _pres3(z_l, patm)[None]
     rho = _eos.density(eos, T, S, pres)
     nt = max(np.asarray(thetao).shape[0], np.asarray(so).shape[0])
     return np.broadcast_to(rho, (nt,) + rho.shape[1:])

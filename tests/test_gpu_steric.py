@@ -477,6 +477,45 @@ def test_one_pass_variants_equal_single_launches_bit_for_bit(ml, nt, tc):
         assert torch.all(eta_n[v][0][wet] == 0.0)  # the reference step: exactly zero, as in the reference
 
 
+@pytest.mark.parametrize("variant", ["steric", "thermosteric", "halosteric"])
+@pytest.mark.parametrize("shape,dtype", [((5, 12, 16, 64), torch.float32), ((3, 7, 9, 13), torch.float64)])
+def test_patm_as_a_2d_field(ml, variant, shape, dtype):
+    """``patm`` given as a sea-level-pressure field (steric.py:96 broadcasts ``z_l * 1e4 + patm`` by dimension name):
+    local and global heights, the reference density and delta_rho against the oracle, for fields that would
+    otherwise take the TMA family and for fp64 storage."""
+    from momlevel_b200 import core, synth
+    from momlevel_b200.labeled import DataArray
+
+    ds = synth.make_dataset(*shape, seed=5, device="cuda", dtype=dtype)
+    ny, nx = shape[2:]
+    rng = np.random.default_rng(42)
+    patm = 101325.0 + rng.normal(0.0, 1500.0, (ny, nx))  # +-15 hPa of weather
+    f64 = lambda k: ds[k].values.astype(np.float64)  # noqa: E731
+    oref = osteric.reference_state(f64("thetao"), f64("so"), f64("volcello"), f64("areacello"), f64("z_l"), patm=patm)
+    eta_o, drho_o = osteric.steric_local(f64("thetao"), f64("so"), f64("z_l"), f64("z_i"), f64("deptho"), oref,
+                                         patm=patm, variant=variant)
+    g_o, href_o, _ = osteric.steric_global(f64("thetao"), f64("so"), f64("z_l"), oref, patm=patm, variant=variant)
+    for arg in (patm, DataArray(patm, ("yh", "xh")), DataArray(patm.T.copy(), ("xh", "yh")), torch.from_numpy(patm).cuda()):
+        res, ref = ml.steric(ds, variant=variant, patm=arg)
+        assert core.last_path() == 1  # the plain-load family carries the per-column offset
+        _close_nan(ref["rho"].values, oref["rho"], rtol=RHO_RTOL)
+        _close_nan(res[variant].values, eta_o, atol=ETA_ATOL)
+    _close_nan(res["delta_rho"].values, drho_o, atol=1e-9)
+    assert float(ref["masso"]) == pytest.approx(float(oref["masso"]), rel=1e-13)
+    gres, _ = ml.steric(ds, variant=variant, domain="global", patm=patm, reference=ref)
+    assert np.max(np.abs(gres[variant].values - g_o)) < ETA_ATOL
+    # the offset is gone after the call: the next one is the plain scalar case again, on the usual family
+    res0, _ = ml.steric(ds, variant=variant)
+    ref0 = osteric.reference_state(f64("thetao"), f64("so"), f64("volcello"), f64("areacello"), f64("z_l"))
+    eta0, _ = osteric.steric_local(f64("thetao"), f64("so"), f64("z_l"), f64("z_i"), f64("deptho"), ref0, variant=variant)
+    _close_nan(res0[variant].values, eta0, atol=ETA_ATOL)
+    assert float(np.nanmax(np.abs(eta0 - eta_o))) > 1e-7  # the field did change the answer
+    with pytest.raises(NotImplementedError):
+        ml.steric(ds, patm=np.zeros((shape[0], ny, nx)))
+    with pytest.raises(ValueError):
+        ml.steric(ds, patm=np.zeros((ny + 1, nx)))
+
+
 # ------------------------------------------------------- size-independent properties
 
 
