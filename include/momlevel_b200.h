@@ -279,6 +279,45 @@ int ml_steric_local_variants_host(int eos, int dtype, const void* T, const void*
                                   int steps_per_window, double* eta_steric, double* eta_thermosteric,
                                   double* eta_halosteric, double* rho_ref_out, double* sums_out);
 
+/* ---------------------------------------------------------------------------------------
+ * ml_host_stream_* -- the host path for fields that arrive block by block.
+ * The reference works on dask-backed Datasets (src/momlevel/derived.py:624-630 `dask="allowed"`;
+ * examples/example.ipynb cell 4 opens the model output with chunks={"time": 1, ...}): the fields never exist as
+ * one array.  begin() takes everything that does not depend on time, push() one block of consecutive time
+ * steps -- staged, packed and copied like a window of ml_steric_local_host while the previous block computes --
+ * and finish() waits for the tail.  ml_steric_local_host, ml_steric_local_variants_host and
+ * ml_steric_global_host are begin + one push per window + finish.
+ *
+ *   domain        ML_DOMAIN_LOCAL: heights eta[nt_block][ncol] per push (steric.py:150-166);
+ *                 ML_DOMAIN_GLOBAL: masses masso[nt_block] per push (steric.py:135)
+ *   variants      bit 0 steric, bit 1 thermosteric, bit 2 halosteric (steric.py:115-121); at least one
+ *   v_ref         host [nz][ncol] of vref_dtype: reference["volcello"]; must stay valid until the first push returns
+ *   T_ref, S_ref, rho_ref   host reference slabs / density of a SUPPLIED reference (steric.py:98-103), or all NULL:
+ *                 the reference state is step 0 of the first block (steric.py:105-107, reference.py:60-80).
+ *                 rho_ref is needed by the local domain, T_ref / S_ref by the thermo- / halosteric variants
+ *   z_i, deptho   host, local domain only;  p_level host [nz]
+ *   max_block_steps   upper bound of nt_block (sizes the two device windows)
+ *   want_reference    bit 0: finish() will be asked for rho_ref_out (every row then crosses as it is);
+ *                     bit 1: global domain with a self-reference: evaluate volo / masso from step 0 (sums_out)
+ * push(): T_block, S_block host [nt_block][nz][ncol] of `dtype` (pinned memory keeps the copies asynchronous;
+ *   pageable memory is staged by the library's own threads); out_* host [nt_block][ncol] (local) or [nt_block]
+ *   (global) for the variants asked for.  The block's memory may be reused once the NEXT push (or finish) has
+ *   returned; the outputs are complete when finish() returns.
+ * finish(): rho_ref_out host [nz][ncol] or NULL; sums_out host fp64[2] {volo, masso} or NULL; frees the stream.
+ * abort(): drains the device and frees the stream (after an error, or to give up).
+ * A stream belongs to the thread that began it; a thread has one open stream at a time.
+ * ------------------------------------------------------------------------------------- */
+#define ML_DOMAIN_LOCAL 0
+#define ML_DOMAIN_GLOBAL 1
+int ml_host_stream_begin(int domain, int eos, int dtype, int variants, const void* v_ref, int vref_dtype,
+                         const void* T_ref, const void* S_ref, const double* rho_ref, const double* z_i,
+                         const double* deptho, const double* p_level, double neg_inv_rhozero, int64_t nz,
+                         int64_t ncol, int64_t max_block_steps, int want_reference, void** stream_out);
+int ml_host_stream_push(void* stream, const void* T_block, const void* S_block, int64_t nt_block,
+                        double* out_steric, double* out_thermosteric, double* out_halosteric);
+int ml_host_stream_finish(void* stream, double* rho_ref_out, double* sums_out);
+int ml_host_stream_abort(void* stream);
+
 /* Frees the device staging buffers, streams and events that the *_host entry points keep per
  * host thread between calls. */
 int ml_host_release(void);

@@ -17,6 +17,7 @@ F32, F64 = 0, 1
 EOS_IDS = {"wright": 0, "linear": 1}
 FUNC_IDS = {"density": 0, "drho_dtemp": 1, "drho_dsal": 2, "alpha": 3, "beta": 4}
 P_SCALAR, P_PER_LEVEL, P_FULL = 0, 1, 2
+DOMAIN_LOCAL, DOMAIN_GLOBAL = 0, 1
 PATH_DIRECT, PATH_TMA = 1, 2
 
 _vp, _i, _i64, _d, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_size_t
@@ -43,6 +44,11 @@ EXPORTS = {
     "ml_steric_local_variants": (_i, [_i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp, _vp, _d, _i64, _i64, _i64, _vp, _vp,
                                       _vp, _vp, _vp, _vp, _sz, _vp]),
     "ml_steric_global": (_i, [_i, _i, _vp, _vp, _i, _i, _vp, _i, _vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "ml_host_stream_begin": (_i, [_i, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _d, _i64, _i64, _i64, _i,
+                                  ctypes.POINTER(ctypes.c_void_p)]),
+    "ml_host_stream_push": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "ml_host_stream_finish": (_i, [_vp, _vp, _vp]),
+    "ml_host_stream_abort": (_i, [_vp]),
     "ml_host_release": (_i, []),
     "ml_host_set_packing": (_i, [_i, _i]),
     "ml_host_last_packed_fraction": (_d, []),

@@ -33,6 +33,9 @@ __all__ = [
     "launch_count",
     "force_direct",
     "variants_chunk",
+    "HostStream",
+    "Pressure",
+    "host_release",
 ]
 
 
@@ -633,3 +636,132 @@ def steric_global_host(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
     _lib.check(L.ml_steric_global_host(_eos_id(eos), _dt_id(T), T.data_ptr(), S.data_ptr(), v_ref.data_ptr(),
                                        p.data_ptr(), nt, nz, ncol, int(steps_per_window), masso.data_ptr()))
     return masso
+
+
+VARIANT_BITS = {"steric": 1, "thermosteric": 2, "halosteric": 4}
+
+
+class HostStream:
+    """The host path for fields that arrive block by block (``ml_host_stream_begin / push / finish``).
+
+    What a dask-backed Dataset is to the reference (derived.py:624-630 ``dask="allowed"``; example.ipynb cell 4 opens
+    the model output with ``chunks={"time": 1, ...}``): the 4-D fields never exist as one array.  ``push`` takes one
+    block of consecutive time steps ``[nt_block, nz, ...]`` of T and S (numpy or CPU tensors; pinned memory keeps
+    the copies asynchronous) and returns the block's outputs -- CPU tensors ``[nt_block, ...]`` per variant for
+    ``domain="local"``, ``[nt_block]`` masses for ``domain="global"`` -- which are complete once :meth:`finish`
+    has returned.  With ``reference=None`` the reference state is step 0 of the first block; otherwise
+    ``reference = {"thetao", "so", "rho"}`` (host arrays) is a supplied reference (steric.py:98-103).
+    The stream holds at most the current and the previous block alive.
+    """
+
+    def __init__(self, domain, v_ref, p_level, z_i=None, deptho=None, variants=("steric",), reference=None,
+                 rhozero=1035.0, eos="Wright", max_block_steps=1, dtype=torch.float32, want_rho_ref=False, want_sums=False):
+        L = _lib.lib()
+        _device()
+        self.local = domain == "local"
+        if domain not in ("local", "global"):
+            raise ValueError(f"Unknown domain '{domain}'")
+        self.variants = tuple(variants)
+        mask = 0
+        for v in self.variants:
+            mask |= VARIANT_BITS[v]
+        self.dtype = dtype
+        host = _host_tensor
+        self._v = host(v_ref)
+        if self._v.dtype not in (torch.float32, torch.float64):
+            self._v = self._v.to(torch.float64)
+        self.nz = int(self._v.shape[0])
+        self.hshape = tuple(self._v.shape[1:])
+        self.ncol = int(np.prod(self.hshape, dtype=np.int64))
+        self._p = host(np.asarray(_host_np(p_level), dtype=np.float64))
+        self._zi = host(np.asarray(_host_np(z_i), dtype=np.float64)) if z_i is not None else None
+        self._depth = host(np.asarray(_host_np(deptho), dtype=np.float64)) if deptho is not None else None
+        if self.local:
+            assert self._zi is not None and self._depth is not None, "the local domain needs z_i and deptho"
+            assert self._zi.numel() == self.nz + 1 and self._depth.numel() == self.ncol
+        assert self._p.numel() == self.nz
+        self._ref = None
+        tref = sref = rref = None
+        if reference is not None:
+            self._ref = {k: host(reference[k]) for k in ("thetao", "so", "rho") if reference.get(k) is not None}
+            if "thetao" in self._ref:
+                self._ref["thetao"] = self._ref["thetao"].to(dtype)
+                self._ref["so"] = self._ref["so"].to(dtype)
+                tref, sref = self._ref["thetao"].data_ptr(), self._ref["so"].data_ptr()
+            if "rho" in self._ref:
+                self._ref["rho"] = self._ref["rho"].to(torch.float64)
+                rref = self._ref["rho"].data_ptr()
+        self.want_rho_ref = bool(want_rho_ref)
+        self.max_block_steps = int(max_block_steps)
+        handle = ctypes.c_void_p()
+        _lib.check(L.ml_host_stream_begin(
+            _lib.DOMAIN_LOCAL if self.local else _lib.DOMAIN_GLOBAL, _eos_id(eos), _dt_id(torch.empty(0, dtype=dtype)), mask,
+            self._v.data_ptr(), _dt_id(self._v), tref, sref, rref,
+            self._zi.data_ptr() if self._zi is not None else None,
+            self._depth.data_ptr() if self._depth is not None else None, self._p.data_ptr(), -1.0 / rhozero, self.nz,
+            self.ncol, self.max_block_steps, (1 if want_rho_ref else 0) | (2 if want_sums else 0), ctypes.byref(handle)))
+        self._h = handle
+        self._blocks = []   # (T, S) of the current and the previous block
+        self._outs = []     # every output tensor, in push order
+        self.steps = 0
+
+    def push(self, T_block, S_block):
+        if self._h is None:
+            raise RuntimeError("the stream is closed")
+        T, S = _host_tensor(T_block).to(self.dtype), _host_tensor(S_block).to(self.dtype)
+        assert T.shape == S.shape and tuple(T.shape[1:]) == (self.nz,) + self.hshape, \
+            f"block of shape {tuple(T.shape)}, expecting [nt, {self.nz}, {self.hshape}]"
+        nt = int(T.shape[0])
+        shape = (nt,) + self.hshape if self.local else (nt,)
+        out = {v: torch.empty(shape, dtype=torch.float64) for v in self.variants}
+        ptr = lambda v: out[v].data_ptr() if v in out else None  # noqa: E731
+        rc = _lib.lib().ml_host_stream_push(self._h, T.data_ptr(), S.data_ptr(), nt, ptr("steric"), ptr("thermosteric"),
+                                            ptr("halosteric"))
+        if rc != 0:
+            msg = _lib.lib().ml_last_error().decode("utf-8", "replace")
+            self.abort()
+            raise _lib.MLError(rc, msg)
+        self._blocks = (self._blocks + [(T, S)])[-2:]  # the previous block is released by the NEXT push
+        self._outs.append(out)
+        self.steps += nt
+        return out
+
+    def finish(self):
+        """Wait for the tail; returns ``(rho_ref [nz, ...] or None, (volo, masso) or None)``."""
+        if self._h is None:
+            raise RuntimeError("the stream is closed")
+        rho = torch.empty((self.nz,) + self.hshape, dtype=torch.float64) if self.want_rho_ref else None
+        sums = torch.zeros(2, dtype=torch.float64)
+        h, self._h = self._h, None
+        _lib.check(_lib.lib().ml_host_stream_finish(h, rho.data_ptr() if rho is not None else None, sums.data_ptr()))
+        self._blocks = []
+        return rho, ((float(sums[0]), float(sums[1])) if self._ref is None else None)
+
+    def abort(self):
+        if self._h is not None:
+            h, self._h = self._h, None
+            _lib.lib().ml_host_stream_abort(h)
+        self._blocks = []
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+def _host_np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def host_release():
+    """Free the device windows, pinned staging, streams and worker threads that the ``*_host`` calls of THIS thread
+    keep between calls (``ml_host_release``).  Registered to run at interpreter exit for the importing thread; a
+    program that calls the host path from short-lived worker threads should call it before each of them ends."""
+    if _lib._LIB is not None:
+        _lib._LIB.ml_host_release()
+
+
+import atexit  # noqa: E402
+
+atexit.register(host_release)

@@ -88,9 +88,28 @@ class Pool {
 // Device staging buffers, pinned host staging, streams, events and the worker threads are kept per host
 // thread between calls (a year of OM4p25 needs ~5 GB of windows; allocating and freeing them costs tens of
 // milliseconds per call) and released by ml_host_release() or at thread exit.
+// Device and pinned-host buffers of a thread's Resources, by name (a slot grows on demand and is kept between calls).
+enum DevSlot {
+  kDevWinT0, kDevWinS0, kDevWinT1, kDevWinS1,  // the two device windows of T and S
+  kDevVol, kDevRho, kDevZi, kDevDepth, kDevP, kDevSums, kDevWs,
+  kDevTref, kDevSref,                          // reference slabs held for the thermo- / halosteric variants
+  kDevOut0,                                    // 6 slots: outputs [window parity][variant]
+  kDevPackT0 = kDevOut0 + 6, kDevPackS0, kDevPackT1, kDevPackS1,  // packed rows [window parity][field]
+  kDevWords, kDevBefore, kDevLvlOff, kDevFlags0, kDevFlags1,
+  kDevSlots
+};
+enum HostSlot {
+  kHostWords, kHostBefore, kHostLvlOff,
+  kHostStageT0, kHostStageS0, kHostStageT1, kHostStageS1,  // pinned staging [window parity][field]; kHostStageT0 doubles as the ring
+  kHostFlags,
+  kHostOut0,                                               // 6 slots: bounce buffers of pageable outputs [parity][variant]
+  kHostVol = kHostOut0 + 6,                                // bounce buffer of a pageable volcello
+  kHostSlots_
+};
+
 struct Resources {
-  static constexpr int kSlots = 28;
-  static constexpr int kHostSlots = 12;
+  static constexpr int kSlots = kDevSlots;
+  static constexpr int kHostSlots = kHostSlots_;
   static constexpr int kRing = 3;  // dense rows in flight on the copy stream
   static constexpr int kStageRing = 6;  // packed rows between the packers and the copy engine (packing mode 3)
   void* buf[kSlots] = {nullptr};
@@ -100,6 +119,7 @@ struct Resources {
   int device = -1;
   cudaStream_t copy = nullptr, comp = nullptr, back = nullptr;  // host->device, kernels, device->host
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  cudaEvent_t out_done[2] = {nullptr, nullptr};  // the outputs of a window of this parity have reached the host
   cudaEvent_t ring[kRing] = {nullptr};
   cudaEvent_t slot_done[kStageRing] = {nullptr};  // the copies out of a slot of the staging ring have finished
   Pool pool;
@@ -108,6 +128,7 @@ struct Resources {
   double last_packed_fraction = 0.0;
   double last_ms[4] = {0.0, 0.0, 0.0, 0.0};  // presence index, windows (host side), drain, whole call
   std::atomic<uint64_t> h2d_bytes{0};
+  bool open_stream = false;  // a ml_host_stream_* computation is using the buffers
   void release() {
     for (int i = 0; i < kSlots; ++i) {
       if (buf[i]) cudaFree(buf[i]);
@@ -122,7 +143,8 @@ struct Resources {
     for (int i = 0; i < 2; ++i) {
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (freed[i]) cudaEventDestroy(freed[i]);
-      copied[i] = freed[i] = nullptr;
+      if (out_done[i]) cudaEventDestroy(out_done[i]);
+      copied[i] = freed[i] = out_done[i] = nullptr;
     }
     for (int i = 0; i < kRing; ++i) {
       if (ring[i]) cudaEventDestroy(ring[i]);
@@ -153,6 +175,7 @@ struct Resources {
     for (int b = 0; b < 2; ++b) {
       if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if (!out_done[b] && (e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
     for (int i = 0; i < kRing; ++i)
       if (!ring[i] && (e = cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming)) != cudaSuccess) return e;
@@ -355,8 +378,8 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / kSegmentGroups));
   const size_t nw = (size_t)nz * (size_t)plan.ngrp;
   void *hw, *hb, *hl;
-  if (r.halloc(0, &hw, nw * 4) != cudaSuccess || r.halloc(1, &hb, nw * 4) != cudaSuccess ||
-      r.halloc(2, &hl, (size_t)(nz + 1) * 8) != cudaSuccess) {
+  if (r.halloc(kHostWords, &hw, nw * 4) != cudaSuccess || r.halloc(kHostBefore, &hb, nw * 4) != cudaSuccess ||
+      r.halloc(kHostLvlOff, &hl, (size_t)(nz + 1) * 8) != cudaSuccess) {
     cudaGetLastError();
     return ML_OK;
   }
@@ -406,7 +429,7 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   for (auto& q : plan.slot_queued) q.store(0, std::memory_order_relaxed);
   if (plan.ring) {
     void* h;
-    if (r.halloc(3, &h, (size_t)Resources::kStageRing * 2 * (size_t)ncol * 4) != cudaSuccess) {
+    if (r.halloc(kHostStageT0, &h, (size_t)Resources::kStageRing * 2 * (size_t)ncol * 4) != cudaSuccess) {
       cudaGetLastError();
       return ML_OK;
     }
@@ -415,27 +438,27 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   for (int b = 0; b < 2; ++b) {
     for (int f = 0; f < 2; ++f) {
       void *h = nullptr, *d;
-      if (!plan.ring && r.halloc(3 + 2 * b + f, &h, stage_bytes) != cudaSuccess) {
+      if (!plan.ring && r.halloc(kHostStageT0 + 2 * b + f, &h, stage_bytes) != cudaSuccess) {
         cudaGetLastError();
         return ML_OK;
       }
-      ML_CUDA(r.alloc(16 + 2 * b + f, &d, stage_bytes));
+      ML_CUDA(r.alloc(kDevPackT0 + 2 * b + f, &d, stage_bytes));
       plan.stage[b][f] = (float*)h;
       plan.d_packed[b][f] = (float*)d;
     }
     void *hf, *df;
-    if (r.halloc(7, &hf, 2 * flag_bytes) != cudaSuccess) {
+    if (r.halloc(kHostFlags, &hf, 2 * flag_bytes) != cudaSuccess) {
       cudaGetLastError();
       return ML_OK;
     }
-    ML_CUDA(r.alloc(23 + b, &df, flag_bytes));
+    ML_CUDA(r.alloc(kDevFlags0 + b, &df, flag_bytes));
     plan.flags[b] = (uint8_t*)hf + (size_t)b * flag_bytes;
     plan.d_flags[b] = (uint8_t*)df;
   }
   void *dw, *db, *dl;
-  ML_CUDA(r.alloc(20, &dw, nw * 4));
-  ML_CUDA(r.alloc(21, &db, nw * 4));
-  ML_CUDA(r.alloc(22, &dl, (size_t)(nz + 1) * 8));
+  ML_CUDA(r.alloc(kDevWords, &dw, nw * 4));
+  ML_CUDA(r.alloc(kDevBefore, &db, nw * 4));
+  ML_CUDA(r.alloc(kDevLvlOff, &dl, (size_t)(nz + 1) * 8));
   plan.d_words = (uint32_t*)dw;
   plan.d_before = (uint32_t*)db;
   plan.d_lvloff = (uint64_t*)dl;
@@ -646,160 +669,394 @@ extern "C" int ml_host_last_timings(double* ms4) {
   return ML_OK;
 }
 
-// eta_thermo / eta_halo: optional extra heights from the same transfer (NULL = steric only)
+// ---------------------------------------------------------------------------------------------------
+// Streamed computation: begin -> push (one block of time steps after the other, as they arrive) -> finish.
+// The whole-array entry points below are begin + one push per window + finish, so there is one code path.
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+struct HostStream {
+  Resources* r = nullptr;
+  std::thread::id owner;
+  int domain = ML_DOMAIN_LOCAL, eos = 0, dtype = 0, vref_dtype = 0;
+  const void* v_host = nullptr;  // the reference volume in host memory that stays valid until the first push
+  size_t es = 4;
+  int64_t nz = 0, ncol = 0, max_steps = 0;
+  bool want[3] = {true, false, false};  // steric, thermosteric, halosteric
+  bool selfref = true;                  // the reference state is step 0 of the first block
+  bool want_rho_ref = false;
+  bool want_sums = true;                // global domain: evaluate volo / masso of the reference state from step 0
+  double coef = 0.0;
+  int64_t blocks = 0, steps = 0;
+  bool failed = false;
+  PackPlan plan;
+  void *dT[2] = {nullptr, nullptr}, *dS[2] = {nullptr, nullptr};
+  void *dV = nullptr, *dRho = nullptr, *dZi = nullptr, *dDepth = nullptr, *dP = nullptr, *dSums = nullptr, *dWs = nullptr;
+  void *dTref = nullptr, *dSref = nullptr;
+  double* dOut[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  size_t ws_bytes = 0;
+  // outputs of a block land in the caller's arrays directly (pinned) or through a pinned bounce buffer (pageable)
+  struct Pending {
+    double *user = nullptr, *bounce = nullptr;
+    size_t bytes = 0;
+  } pending[2][3];
+  int nthreads = 1;
+  bool release_previous = true;  // push(k) returns once block k - 1 has left the caller's memory
+  double t_begin = 0.0, t_plan = 0.0;
+};
+
+// an error leaves copies and kernels in flight that read the caller's block and write buffers the next call reuses
+int stream_fail(HostStream* hs, int rc) {
+  if (hs->r) {
+    cudaStreamSynchronize(hs->r->copy);
+    cudaStreamSynchronize(hs->r->comp);
+    cudaStreamSynchronize(hs->r->back);
+  }
+  hs->failed = true;
+  return rc;
+}
+
+// pageable outputs of the block that used parity b: bounce buffer -> caller's array (the copies behind out_done[b] are done)
+void flush_pending(HostStream* hs, int b) {
+  for (int v = 0; v < 3; ++v) {
+    HostStream::Pending& p = hs->pending[b][v];
+    if (p.user != nullptr && p.bounce != nullptr && p.bytes) parallel_copy(*hs->r, p.user, p.bounce, p.bytes, hs->nthreads);
+    p = HostStream::Pending();
+  }
+}
+
+}  // namespace
+
+extern "C" int ml_host_stream_begin(int domain, int eos, int dtype, int variants, const void* v_ref, int vref_dtype,
+                                    const void* T_ref, const void* S_ref, const double* rho_ref, const double* z_i,
+                                    const double* deptho,
+                                    const double* p_level, double neg_inv_rhozero, int64_t nz, int64_t ncol,
+                                    int64_t max_block_steps, int want_reference, void** stream_out) {
+  using namespace ml;
+  ML_REQUIRE_PTR(stream_out);
+  *stream_out = nullptr;
+  if (domain != ML_DOMAIN_LOCAL && domain != ML_DOMAIN_GLOBAL) return fail(ML_ERR_MODE, "unknown domain %d", domain);
+  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  if (vref_dtype != ML_F32 && vref_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown vref dtype id %d", vref_dtype);
+  if ((variants & 7) == 0 || (variants & ~7)) return fail(ML_ERR_MODE, "variants mask %d: bit 0 steric, 1 thermosteric, 2 halosteric", variants);
+  ML_REQUIRE_PTR(v_ref);
+  ML_REQUIRE_PTR(p_level);
+  const bool local = domain == ML_DOMAIN_LOCAL;
+  if (local) {
+    ML_REQUIRE_PTR(z_i);
+    ML_REQUIRE_PTR(deptho);
+  }
+  if (nz <= 0 || ncol <= 0 || max_block_steps < 1)
+    return fail(ML_ERR_SHAPE, "bad extents nz=%lld ncol=%lld block=%lld", (long long)nz, (long long)ncol, (long long)max_block_steps);
+  // a supplied reference: the slabs that the thermo- / halosteric variants hold fixed, and (local) its density
+  const bool supplied = T_ref != nullptr || S_ref != nullptr || rho_ref != nullptr;
+  const bool others = (variants & 6) != 0;
+  if (supplied) {
+    if (local) ML_REQUIRE_PTR(rho_ref);
+    if (others) {
+      ML_REQUIRE_PTR(T_ref);
+      ML_REQUIRE_PTR(S_ref);
+    }
+  }
+
+  Resources& r = resources();
+  if (r.open_stream) return fail(ML_ERR_MODE, "this thread already has an open host stream (finish or abort it first)");
+  HostStream* hs = new HostStream();
+  hs->r = &r;
+  hs->owner = std::this_thread::get_id();
+  hs->domain = domain;
+  hs->eos = eos;
+  hs->dtype = dtype;
+  hs->es = (size_t)elem_size(dtype);
+  hs->vref_dtype = vref_dtype;
+  hs->nz = nz;
+  hs->ncol = ncol;
+  hs->max_steps = max_block_steps;
+  for (int v = 0; v < 3; ++v) hs->want[v] = (variants >> v) & 1;
+  hs->selfref = !supplied;
+  hs->want_rho_ref = (want_reference & 1) != 0;
+  hs->want_sums = (want_reference & 2) != 0 || local;
+  hs->coef = neg_inv_rhozero;
+  hs->nthreads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
+  const size_t es = hs->es, lvl = (size_t)nz * (size_t)ncol, ves = (size_t)elem_size(vref_dtype);
+  const size_t win_bytes = (size_t)max_block_steps * lvl * es;
+  hs->ws_bytes = ml_workspace_bytes(local ? 2 : std::max<int64_t>(2, max_block_steps), nz, ncol);
+  auto bail = [&](int rc) {
+    stream_fail(hs, rc);
+    delete hs;
+    return rc;
+  };
+#define ML_HS_CUDA(call)                                      \
+  do {                                                        \
+    cudaError_t e__ = (call);                                 \
+    if (e__ != cudaSuccess) return bail(cuda_fail(e__, #call)); \
+  } while (0)
+  ML_HS_CUDA(r.prepare());
+  for (int b = 0; b < 2; ++b) {
+    ML_HS_CUDA(r.alloc(kDevWinT0 + 2 * b, &hs->dT[b], win_bytes));
+    ML_HS_CUDA(r.alloc(kDevWinS0 + 2 * b, &hs->dS[b], win_bytes));
+    const size_t out_bytes = (size_t)max_block_steps * (local ? (size_t)ncol : 1) * sizeof(double);
+    for (int v = 0; v < 3; ++v) {
+      void* d = nullptr;
+      if (hs->want[v]) ML_HS_CUDA(r.alloc(kDevOut0 + 3 * b + v, &d, out_bytes));
+      hs->dOut[b][v] = (double*)d;
+    }
+  }
+  ML_HS_CUDA(r.alloc(kDevVol, &hs->dV, lvl * ves));
+  ML_HS_CUDA(r.alloc(kDevP, &hs->dP, (size_t)nz * sizeof(double)));
+  ML_HS_CUDA(r.alloc(kDevWs, &hs->dWs, hs->ws_bytes));
+  ML_HS_CUDA(r.alloc(kDevSums, &hs->dSums, 2 * sizeof(double)));
+  // the reference density: read by every local window; evaluated for the scalars of a self-referenced global series
+  if (local || (!supplied && hs->want_sums)) ML_HS_CUDA(r.alloc(kDevRho, &hs->dRho, lvl * sizeof(double)));
+  if (local) {
+    ML_HS_CUDA(r.alloc(kDevZi, &hs->dZi, (size_t)(nz + 1) * sizeof(double)));
+    ML_HS_CUDA(r.alloc(kDevDepth, &hs->dDepth, (size_t)ncol * sizeof(double)));
+  }
+  if (others) {
+    ML_HS_CUDA(r.alloc(kDevTref, &hs->dTref, lvl * es));
+    ML_HS_CUDA(r.alloc(kDevSref, &hs->dSref, lvl * es));
+  }
+
+  r.h2d_bytes = 0;
+  r.last_packed_fraction = 0.0;
+  hs->t_begin = now_ms();
+  if (local) {
+    ML_HS_CUDA(cudaMemcpyAsync(hs->dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+    ML_HS_CUDA(cudaMemcpyAsync(hs->dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+    r.h2d_bytes += (size_t)(nz + 1 + ncol) * sizeof(double);
+  }
+  ML_HS_CUDA(cudaMemcpyAsync(hs->dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+  // Pageable memory (plain numpy) on either end of a copy makes it a synchronous bounce through the driver that
+  // holds this thread -- and with it the pipeline -- for the length of the copy.  Unless packing is off such
+  // operands go through pinned buffers of our own, filled / emptied by the worker threads.
+  const void* v_src = v_ref;
+  if (r.pack_mode != 0 && is_pageable(v_ref)) {
+    void* hv;
+    if (r.halloc(kHostVol, &hv, lvl * ves) == cudaSuccess) {
+      parallel_copy(r, hv, v_ref, lvl * ves, hs->nthreads);
+      v_src = hv;
+    } else {
+      cudaGetLastError();
+    }
+  }
+  ML_HS_CUDA(cudaMemcpyAsync(hs->dV, v_src, lvl * ves, cudaMemcpyHostToDevice, r.copy));
+  hs->v_host = v_src;
+  r.h2d_bytes += (size_t)nz * sizeof(double) + lvl * ves;
+  if (supplied) {
+    if (local) ML_HS_CUDA(cudaMemcpyAsync(hs->dRho, rho_ref, lvl * sizeof(double), cudaMemcpyHostToDevice, r.copy));
+    if (others) {
+      ML_HS_CUDA(cudaMemcpyAsync(hs->dTref, T_ref, lvl * es, cudaMemcpyHostToDevice, r.copy));
+      ML_HS_CUDA(cudaMemcpyAsync(hs->dSref, S_ref, lvl * es, cudaMemcpyHostToDevice, r.copy));
+    }
+    r.h2d_bytes += (local ? lvl * sizeof(double) : 0) + (others ? 2 * lvl * es : 0);
+  }
+#undef ML_HS_CUDA
+  // the packing plan is made at the first push: it depends on where the blocks live (pinned or pageable memory)
+  r.open_stream = true;
+  *stream_out = hs;
+  return ML_OK;
+}
+
+
+extern "C" int ml_host_stream_push(void* stream, const void* T_block, const void* S_block, int64_t nt_block,
+                                   double* out_steric, double* out_thermosteric, double* out_halosteric) {
+  using namespace ml;
+  ML_REQUIRE_PTR(stream);
+  HostStream* hs = static_cast<HostStream*>(stream);
+  if (hs->failed) return fail(ML_ERR_MODE, "the stream has failed; abort it");
+  if (hs->owner != std::this_thread::get_id()) return fail(ML_ERR_MODE, "a host stream belongs to the thread that began it");
+  ML_REQUIRE_PTR(T_block);
+  ML_REQUIRE_PTR(S_block);
+  if (nt_block < 1 || nt_block > hs->max_steps)
+    return fail(ML_ERR_SHAPE, "block of %lld steps, the stream takes 1 ... %lld", (long long)nt_block, (long long)hs->max_steps);
+  double* user_out[3] = {out_steric, out_thermosteric, out_halosteric};
+  for (int v = 0; v < 3; ++v)
+    if (hs->want[v] && user_out[v] == nullptr) return fail(ML_ERR_NULL, "output %d of the stream is NULL", v);
+  Resources& r = *hs->r;
+  const int64_t w = hs->blocks, nz = hs->nz, ncol = hs->ncol;
+  const int b = (int)(w & 1);
+  const bool local = hs->domain == ML_DOMAIN_LOCAL;
+  const size_t lvl = (size_t)nz * (size_t)ncol, es = hs->es;
+  const bool others = hs->want[1] || hs->want[2];
+  const int eos = hs->eos, dtype = hs->dtype, vdt = hs->vref_dtype;
+#define ML_HS_CUDA(call)                                                   \
+  do {                                                                     \
+    cudaError_t e__ = (call);                                              \
+    if (e__ != cudaSuccess) return stream_fail(hs, cuda_fail(e__, #call)); \
+  } while (0)
+#define ML_HS_RC(call)                       \
+  do {                                       \
+    int rc__ = (call);                       \
+    if (rc__) return stream_fail(hs, rc__);  \
+  } while (0)
+  if (w == 0) {
+    // rho_ref is defined where the volume is missing too (reference.py:71), so a stream that hands it back moves
+    // every row as it is; so does one whose reference volume is not stored like the fields
+    const bool pageable = is_pageable(T_block) || is_pageable(S_block);
+    ML_HS_RC(plan_packing(r, hs->plan, vdt == dtype ? dtype : ML_F64, hs->v_host, nz, ncol, hs->max_steps, !hs->want_rho_ref,
+                          pageable));
+    hs->v_host = nullptr;
+    hs->t_plan = now_ms();
+  }
+  if (w >= 2) {  // the outputs of block w - 2 have reached the host: its device output buffers and bounce buffers are free
+    ML_HS_CUDA(cudaEventSynchronize(r.out_done[b]));
+    flush_pending(hs, b);
+  }
+  ML_HS_RC(stage_window(r, hs->plan, b, w, T_block, S_block, nt_block, es, nz, ncol, hs->dT[b], hs->dS[b]));
+
+  const double *dZi = (const double*)hs->dZi, *dDepth = (const double*)hs->dDepth, *dP = (const double*)hs->dP;
+  const bool first_selfref = hs->selfref && w == 0;
+  if (!local && first_selfref && hs->want_sums) {
+    // the scalars of the reference state (reference.py:74-80) from step 0 of the first block
+    ML_HS_RC(ml_reference_state(eos, dtype, hs->dT[0], hs->dS[0], hs->dV, dP, nz, ncol, (double*)hs->dRho, (double*)hs->dSums,
+                                hs->dWs, hs->ws_bytes, r.comp));
+  }
+  if (first_selfref && others) {  // keep the reference slabs before window 0 is recycled (steric.py:115-121)
+    ML_HS_CUDA(cudaMemcpyAsync(hs->dTref, hs->dT[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
+    ML_HS_CUDA(cudaMemcpyAsync(hs->dSref, hs->dS[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
+  }
+  for (int v = 0; v < 3; ++v) {
+    if (!hs->want[v]) continue;
+    // thermosteric holds S at the reference slab, halosteric holds T
+    const void* Tv = v == 2 ? hs->dTref : hs->dT[b];
+    const void* Sv = v == 1 ? hs->dSref : hs->dS[b];
+    const int tb = v == 2, sb = v == 1;
+    double* out = hs->dOut[b][v];
+    if (!local) {
+      ML_HS_RC(ml_steric_global(eos, dtype, Tv, Sv, tb, sb, hs->dV, vdt, dP, nt_block, nz, ncol, out, hs->dWs, hs->ws_bytes,
+                                r.comp));
+    } else if (first_selfref) {
+      // the window that starts at the reference step: the fused self-reference pass (for every variant, so that
+      // each step-0 height is exactly zero; it rewrites rho_ref / sums with the same values)
+      ML_HS_RC(ml_steric_local_selfref(eos, dtype, Tv, Sv, tb, sb, hs->dV, vdt, dZi, dDepth, dP, hs->coef, nt_block, nz, ncol,
+                                       out, (double*)hs->dRho, (double*)hs->dSums, hs->dWs, hs->ws_bytes, r.comp));
+    } else {
+      ML_HS_RC(ml_steric_local(eos, dtype, Tv, Sv, tb, sb, (const double*)hs->dRho, hs->dV, vdt, dZi, dDepth, dP, hs->coef,
+                               nt_block, nz, ncol, out, nullptr, r.comp));
+    }
+  }
+  ML_HS_CUDA(cudaEventRecord(r.freed[b], r.comp));
+  // the results of this block go home while the next blocks come in (PCIe carries both directions)
+  ML_HS_CUDA(cudaStreamWaitEvent(r.back, r.freed[b], 0));
+  const size_t out_bytes = (size_t)nt_block * (local ? (size_t)ncol : 1) * sizeof(double);
+  for (int v = 0; v < 3; ++v) {
+    if (!hs->want[v]) continue;
+    double* dst = user_out[v];
+    HostStream::Pending& pend = hs->pending[b][v];
+    pend = HostStream::Pending();
+    if (is_pageable(dst)) {  // a copy to pageable memory would hold this thread until the block's kernels are done
+      void* hb;
+      if (r.halloc(kHostOut0 + 3 * b + v, &hb, (size_t)hs->max_steps * (local ? (size_t)ncol : 1) * sizeof(double)) == cudaSuccess) {
+        pend.user = dst;
+        pend.bounce = (double*)hb;
+        pend.bytes = out_bytes;
+        dst = (double*)hb;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    ML_HS_CUDA(cudaMemcpyAsync(dst, hs->dOut[b][v], out_bytes, cudaMemcpyDeviceToHost, r.back));
+  }
+  ML_HS_CUDA(cudaEventRecord(r.out_done[b], r.back));
+  // The caller may reuse the PREVIOUS block's memory once this call returns: its copies were queued in front of
+  // this block's, so waiting for them does not stall the copy engine, which already has this block's rows to move.
+  if (w >= 1 && hs->release_previous) ML_HS_CUDA(cudaEventSynchronize(r.copied[b ^ 1]));
+#undef ML_HS_CUDA
+#undef ML_HS_RC
+  hs->blocks++;
+  hs->steps += nt_block;
+  return ML_OK;
+}
+
+extern "C" int ml_host_stream_finish(void* stream, double* rho_ref_out, double* sums_out) {
+  using namespace ml;
+  ML_REQUIRE_PTR(stream);
+  HostStream* hs = static_cast<HostStream*>(stream);
+  if (hs->owner != std::this_thread::get_id()) return fail(ML_ERR_MODE, "a host stream belongs to the thread that began it");
+  Resources& r = *hs->r;
+  int rc = ML_OK;
+  const size_t lvl = (size_t)hs->nz * (size_t)hs->ncol;
+  if (hs->failed) rc = fail(ML_ERR_MODE, "the stream has failed");
+  if (rc == ML_OK && rho_ref_out != nullptr && !(hs->want_rho_ref && hs->dRho != nullptr))
+    rc = fail(ML_ERR_MODE, "rho_ref_out needs want_rho_ref at ml_host_stream_begin");
+  const double t_windows = now_ms();
+  cudaError_t e = cudaSuccess;
+  if (rc == ML_OK && hs->blocks > 0) {
+    if (sums_out && hs->selfref && hs->want_sums) e = cudaMemcpyAsync(sums_out, hs->dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp);
+    if (e == cudaSuccess && rho_ref_out)
+      e = cudaMemcpyAsync(rho_ref_out, hs->dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp);
+  }
+  cudaError_t e2 = cudaStreamSynchronize(r.comp);
+  cudaError_t e3 = cudaStreamSynchronize(r.back);
+  cudaError_t e4 = cudaStreamSynchronize(r.copy);
+  for (cudaError_t x : {e, e2, e3, e4})
+    if (rc == ML_OK && x != cudaSuccess) rc = cuda_fail(x, "ml_host_stream_finish");
+  if (rc == ML_OK) {
+    flush_pending(hs, 0);
+    flush_pending(hs, 1);
+  }
+  r.last_packed_fraction = hs->plan.rows_total ? (double)hs->plan.rows_packed / (double)hs->plan.rows_total : 0.0;
+  const double t_end = now_ms();
+  r.last_ms[0] = (hs->t_plan > 0.0 ? hs->t_plan : t_windows) - hs->t_begin;
+  r.last_ms[1] = t_windows - (hs->t_plan > 0.0 ? hs->t_plan : t_windows);
+  r.last_ms[2] = t_end - t_windows;
+  r.last_ms[3] = t_end - hs->t_begin;
+  r.open_stream = false;
+  delete hs;
+  return rc;
+}
+
+extern "C" int ml_host_stream_abort(void* stream) {
+  if (stream == nullptr) return ML_OK;
+  HostStream* hs = static_cast<HostStream*>(stream);
+  stream_fail(hs, ML_OK);
+  hs->r->open_stream = false;
+  delete hs;
+  return ML_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Whole arrays in host memory: begin + one push per window + finish.
+// ---------------------------------------------------------------------------------------------------
+static int run_windows(void* hs, const void* T, const void* S, size_t step_bytes, int64_t nt, int64_t spw, double* out[3],
+                       size_t out_stride) {
+  for (int64_t t = 0; t < nt; t += spw) {
+    const int64_t n = t + spw <= nt ? spw : nt - t;
+    double* o[3];
+    for (int v = 0; v < 3; ++v) o[v] = out[v] ? out[v] + (size_t)t * out_stride : nullptr;
+    int rc = ml_host_stream_push(hs, (const char*)T + (size_t)t * step_bytes, (const char*)S + (size_t)t * step_bytes, n, o[0],
+                                 o[1], o[2]);
+    if (rc) {
+      ml_host_stream_abort(hs);
+      return rc;
+    }
+  }
+  return ML_OK;
+}
+
 static int steric_local_host_impl(int eos, int dtype, const void* T, const void* S, const void* v0, const double* z_i,
                                   const double* deptho, const double* p_level, double neg_inv_rhozero, int64_t nt,
                                   int64_t nz, int64_t ncol, int steps_per_window, double* eta, double* eta_thermo,
                                   double* eta_halo, double* rho_ref_out, double* sums_out) {
   using namespace ml;
-  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
-  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
   ML_REQUIRE_PTR(T);
   ML_REQUIRE_PTR(S);
-  ML_REQUIRE_PTR(v0);
-  ML_REQUIRE_PTR(z_i);
-  ML_REQUIRE_PTR(deptho);
-  ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(eta);
   if (nt <= 0 || nz <= 0 || ncol <= 0 || steps_per_window < 1)
     return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld window=%d", (long long)nt, (long long)nz,
                 (long long)ncol, steps_per_window);
-
-  const size_t es = (size_t)elem_size(dtype);
-  const size_t lvl = (size_t)nz * (size_t)ncol;
   const int64_t spw = steps_per_window < nt ? steps_per_window : nt;
-  const size_t win_bytes = (size_t)spw * lvl * es;
-  const size_t ws_bytes = ml_workspace_bytes(2, nz, ncol);
-
-  Resources& r = resources();
-  ML_CUDA(r.prepare());
-  void *dT[2], *dS[2], *dV, *dRho, *dEta, *dZi, *dDepth, *dP, *dSums, *dWs;
-  for (int b = 0; b < 2; ++b) {
-    ML_CUDA(r.alloc(2 * b, &dT[b], win_bytes));
-    ML_CUDA(r.alloc(2 * b + 1, &dS[b], win_bytes));
-  }
-  ML_CUDA(r.alloc(4, &dV, lvl * es));
-  ML_CUDA(r.alloc(5, &dRho, lvl * sizeof(double)));
-  ML_CUDA(r.alloc(6, &dEta, (size_t)nt * ncol * sizeof(double)));
-  ML_CUDA(r.alloc(7, &dZi, (size_t)(nz + 1) * sizeof(double)));
-  ML_CUDA(r.alloc(8, &dDepth, (size_t)ncol * sizeof(double)));
-  ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
-  ML_CUDA(r.alloc(10, &dSums, 2 * sizeof(double)));
-  ML_CUDA(r.alloc(11, &dWs, ws_bytes));
-  // the other two variants hold one field at the reference slab (steric.py:115-121), so step 0 of T and S
-  // stays on the device for the whole call, next to one more height field per variant
-  const bool variants = eta_thermo != nullptr || eta_halo != nullptr;
-  void *dT0 = nullptr, *dS0 = nullptr, *dEtaT = nullptr, *dEtaH = nullptr;
-  if (variants) {
-    ML_CUDA(r.alloc(12, &dT0, lvl * es));
-    ML_CUDA(r.alloc(13, &dS0, lvl * es));
-    if (eta_thermo) ML_CUDA(r.alloc(14, &dEtaT, (size_t)nt * ncol * sizeof(double)));
-    if (eta_halo) ML_CUDA(r.alloc(15, &dEtaH, (size_t)nt * ncol * sizeof(double)));
-  }
-
-  r.h2d_bytes = 0;
-  r.last_packed_fraction = 0.0;
-  const double t_call = now_ms();
-  ML_CUDA(cudaMemcpyAsync(dZi, z_i, (size_t)(nz + 1) * sizeof(double), cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(dDepth, deptho, (size_t)ncol * sizeof(double), cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
-  // Pageable memory (plain numpy) on either end of a copy makes it a synchronous bounce through the driver that
-  // holds this thread -- and with it the pipeline -- for the length of the copy.  Unless packing is off such
-  // operands go through pinned buffers of our own, filled / emptied by the worker threads.
-  const int nthreads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
-  const void* v0_src = v0;
-  if (r.pack_mode != 0 && is_pageable(v0)) {
-    void* hv;
-    if (r.halloc(11, &hv, lvl * es) == cudaSuccess) {
-      parallel_copy(r, hv, v0, lvl * es, nthreads);
-      v0_src = hv;
-    } else {
-      cudaGetLastError();
-    }
-  }
-  ML_CUDA(cudaMemcpyAsync(dV, v0_src, lvl * es, cudaMemcpyHostToDevice, r.copy));
-  r.h2d_bytes += (size_t)(2 * nz + 1 + ncol) * sizeof(double) + lvl * es;
-  double* user_eta[3] = {eta, eta_thermo, eta_halo};
-  double* host_eta[3] = {eta, eta_thermo, eta_halo};  // where the device->host copies land
-  const size_t eta_bytes = (size_t)nt * ncol * sizeof(double);
-  for (int v = 0; v < 3; ++v) {
-    void* hb;
-    if (user_eta[v] == nullptr || r.pack_mode == 0 || !is_pageable(user_eta[v])) continue;
-    if (r.halloc(8 + v, &hb, eta_bytes) == cudaSuccess)
-      host_eta[v] = (double*)hb;
-    else
-      cudaGetLastError();
-  }
-  // rho_ref is defined where the volume is missing too (reference.py:71), so a call that wants it back
-  // moves every row as it is
-  PackPlan plan;
-  if (int rc = plan_packing(r, plan, dtype, v0, nz, ncol, spw, rho_ref_out == nullptr,
-                            is_pageable(T) || is_pageable(S))) return rc;
-  const double t_plan = now_ms();
-
-  const int64_t nwin = (nt + spw - 1) / spw;
-  for (int64_t w = 0; w < nwin; ++w) {
-    const int b = (int)(w & 1);
-    const int64_t t_first = w * spw;
-    const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
-    const size_t off = (size_t)t_first * lvl * es;
-    int rc = stage_window(r, plan, b, w, (const char*)T + off, (const char*)S + off, nt_w, es, nz, ncol, dT[b], dS[b]);
-    if (rc) return rc;
-    if (w == 0)  // the window that starts at the reference step (reference.py:60-80): fused pass
-      rc = ml_steric_local_selfref(eos, dtype, dT[0], dS[0], 0, 0, dV, dtype, (const double*)dZi,
-                                   (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
-                                   (double*)dEta, (double*)dRho, (double*)dSums, dWs, ws_bytes, r.comp);
-    else
-      rc = ml_steric_local(eos, dtype, dT[b], dS[b], 0, 0, (const double*)dRho, dV, dtype, (const double*)dZi,
-                           (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
-                           (double*)dEta + (size_t)t_first * ncol, nullptr, r.comp);
-    if (rc) return rc;
-    if (variants) {
-      if (w == 0) {  // keep the reference slabs before window 0 is recycled
-        ML_CUDA(cudaMemcpyAsync(dT0, dT[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
-        ML_CUDA(cudaMemcpyAsync(dS0, dS[0], lvl * es, cudaMemcpyDeviceToDevice, r.comp));
-      }
-      // window 0 starts at the reference step: the fused self-reference pass again, so that the step-0
-      // heights of these variants are exactly zero as well (it rewrites rho_ref / sums with the same values)
-      for (int v = 0; v < 2; ++v) {
-        double* out = (double*)(v == 0 ? dEtaT : dEtaH);
-        if ((v == 0 ? eta_thermo : eta_halo) == nullptr) continue;
-        const void* Tv = v == 0 ? dT[b] : dT0;
-        const void* Sv = v == 0 ? dS0 : dS[b];
-        if (w == 0)
-          rc = ml_steric_local_selfref(eos, dtype, Tv, Sv, v == 1, v == 0, dV, dtype, (const double*)dZi,
-                                       (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol, out,
-                                       (double*)dRho, (double*)dSums, dWs, ws_bytes, r.comp);
-        else
-          rc = ml_steric_local(eos, dtype, Tv, Sv, v == 1, v == 0, (const double*)dRho, dV, dtype, (const double*)dZi,
-                               (const double*)dDepth, (const double*)dP, neg_inv_rhozero, nt_w, nz, ncol,
-                               out + (size_t)t_first * ncol, nullptr, r.comp);
-        if (rc) return rc;
-      }
-    }
-    ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
-    // the heights of this window go home while the next windows come in (PCIe carries both directions)
-    const size_t eoff = (size_t)t_first * ncol, ebytes = (size_t)nt_w * ncol * sizeof(double);
-    ML_CUDA(cudaStreamWaitEvent(r.back, r.freed[b], 0));
-    ML_CUDA(cudaMemcpyAsync(host_eta[0] + eoff, (double*)dEta + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
-    if (eta_thermo) ML_CUDA(cudaMemcpyAsync(host_eta[1] + eoff, (double*)dEtaT + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
-    if (eta_halo) ML_CUDA(cudaMemcpyAsync(host_eta[2] + eoff, (double*)dEtaH + eoff, ebytes, cudaMemcpyDeviceToHost, r.back));
-  }
-  const double t_windows = now_ms();
-  if (sums_out) ML_CUDA(cudaMemcpyAsync(sums_out, dSums, 2 * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
-  if (rho_ref_out) ML_CUDA(cudaMemcpyAsync(rho_ref_out, dRho, lvl * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
-  ML_CUDA(cudaStreamSynchronize(r.comp));
-  ML_CUDA(cudaStreamSynchronize(r.back));
-  ML_CUDA(cudaStreamSynchronize(r.copy));
-  for (int v = 0; v < 3; ++v)
-    if (user_eta[v] != nullptr && host_eta[v] != user_eta[v]) parallel_copy(r, user_eta[v], host_eta[v], eta_bytes, nthreads);
-  r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
-  const double t_end = now_ms();
-  r.last_ms[0] = t_plan - t_call;
-  r.last_ms[1] = t_windows - t_plan;
-  r.last_ms[2] = t_end - t_windows;
-  r.last_ms[3] = t_end - t_call;
-  return ML_OK;
+  const int variants = 1 | (eta_thermo ? 2 : 0) | (eta_halo ? 4 : 0);
+  void* hs = nullptr;
+  int rc = ml_host_stream_begin(ML_DOMAIN_LOCAL, eos, dtype, variants, v0, dtype, nullptr, nullptr, nullptr, z_i, deptho,
+                                p_level, neg_inv_rhozero, nz, ncol, spw, rho_ref_out != nullptr ? 1 : 0, &hs);
+  if (rc) return rc;
+  static_cast<HostStream*>(hs)->release_previous = false;  // the caller's arrays outlive the call
+  double* out[3] = {eta, eta_thermo, eta_halo};
+  const size_t step_bytes = (size_t)nz * (size_t)ncol * (size_t)elem_size(dtype);
+  if ((rc = run_windows(hs, T, S, step_bytes, nt, spw, out, (size_t)ncol))) return rc;
+  return ml_host_stream_finish(hs, rho_ref_out, sums_out);
 }
 
 extern "C" int ml_steric_local_host(int eos, int dtype, const void* T, const void* S, const void* v0,
@@ -826,58 +1083,21 @@ extern "C" int ml_steric_global_host(int eos, int dtype, const void* T, const vo
                                      const double* p_level, int64_t nt, int64_t nz, int64_t ncol,
                                      int steps_per_window, double* masso) {
   using namespace ml;
-  if (eos != ML_EOS_WRIGHT && eos != ML_EOS_LINEAR) return fail(ML_ERR_EOS, "unknown equation of state id %d", eos);
-  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
   ML_REQUIRE_PTR(T);
   ML_REQUIRE_PTR(S);
-  ML_REQUIRE_PTR(v_ref);
-  ML_REQUIRE_PTR(p_level);
   ML_REQUIRE_PTR(masso);
   if (nt <= 0 || nz <= 0 || ncol <= 0 || steps_per_window < 1)
     return fail(ML_ERR_SHAPE, "bad extents nt=%lld nz=%lld ncol=%lld window=%d", (long long)nt, (long long)nz,
                 (long long)ncol, steps_per_window);
-  const size_t es = (size_t)elem_size(dtype);
-  const size_t lvl = (size_t)nz * (size_t)ncol;
   const int64_t spw = steps_per_window < nt ? steps_per_window : nt;
-  const size_t win_bytes = (size_t)spw * lvl * es;
-  const size_t ws_bytes = ml_workspace_bytes(spw, nz, ncol);
-
-  Resources& r = resources();
-  ML_CUDA(r.prepare());
-  void *dT[2], *dS[2], *dV, *dM, *dP, *dWs;
-  for (int b = 0; b < 2; ++b) {
-    ML_CUDA(r.alloc(2 * b, &dT[b], win_bytes));
-    ML_CUDA(r.alloc(2 * b + 1, &dS[b], win_bytes));
-  }
-  ML_CUDA(r.alloc(4, &dV, lvl * es));
-  ML_CUDA(r.alloc(6, &dM, (size_t)nt * sizeof(double)));
-  ML_CUDA(r.alloc(9, &dP, (size_t)nz * sizeof(double)));
-  ML_CUDA(r.alloc(11, &dWs, ws_bytes));
-  r.h2d_bytes = 0;
-  r.last_packed_fraction = 0.0;
-  ML_CUDA(cudaMemcpyAsync(dP, p_level, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(dV, v_ref, lvl * es, cudaMemcpyHostToDevice, r.copy));
-  r.h2d_bytes += (size_t)nz * sizeof(double) + lvl * es;
-  // rho * volcello is skipped where the reference volume is missing (derived.py:435-438)
-  PackPlan plan;
-  if (int rc = plan_packing(r, plan, dtype, v_ref, nz, ncol, spw, true, is_pageable(T) || is_pageable(S))) return rc;
-
-  const int64_t nwin = (nt + spw - 1) / spw;
-  for (int64_t w = 0; w < nwin; ++w) {
-    const int b = (int)(w & 1);
-    const int64_t t_first = w * spw;
-    const int64_t nt_w = (t_first + spw <= nt) ? spw : (nt - t_first);
-    const size_t off = (size_t)t_first * lvl * es;
-    int rc = stage_window(r, plan, b, w, (const char*)T + off, (const char*)S + off, nt_w, es, nz, ncol, dT[b], dS[b]);
-    if (rc) return rc;
-    rc = ml_steric_global(eos, dtype, dT[b], dS[b], 0, 0, dV, dtype, (const double*)dP, nt_w, nz, ncol,
-                              (double*)dM + t_first, dWs, ws_bytes, r.comp);
-    if (rc) return rc;
-    ML_CUDA(cudaEventRecord(r.freed[b], r.comp));
-  }
-  ML_CUDA(cudaMemcpyAsync(masso, dM, (size_t)nt * sizeof(double), cudaMemcpyDeviceToHost, r.comp));
-  ML_CUDA(cudaStreamSynchronize(r.comp));
-  ML_CUDA(cudaStreamSynchronize(r.copy));
-  r.last_packed_fraction = plan.rows_total ? (double)plan.rows_packed / (double)plan.rows_total : 0.0;
-  return ML_OK;
+  // the masses need the reference VOLUME only, which the caller hands in: no reference-state pass
+  void* hs = nullptr;
+  int rc = ml_host_stream_begin(ML_DOMAIN_GLOBAL, eos, dtype, 1, v_ref, dtype, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                p_level, 0.0, nz, ncol, spw, 0, &hs);
+  if (rc) return rc;
+  static_cast<HostStream*>(hs)->release_previous = false;
+  double* out[3] = {masso, nullptr, nullptr};
+  const size_t step_bytes = (size_t)nz * (size_t)ncol * (size_t)elem_size(dtype);
+  if ((rc = run_windows(hs, T, S, step_bytes, nt, spw, out, 1))) return rc;
+  return ml_host_stream_finish(hs, nullptr, nullptr);
 }

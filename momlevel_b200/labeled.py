@@ -13,7 +13,7 @@ computation goes through ``momlevel_b200.core`` to the CUDA library.
 import numpy as np
 import torch
 
-__all__ = ["DataArray", "Dataset"]
+__all__ = ["ChunkedArray", "DataArray", "Dataset"]
 
 
 def _is_tensor(x):
@@ -26,8 +26,76 @@ def _to_numpy(x):
     return np.asarray(x)
 
 
+class ChunkedArray:
+    """A field that exists as consecutive blocks along its first axis -- what a dask-backed xarray variable is.
+
+    ``blocks`` is a callable that returns a fresh iterator over the blocks (numpy arrays ``[n_i, ...]`` whose lengths
+    are ``chunks``); nothing is read until somebody iterates.  ``steric()`` streams such fields through the device
+    block by block (``core.HostStream``) instead of asking for the whole array, which for a daily global series
+    (BASELINE config 4: 1.4 TB) does not exist anywhere.  Indexing a step range reads only the blocks it touches;
+    ``numpy.asarray`` concatenates everything (the fallback for code that is not block-aware).
+    """
+
+    def __init__(self, shape, dtype, chunks, blocks):
+        self.shape = tuple(int(n) for n in shape)
+        self.dtype = np.dtype(dtype)
+        self.chunks = tuple(int(c) for c in chunks)
+        assert sum(self.chunks) == self.shape[0], "the blocks must cover the first axis"
+        self._blocks = blocks
+        self.blocks_read = 0  # accounting for tests: how many blocks have been produced
+
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        return int(np.prod(self.shape, dtype=np.int64))
+
+    @property
+    def flags(self):
+        return {"C_CONTIGUOUS": True}
+
+    def blocks(self):
+        for blk in self._blocks():
+            self.blocks_read += 1
+            yield np.asarray(blk)
+
+    def _steps(self, start, stop):
+        """Steps ``[start, stop)`` as one numpy array, reading only the blocks that hold them."""
+        out, t0 = [], 0
+        for n, blk in zip(self.chunks, self.blocks()):
+            lo, hi = max(start, t0), min(stop, t0 + n)
+            if lo < hi:
+                out.append(np.asarray(blk)[lo - t0: hi - t0])
+            t0 += n
+            if t0 >= stop:
+                break
+        return np.concatenate(out) if len(out) != 1 else out[0]
+
+    def __getitem__(self, key):
+        if not isinstance(key, tuple):
+            key = (key,)
+        k0, rest = key[0], key[1:]
+        if isinstance(k0, (int, np.integer)):
+            i = int(k0) % self.shape[0]
+            first = self._steps(i, i + 1)[0]
+            return first[rest] if rest else first
+        start, stop, step = k0.indices(self.shape[0])
+        assert step == 1, "a chunked field is sliced in whole step ranges"
+        sub = self._steps(start, stop)
+        return sub[(slice(None),) + rest] if rest else sub
+
+    def __array__(self, dtype=None, copy=None):
+        full = np.concatenate(list(self.blocks())) if self.chunks else np.empty(self.shape, self.dtype)
+        return full.astype(dtype) if dtype is not None else full
+
+    def __repr__(self):
+        return f"<momlevel_b200.ChunkedArray {self.shape} {self.dtype} in {len(self.chunks)} blocks>"
+
+
 class DataArray:
-    """N-d array with dimension names. ``data`` is a numpy array or a torch tensor."""
+    """N-d array with dimension names. ``data`` is a numpy array, a torch tensor or a :class:`ChunkedArray`."""
 
     __array_priority__ = 50
 
@@ -37,7 +105,7 @@ class DataArray:
             attrs = dict(data.attrs) if attrs is None else attrs
             coords = dict(data.coords) if coords is None else coords
             data = data._data
-        if not _is_tensor(data) and not callable(data):
+        if not _is_tensor(data) and not callable(data) and not isinstance(data, ChunkedArray):
             data = np.asarray(data)
         self._data = data
         self._lazy_shape = None

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import core
-from .labeled import DataArray, Dataset
+from .labeled import ChunkedArray, DataArray, Dataset
 from .reference import _pressure, setup_reference_state
 from .util import annual_average, calendar_axis, default_coords, validate_dataset, whole_years_in_order
 
@@ -48,7 +48,11 @@ def steric(
         from . import xarray_io
 
         dset_x = dset
-        dset = xarray_io.from_xarray(dset)
+        # only what the path reads is converted; dask-backed fields stay in blocks (labeled.ChunkedArray)
+        t_, z_, zb_ = default_coords(coord_names)
+        needed = {"thetao", "so", "volcello", "areacello", "deptho", t_, z_, zb_}
+        needed |= {k for k, v in (varname_map or {}).items() if v in needed}
+        dset = xarray_io.from_xarray(dset, names=sorted(needed))
         if reference is not None:
             assert type(reference).__module__.startswith("xarray"), "`reference` must be an xarray Dataset"
             reference = xarray_io.from_xarray(reference)
@@ -70,8 +74,18 @@ def steric(
 
     # steric.py:98-112
     fused_eta = None
+    streamed = None    # heights / masses of fields that arrive block by block (dask-backed variables)
     area_total = None  # areacello.sum(), when the fused path has already read it back
-    if reference is not None:
+    if variant in VARIANTS and _chunked(dset):
+        # the fields exist only as blocks along time: streamed through the device as they are produced
+        # (core.HostStream), never asked for as whole arrays
+        if reference is not None:
+            assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
+        reference, streamed = _streamed(dset, reference, pres, equation_of_state, variant, domain, rhozero, tcoord,
+                                        zcoord, zbounds, verbose)
+        if domain != "global":
+            fused_eta = streamed
+    elif reference is not None:
         assert isinstance(reference, Dataset), "`reference` must be an xarray Dataset"
         if verbose:
             print("Using supplied reference state")
@@ -111,7 +125,9 @@ def steric(
     if domain == "global":
         # steric.py:134-147
         v_ref = reference["volcello"].data
-        if (variant == "steric" and not isinstance(pres, core.Pressure)
+        if streamed is not None:
+            masso = streamed.numpy()
+        elif (variant == "steric" and not isinstance(pres, core.Pressure)
                 and _host_resident(dset, tcoord, zcoord, zbounds, need_depth=False)
                 and not (isinstance(v_ref, torch.Tensor) and v_ref.is_cuda)):
             # fields in host memory (a daily series does not fit in HBM): streamed through device windows,
@@ -145,8 +161,14 @@ def steric(
             return core.delta_rho(thetao.data, so.data, reference["rho"].data, reference["volcello"].data, pres,
                                   eos=equation_of_state, t_bcast=t_bcast, s_bcast=s_bcast)
 
+        if streamed is not None:
+            def _delta_rho():  # noqa: F811 -- block by block again; the result is as large as the inputs
+                return _delta_rho_streamed(thetao, so, reference, pres, equation_of_state, t_bcast, s_bcast)
+
         drho_shape = full.shape
-        if annual and days_in_month is None and tcoord in dset.variables:
+        if streamed is not None:
+            fused_weights = None  # blocks need not hold whole years: the monthly anomaly is averaged when it is read
+        elif annual and days_in_month is None and tcoord in dset.variables:
             # util.py:79-87: year and days-in-month of every step come from the calendar objects of the time axis
             cal = calendar_axis(dset[tcoord].values)
             if cal is not None and whole_years_in_order(cal[0]):
@@ -338,6 +360,147 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferre
         assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
         sums = host[4:6]
     return _reference_from_pass(dset, tcoord, eos, rho, sums, pres), eta, area_total
+
+
+def _chunked(dset):
+    """Whether thetao or so exists only as blocks along time (a dask-backed variable, ``labeled.ChunkedArray``)."""
+    try:
+        return any(isinstance(dset[n]._data, ChunkedArray) for n in ("thetao", "so"))
+    except (KeyError, AttributeError):
+        return False
+
+
+def _block_iter(arr):
+    """``(chunks, iterator of numpy blocks)`` of a field: its own blocks, or the whole host array as one block."""
+    if isinstance(arr, ChunkedArray):
+        return arr.chunks, arr.blocks()
+    a = arr.detach().cpu().numpy() if isinstance(arr, torch.Tensor) else np.asarray(arr)
+    return (a.shape[0],), iter([a])
+
+
+def _aligned_blocks(T, S):
+    """Blocks of T and S cut at the union of their block boundaries (views, no copies): ``(max_len, iterator)``."""
+    ct, it_t = _block_iter(T)
+    cs, it_s = _block_iter(S)
+    assert sum(ct) == sum(cs), "thetao and so must have the same number of time steps"
+    cuts = sorted(set(np.cumsum(ct).tolist()) | set(np.cumsum(cs).tolist()))
+    lens = np.diff([0] + cuts).tolist()
+
+    def gen():
+        bt = bs = None
+        ot = os_ = 0
+        for n in lens:
+            if bt is None or ot >= bt.shape[0]:
+                bt, ot = next(it_t), 0
+            if bs is None or os_ >= bs.shape[0]:
+                bs, os_ = next(it_s), 0
+            yield bt[ot: ot + n], bs[os_: os_ + n]
+            ot += n
+            os_ += n
+
+    return (max(lens) if lens else 1), gen()
+
+
+def _host_array(x):
+    x = x.data if isinstance(x, DataArray) else x
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+def _streamed(dset, reference, pres, eos, variant, domain, rhozero, tcoord, zcoord, zbounds, verbose=False):
+    """The heights (local) or masses (global) of fields that arrive block by block, and the reference Dataset.
+
+    One pass over the blocks of ``thetao`` / ``so`` through ``core.HostStream``: a block is packed, copied and
+    integrated while the next one is being produced, and at most two blocks are alive at a time.  With
+    ``reference=None`` the reference state is step 0 of the first block (steric.py:105-107).
+    Returns ``(reference, CPU tensor)``.
+    """
+    from .util import eos_func_from_str
+
+    eos_func_from_str(eos)
+    if isinstance(pres, core.Pressure):
+        raise NotImplementedError("a 2-D `patm` together with chunked (dask-backed) fields")
+    local = domain != "global"
+    if local:
+        _check_depths(dset, zcoord, zbounds)
+    T, S = dset["thetao"], dset["so"]
+    if not (T.dims == S.dims and T.ndim == 4 and T.dims[0] == tcoord and T.dims[1] == zcoord and T.shape == S.shape):
+        raise ValueError(f"expecting fields laid out ({tcoord}, {zcoord}, y, x), got {T.dims} and {S.dims}")
+    supplied = reference is not None
+    if supplied:
+        if verbose:
+            print("Using supplied reference state")
+        V0 = _host_array(reference["volcello"])
+        ref = {"rho": _host_array(reference["rho"])} if local else {}
+        if variant != "steric":
+            ref.update(thetao=_host_array(reference["thetao"]), so=_host_array(reference["so"]))
+        if not ref:  # the masses of the steric variant need the reference volume only
+            ref = None
+    else:
+        if verbose:
+            print("Generating reference state from first timestep")
+        V0 = _host_array(dset["volcello"].isel({tcoord: 0}).squeeze())
+        ref = None
+    max_len, blocks = _aligned_blocks(T._data, S._data)
+    dt = torch.float32 if str(T._data.dtype).endswith("float32") and str(S._data.dtype).endswith("float32") else torch.float64
+    hs = core.HostStream("local" if local else "global", V0, _host_numpy(pres),
+                         z_i=_host_array(dset[zbounds]) if local else None,
+                         deptho=_host_array(dset["deptho"]) if local else None, variants=(variant,), reference=ref,
+                         rhozero=rhozero, eos=eos, max_block_steps=max_len, dtype=dt, want_sums=not supplied)
+    outs, first = [], None
+    try:
+        for Tb, Sb in blocks:
+            if first is None and not supplied:  # step 0 becomes the reference Dataset (reference.py:60-68)
+                first = (np.array(Tb[0]), np.array(Sb[0]))
+            outs.append(hs.push(Tb, Sb)[variant])
+        _, sums = hs.finish()
+    except BaseException:
+        hs.abort()
+        raise
+    out = torch.cat(outs) if len(outs) != 1 else outs[0]
+    if not supplied:
+        sub = Dataset()
+        hdims = T.dims[1:]
+        sub["thetao"] = DataArray(first[0], hdims, attrs=T.attrs)
+        sub["so"] = DataArray(first[1], hdims, attrs=S.attrs)
+        sub["volcello"] = DataArray(V0, hdims, attrs=dset["volcello"].attrs)
+        sub["areacello"] = dset["areacello"]
+        for name in hdims:
+            if name in dset.variables:
+                sub[name] = dset[name]
+        sub = _with_time_axis(sub, tcoord)
+        reference = _reference_from_pass(sub, tcoord, eos, None, torch.tensor(sums, dtype=torch.float64), pres)
+    return reference, out
+
+
+def _with_time_axis(sub, tcoord):
+    """A one-step Dataset around the reference slabs, so that ``_reference_from_pass`` can take its step 0."""
+    out = Dataset()
+    for k, v in sub.variables.items():
+        if k in ("thetao", "so", "volcello"):
+            d = v.data
+            out[k] = DataArray(d[None] if not isinstance(d, torch.Tensor) else d.unsqueeze(0), (tcoord,) + v.dims, attrs=v.attrs)
+        else:
+            out[k] = v
+    return out
+
+
+def _delta_rho_streamed(thetao, so, reference, pres, eos, t_bcast, s_bcast):
+    """``delta_rho`` (steric.py:151-158) of chunked fields: one ``ml_delta_rho`` per block, gathered on the host."""
+    full = so if t_bcast else thetao
+    rho_ref, v_ref = reference["rho"].data, reference["volcello"].data
+    parts = []
+    if t_bcast or s_bcast:
+        fixed = (thetao if t_bcast else so).data
+        _, it = _block_iter(full._data)
+        for blk in it:
+            a = core.delta_rho(fixed if t_bcast else blk, blk if t_bcast else fixed, rho_ref, v_ref, pres, eos=eos,
+                               t_bcast=t_bcast, s_bcast=s_bcast)
+            parts.append(a.cpu())
+    else:
+        _, it = _aligned_blocks(thetao._data, so._data)
+        for Tb, Sb in it:
+            parts.append(core.delta_rho(Tb, Sb, rho_ref, v_ref, pres, eos=eos).cpu())
+    return torch.cat(parts)
 
 
 VARIANTS = ("steric", "thermosteric", "halosteric")

@@ -10,21 +10,74 @@ import numpy as np
 __version__ = "0.0-stub"
 
 
+class ChunkedNumpy:
+    """Stands in for a dask array: knows its ``chunks``, computes only what is sliced out of it, and keeps
+    count of what it was asked to materialise (``largest_compute``: the biggest single request, in elements)."""
+
+    largest_compute = 0
+    total_computed = 0
+
+    def __init__(self, array, chunks0):
+        self._a = array
+        self.chunks = (tuple(chunks0),) + tuple((n,) for n in array.shape[1:])
+        assert sum(chunks0) == array.shape[0]
+
+    shape = property(lambda self: self._a.shape)
+    dtype = property(lambda self: self._a.dtype)
+    ndim = property(lambda self: self._a.ndim)
+
+    def __getitem__(self, key):
+        sub = self._a[key]
+        return ChunkedNumpy(sub, (sub.shape[0],)) if sub.ndim == self._a.ndim else sub
+
+    def compute(self):
+        ChunkedNumpy.largest_compute = max(ChunkedNumpy.largest_compute, self._a.size)
+        ChunkedNumpy.total_computed += self._a.size
+        return np.array(self._a)
+
+    def __array__(self, dtype=None, copy=None):
+        out = self.compute()
+        return out.astype(dtype) if dtype is not None else out
+
+
 class Variable:
     def __init__(self, values, dims, attrs=None):
-        self.values = np.asarray(values)
+        self._data = values if isinstance(values, ChunkedNumpy) else np.asarray(values)
         self.dims = tuple(dims)
         self.attrs = dict(attrs or {})
         self.encoding = {}
 
     @property
+    def data(self):
+        return self._data
+
+    @property
+    def values(self):
+        return np.asarray(self._data)
+
+    @property
     def shape(self):
-        return self.values.shape
+        return self._data.shape
+
+    @property
+    def ndim(self):
+        return self._data.ndim
+
+    @property
+    def dtype(self):
+        return self._data.dtype
+
+    def __getitem__(self, key):
+        sub = self._data[key]
+        keys = key if isinstance(key, tuple) else (key,)
+        dims = tuple(d for d, k in zip(self.dims, keys + (slice(None),) * (len(self.dims) - len(keys)))
+                     if not isinstance(k, (int, np.integer)))
+        return Variable(sub, dims, self.attrs)
 
 
 class DataArray(Variable):
     def __init__(self, data, dims=None, attrs=None, coords=None, name=None):
-        data = np.asarray(data)
+        data = data if isinstance(data, ChunkedNumpy) else np.asarray(data)
         super().__init__(data, dims if dims is not None else tuple(f"dim_{i}" for i in range(data.ndim)), attrs)
         self.name = name
 

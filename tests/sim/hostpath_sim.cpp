@@ -60,13 +60,13 @@ static void toy_reference(const float* T, const float* S, const float* V, int64_
   sums[1] = masso;
 }
 
-static void toy_global(const float* T, const float* S, const float* V, int64_t nt, int64_t nz, int64_t ncol,
+static void toy_global(const float* T, const float* S, int tb, int sb, const float* V, int64_t nt, int64_t nz, int64_t ncol,
                        double* masso) {
   for (int64_t t = 0; t < nt; ++t) {
     double m = 0.0;
     for (size_t i = 0; i < (size_t)nz * ncol; ++i) {
       if (!present(V[i])) continue;
-      const double x = toy_rho(T[(size_t)t * nz * ncol + i], S[(size_t)t * nz * ncol + i]) * V[i];
+      const double x = toy_rho(T[(tb ? 0 : (size_t)t * nz * ncol) + i], S[(sb ? 0 : (size_t)t * nz * ncol) + i]) * V[i];
       if (!std::isnan(x)) m += x;
     }
     masso[t] = m;
@@ -96,9 +96,15 @@ extern "C" int ml_steric_local_selfref(int, int, const void* T, const void* S, i
   return 0;
 }
 
-extern "C" int ml_steric_global(int, int, const void* T, const void* S, int, int, const void* v_ref, int, const double*,
+extern "C" int ml_steric_global(int, int, const void* T, const void* S, int tb, int sb, const void* v_ref, int, const double*,
                                 int64_t nt, int64_t nz, int64_t ncol, double* masso, void*, size_t, void* stream) {
-  ((cudaStream_t)stream)->enqueue([=] { toy_global((const float*)T, (const float*)S, (const float*)v_ref, nt, nz, ncol, masso); });
+  ((cudaStream_t)stream)->enqueue([=] { toy_global((const float*)T, (const float*)S, tb, sb, (const float*)v_ref, nt, nz, ncol, masso); });
+  return 0;
+}
+
+extern "C" int ml_reference_state(int, int, const void* T0, const void* S0, const void* V0, const double*, int64_t nz,
+                                  int64_t ncol, double* rho_ref, double* sums, void*, size_t, void* stream) {
+  ((cudaStream_t)stream)->enqueue([=] { toy_reference((const float*)T0, (const float*)S0, (const float*)V0, nz, ncol, rho_ref, sums); });
   return 0;
 }
 
@@ -192,7 +198,7 @@ int main() {
       toy_local(T, S, 0, 0, rho_ref.data(), V, nt, nz, ncol, want[0].data());
       toy_local(T, S, 0, 1, rho_ref.data(), V, nt, nz, ncol, want[1].data());  // thermosteric: S held at step 0
       toy_local(T, S, 1, 0, rho_ref.data(), V, nt, nz, ncol, want[2].data());  // halosteric: T held at step 0
-      toy_global(T, S, V, nt, nz, ncol, want_m.data());
+      toy_global(T, S, 0, 0, V, nt, nz, ncol, want_m.data());
       std::vector<double> z_i(nz + 1, 0.0), depth(ncol, 1.0), p(nz, 0.0), masso(nt), rho_out(lvl);
       int packable = 0;  // levels with less than 90 % of their cells present: what mode 2 packs from pinned memory
       for (int64_t z = 0; z < nz; ++z) {
@@ -238,6 +244,85 @@ int main() {
                        (long long)nt, (long long)nz, (long long)ncol, pinned, mode, threads, spw, slow, frac);
               }
             }
+      // ---- the same fields pushed block by block (ml_host_stream_*): blocks of uneven length travel through two
+      // scratch buffers, and a buffer is scribbled over as soon as the contract allows it (after the NEXT push returns)
+      {
+        std::vector<double> want_g[3];
+        for (auto& w : want_g) w.resize((size_t)nt);
+        toy_global(T, S, 0, 0, V, nt, nz, ncol, want_g[0].data());
+        toy_global(T, S, 0, 1, V, nt, nz, ncol, want_g[1].data());
+        toy_global(T, S, 1, 0, V, nt, nz, ncol, want_g[2].data());
+        const int64_t maxb = 3;
+        float* sc[2][2];
+        for (int b = 0; b < 2; ++b)
+          for (int f = 0; f < 2; ++f) sc[b][f] = alloc<float>((size_t)maxb * lvl, pinned);
+        double* out_s[3];
+        for (auto& o : out_s) o = alloc<double>((size_t)nt * ncol, pinned);
+        for (int mode : {0, 1, 2, 4})
+          for (int threads : {1, 3})
+            for (int domain = 0; domain < 2; ++domain)
+              for (int supplied = 0; supplied < 2; ++supplied)
+                for (int slow = 0; slow < 2; ++slow) {
+                  if (mode == 0 && threads != 1) continue;
+                  simcuda::copy_ns_per_kib() = slow ? 300 : 0;
+                  ml_host_set_packing(mode, threads);
+                  for (auto& o : out_s) memset(o, 0, (size_t)nt * ncol * sizeof(double));
+                  void* hs = nullptr;
+                  double sums[2] = {0, 0};
+                  int rc = ml_host_stream_begin(domain, 0, ML_F32, 7, V, ML_F32, supplied ? T : nullptr, supplied ? S : nullptr,
+                                                supplied ? rho_ref.data() : nullptr, z_i.data(), depth.data(), p.data(), -1.0, nz,
+                                                ncol, maxb, domain == 1 ? 2 : 0, &hs);
+                  bool ok = rc == 0;
+                  int64_t t = 0;
+                  for (int k = 0; ok && t < nt; ++k) {
+                    const int64_t n = std::min<int64_t>(nt - t, 1 + (k % maxb));  // 1, 2, 3, 1, ... steps
+                    memcpy(sc[k & 1][0], T + (size_t)t * lvl, (size_t)n * lvl * sizeof(float));
+                    memcpy(sc[k & 1][1], S + (size_t)t * lvl, (size_t)n * lvl * sizeof(float));
+                    const size_t o = (size_t)t * (domain == 0 ? (size_t)ncol : 1);
+                    rc = ml_host_stream_push(hs, sc[k & 1][0], sc[k & 1][1], n, out_s[0] + o, out_s[1] + o, out_s[2] + o);
+                    ok = ok && rc == 0;
+                    if (k >= 1)  // the previous block's memory is the caller's again
+                      for (int f = 0; f < 2; ++f)
+                        for (size_t i = 0; i < (size_t)maxb * lvl; ++i) sc[(k - 1) & 1][f][i] = -1234.5f;
+                    t += n;
+                  }
+                  if (ok) {
+                    rc = ml_host_stream_finish(hs, nullptr, sums);
+                    ok = rc == 0;
+                  } else if (hs) {
+                    ml_host_stream_abort(hs);
+                  }
+                  for (int v = 0; v < 3 && ok; ++v)
+                    ok = domain == 0 ? same(out_s[v], want[v].data(), (size_t)nt * ncol) : same(out_s[v], want_g[v].data(), (size_t)nt);
+                  if (ok && !supplied) ok = sums[0] == want_sums[0] && sums[1] == want_sums[1];
+                  ++runs;
+                  if (!ok) {
+                    ++bad;
+                    printf("STREAM MISMATCH nt=%lld nz=%lld ncol=%lld pinned=%d mode=%d threads=%d domain=%d supplied=%d slow=%d rc=%d %s\n",
+                           (long long)nt, (long long)nz, (long long)ncol, pinned, mode, threads, domain, supplied, slow, rc,
+                           ml::tls().err);
+                  }
+                }
+        // misuse: a second stream on the same thread, a block that is too long, a missing output
+        {
+          void *a = nullptr, *b2 = nullptr;
+          int rc = ml_host_stream_begin(1, 0, ML_F32, 1, V, ML_F32, nullptr, nullptr, nullptr, nullptr, nullptr, p.data(), 0.0, nz,
+                                        ncol, 2, 0, &a);
+          bool ok = rc == 0 && ml_host_stream_begin(1, 0, ML_F32, 1, V, ML_F32, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                    p.data(), 0.0, nz, ncol, 2, 0, &b2) != 0;
+          ok = ok && ml_host_stream_push(a, T, S, 3, out_s[0], nullptr, nullptr) != 0;   // longer than max_block_steps
+          ok = ok && ml_host_stream_push(a, T, S, 1, nullptr, nullptr, nullptr) != 0;    // no output
+          ok = ok && ml_host_stream_abort(a) == 0;
+          ++runs;
+          if (!ok) {
+            ++bad;
+            printf("STREAM MISUSE not rejected\n");
+          }
+        }
+        for (int b = 0; b < 2; ++b)
+          for (int f = 0; f < 2; ++f) release(sc[b][f], pinned);
+        for (auto& o : out_s) release(o, pinned);
+      }
       release(T, pinned);
       release(S, pinned);
       release(V, pinned);

@@ -1090,3 +1090,98 @@ def test_reference_density_is_produced_on_demand(ml):
     out = core.steric_local_selfref(dsr["thetao"].data, dsr["so"].data, dsr["volcello"].data[0], dsr["z_i"].data,
                                     dsr["deptho"].data, pres, want_rho_ref=False)
     assert out[1] is not None and core.last_path() == 1
+
+
+# ------------------------------------------------- fields that arrive block by block (core.HostStream, ChunkedArray)
+
+
+def _chunked_dataset(ds, chunks):
+    """The same labelled Dataset with thetao / so / volcello held as blocks along time (what dask-backed variables are)."""
+    from momlevel_b200.labeled import ChunkedArray, DataArray
+
+    out = ds.copy()
+    made = {}
+    for name in ("thetao", "so", "volcello"):
+        full = ds[name].values
+        cuts = np.cumsum((0,) + tuple(chunks))
+
+        def blocks(full=full, cuts=cuts):
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                yield np.array(full[a:b])
+
+        made[name] = ChunkedArray(full.shape, full.dtype, chunks, blocks)
+        out[name] = DataArray(made[name], ds[name].dims, attrs=ds[name].attrs)
+    return out, made
+
+
+@pytest.mark.parametrize("variant", ["steric", "thermosteric", "halosteric"])
+@pytest.mark.parametrize("domain", ["local", "global"])
+@pytest.mark.parametrize("shape,chunks", [((7, 12, 16, 64), (1, 2, 3, 1)), ((5, 6, 9, 13), (5,)), ((6, 75, 8, 96), (2, 2, 2))])
+def test_chunked_fields_are_streamed_block_by_block(ml, variant, domain, shape, chunks):
+    """steric(dset) on fields that exist only as blocks along time equals the call on whole arrays bit for bit --
+    heights, masses, reference scalars -- for a self-reference and for a supplied reference, and reads every block
+    of T and S exactly once (volcello: its first block only)."""
+    from momlevel_b200 import synth
+
+    ds = synth.make_dataset(*shape, seed=8, device="cpu", dtype=torch.float32)
+    want, wref = ml.steric(ds, variant=variant, domain=domain)
+    cds, made = _chunked_dataset(ds, chunks)
+    got, gref = ml.steric(cds, variant=variant, domain=domain)
+    assert made["thetao"].blocks_read == len(chunks) and made["so"].blocks_read == len(chunks)
+    assert made["volcello"].blocks_read == 1
+    assert np.array_equal(got[variant].values, want[variant].values, equal_nan=True)
+    for k in ("volo", "masso", "rhoga"):
+        assert float(gref[k]) == float(wref[k])
+    assert np.array_equal(gref["rho"].values, wref["rho"].values, equal_nan=True)
+    if domain == "local":
+        assert np.array_equal(got["delta_rho"].values, want["delta_rho"].values, equal_nan=True)
+    else:
+        assert float(got["reference_height"]) == float(want["reference_height"])
+    # a supplied reference (steric.py:98-103): another pass over the blocks, same numbers
+    again, _ = ml.steric(cds, variant=variant, domain=domain, reference=wref)
+    again_w, _ = ml.steric(ds, variant=variant, domain=domain, reference=wref)
+    assert np.array_equal(again[variant].values, again_w[variant].values, equal_nan=True)
+    # and the oracle
+    ref_o, eta_o, _, g_o, _, _ = _oracle_case(ds, variant, "Wright")
+    if domain == "local":
+        _close_nan(got[variant].values, eta_o, atol=ETA_ATOL)
+    else:
+        assert np.max(np.abs(got[variant].values - g_o)) < ETA_ATOL
+
+
+def test_host_stream_global_series_longer_than_memory_budget(ml):
+    """BASELINE config 4 in miniature through core.HostStream: a daily global series pushed one day at a time from a
+    generator, three variants at once, with at most two blocks alive; equals the resident call bit for bit."""
+    from momlevel_b200 import core, synth
+
+    nt, nz, ny, nx = 40, 10, 16, 64
+    grid = synth.make_grid(nz, ny, nx, seed=3, device="cpu")
+    pres = (grid["z_l"] * 1.0e4 + 101325.0).numpy()
+    T, S, V = synth.make_fields(grid, nt, seed=3, dtype=torch.float32)
+    want = {v: core.steric_global(T.cuda() if v != "halosteric" else T[0].cuda(), S.cuda() if v != "thermosteric" else S[0].cuda(),
+                                  V.cuda(), pres, t_bcast=v == "halosteric", s_bcast=v == "thermosteric").cpu()
+            for v in ("steric", "thermosteric", "halosteric")}
+    rho_w, sums_w = core.reference_state(T[0].cuda(), S[0].cuda(), V.cuda(), pres)
+    hs = core.HostStream("global", V, pres, variants=("steric", "thermosteric", "halosteric"), max_block_steps=3,
+                         want_sums=True)
+    outs = []
+    t = 0
+    import weakref
+
+    alive = []
+    for n in [1, 3, 2] * 7:
+        n = min(n, nt - t)
+        if n <= 0:
+            break
+        blk = (T[t:t + n].clone().numpy(), S[t:t + n].clone().numpy())  # a fresh block, as a reader would produce it
+        alive.append(weakref.ref(blk[0]))
+        outs.append(hs.push(*blk))
+        del blk
+        t += n
+        assert sum(r() is not None for r in alive) <= 2  # the stream keeps the current and the previous block only
+    rho, sums = hs.finish()
+    for v in want:
+        assert torch.equal(torch.cat([o[v] for o in outs]), want[v])
+    assert sums == (float(sums_w[0]), float(sums_w[1]))
+    with pytest.raises(RuntimeError):
+        hs.push(T[:1].numpy(), S[:1].numpy())  # closed

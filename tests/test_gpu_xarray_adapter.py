@@ -68,3 +68,37 @@ def test_xarray_annual_average_with_a_calendar_axis(xr):
     assert np.asarray(result["time"].values).shape == (2,)
     assert float(np.nansum(result["steric"].values)) == pytest.approx(1.07892738, abs=5e-9)
     assert float(np.nansum(result["delta_rho"].values)) == pytest.approx(-4.15906613, abs=5e-9)
+
+
+def test_dask_backed_fields_are_never_loaded_whole(xr):
+    """A Dataset whose 4-D variables are dask-like (chunked along time, as `xr.open_mfdataset(..., chunks={"time": 1})`
+    gives them): the adapter keeps them in blocks, steric() streams them, and no request ever asks for more than one
+    block.  Variables the path does not read are not touched at all."""
+    import momlevel_b200 as ml
+    from momlevel_b200 import synth
+
+    if not hasattr(xr, "ChunkedNumpy"):
+        pytest.skip("needs the stub's dask stand-in (real xarray + dask is exercised the same way by its own chunks)")
+    lab = synth.make_dataset(6, 10, 16, 64, seed=12, device="cpu", dtype=__import__("torch").float32)
+    ds = xr.Dataset()
+    for name, var in lab.variables.items():
+        vals = np.asarray(var.values)
+        data = xr.ChunkedNumpy(vals, (1,) * 6) if vals.ndim == 4 else vals
+        ds[name] = xr.DataArray(data, dims=var.dims, attrs=dict(var.attrs))
+
+    class Untouchable(xr.ChunkedNumpy):
+        def compute(self):
+            raise AssertionError("a variable the path does not read was loaded")
+
+    ds["uo"] = xr.DataArray(Untouchable(np.zeros((6, 10, 16, 64), np.float32), (1,) * 6), dims=lab["thetao"].dims)
+    xr.ChunkedNumpy.largest_compute = 0
+    result, reference = ml.steric(ds)
+    one_block = 10 * 16 * 64
+    assert 0 < xr.ChunkedNumpy.largest_compute <= one_block
+    want, wref = ml.steric(lab)
+    assert np.array_equal(np.asarray(result["steric"].values), want["steric"].values, equal_nan=True)
+    assert float(reference["masso"].values) == float(wref["masso"])
+    g, _ = ml.steric(ds, domain="global", variant="halosteric")
+    gw, _ = ml.steric(lab, domain="global", variant="halosteric")
+    assert np.array_equal(np.asarray(g["halosteric"].values), gw["halosteric"].values)
+    assert xr.ChunkedNumpy.largest_compute <= one_block
