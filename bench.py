@@ -583,6 +583,13 @@ def run_ours(args):
         extras["calc_n2_gpts"] = half * N / ms / 1e6
         ms = timed(lambda: core.calc_n2(T[:half], S[:half], z_l, adjust_negative=True))
         extras["calc_n2_adjusted_gpts"] = half * N / ms / 1e6
+        # fields stored as fp64 (the reference's own test data; anything xarray arithmetic has touched): 16 B per point
+        T64, S64, V64 = T[:half].double(), S[:half].double(), V.double()
+        ms = timed(lambda: core.steric_local_selfref(T64, S64, V64, z_i, depth, pres, want_rho_ref=False))
+        extras["steric_local_selfref_fp64_storage_gpts"] = half * N / ms / 1e6
+        extras["steric_local_selfref_fp64_storage_hbm_frac"] = (half * N * 16 + N * 8 + ncol * 8 * (half + 1)) / (ms * 1e-3) / 1e9 / peak
+        extras["steric_local_selfref_fp64_storage_family"] = {1: "direct", 2: "tma"}.get(core.last_path(), "none")
+        del T64, S64, V64
         extras["steric_local_selfref_call_gpts"] = points / k3_avg_ms / 1e6
         # the public call with everything around the kernel: validation, variant select, result Datasets,
         # the read-back of volo / masso (wall clock, synchronised on both sides)

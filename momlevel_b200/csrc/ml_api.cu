@@ -740,8 +740,9 @@ int ml_steric_local_selfref(int eos, int dtype, const void* T, const void* S, in
   // rho_ref is an output the caller may not want (8 bytes per reference point, 7 % of the traffic of a
   // 12-step call).  It can be left out when one fused chunk serves the whole call; longer series and the
   // direct family read it back for the later steps.
-  if (rho_ref == nullptr && !(tma_ok && nt <= 12))
-    return fail(ML_ERR_NULL, "rho_ref is NULL: it may only be omitted for fp32, aligned fields of at most 12 steps");
+  if (rho_ref == nullptr && !(tma_ok && nt <= (dtype == ML_F32 ? 12 : 6)))
+    return fail(ML_ERR_NULL, "rho_ref is NULL: it may only be omitted when one fused chunk serves the call "
+                             "(aligned fields of at most 12 steps, 6 if stored as fp64)");
   if (tma_ok) {
     tls().last_path = ML_PATH_TMA;
     return tma::launch_selfref(eos, T, S, t_bcast, s_bcast, v_ref, vref_dtype, z_i, deptho, p_level, neg_inv_rhozero,

@@ -18,9 +18,10 @@
 // The columns of a tile are sorted by wet depth first (ML_TMA_SORT) so that dry columns share
 // warps with other dry columns instead of riding along in wet ones.
 //
-// Eligibility: fp32 fields, 16-byte aligned bases, ncol % 4 == 0 (TMA global strides are
-// multiples of 16 bytes), ncol >= kTile, no delta_rho output.  Everything else takes the
-// direct family in ml_api.cu.
+// Eligibility: fields and volcello stored alike (fp32, or fp64 -- what the reference's own test data and any
+// xarray arithmetic on model output produce -- with half as many steps per chunk), 16-byte aligned bases,
+// rows a multiple of 16 bytes (TMA global strides), ncol >= kTile, no delta_rho output.  Everything else
+// takes the direct family in ml_api.cu.
 #include "ml_tma_dev.cuh"
 #include "ml_tma.cuh"
 
@@ -52,16 +53,17 @@ __host__ __device__ constexpr int ctas_per_sm_of(int mode) { return mode == 1 /*
 
 
 struct Params {
-  const float* T;         // the fields themselves (the streaming path goes through the tensor maps;
-  const float* S;         //  these are for the repair pass of a column that met a missing value)
+  const void* T;          // the fields themselves (the streaming path goes through the tensor maps;
+  const void* S;          //  these are for the repair pass of a column that met a missing value); fp32 or fp64
   const double* rho_ref;  // kLocal: read
   double* rho_ref_out;    // kSelfRef: written (may be NULL)
-  const float* v_ref;     // fp32 volcello of the reference state
+  const void* v_ref;      // volcello of the reference state, stored like the fields
   const double* z_i;      // local modes
   const double* deptho;   // local modes
   const double* p_level;
   double coef;
   int nt, nz;
+  int es;                 // bytes per stored value of T, S and v_ref: 4 or 8
   int t_start;            // first time step covered by this launch
   int first_is_reference; // kLocal: step 0 of the field IS the reference state -> its height is exactly zero
   unsigned nchunks;       // time chunks covered by this launch; grid = tiles * nchunks, chunk fastest
@@ -87,7 +89,7 @@ enum Mode { kLocal = 0, kGlobal = 1, kSelfRef = 2 };
 #define ML_TMA_KERNEL_ATTR __launch_bounds__(kThreads, ctas_per_sm_of(MODE))
 #endif
 
-template <int EOS, int TC, int BC, int MODE>
+template <typename TIn, int EOS, int TC, int BC, int MODE>
 __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
@@ -96,12 +98,16 @@ __global__ void ML_TMA_KERNEL_ATTR
   constexpr int SORT = ML_TMA_SORT;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
-  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(float);
-  constexpr int kStageFloats = (int)(kStageBytes / sizeof(float));
+  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(TIn);
+  constexpr int kStageFloats = (int)(kStageBytes / sizeof(TIn));
   constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* stage_base = reinterpret_cast<float*>(smem_raw);
+  TIn* stage_base = reinterpret_cast<TIn*>(smem_raw);
+  const TIn* const gT = static_cast<const TIn*>(P.T);
+  const TIn* const gS = static_cast<const TIn*>(P.S);
+  const TIn* const gV = static_cast<const TIn*>(P.v_ref);
+  typedef typename RawBits<TIn>::type vbits;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kStages * kStageBytes);
   uint64_t* empty = full + kStages;                            // [kStages] "every warp has left the stage"
   int* released = reinterpret_cast<int*>(full + 2 * kStages);  // [kStages] warps that are done with the stage
@@ -126,8 +132,8 @@ __global__ void ML_TMA_KERNEL_ATTR
   // spinning on "empty" barriers and taking registers and issue slots from the math warps.
   auto refill_stage = [&](int z) {
     const int s = z % kStages;
-    float* dT = stage_base + (size_t)s * kStageFloats;
-    float* dS = dT + kRowsT * kTile;
+    TIn* dT = stage_base + (size_t)s * kStageFloats;
+    TIn* dS = dT + kRowsT * kTile;
     mbar_expect_tx(full + s, kStageBytes);
     if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
     if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
@@ -157,7 +163,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     int key = 0;
     if (GLOBAL) {
       if (cg < P.ncol)
-        for (int z = 0; z < nz; ++z) key += vraw_isnan(ld_vraw(P.v_ref, (i64)z * P.ncol + cg)) ? 0 : 1;
+        for (int z = 0; z < nz; ++z) key += vraw_isnan(ld_vraw(gV, (i64)z * P.ncol + cg)) ? 0 : 1;
     } else {
       key = wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
     }
@@ -180,7 +186,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     }
     // per-level operands, fetched one level ahead (raw bits, see ld_vraw)
     double rref_n = 0.0;
-    unsigned v_n = ld_vraw(P.v_ref, cc);
+    vbits v_n = ld_vraw(gV, cc);
     if (MODE == kLocal) rref_n = __ldg(P.rho_ref + cc);
     const bool surface_wet = !vraw_isnan(v_n);  // steric.py:166
     const bool zero_first = MODE == kLocal && P.first_is_reference != 0 && t0 == 0;
@@ -190,16 +196,16 @@ __global__ void ML_TMA_KERNEL_ATTR
     double sub_n = 0.0;
     if (SELFREF) {
       mbar_wait(full + 0, 0u);
-      const float* row = stage_base + col;
+      const TIn* row = stage_base + col;
       sub_n = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[0]);  // reference.py:60-71
       if (in && P.rho_ref_out) P.rho_ref_out[c] = sub_n;
     }
     for (int z = 0; z < nz; ++z) {
       const double rref_z = SELFREF ? sub_n : rref_n;
-      const unsigned v_z = v_n;
+      const vbits v_z = v_n;
       if (z + 1 < nz) {
         const i64 j = (i64)(z + 1) * P.ncol + cc;
-        v_n = ld_vraw(P.v_ref, j);
+        v_n = ld_vraw(gV, j);
         if (MODE == kLocal) rref_n = __ldg(P.rho_ref + j);
       }
       // weight of this cell in the sum and the value subtracted from rho
@@ -228,7 +234,7 @@ __global__ void ML_TMA_KERNEL_ATTR
       // recomputed and discarded) -- wait for it up front so that the reference point and the
       // TC - 1 points below form one straight-line block
       const int zn = (z + 1 < nz) ? z + 1 : z;
-      const float* rowN = stage_base + (size_t)(zn % kStages) * kStageFloats + col;
+      const TIn* rowN = stage_base + (size_t)(zn % kStages) * kStageFloats + col;
       const double p_next = s_p[zn];
       const int s = z % kStages;
       if (SELFREF && (ML_TMA_EXPERIMENT != 1 || zn < kStages)) mbar_wait(full + (zn % kStages), (uint32_t)(zn / kStages) & 1u);
@@ -241,8 +247,8 @@ __global__ void ML_TMA_KERNEL_ATTR
         // of the thermo- / halosteric kernels.  A hole at a WET cell does reach the sums; it is
         // caught after the sweep and that column is redone with the skipna rule (repair pass below).
         const int first_wet = __shfl_sync(0xffffffffu, col, __ffs(live_lanes) - 1);  // every lane takes part
-        const float* sT = stage_base + (size_t)s * kStageFloats + (live ? col : first_wet);
-        const float* sS = sT + kRowsT * kTile;
+        const TIn* sT = stage_base + (size_t)s * kStageFloats + (live ? col : first_wet);
+        const TIn* sS = sT + kRowsT * kTile;
         if (SELFREF) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
         // a time-invariant operand is folded into the polynomial's coefficients once per level
         // (thermosteric +15 %, halosteric +16 %)
@@ -260,7 +266,7 @@ __global__ void ML_TMA_KERNEL_ATTR
       } else if (SELFREF) {
         // a warp without water still owes rho_ref of the next level (reference.py:71 evaluates the
         // EOS everywhere); over land T, S are missing and so is the result -- no arithmetic needed
-        const float tN = rowN[0], sN = rowN[kRowsT * kTile];
+        const TIn tN = rowN[0], sN = rowN[kRowsT * kTile];
         sub_n = nan("");
         if (__any_sync(0xffffffffu, !(isnan(tN) || isnan(sN)))) sub_n = eos.rho_at((double)tN, (double)sN, p_next);
       }
@@ -285,7 +291,7 @@ __global__ void ML_TMA_KERNEL_ATTR
       const i64 lvl = (i64)nz * P.ncol;
       for (int z = 0; z < nz; ++z) {
         const i64 j = (i64)z * P.ncol + c;
-        const unsigned v = ld_vraw(P.v_ref, j);
+        const vbits v = ld_vraw(gV, j);
         double w, sub = 0.0;
         if (GLOBAL) {
           w = vraw_isnan(v) ? 0.0 : vraw_value(v);
@@ -296,17 +302,17 @@ __global__ void ML_TMA_KERNEL_ATTR
         if (!nonzero(w)) continue;
         eos.set_level(s_p[z]);
         if (SELFREF)  // the reference density again, from step 0 of this column (same arithmetic as in the sweep)
-          sub = eos.rho((double)__ldg(P.T + j), (double)__ldg(P.S + j));
+          sub = eos.rho((double)__ldg(gT + j), (double)__ldg(gS + j));
         // the same evaluation as the sweep (a pinned operand folded into the coefficients), so that a repaired
         // column does not depend on how the time axis was cut into chunks
         typename Eos<EOS>::Pinned pin = {};
-        if (BC == 1) pin = eos.pin_t((double)__ldg(P.T + j));
-        if (BC == 2) pin = eos.pin_s((double)__ldg(P.S + j));
+        if (BC == 1) pin = eos.pin_t((double)__ldg(gT + j));
+        if (BC == 2) pin = eos.pin_s((double)__ldg(gS + j));
 #pragma unroll
         for (int k = SELFREF ? 1 : 0; k < TC; ++k) {
           if (t0 + k >= P.nt || (k == 0 && zero_first)) continue;
-          const double Tv = (double)__ldg(P.T + (BC == 1 ? 0 : (i64)(t0 + k) * lvl) + j);
-          const double Sv = (double)__ldg(P.S + (BC == 2 ? 0 : (i64)(t0 + k) * lvl) + j);
+          const double Tv = (double)__ldg(gT + (BC == 1 ? 0 : (i64)(t0 + k) * lvl) + j);
+          const double Sv = (double)__ldg(gS + (BC == 2 ? 0 : (i64)(t0 + k) * lvl) + j);
           const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
           fma_skipnan(acc[k], w, GLOBAL ? rho : rho - sub);
         }
@@ -350,14 +356,15 @@ __global__ void ML_TMA_KERNEL_ATTR
 
 static bool common_eligible(int dtype, int vref_dtype, const void* T, const void* S, int64_t nt, int64_t nz,
                             int64_t ncol) {
-  if (dtype != ML_F32 || vref_dtype != ML_F32) return false;
+  if ((dtype != ML_F32 && dtype != ML_F64) || vref_dtype != dtype) return false;  // volcello stored like the fields
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
-  if (ncol % 4 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
+  const int per16 = dtype == ML_F32 ? 4 : 2;  // TMA global strides are multiples of 16 bytes
+  if (ncol % per16 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
   if (nt < 1 || nz < 1 || nz > 512) return false;
   // grid.x = tiles * time chunks (chunks of at least 4 steps)
   if ((double)((ncol + kTile - 1) / kTile) * (double)((nt + 3) / 4) > 2147483647.0) return false;
   // TMA global strides must stay below 2^40 bytes
-  if ((double)ncol * (double)nz * 4.0 >= 1099511627776.0) return false;
+  if ((double)ncol * (double)nz * 8.0 >= 1099511627776.0) return false;
   return encode_fn() != nullptr;
 }
 
@@ -372,17 +379,17 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
 }
 
 template <int TC>
-inline size_t smem_bytes(int bc, int nz, int mode) {
+inline size_t smem_bytes(int bc, int nz, int mode, int es) {
   const int kStages = stages_of(mode);
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * 4) + 3 * kStages * sizeof(uint64_t) +
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * es) + 3 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 
-template <int EOS, int TC, int BC, int MODE>
+template <typename TIn, int EOS, int TC, int BC, int MODE>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
-  auto kern = k_steric_tma<EOS, TC, BC, MODE>;
-  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE);
+  auto kern = k_steric_tma<TIn, EOS, TC, BC, MODE>;
+  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn));
   // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
   // is set on every launch (a host-side table lookup) rather than cached in a static
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -394,16 +401,16 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
   return launched("k_steric_tma");
 }
 
-template <int EOS, int TC, int MODE>
+template <typename TIn, int EOS, int TC, int MODE>
 static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles,
                      unsigned chunks, cudaStream_t st) {
-#ifdef ML_TMA_FAST_BUILD  // experiment builds: only the Wright / 12-step / no-broadcast kernels
-  if (EOS != 0 || TC != 12 || bc != 0) return fail(ML_ERR_MODE, "kernel not instantiated in a fast build");
-  return launch_one<0, 12, 0, MODE>(mT, mS, P, tiles, chunks, st);
+#ifdef ML_TMA_FAST_BUILD  // experiment builds: only the fp32 / Wright / 12-step / no-broadcast kernels
+  if (sizeof(TIn) != 4 || EOS != 0 || TC != 12 || bc != 0) return fail(ML_ERR_MODE, "kernel not instantiated in a fast build");
+  return launch_one<float, 0, 12, 0, MODE>(mT, mS, P, tiles, chunks, st);
 #else
-  if (bc == 0) return launch_one<EOS, TC, 0, MODE>(mT, mS, P, tiles, chunks, st);
-  if (bc == 1) return launch_one<EOS, TC, 1, MODE>(mT, mS, P, tiles, chunks, st);
-  return launch_one<EOS, TC, 2, MODE>(mT, mS, P, tiles, chunks, st);
+  if (bc == 0) return launch_one<TIn, EOS, TC, 0, MODE>(mT, mS, P, tiles, chunks, st);
+  if (bc == 1) return launch_one<TIn, EOS, TC, 1, MODE>(mT, mS, P, tiles, chunks, st);
+  return launch_one<TIn, EOS, TC, 2, MODE>(mT, mS, P, tiles, chunks, st);
 #endif
 }
 
@@ -411,13 +418,18 @@ static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const
 // is cut into 12-step chunks plus ONE remainder chunk of the smallest width in {4, 8, 12} that holds
 // what is left: rows past nt are zero-filled by the TMA unit and cost no bytes, but they do cost
 // arithmetic, so a 10-step window runs as one 12-step chunk (2 idle rows), not as 8 + 8 (6 idle).
+// Fields stored as fp64 take twice the shared memory per step: 6-step chunks, remainder in {4, 6}.
 struct Segment {
   CUtensorMap mT, mS;
   int tc, t_start;
   unsigned chunks;
 };
 
-static int remainder_tc(int steps) { return steps <= 4 ? 4 : (steps <= 8 ? 8 : 12); }
+static int main_tc(int es) { return es == 4 ? 12 : 6; }
+static int remainder_tc(int steps, int es) {
+  if (es == 4) return steps <= 4 ? 4 : (steps <= 8 ? 8 : 12);
+  return steps <= 4 ? 4 : 6;
+}
 
 struct Plan {
   int bc;
@@ -432,8 +444,8 @@ static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int 
   g.tc = tc;
   g.t_start = t_start;
   g.chunks = chunks;
-  const bool okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc);
-  const bool okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc);
+  const bool okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
+  const bool okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
   return (okT && okS) ? ML_OK : fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
 }
 
@@ -442,25 +454,39 @@ static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_
   pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
   pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
   pl->nseg = 0;
-  const int steps = P.nt - t_begin, full = steps / 12, rest = steps % 12;
+  const int mtc = main_tc(P.es);
+  const int steps = P.nt - t_begin, full = steps / mtc, rest = steps % mtc;
   int rc = ML_OK;
-  if (full > 0) rc = add_segment(pl, T, S, t_bcast, s_bcast, P, 12, t_begin, (unsigned)full);
-  if (rc == ML_OK && rest > 0) rc = add_segment(pl, T, S, t_bcast, s_bcast, P, remainder_tc(rest), t_begin + 12 * full, 1u);
+  if (full > 0) rc = add_segment(pl, T, S, t_bcast, s_bcast, P, mtc, t_begin, (unsigned)full);
+  if (rc == ML_OK && rest > 0)
+    rc = add_segment(pl, T, S, t_bcast, s_bcast, P, remainder_tc(rest, P.es), t_begin + mtc * full, 1u);
   return rc;
 }
 
 template <int MODE>
 static int launch_segment(int eos, const Plan& pl, const Segment& g, Params P, cudaStream_t st) {
   P.t_start = g.t_start;
-#define ML_TMA_GO(E, TCV) return launch_bc<E, TCV, MODE>(pl.bc, g.mT, g.mS, P, pl.tiles, g.chunks, st)
-  if (eos == ML_EOS_WRIGHT) {
-    if (g.tc == 12) ML_TMA_GO(0, 12);
-    if (g.tc == 8) ML_TMA_GO(0, 8);
-    ML_TMA_GO(0, 4);
+#define ML_TMA_GO(TIN, E, TCV) return launch_bc<TIN, E, TCV, MODE>(pl.bc, g.mT, g.mS, P, pl.tiles, g.chunks, st)
+  if (P.es == 8) {  // fields stored as fp64
+#ifndef ML_TMA_FAST_BUILD
+    if (eos == ML_EOS_WRIGHT) {
+      if (g.tc == 6) ML_TMA_GO(double, 0, 6);
+      ML_TMA_GO(double, 0, 4);
+    }
+    if (g.tc == 6) ML_TMA_GO(double, 1, 6);
+    ML_TMA_GO(double, 1, 4);
+#else
+    return fail(ML_ERR_MODE, "kernel not instantiated in a fast build");
+#endif
   }
-  if (g.tc == 12) ML_TMA_GO(1, 12);
-  if (g.tc == 8) ML_TMA_GO(1, 8);
-  ML_TMA_GO(1, 4);
+  if (eos == ML_EOS_WRIGHT) {
+    if (g.tc == 12) ML_TMA_GO(float, 0, 12);
+    if (g.tc == 8) ML_TMA_GO(float, 0, 8);
+    ML_TMA_GO(float, 0, 4);
+  }
+  if (g.tc == 12) ML_TMA_GO(float, 1, 12);
+  if (g.tc == 8) ML_TMA_GO(float, 1, 8);
+  ML_TMA_GO(float, 1, 4);
 #undef ML_TMA_GO
 }
 
@@ -476,12 +502,12 @@ static int launch_plan(int eos, const Plan& pl, const Params& P, cudaStream_t st
 static Params base_params(const void* T, const void* S, const void* v_ref, int vref_dtype, const double* p_level,
                           int nt, int nz, int64_t ncol) {
   Params P;
-  P.T = static_cast<const float*>(T);
-  P.S = static_cast<const float*>(S);
+  P.T = T;
+  P.S = S;
+  P.es = vref_dtype == ML_F64 ? 8 : 4;  // eligibility guarantees fields and volcello share a dtype
   P.rho_ref = nullptr;
   P.rho_ref_out = nullptr;
-  P.v_ref = static_cast<const float*>(v_ref);
-  (void)vref_dtype;  // eligibility guarantees fp32
+  P.v_ref = v_ref;
   P.z_i = nullptr;
   P.deptho = nullptr;
   P.p_level = p_level;
@@ -530,7 +556,7 @@ int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bca
   first.bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
   first.tiles = (unsigned)((ncol + kTile - 1) / kTile);
   first.nseg = 0;
-  const int tc0 = nt >= 12 ? 12 : remainder_tc(nt);
+  const int tc0 = nt >= main_tc(P.es) ? main_tc(P.es) : remainder_tc(nt, P.es);
   int rc = add_segment(&first, T, S, t_bcast, s_bcast, P, tc0, 0, 1u);
   if (rc) return rc;
   if ((rc = launch_plan<kSelfRef>(eos, first, P, st))) return rc;

@@ -61,10 +61,53 @@ struct Params3 {
 __host__ __device__ constexpr int ctas_per_sm3(int tc, int tile = 256) { return (tc > 8 ? 1 : 2) * (256 / tile); }
 __host__ __device__ constexpr int stages3(int tc) { return tc > 8 ? 6 : 4; }
 
+// Repair pass (rare: consistent model output has no holes at wet cells).  A hole turned some of the column's sums
+// into NaN; xarray's sum skips the missing term (steric.py:163), so those heights are integrated again from global
+// memory with that rule and stored from here.  Each height is repaired on its own, as its single-height kernel would
+// (a hole in T does not touch the halosteric sums, which hold T at the reference slab), with the sweep's evaluation,
+// so that a repaired column does not depend on how the time axis was cut into chunks.  Out of line: the sweep's
+// register allocation should not pay for a path that almost never runs.
+template <int EOS, int TC, bool SELFREF>
+__device__ __noinline__ void repair_column3(const Params3& P, int t0, bool chunk0, i64 c, double depth, const double* s_zi,
+                                            const double* s_p, bool surface_wet, unsigned poisoned) {
+  Eos<EOS> eos;
+  const int nz = P.nz;
+  const i64 lvl = (i64)nz * P.ncol;
+  for (int v = 0; v < 3; ++v) {
+    if (!((poisoned >> v) & 1u) || P.eta[v] == nullptr) continue;
+    double acc[TC];
+#pragma unroll
+    for (int k = 0; k < TC; ++k) acc[k] = 0.0;
+    for (int z = 0; z < nz; ++z) {
+      const i64 j = (i64)z * P.ncol + c;
+      const unsigned vr = ld_vraw(P.v_ref, j);
+      const double w = vraw_isnan(vr) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
+      if (!nonzero(w)) continue;
+      eos.set_level(s_p[z]);
+      const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
+      const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
+      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
+      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
+#pragma unroll
+      for (int k = 0; k < TC; ++k) {
+        if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
+        const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
+        const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
+        const double rho = v == 0 ? eos.rho(Tv, Sv) : (v == 1 ? eos.rho_pinned_s(qs, Tv) : eos.rho_pinned_t(qt, Sv));
+        fma_skipnan(acc[k], w, rho - sub);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < TC; ++k)
+      if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[k] : nan("");
+  }
+}
+
 template <int EOS, int TC, int MODE, int TILE>
 __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
     k_steric_tma3(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS,
-                  const __grid_constant__ CUtensorMap mapTr, const __grid_constant__ CUtensorMap mapSr, const Params3 P) {
+                  const __grid_constant__ CUtensorMap mapTr, const __grid_constant__ CUtensorMap mapSr,
+                  const __grid_constant__ Params3 P) {
   constexpr bool SELFREF = MODE == kSelfRef3;
   constexpr int kWarpsT = TILE / 32;
   constexpr int kStages = stages3(TC);
@@ -217,52 +260,24 @@ __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
       refill_stage(z + kStages);
   }
 
-  // Repair pass (rare): a hole at a wet cell turned the column's sums into NaN; xarray's sum skips the
-  // missing term (steric.py:163), so the column is integrated again from global memory with that rule.
-  // Each height is repaired on its own, as its single-height kernel would (a hole in T does not touch the
-  // halosteric sums, which hold T at the reference slab).
-  bool poisoned[3] = {false, false, false};
+  // a hole at a wet cell turned some sums into NaN: those heights are redone out of line (repair_column3)
+  unsigned poisoned = 0u;
 #pragma unroll
-  for (int v = 0; v < 3; ++v)
+  for (int v = 0; v < 3; ++v) {
+    bool bad = false;
 #pragma unroll
-    for (int k = 0; k < TC; ++k) poisoned[v] |= is_nan_q(acc[v][k]);
-  if ((poisoned[0] || poisoned[1] || poisoned[2]) && in) {
-#pragma unroll
-    for (int v = 0; v < 3; ++v)
-#pragma unroll
-      for (int k = 0; k < TC; ++k)
-        if (poisoned[v]) acc[v][k] = 0.0;
-    const i64 lvl = (i64)nz * P.ncol;
-    for (int z = 0; z < nz; ++z) {
-      const i64 j = (i64)z * P.ncol + c;
-      const unsigned v = ld_vraw(P.v_ref, j);
-      const double w = vraw_isnan(v) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
-      if (!nonzero(w)) continue;
-      eos.set_level(s_p[z]);
-      const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
-      const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
-      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
-      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
-#pragma unroll
-      for (int k = 0; k < TC; ++k) {
-        if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
-        const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
-        const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
-        // the sweep's evaluation (as in the single-height kernels): a repaired column does not depend on the chunking
-        if (poisoned[0]) fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
-        if (poisoned[1]) fma_skipnan(acc[1][k], w, eos.rho_pinned_s(qs, Tv) - sub);
-        if (poisoned[2]) fma_skipnan(acc[2][k], w, eos.rho_pinned_t(qt, Sv) - sub);
-      }
-    }
+    for (int k = 0; k < TC; ++k) bad |= is_nan_q(acc[v][k]);
+    poisoned |= bad ? (1u << v) : 0u;
   }
   if (in) {
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-      if (P.eta[v] == nullptr) continue;
+      if (P.eta[v] == nullptr || ((poisoned >> v) & 1u)) continue;
 #pragma unroll
       for (int k = 0; k < TC; ++k)
         if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[v][k] : nan("");
     }
+    if (poisoned != 0u) repair_column3<EOS, TC, SELFREF>(P, t0, chunk0, c, depth, s_zi, s_p, surface_wet, poisoned);
   }
   if (SELFREF && chunk0) {  // uniform per CTA
     vol = warp_sum(vol);
@@ -373,6 +388,7 @@ static int launch_all3(int eos, const void* T, const void* S, const void* Tr, co
 
 bool variants_eligible(int dtype, const void* T, const void* S, const void* Tr, const void* Sr, int vref_dtype,
                        int64_t nt, int64_t nz, int64_t ncol) {
+  if (dtype != ML_F32 || vref_dtype != ML_F32) return false;  // the one-pass kernel stages fp32 rows only
   if ((reinterpret_cast<uintptr_t>(Tr) | reinterpret_cast<uintptr_t>(Sr)) & 15u) return false;
   return local_eligible(dtype, T, S, 0, 0, nullptr, nullptr, vref_dtype, nt, nz, ncol, nullptr, nullptr);
 }

@@ -87,6 +87,22 @@ __device__ __forceinline__ void fma_skipnan(double& acc, double w, double d) {
 __device__ __forceinline__ unsigned ld_vraw(const float* v, i64 i) { return __ldg(reinterpret_cast<const unsigned*>(v) + i); }
 __device__ __forceinline__ bool vraw_isnan(unsigned w) { return (w & 0x7fffffffu) > 0x7f800000u; }
 __device__ __forceinline__ double vraw_value(unsigned w) { return (double)__uint_as_float(w); }
+// the same for a reference volume stored as fp64
+__device__ __forceinline__ unsigned long long ld_vraw(const double* v, i64 i) {
+  return __ldg(reinterpret_cast<const unsigned long long*>(v) + i);
+}
+__device__ __forceinline__ bool vraw_isnan(unsigned long long w) { return (w & 0x7fffffffffffffffull) > 0x7ff0000000000000ull; }
+__device__ __forceinline__ double vraw_value(unsigned long long w) { return __longlong_as_double((long long)w); }
+template <typename T>
+struct RawBits;
+template <>
+struct RawBits<float> {
+  typedef unsigned type;
+};
+template <>
+struct RawBits<double> {
+  typedef unsigned long long type;
+};
 
 // partial-cell thickness, derived.py:308-318 for top = 0 / bottom = None, written with plain
 // compares: depth and z_i are never NaN here (deptho is NaN-filled with 0 on entry, derived.py:295)
@@ -165,14 +181,16 @@ static EncodeTiledFn encode_fn() {
 }
 
 // fp32 field [nt][nz][ncol] (rank 3) or [nz][ncol] (rank 2); box = {kTile, 1, tc}
-static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc, int tile = kTile) {
+static bool make_map(CUtensorMap* map, const void* base, int rank, i64 ncol, i64 nz, i64 nt, int tc, int tile = kTile,
+                     int elem_bytes = 4) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return false;
+  const cuuint64_t es = (cuuint64_t)elem_bytes;
   cuuint64_t dims[3] = {(cuuint64_t)ncol, (cuuint64_t)nz, (cuuint64_t)nt};
-  cuuint64_t strides[2] = {(cuuint64_t)ncol * 4, (cuuint64_t)ncol * (cuuint64_t)nz * 4};
+  cuuint64_t strides[2] = {(cuuint64_t)ncol * es, (cuuint64_t)ncol * (cuuint64_t)nz * es};
   cuuint32_t box[3] = {(cuuint32_t)tile, 1, (cuuint32_t)tc};
   cuuint32_t estr[3] = {1, 1, 1};
-  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
+  return fn(map, elem_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }

@@ -386,7 +386,8 @@ def test_time_axis_partition(ml, nt):
 @pytest.mark.parametrize("shape,dtype", [((13, 12, 16, 64), torch.float32),   # TMA family, 4-step chunks + a short one
                                          ((5, 75, 8, 96), torch.float32),     # full 75-level column
                                          ((3, 10, 37, 53), torch.float32),    # ragged: single-variant fallback
-                                         ((6, 9, 16, 64), torch.float64)])    # fp64 storage: fallback
+                                         ((6, 9, 16, 64), torch.float64),     # fp64 storage: one TMA launch per height
+                                         ((9, 9, 3, 97), torch.float64)])     # fp64, odd ncol: the direct family
 @pytest.mark.parametrize("eos", ["Wright", "linear"])
 def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     """steric_variants == steric + thermosteric + halosteric called one by one, and the oracle."""
@@ -396,7 +397,8 @@ def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     ds["thetao"].data[shape[0] // 2, 1, 3, 5] = float("nan")  # a hole at one step
     res, ref = ml.steric_variants(ds, equation_of_state=eos)
     path = core.last_path()
-    assert path == (2 if dtype == torch.float32 and (shape[2] * shape[3]) % 4 == 0 and shape[2] * shape[3] >= 256 else 1)
+    ncol = shape[2] * shape[3]
+    assert path == (2 if ncol % (4 if dtype == torch.float32 else 2) == 0 and ncol >= 256 else 1)
     one, ref1 = ml.steric(ds, equation_of_state=eos)
     _close_nan(ref["rho"].values, ref1["rho"].values, rtol=1e-15)
     assert float(ref["volo"]) == pytest.approx(float(ref1["volo"]), rel=1e-13)
@@ -998,18 +1000,21 @@ def test_steric_takes_the_host_route_for_host_resident_fields(ml, monkeypatch):
 
 
 @pytest.mark.parametrize("seed", range(12))
-def test_random_shapes_tma_against_direct(ml, seed):
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_random_shapes_tma_against_direct(ml, seed, dtype):
     """Shapes drawn at random around the TMA family's edges -- a last tile with a few columns, one or two
-    levels, a single step, more levels than the ring is deep -- must agree with the direct family."""
+    levels, a single step, more levels than the ring is deep -- must agree with the direct family, for fields
+    stored as fp32 (12-step chunks) and as fp64 (6-step chunks, rows a multiple of two values)."""
     from momlevel_b200 import core, synth
 
     rng = np.random.default_rng(1000 + seed)
     nt = int(rng.choice([1, 2, 3, 5, 11, 12, 13, 17, 29]))
     nz = int(rng.choice([1, 2, 3, 4, 5, 9, 33, 75, 130]))
     ny = int(rng.integers(1, 9))
-    nx = 4 * int(rng.integers(64 // ny + 1, 200))  # ncol % 4 == 0 and >= 256
+    per16 = 4 if dtype == torch.float32 else 2
+    nx = per16 * int(rng.integers(256 // (per16 * ny) + 1, 800 // per16))  # rows of whole 16-byte units, ncol >= 256
     grid = synth.make_grid(nz, ny, nx, seed=seed, device="cuda")
-    T, S, V = synth.make_fields(grid, nt, seed=seed, dtype=torch.float32)
+    T, S, V = synth.make_fields(grid, nt, seed=seed, dtype=dtype)
     if nt > 1 and nz > 1:
         T[nt - 1, nz // 2, 0, nx // 2] = float("nan")
     pres = grid["z_l"] * 1.0e4 + 101325.0
