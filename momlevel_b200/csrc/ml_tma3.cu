@@ -61,53 +61,10 @@ struct Params3 {
 __host__ __device__ constexpr int ctas_per_sm3(int tc, int tile = 256) { return (tc > 8 ? 1 : 2) * (256 / tile); }
 __host__ __device__ constexpr int stages3(int tc) { return tc > 8 ? 6 : 4; }
 
-// Repair pass (rare: consistent model output has no holes at wet cells).  A hole turned some of the column's sums
-// into NaN; xarray's sum skips the missing term (steric.py:163), so those heights are integrated again from global
-// memory with that rule and stored from here.  Each height is repaired on its own, as its single-height kernel would
-// (a hole in T does not touch the halosteric sums, which hold T at the reference slab), with the sweep's evaluation,
-// so that a repaired column does not depend on how the time axis was cut into chunks.  Out of line: the sweep's
-// register allocation should not pay for a path that almost never runs.
-template <int EOS, int TC, bool SELFREF>
-__device__ __noinline__ void repair_column3(const Params3& P, int t0, bool chunk0, i64 c, double depth, const double* s_zi,
-                                            const double* s_p, bool surface_wet, unsigned poisoned) {
-  Eos<EOS> eos;
-  const int nz = P.nz;
-  const i64 lvl = (i64)nz * P.ncol;
-  for (int v = 0; v < 3; ++v) {
-    if (!((poisoned >> v) & 1u) || P.eta[v] == nullptr) continue;
-    double acc[TC];
-#pragma unroll
-    for (int k = 0; k < TC; ++k) acc[k] = 0.0;
-    for (int z = 0; z < nz; ++z) {
-      const i64 j = (i64)z * P.ncol + c;
-      const unsigned vr = ld_vraw(P.v_ref, j);
-      const double w = vraw_isnan(vr) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
-      if (!nonzero(w)) continue;
-      eos.set_level(s_p[z]);
-      const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
-      const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
-      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
-      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
-#pragma unroll
-      for (int k = 0; k < TC; ++k) {
-        if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
-        const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
-        const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
-        const double rho = v == 0 ? eos.rho(Tv, Sv) : (v == 1 ? eos.rho_pinned_s(qs, Tv) : eos.rho_pinned_t(qt, Sv));
-        fma_skipnan(acc[k], w, rho - sub);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < TC; ++k)
-      if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[k] : nan("");
-  }
-}
-
 template <int EOS, int TC, int MODE, int TILE>
 __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
     k_steric_tma3(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS,
-                  const __grid_constant__ CUtensorMap mapTr, const __grid_constant__ CUtensorMap mapSr,
-                  const __grid_constant__ Params3 P) {
+                  const __grid_constant__ CUtensorMap mapTr, const __grid_constant__ CUtensorMap mapSr, const Params3 P) {
   constexpr bool SELFREF = MODE == kSelfRef3;
   constexpr int kWarpsT = TILE / 32;
   constexpr int kStages = stages3(TC);
@@ -164,7 +121,9 @@ __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
   {
     const i64 cg = (i64)c0 + tid;
     const int key = wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
-    col = sorted_column_t<TILE>(key, reinterpret_cast<unsigned*>(s_key), s_col);
+    // CTAs that share an SM should not all put their deepest band on the same sub-partition (2 % with two CTAs per SM)
+    const int rot = (int)((blockIdx.x * 2654435761u) >> 20) & 3;
+    col = sorted_column_t<TILE>(key, reinterpret_cast<unsigned*>(s_key), s_col, rot);
   }
 
   const i64 c = (i64)c0 + col;
@@ -187,11 +146,13 @@ __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
   for (int z = 0; z < nz; ++z) {
     const double rref_z = rref_n;
     const unsigned v_z = v_n;
+#ifndef ML_TMA3_PREFETCH_LATE
     if (z + 1 < nz) {
       const i64 j = (i64)(z + 1) * P.ncol + cc;
       v_n = ld_vraw(P.v_ref, j);
       if (!SELFREF) rref_n = __ldg(P.rho_ref + j);
     }
+#endif
     const bool dry = vraw_isnan(v_z);
     double w = level_dz(depth, s_zi[z], s_zi[z + 1]);
     if (dry || (!SELFREF && isnan(rref_z))) w = 0.0;  // steric.py:151-153
@@ -258,26 +219,61 @@ __global__ void __launch_bounds__(TILE, ctas_per_sm3(TC, TILE))
     __syncwarp();
     if (lane == 0 && stage_done(empty + s, released + s, kWarpsT, (uint32_t)(z / kStages) & 1u) && z + kStages < nz)
       refill_stage(z + kStages);
+#ifdef ML_TMA3_PREFETCH_LATE
+    if (z + 1 < nz) {  // behind the release: it then has no load of this thread to wait for
+      const i64 j = (i64)(z + 1) * P.ncol + cc;
+      v_n = ld_vraw(P.v_ref, j);
+      if (!SELFREF) rref_n = __ldg(P.rho_ref + j);
+    }
+#endif
   }
 
-  // a hole at a wet cell turned some sums into NaN: those heights are redone out of line (repair_column3)
-  unsigned poisoned = 0u;
+  // Repair pass (rare: consistent model output has no holes at wet cells).  A hole at a wet cell turned some of the
+  // column's sums into NaN; xarray's sum skips the missing term (steric.py:163), so the column is integrated again
+  // from global memory with that rule -- all three heights, with the sweep's own evaluation: a height that met no
+  // hole comes out as it was, and a repaired one does not depend on how the time axis was cut into chunks, so the
+  // fields stay identical to the single-height kernels'.  (Kept in this simple form on purpose: repairing per height,
+  // or out of line, changed the register allocation of the sweep above and cost it 4 %.)
+  bool poisoned = false;
 #pragma unroll
-  for (int v = 0; v < 3; ++v) {
-    bool bad = false;
+  for (int v = 0; v < 3; ++v)
 #pragma unroll
-    for (int k = 0; k < TC; ++k) bad |= is_nan_q(acc[v][k]);
-    poisoned |= bad ? (1u << v) : 0u;
+    for (int k = 0; k < TC; ++k) poisoned |= is_nan_q(acc[v][k]);
+  if (poisoned && in) {
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+      for (int k = 0; k < TC; ++k) acc[v][k] = 0.0;
+    const i64 lvl = (i64)nz * P.ncol;
+    for (int z = 0; z < nz; ++z) {
+      const i64 j = (i64)z * P.ncol + c;
+      const unsigned v = ld_vraw(P.v_ref, j);
+      const double w = vraw_isnan(v) ? 0.0 : level_dz(depth, s_zi[z], s_zi[z + 1]);
+      if (!nonzero(w)) continue;
+      eos.set_level(s_p[z]);
+      const double Tr = (double)__ldg(P.Tref + j), Sr = (double)__ldg(P.Sref + j);
+      const double sub = SELFREF ? eos.rho(Tr, Sr) : __ldg(P.rho_ref + j);
+      const typename Eos<EOS>::Pinned qs = eos.pin_s(Sr);
+      const typename Eos<EOS>::Pinned qt = eos.pin_t(Tr);
+#pragma unroll
+      for (int k = 0; k < TC; ++k) {
+        if (t0 + k >= P.nt || (chunk0 && k == 0)) continue;
+        const double Tv = (double)__ldg(P.T + (i64)(t0 + k) * lvl + j);
+        const double Sv = (double)__ldg(P.S + (i64)(t0 + k) * lvl + j);
+        fma_skipnan(acc[0][k], w, eos.rho(Tv, Sv) - sub);
+        fma_skipnan(acc[1][k], w, eos.rho_pinned_s(qs, Tv) - sub);
+        fma_skipnan(acc[2][k], w, eos.rho_pinned_t(qt, Sv) - sub);
+      }
+    }
   }
   if (in) {
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
-      if (P.eta[v] == nullptr || ((poisoned >> v) & 1u)) continue;
+      if (P.eta[v] == nullptr) continue;
 #pragma unroll
       for (int k = 0; k < TC; ++k)
         if (t0 + k < P.nt) P.eta[v][(i64)(t0 + k) * P.ncol + c] = surface_wet ? P.coef * acc[v][k] : nan("");
     }
-    if (poisoned != 0u) repair_column3<EOS, TC, SELFREF>(P, t0, chunk0, c, depth, s_zi, s_p, surface_wet, poisoned);
   }
   if (SELFREF && chunk0) {  // uniform per CTA
     vol = warp_sum(vol);
@@ -319,8 +315,10 @@ static int launch_one3(const CUtensorMap maps[4], const Params3& P, unsigned til
 // chunk widths of a launch sequence: whole main-width chunks, then one remainder chunk of the smallest width
 // in {4, 6, 8, 12} that holds what is left (rows past nt are zero-filled by the TMA unit and cost arithmetic only).
 // The main width can be overridden for experiments (ML_TMA3_TC = 4 | 6 | 8 | 12 in the environment).
+// Measured on OM4p25 x 12 (profiles/r02_experiments.md): 12-step chunks, one CTA per SM: 4.13 ms; 6-step chunks, two
+// CTAs per SM: 4.27-4.36 ms (the per-level stage release weighs twice as much); three single-height launches: 4.79 ms.
 #ifndef ML_TMA3_TC
-#define ML_TMA3_TC 6
+#define ML_TMA3_TC 12
 #endif
 // columns per CTA: 256 or 128 (ML_TMA3_TILE in the environment, or 100 added to the value given to
 // ml_set_variants_chunk, e.g. 106 = 128-column tiles with 6-step chunks)

@@ -131,7 +131,7 @@ __device__ __forceinline__ int wet_levels(double depth, const double* s_zi, int 
 // 0 1 2 3 7 6 5 4 (by depth band p / 32), so that the two warps an SM sub-partition hosts (w and
 // w + 4) carry a deep and a shallow band.  Every thread of the CTA must call it.
 template <int TILE>
-__device__ __forceinline__ int sorted_column_t(int key, unsigned* s_key, int* s_col) {
+__device__ __forceinline__ int sorted_column_t(int key, unsigned* s_key, int* s_col, int rot = 0) {
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned v = ((unsigned)key << 8) | (unsigned)(TILE - 1 - tid);
   for (int k = 2; k <= TILE; k <<= 1) {
@@ -152,7 +152,10 @@ __device__ __forceinline__ int sorted_column_t(int key, unsigned* s_key, int* s_
   const int band = tid >> 5;
   // 256 columns: bands to warp slots 0 1 2 3 7 6 5 4 (a deep and a shallow band per SM sub-partition);
   // 128 columns: one warp per sub-partition, bands in order
-  const int slot = TILE == 256 ? (band < 4 ? band : 11 - band) : band;
+  // rot (0..3) turns the assignment round the four sub-partitions: CTAs that share an SM then put their deep
+  // bands on different sub-partitions instead of all on the first one
+  int slot = TILE == 256 ? (band < 4 ? band : 11 - band) : band;
+  slot = (slot & ~3) | ((slot + rot) & 3);
   s_col[slot * 32 + lane] = TILE - 1 - (int)(v & 255u);
   __syncthreads();
   return s_col[tid];

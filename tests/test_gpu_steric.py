@@ -387,7 +387,7 @@ def test_time_axis_partition(ml, nt):
                                          ((5, 75, 8, 96), torch.float32),     # full 75-level column
                                          ((3, 10, 37, 53), torch.float32),    # ragged: single-variant fallback
                                          ((6, 9, 16, 64), torch.float64),     # fp64 storage: one TMA launch per height
-                                         ((9, 9, 3, 97), torch.float64)])     # fp64, odd ncol: the direct family
+                                         ((9, 9, 5, 59), torch.float64)])     # fp64, odd ncol: the direct family
 @pytest.mark.parametrize("eos", ["Wright", "linear"])
 def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     """steric_variants == steric + thermosteric + halosteric called one by one, and the oracle."""
