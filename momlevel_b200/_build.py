@@ -46,7 +46,12 @@ def build(force=False, verbose=False):
     """Compile every CUDA source into one shared library. Returns the library path."""
     if not force and not needs_build():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else [])
+    import os
+    import shlex
+
+    # extra flags for experiment builds, e.g. MOMLEVEL_B200_NVCC_FLAGS="-DML_TMA_FENCED_RELEASE" (csrc/ml_tma_dev.cuh)
+    extra = shlex.split(os.environ.get("MOMLEVEL_B200_NVCC_FLAGS", ""))
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else [])
     cmd += ["-o", str(LIB)] + [str(CSRC / s) for s in SOURCES if (CSRC / s).exists()]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:

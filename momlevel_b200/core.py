@@ -193,14 +193,16 @@ def eos_eval(eos, func, T, S, p=None, z_axis=None, t_bcast=False, s_bcast=False)
     return out
 
 
-def flament_spice(T, S):
-    """``momlevel.spice.flament.spice`` (flament.py:43-95)."""
+def flament_spice(T, S, out=None):
+    """``momlevel.spice.flament.spice`` (flament.py:43-95); ``out`` may hand in the fp64 result tensor."""
     L = _lib.lib()
     T, S = to_device(T), to_device(S)
     assert T.shape == S.shape, "thetao and so must have the same shape"  # flament.py:75
     dt = _field_dtype(T, S)
     T, S = T.to(dt), S.to(dt)
-    out = torch.empty(T.shape, dtype=torch.float64, device=T.device)
+    if out is None:
+        out = torch.empty(T.shape, dtype=torch.float64, device=T.device)
+    assert out.dtype == torch.float64 and out.is_contiguous() and out.numel() == T.numel() and out.device == T.device
     _lib.check(L.ml_flament_spice(_dt_id(T), T.data_ptr(), S.data_ptr(), T.numel(), out.data_ptr(), _stream()))
     return out
 

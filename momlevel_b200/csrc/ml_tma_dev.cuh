@@ -51,22 +51,37 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 
 // A warp has finished reading a ring stage (call from lane 0, after a __syncwarp() that gathers the warp's reads).
 // Returns true in the lane whose warp is the LAST of the CTA to leave the stage: that lane issues the TMA refill,
-// an async-proxy write into memory the other warps have just read through the generic proxy.  Ordering: every warp
-// ARRIVES (release) on the stage's "empty" mbarrier before it bumps the election counter, and the elected lane
-// WAITS (acquire) for that phase before it returns -- all arrivals precede its own bump, so the wait falls
-// through -- which puts every warp's reads before the refill without a MEMBAR in the loop (an acq_rel atomic on
-// the counter compiles to MEMBAR.ALL.CTA + ATOMS and cost the thermo- / halosteric kernels 5-11 %).
-// ML_TMA_RELAXED_RELEASE keeps only the relaxed counter (round 1's scheme) for an A/B.
+// an async-proxy write into memory the other warps have just read through the generic proxy.
+//
+// Default: a relaxed shared-memory counter elects the last warp.  What keeps the refill behind the reads is the
+// hardware's order, not the PTX memory model: a warp's LDS and its ATOMS go through the same in-order shared-memory
+// pipe (the __syncwarp() keeps the compiler from sinking a read below the atomic), the refill is issued only after
+// the eighth ATOMS has RETURNED, and the copy it starts needs hundreds of nanoseconds to come back from L2 / HBM.
+//
+// -DML_TMA_FENCED_RELEASE builds the version that is also right by the memory model: every warp ARRIVES (release)
+// on the stage's "empty" mbarrier (initialised to the number of warps); the state the arrive returns holds the
+// pending count from before it, so the warp that finds 1 there is the last one, and it WAITS (acquire) on the
+// phase it has just completed before it issues the refill.  All GPU tests pass with either build.  The fenced
+// one is 3 % slower on the headline step (1.94-1.97 against 1.88-1.91 ms, four alternating runs,
+// profiles/r02_experiments.md): a release has to wait for the thread's loads in flight, and the next level's
+// volcello / rho_ref prefetch -- issued one level ahead precisely so that nobody waits for it -- is in flight
+// then.  (An acq_rel atomic on the counter, MEMBAR.ALL.CTA + ATOMS, cost the thermo- / halosteric kernels 5-11 %.)
 __device__ __forceinline__ bool stage_done(uint64_t* empty_bar, int* counter, int nwarps, uint32_t parity) {
-#ifndef ML_TMA_RELAXED_RELEASE
-  mbar_arrive(empty_bar);
-#endif
-  const int before = atomicAdd(counter, 1);
-  if ((before & (nwarps - 1)) != nwarps - 1) return false;
-#ifndef ML_TMA_RELAXED_RELEASE
+#ifndef ML_TMA_FENCED_RELEASE
+  (void)empty_bar;
+  (void)parity;
+  return (atomicAdd(counter, 1) & (nwarps - 1)) == nwarps - 1;
+#else
+  (void)counter;
+  (void)nwarps;
+  uint64_t state;
+  uint32_t pending;
+  asm volatile("mbarrier.arrive.shared::cta.b64 %0, [%1];" : "=l"(state) : "r"(smem_u32(empty_bar)) : "memory");
+  asm volatile("mbarrier.pending_count.b64 %0, %1;" : "=r"(pending) : "l"(state));
+  if (pending != 1u) return false;
   mbar_wait(empty_bar, parity);
-#endif
   return true;
+#endif
 }
 
 // acc += w * d unless d is NaN (xarray's skipna sum).  d comes out of fp64 arithmetic, so a
