@@ -826,6 +826,11 @@ static int delta_rho_impl(int eos, int dtype, const void* T, const void* S, int 
   const int v_f32 = vref_dtype == ML_F32;
   const uintptr_t bits = reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S) |
                          reinterpret_cast<uintptr_t>(rho_ref) | reinterpret_cast<uintptr_t>(delta_rho);
+  // fp32 fields, monthly output: the ring-staged streaming kernel (ml_stream.cu)
+  if (weights == nullptr && dtype == ML_F32 && !direct_only() && stream::eligible(T, S, rho_ref, delta_rho, ncol) &&
+      (reinterpret_cast<uintptr_t>(v_ref) & 15u) == 0 && nt <= INT32_MAX)
+    return stream::launch_delta_rho(eos, (const float*)T, (const float*)S, ts, ss, rho_ref, v_ref, v_f32, p_level, (int)nt, nz,
+                                    ncol, delta_rho, st);
   const bool vec = ncol % 4 == 0 && (bits & 15u) == 0 && tls().p_col == nullptr;
   const i64 gx = cdiv(vec ? ncol / 4 : ncol, kBlock);
   i64 gy = cdiv(148 * 16, gx);

@@ -229,6 +229,85 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 }
 
+// ------------------------------------------------------------------------------ density anomaly
+// delta_rho[t][z][col] = V_ref notnull ? rho(T, S, p_z) - rho_ref : NaN (steric.py:151-153).  A CTA owns (level,
+// column segment) pairs; rho_ref and the volume mask of a pair are read once into registers and reused for every
+// time step, whose T and S tiles stream through the ring (the sequence runs on across pair boundaries, so the ring
+// never drains).
+template <int EOS, typename TV>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_stream_delta_rho(const float* __restrict__ T, const float* __restrict__ S, i64 t_stride, i64 s_stride,
+                       const double* __restrict__ rho_ref, const TV* __restrict__ v_ref,
+                       const double* __restrict__ p_level, int nt, Geom g, double* __restrict__ out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Ring<2> ring;
+  ring.init(smem_raw);
+  const int tid = threadIdx.x;
+  const i64 npairs = g.ntiles;                         // (level, segment) pairs; g.nz rows
+  const i64 mine = npairs > (i64)blockIdx.x ? (npairs - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const i64 nseq = mine * nt;                          // tiles this CTA streams, time fastest
+  auto issue = [&](i64 q, int s) {
+    const i64 pair = (i64)blockIdx.x + (q / nt) * gridDim.x;
+    const int t = (int)(q % nt);
+    const i64 row = pair / g.tiles_per_row;            // level
+    const i64 col0 = (pair - row * g.tiles_per_row) * kTile;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    const uint32_t bytes = (uint32_t)len * 4u;
+    const i64 off = row * g.ncol + col0;
+    tma::mbar_expect_tx(ring.full + s, 2 * bytes);
+    bulk_load(ring.stage(s, 0), T + (i64)t * t_stride + off, bytes, ring.full + s);
+    bulk_load(ring.stage(s, 1), S + (i64)t * s_stride + off, bytes, ring.full + s);
+  };
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < kStages && s < nseq; ++s) issue(s, s);
+  Eos<EOS> eos;
+  const i64 lvl = (i64)g.nz * g.ncol;
+  i64 q = 0;
+  for (i64 i = 0; i < mine; ++i) {
+    const i64 pair = (i64)blockIdx.x + i * gridDim.x;
+    const i64 row = pair / g.tiles_per_row;
+    const i64 col0 = (pair - row * g.tiles_per_row) * kTile;
+    const i64 len = g.ncol - col0 < kTile ? g.ncol - col0 : kTile;
+    const i64 off = row * g.ncol + col0;
+    eos.set_level(__ldg(p_level + row));
+    double ref[2][4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int qd = tid + h * kThreads;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) ref[h][j] = nan("");
+      if (4 * qd < len) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(rho_ref + off + 4 * qd));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(rho_ref + off + 4 * qd) + 1);
+        const double r4[4] = {a.x, a.y, b.x, b.y};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ref[h][j] = isnan(__ldg(v_ref + off + 4 * qd + j)) ? nan("") : r4[j];
+      }
+    }
+    for (int t = 0; t < nt; ++t, ++q) {
+      const int s = (int)(q % kStages);
+      tma::mbar_wait(ring.full + s, (uint32_t)(q / kStages) & 1u);
+      const float4* sT = reinterpret_cast<const float4*>(ring.stage(s, 0));
+      const float4* sS = reinterpret_cast<const float4*>(ring.stage(s, 1));
+      double* o = out + (i64)t * lvl + off;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int qd = tid + h * kThreads;
+        if (4 * qd < len) {
+          const float4 a = sT[qd], b = sS[qd];
+          st4(o + 4 * qd, eos.rho((double)a.x, (double)b.x) - ref[h][0], eos.rho((double)a.y, (double)b.y) - ref[h][1],
+              eos.rho((double)a.z, (double)b.z) - ref[h][2], eos.rho((double)a.w, (double)b.w) - ref[h][3]);
+        }
+      }
+      if (last_to_leave(ring.empty + s, ring.released + s, (uint32_t)(q / kStages) & 1u)) {
+        const i64 next = q + kStages;
+        if (next < nseq) issue(next, s);
+      }
+    }
+  }
+}
+
 // ----------------------------------------------------------------------- host side
 static Geom geometry(i64 nrows, int nz, i64 ncol) {
   Geom g;
@@ -302,6 +381,26 @@ int launch_refstate(int eos, const float* T0, const float* S0, const float* V0, 
     kern<<<grid, kThreads, ring_bytes<3>(), st>>>(T0, S0, V0, p_level, g, rho_ref, partials);
   }
   return launched("k_stream_refstate");
+}
+
+int launch_delta_rho(int eos, const float* T, const float* S, i64 t_stride, i64 s_stride, const double* rho_ref,
+                     const void* v_ref, int v_f32, const double* p_level, int nt, i64 nz, i64 ncol, double* out,
+                     cudaStream_t st) {
+  const Geom g = geometry(nz, (int)nz, ncol);
+  const unsigned grid = persistent_grid(g.ntiles, 2);
+#define ML_STREAM_DRHO(E, TV)                                                                                     \
+  do {                                                                                                            \
+    auto kern = k_stream_delta_rho<E, TV>;                                                                        \
+    if (int rc = opt_in(kern, ring_bytes<2>())) return rc;                                                        \
+    kern<<<grid, kThreads, ring_bytes<2>(), st>>>(T, S, t_stride, s_stride, rho_ref, (const TV*)v_ref, p_level, nt, g, out); \
+  } while (0)
+  if (eos == ML_EOS_WRIGHT) {
+    if (v_f32) ML_STREAM_DRHO(0, float); else ML_STREAM_DRHO(0, double);
+  } else {
+    if (v_f32) ML_STREAM_DRHO(1, float); else ML_STREAM_DRHO(1, double);
+  }
+#undef ML_STREAM_DRHO
+  return launched("k_stream_delta_rho");
 }
 
 }  // namespace stream

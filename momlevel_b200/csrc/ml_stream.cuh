@@ -21,5 +21,11 @@ int refstate_blocks(long long nz, long long ncol);
 int launch_refstate(int eos, const float* T0, const float* S0, const float* V0, const double* p_level, long long nz,
                     long long ncol, double* rho_ref, double* partials, cudaStream_t st);
 
+// delta_rho[t][z][col] = rho(T, S, p_z) - rho_ref where the reference volume is present, NaN elsewhere (steric.py:151-153);
+// t_stride / s_stride = 0 for an operand held at the reference slab
+int launch_delta_rho(int eos, const float* T, const float* S, long long t_stride, long long s_stride, const double* rho_ref,
+                     const void* v_ref, int v_f32, const double* p_level, int nt, long long nz, long long ncol, double* out,
+                     cudaStream_t st);
+
 }  // namespace stream
 }  // namespace ml

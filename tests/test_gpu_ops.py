@@ -335,3 +335,44 @@ def test_stream_reference_state(ml, eos, shape):
     V64 = V.astype(np.float64)
     assert float(sums[0]) == pytest.approx(np.nansum(V64), rel=1e-13)
     assert float(sums[1]) == pytest.approx(np.nansum(want * V64), rel=1e-13)
+
+
+@pytest.mark.parametrize("eos", ["Wright", "linear"])
+@pytest.mark.parametrize("shape,bcast", [((7, 5, 4, 1028), None), ((3, 75, 8, 160), "t"), ((3, 75, 8, 160), "s"),
+                                         ((1, 2, 1, 4), None), ((9, 3, 2, 2052), None)])
+def test_stream_delta_rho(ml, eos, shape, bcast):
+    """steric.py:151-153 through the ring-staged kernel: rows that are not whole tiles, more (level, segment) pairs than
+    CTAs, a broadcast operand, a volume mask -- bit for bit with the plain kernel, and against the oracle."""
+    from momlevel_b200 import core
+    from oracle import eos as oeos
+
+    nt, nz, ny, nx = shape
+    rng = np.random.default_rng(nt * 100 + nz)
+    T = rng.uniform(-2, 32, shape).astype(np.float32)
+    S = rng.uniform(30, 40, shape).astype(np.float32)
+    V = rng.uniform(1e6, 1e9, shape[1:]).astype(np.float32)
+    V[:, 0, :2] = np.nan
+    if nt > 1:
+        T[nt - 1, 0, 0, 3] = np.nan
+    p = np.linspace(1e5, 6e7, nz)
+    Td, Sd, Vd = (torch.from_numpy(x).cuda() for x in (T, S, V))
+    rho_ref, _ = core.reference_state(Td[0], Sd[0], Vd, p, eos=eos)
+    Tin = Td[0].contiguous() if bcast == "t" else Td
+    Sin = Sd[0].contiguous() if bcast == "s" else Sd
+    kw = dict(eos=eos, t_bcast=bcast == "t", s_bcast=bcast == "s")
+    got = core.delta_rho(Tin, Sin, rho_ref, Vd, p, **kw)
+    prev = core.force_direct(1)
+    try:
+        plain = core.delta_rho(Tin, Sin, rho_ref, Vd, p, **kw)
+    finally:
+        core.force_direct(prev)
+    assert torch.equal(torch.nan_to_num(got, nan=-7.0), torch.nan_to_num(plain, nan=-7.0))
+    T64 = (T[0:1] if bcast == "t" else T).astype(np.float64)
+    S64 = (S[0:1] if bcast == "s" else S).astype(np.float64)
+    rho = np.broadcast_to(oeos.density(eos, T64, S64, p[None, :, None, None]), shape)
+    ref = oeos.density(eos, T[0].astype(np.float64), S[0].astype(np.float64), p[:, None, None])
+    want = np.where(~np.isnan(V)[None], rho - ref[None], np.nan)
+    g = got.cpu().numpy()
+    assert np.array_equal(np.isnan(g), np.isnan(want))
+    ok = ~np.isnan(want)
+    assert np.max(np.abs(g[ok] - want[ok])) < 1e-9

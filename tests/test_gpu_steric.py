@@ -636,6 +636,38 @@ def test_subsample_parity_at_size(ml, big):
     _close_nan(result["steric"].data[:, ys, :].cpu().numpy(), eta, atol=ETA_ATOL)
 
 
+def _sampled_columns(ncol, n_stride=96, tile=256):
+    """Columns from every part of the grid: both ends of the first, second, middle and last 256-column tile of the
+    TMA family and a stride across everything in between (not one slab of rows from the middle)."""
+    tiles = (ncol + tile - 1) // tile
+    picks = {0, 1, tile - 1, tile, tile + 1, 2 * tile - 1, (tiles // 2) * tile - 1, (tiles // 2) * tile,
+             (tiles - 1) * tile - 1, (tiles - 1) * tile, (tiles - 1) * tile + 1, ncol - 2, ncol - 1}
+    picks |= {int(x) for x in np.linspace(0, ncol - 1, n_stride)}
+    return np.array(sorted(p for p in picks if 0 <= p < ncol), dtype=np.int64)
+
+
+def _oracle_on_columns(T, S, V, grid, cols, eos="Wright", variants=("steric",), T_ref=None, S_ref=None):
+    """The oracle (fp64-upcast inputs) on the sampled columns of device-resident fields ``[t][z][y][x]``.
+    Returns ``(reference dict, {variant: eta[t][col]}, masso[t] of these columns)``."""
+    idx = torch.as_tensor(cols, device=T.device)
+    f64 = lambda x: x.double().cpu().numpy()  # noqa: E731
+    Tc = f64(T.flatten(2)[:, :, idx])[:, :, None, :]
+    Sc = f64(S.flatten(2)[:, :, idx])[:, :, None, :]
+    Vc = f64(V.flatten(1)[:, idx])[None, :, None, :]
+    depth = f64(grid["deptho"].flatten()[idx])[None, :]
+    area = f64(grid["areacello"].flatten()[idx])[None, :]
+    z_l, z_i = f64(grid["z_l"]), f64(grid["z_i"])
+    if T_ref is None:
+        oref = osteric.reference_state(Tc, Sc, Vc, area, z_l, eos=eos)
+    else:
+        T0 = f64(T_ref.flatten(1)[:, idx])[None, :, None, :]
+        S0 = f64(S_ref.flatten(1)[:, idx])[None, :, None, :]
+        oref = osteric.reference_state(T0, S0, Vc, area, z_l, eos=eos)
+    etas = {v: osteric.steric_local(Tc, Sc, z_l, z_i, depth, oref, eos=eos, variant=v)[0][:, 0, :] for v in variants}
+    _, _, masso = osteric.steric_global(Tc, Sc, z_l, oref, eos=eos)
+    return oref, etas, masso
+
+
 def test_full_size_om4p25_properties(ml):
     """BASELINE config 2 at full size (1440x1080x75 x 12): size-independent properties + a slab vs the oracle."""
     from momlevel_b200 import synth
@@ -660,15 +692,34 @@ def test_full_size_om4p25_properties(ml):
     # checksum of checksums: the global mass series from the 4-D field equals the kernel's
     g, _ = ml.steric(ds, domain="global", reference=reference)
     assert abs(float(g["steric"].values[0])) < 1e-10 and np.all(np.isfinite(g["steric"].values))
-    # a slab against the oracle
-    ys = slice(600, 604)
-    f64 = lambda k: ds[k].data[..., ys, :].cpu().numpy().astype(np.float64)  # noqa: E731
-    oref = osteric.reference_state(f64("thetao"), f64("so"), f64("volcello"), ds["areacello"].values[ys],
-                                   ds["z_l"].values)
-    oeta, _ = osteric.steric_local(f64("thetao"), f64("so"), ds["z_l"].values, ds["z_i"].values,
-                                   ds["deptho"].values[ys], oref)
-    _close_nan(eta[:, ys, :].cpu().numpy(), oeta, atol=ETA_ATOL)
-    _close_nan(reference["rho"].data[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
+    # columns from every part of the grid against the oracle: the three heights (BASELINE config 2 names them
+    # together; the one-pass kernel serves the call) and the reference density
+    grid = {k: ds[k].data for k in ("deptho", "areacello", "z_l", "z_i")}
+    T, S, V = ds["thetao"].data, ds["so"].data, ds["volcello"].data[0]
+    cols = _sampled_columns(1080 * 1440)
+    oref, oetas, _ = _oracle_on_columns(T, S, V, grid, cols, variants=("steric", "thermosteric", "halosteric"))
+    idx = torch.as_tensor(cols, device="cuda")
+    _close_nan(eta.flatten(1)[:, idx].cpu().numpy(), oetas["steric"], atol=ETA_ATOL)
+    _close_nan(reference["rho"].data.flatten(1)[:, idx].cpu().numpy(), oref["rho"][:, 0, :], rtol=RHO_RTOL)
+    all3, _ = ml.steric_variants(ds)
+    for v in ("steric", "thermosteric", "halosteric"):
+        _close_nan(all3[v].data.flatten(1)[:, idx].cpu().numpy(), oetas[v], atol=ETA_ATOL)
+    assert torch.equal(torch.nan_to_num(all3["steric"].data), torch.nan_to_num(eta))
+    # BASELINE config 5 on the same fields: the linear EOS height and Flament spiciness against the oracle
+    lidx = idx
+    _, letas, _ = _oracle_on_columns(T, S, V, grid, cols, eos="linear")
+    _close_nan(lin["steric"].data.flatten(1)[:, lidx].cpu().numpy(), letas["steric"], atol=ETA_ATOL)
+    half = ml.core.flament_spice(T[:6], S[:6])
+    pts = torch.arange(0, half.numel(), 997, device="cuda")
+    Tp, Sp = (x[:6].flatten()[pts].double().cpu().numpy() for x in (T, S))
+    m = ~(np.isnan(Tp) | np.isnan(Sp))
+    from oracle import spice as ospice
+
+    got = half.flatten()[pts].cpu().numpy()
+    assert np.all(np.isnan(got[~m]))
+    want = ospice.flament_spice(Tp[m], Sp[m])
+    assert np.max(np.abs(got[m] - want) / np.maximum(np.abs(want), 1.0)) < 1e-12
+    del half
 
 
 def test_full_size_spear_member(ml):
@@ -685,14 +736,17 @@ def test_full_size_spear_member(ml):
     assert core.last_path() == 2
     wet = ~torch.isnan(V[0])
     assert torch.all(eta[0][wet] == 0.0) and torch.equal(torch.isnan(eta[77]), ~wet)
-    ys = slice(150, 154)
-    f64 = lambda x: x[..., ys, :].double().cpu().numpy()  # noqa: E731
-    z_l, z_i = grid["z_l"].cpu().numpy(), grid["z_i"].cpu().numpy()
-    V4 = np.broadcast_to(f64(V), (nt,) + f64(V).shape)
-    oref = osteric.reference_state(f64(T), f64(S), V4, grid["areacello"][ys].cpu().numpy(), z_l)
-    oeta, _ = osteric.steric_local(f64(T), f64(S), z_l, z_i, grid["deptho"][ys].cpu().numpy(), oref)
-    _close_nan(eta[:, ys, :].cpu().numpy(), oeta, atol=ETA_ATOL)
-    _close_nan(rho[:, ys, :].cpu().numpy(), oref["rho"], rtol=RHO_RTOL)
+    cols = _sampled_columns(ny * nx)
+    idx = torch.as_tensor(cols, device="cuda")
+    oref, oetas, _ = _oracle_on_columns(T, S, V, grid, cols)
+    _close_nan(eta.flatten(1)[:, idx].cpu().numpy(), oetas["steric"], atol=ETA_ATOL)
+    _close_nan(rho.flatten(1)[:, idx].cpu().numpy(), oref["rho"][:, 0, :], rtol=RHO_RTOL)
+    # a block of the member that does not start at its step 0 (distributed.assign_member_blocks): reference from
+    # the step-0 slabs, then the block against it
+    (e3, r3, s3), = mld.steric_local_pieces([(T[36:].contiguous(), S[36:].contiguous(), V, (T[0].contiguous(), S[0].contiguous()))],
+                                            grid["z_i"], grid["deptho"], pres)
+    assert torch.equal(torch.nan_to_num(r3), torch.nan_to_num(rho))
+    assert float(torch.nan_to_num(e3 - eta[36:]).abs().max()) < 1e-12
     (e2, r2, s2), = mld.steric_local_members([(T, S, V)], grid["z_i"], grid["deptho"], pres)
     assert torch.equal(torch.nan_to_num(e2), torch.nan_to_num(eta)) and torch.equal(s2, sums)
 
@@ -719,13 +773,13 @@ def test_full_size_om4p125_window(ml):
         want = torch.nansum(rho * V.double())
         assert float((masso[t] - want).abs() / want) < 1e-12
         del rho
-    ys = slice(1000, 1002)
-    f64 = lambda x: x[..., ys, :].double().cpu().numpy()  # noqa: E731
-    z_l = grid["z_l"].cpu().numpy()
-    V4 = np.broadcast_to(f64(V), (nt,) + f64(V).shape)
-    oref = osteric.reference_state(f64(T), f64(S), V4, grid["areacello"][ys].cpu().numpy(), z_l)
-    _, _, omass = osteric.steric_global(f64(T), f64(S), z_l, oref)
-    got = core.steric_global(T[..., ys, :].contiguous(), S[..., ys, :].contiguous(), V[:, ys, :].contiguous(), pres)
+    # the masses of a sub-grid made of columns from every part of the grid, against the oracle
+    cols = _sampled_columns(ny * nx, n_stride=1024)
+    cols = cols[: len(cols) // 4 * 4]  # rows of whole 16-byte units: the sub-grid takes the TMA family too
+    idx = torch.as_tensor(cols, device="cuda")
+    _, _, omass = _oracle_on_columns(T, S, V, grid, cols)
+    got = core.steric_global(T.flatten(2)[:, :, idx].contiguous(), S.flatten(2)[:, :, idx].contiguous(),
+                             V.flatten(1)[:, idx].contiguous(), pres)
     assert np.allclose(got.cpu().numpy(), omass, rtol=1e-12, atol=0)
 
 
