@@ -21,8 +21,18 @@
 namespace ml {
 namespace stream {
 
+// experiment knobs (tools/ab_stream.sh): ring depth, CTAs per SM of the map kernel, cache hint of the result stores
+#ifndef ML_STREAM_STAGES
+#define ML_STREAM_STAGES 4
+#endif
+#ifndef ML_STREAM_CTAS
+#define ML_STREAM_CTAS 3
+#endif
+#ifndef ML_STREAM_ST
+#define ML_STREAM_ST 0
+#endif
 constexpr int kTile = 2048;     // points per tile: 8 KB per fp32 operand
-constexpr int kStages = 4;
+constexpr int kStages = ML_STREAM_STAGES;
 constexpr int kThreads = 256;   // two quads of a tile per thread
 constexpr int kWarps = kThreads / 32;
 
@@ -35,8 +45,14 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 // four results of a quad leave as ONE 256-bit store (sm_100: STG.256): a lane writes a whole 32-byte sector and a
 // warp 1 KB in a row; two 128-bit stores per lane would each write half of every sector they touch
 __device__ __forceinline__ void st4(double* p, double a, double b, double c, double d) {
+#if ML_STREAM_ST == 1
+  asm volatile("st.global.cs.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#elif ML_STREAM_ST == 2
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
   asm volatile("st.global.L1::no_allocate.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d)
                : "memory");
+#endif
 }
 // A warp is done with a stage: true in lane 0 of the warp that is the LAST of the CTA to leave it (that lane
 // refills the stage); tma::stage_done orders every warp's reads of the stage before the refill.
@@ -86,7 +102,7 @@ constexpr size_t ring_bytes() {
 // ------------------------------------------------------------------------------ spice / density
 // OP 0: Flament spiciness (T, S).  OP 1: density of EOS (T, S, p per row: scalar or per level).
 template <int OP, int EOS>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, ML_STREAM_CTAS)
     k_stream_map(const float* __restrict__ T, const float* __restrict__ S, i64 t_stride, i64 s_stride,
                  const double* __restrict__ p, int pmode, Geom g, double* __restrict__ out) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -342,14 +358,14 @@ int launch_spice(const float* T, const float* S, i64 n, double* out, cudaStream_
   const Geom g = geometry(1, 1, n);
   auto kern = k_stream_map<0, 0>;
   if (int rc = opt_in(kern, ring_bytes<2>())) return rc;
-  kern<<<persistent_grid(g.ntiles, 3), kThreads, ring_bytes<2>(), st>>>(T, S, 0, 0, nullptr, 0, g, out);
+  kern<<<persistent_grid(g.ntiles, ML_STREAM_CTAS), kThreads, ring_bytes<2>(), st>>>(T, S, 0, 0, nullptr, 0, g, out);
   return launched("k_stream_map(spice)");
 }
 
 int launch_density(int eos, const float* T, const float* S, i64 t_stride, i64 s_stride, const double* p, int pmode,
                    i64 nrows, int nz, i64 ncol, double* out, cudaStream_t st) {
   const Geom g = geometry(nrows, nz, ncol);
-  const unsigned grid = persistent_grid(g.ntiles, 3);
+  const unsigned grid = persistent_grid(g.ntiles, ML_STREAM_CTAS);
   if (eos == ML_EOS_WRIGHT) {
     auto kern = k_stream_map<1, 0>;
     if (int rc = opt_in(kern, ring_bytes<2>())) return rc;

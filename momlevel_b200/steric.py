@@ -127,15 +127,13 @@ def steric(
         v_ref = reference["volcello"].data
         if streamed is not None:
             masso = streamed.numpy()
-        elif (variant == "steric" and not isinstance(pres, core.Pressure)
+        elif (variant in VARIANTS and not isinstance(pres, core.Pressure)
                 and _host_resident(dset, tcoord, zcoord, zbounds, need_depth=False)
                 and not (isinstance(v_ref, torch.Tensor) and v_ref.is_cuda)):
-            # fields in host memory (a daily series does not fit in HBM): streamed through device windows,
-            # level rows packed to the cells of the reference volume on the way (ml_steric_global_host)
-            step_bytes = 2 * int(np.prod(full.shape[1:])) * 4
-            spw = int(min(max(1, -(-(1 << 28) // step_bytes)), full.shape[0]))
-            masso = core.steric_global_host(thetao.data, so.data, v_ref, _host_numpy(pres), eos=equation_of_state,
-                                            steps_per_window=spw).numpy()
+            # fields in host memory (a daily series does not fit in HBM): streamed through device windows, level rows
+            # packed to the cells of the reference volume on the way; the thermo- / halosteric variants keep their
+            # reference slab on the device for the whole series (ml_host_stream_*)
+            masso = _global_host(dset, reference, variant, pres, equation_of_state).numpy()
         else:
             masso = core.steric_global(thetao.data, so.data, v_ref, pres, eos=equation_of_state,
                                        t_bcast=t_bcast, s_bcast=s_bcast).cpu().numpy()
@@ -360,6 +358,29 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferre
         assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
         sums = host[4:6]
     return _reference_from_pass(dset, tcoord, eos, rho, sums, pres), eta, area_total
+
+
+def _global_host(dset, reference, variant, pres, eos):
+    """``calc_masso(rho, reference.volcello)`` per step (steric.py:135) for fields in host memory, any variant."""
+    T, S = dset["thetao"].data, dset["so"].data
+    nt = int(T.shape[0])
+    step_bytes = 2 * int(np.prod(T.shape[1:])) * (4 if str(T.dtype).endswith("float32") else 8)
+    spw = int(min(max(1, -(-(1 << 28) // step_bytes)), nt))  # windows of >= 256 MB
+    ref = None
+    if variant != "steric":
+        ref = {"thetao": _host_array(reference["thetao"]), "so": _host_array(reference["so"])}
+    f32 = str(T.dtype).endswith("float32") and str(S.dtype).endswith("float32")
+    hs = core.HostStream("global", _host_array(reference["volcello"]), _host_numpy(pres), variants=(variant,), reference=ref,
+                         eos=eos, max_block_steps=spw, dtype=torch.float32 if f32 else torch.float64)
+    outs = []
+    try:
+        for t in range(0, nt, spw):
+            outs.append(hs.push(T[t: t + spw], S[t: t + spw])[variant])
+        hs.finish()
+    except BaseException:
+        hs.abort()
+        raise
+    return torch.cat(outs) if len(outs) != 1 else outs[0]
 
 
 def _chunked(dset):

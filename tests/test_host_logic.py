@@ -253,20 +253,37 @@ def test_steric_routes_host_resident_fields_to_the_host_entry(monkeypatch):
     ref_in["areacello"] = small["areacello"]
     gcalls = []
 
-    def fake_global(T, S, v_ref, p_level, eos="Wright", steps_per_window=1):
-        gcalls.append((tuple(T.shape), tuple(v_ref.shape), type(p_level).__name__, steps_per_window, eos))
-        return torch.full((T.shape[0],), float(o["masso"]), dtype=torch.float64)
+    class FakeStream:  # stands in for core.HostStream (ml_host_stream_*): records what steric() hands it
+        def __init__(self, domain, v_ref, p_level, variants=("steric",), reference=None, eos="Wright", max_block_steps=1,
+                     dtype=torch.float32, **kw):
+            self.variants = variants
+            gcalls.append(["begin", domain, tuple(np.shape(v_ref)), type(p_level).__name__, variants,
+                           None if reference is None else sorted(reference), eos, max_block_steps])
 
-    monkeypatch.setattr(core, "steric_global_host", fake_global)
+        def push(self, T, S):
+            gcalls.append(["push", tuple(T.shape)])
+            return {v: torch.full((T.shape[0],), float(o["masso"]), dtype=torch.float64) for v in self.variants}
+
+        def finish(self):
+            gcalls.append(["finish"])
+            return None, None
+
+        def abort(self):
+            gcalls.append(["abort"])
+
+    monkeypatch.setattr(core, "HostStream", FakeStream)
     calls.clear()
     res, _ = ml.steric(small, domain="global", reference=ref_in)
-    assert gcalls == [((5, 12, 20, 32), (12, 20, 32), "ndarray", 5, "Wright")] and calls == []
+    assert gcalls == [["begin", "global", (12, 20, 32), "ndarray", ("steric",), None, "Wright", 5],
+                      ["push", (5, 12, 20, 32)], ["finish"]] and calls == []
     assert res["steric"].shape == (5,) and np.allclose(res["steric"].values, 0.0, atol=1e-12)  # M(t) = M_ref
     assert float(res["reference_height"]) == pytest.approx(o["volo"] / small["areacello"].values.sum())
-    # thermosteric / halosteric in the global domain hold one field at its reference slab: the ordinary route
-    with pytest.raises(ml._lib.MLError):  # reaches its device check
-        ml.steric(small, domain="global", reference=ref_in, variant="thermosteric")
-    assert len(gcalls) == 1
+    # thermosteric / halosteric in the global domain hold one field at its reference slab, which the stream keeps on
+    # the device for the whole series (steric.py:115-121)
+    gcalls.clear()
+    res, _ = ml.steric(small, domain="global", reference=ref_in, variant="thermosteric")
+    assert gcalls[0] == ["begin", "global", (12, 20, 32), "ndarray", ("thermosteric",), ["so", "thetao"], "Wright", 5]
+    assert res["thermosteric"].shape == (5,)
 
 
 def test_annual_average_reads_a_calendar_time_axis():
