@@ -1042,12 +1042,12 @@ def test_steric_takes_the_host_route_for_host_resident_fields(ml, monkeypatch):
             _close_nan(ref["rho"].values, oref["rho"], rtol=RHO_RTOL)
             assert got["delta_rho"].shape == shape
         # the global domain from host memory, every variant (ml_host_stream_*: the pinned operand's reference slab
-        # stays on the device): the device-resident call bit for bit, and the oracle
+        # stays on the device): against the device-resident call and the oracle
         before = core.launch_count()
         gh, _ = ml.steric(host, variant=variant, domain="global", reference=ref)
         assert core.host_last_transfer()[0] > 0 and core.launch_count() > before
         gd, _ = ml.steric(dev, variant=variant, domain="global", reference=wref)
-        assert np.array_equal(gh[variant].values, gd[variant].values)
+        assert np.max(np.abs(gh[variant].values - gd[variant].values)) < 1e-12  # (the two references' scalars differ by an ulp)
         g_o, _, _ = osteric.steric_global(T64, S64, z_l, oref, variant=variant)
         assert np.max(np.abs(gh[variant].values - g_o)) < ETA_ATOL
     # small datasets are simply copied to the device; forcing the route shows the same numbers
