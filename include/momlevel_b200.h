@@ -242,6 +242,17 @@ int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bca
                      size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * ml_calc_masso -- skipna sums of a field that already exists: out[r] = sum_i rho[r][i] * volcello[i].
+ * Replaces derived.calc_masso (src/momlevel/derived.py:414-444: `(rho * volcello).sum(...)` per time step, without
+ * the rho * volcello temporary) and, with volcello == NULL, derived.calc_volo (derived.py:769-795:
+ * `volcello.sum()`, the field passed as `rho` with nrows = 1).  Two fixed-order stages: bitwise reproducible.
+ *   rho        device [nrows][n] of `dtype`;  volcello device [n] of `w_dtype` or NULL
+ *   out        device fp64[nrows];  workspace: nrows * 1184 doubles are always enough
+ * ------------------------------------------------------------------------------------- */
+int ml_calc_masso(int dtype, const void* rho, int w_dtype, const void* volcello, int64_t nrows, int64_t n,
+                  double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * ml_steric_local_host -- the same computation as reference_state + steric_local for
  * variant="steric" on HOST buffers: time steps are staged to the device through two
  * pinned/registered windows so the copy of step k+1 overlaps the kernels of step k.

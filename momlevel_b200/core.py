@@ -34,6 +34,7 @@ __all__ = [
     "force_direct",
     "variants_chunk",
     "HostStream",
+    "weighted_nansum",
     "Pressure",
     "host_release",
 ]
@@ -333,6 +334,25 @@ def reference_state(T0, S0, V0, p_level, eos="Wright", out=None):
                                  ncol, rho.data_ptr(), sums.data_ptr(), ws.data_ptr(), nbytes, _stream())
         )
     return rho, sums
+
+
+def weighted_nansum(a, w=None, nrows=1):
+    """``out[r] = nansum(a[r] * w)`` (``w=None``: ``nansum(a[r])``) for ``a`` viewed as ``[nrows, n]`` -- the sums of
+    ``derived.calc_masso`` (derived.py:435-438) and ``derived.calc_volo`` (:787-789) on fields that already exist,
+    in two fixed-order stages and without the ``rho * volcello`` temporary.  fp64 ``[nrows]`` on the device."""
+    L = _lib.lib()
+    a = to_device(a)
+    n = a.numel() // max(int(nrows), 1)
+    wt = None
+    if w is not None:
+        wt = to_device(w)
+        assert wt.numel() == n, "one weight per point of a row"
+    out = torch.empty(int(nrows), dtype=torch.float64, device=a.device)
+    ws = torch.empty(int(nrows) * 1184, dtype=torch.float64, device=a.device)
+    _lib.check(L.ml_calc_masso(_dt_id(a), a.data_ptr(), _dt_id(wt) if wt is not None else 0,
+                               wt.data_ptr() if wt is not None else None, int(nrows), n, out.data_ptr(), ws.data_ptr(),
+                               ws.numel() * 8, _stream()))
+    return out
 
 
 def _steric_operands(T, S, t_bcast, s_bcast):

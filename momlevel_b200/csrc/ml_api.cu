@@ -219,6 +219,25 @@ __global__ void __launch_bounds__(kBlock) k_calc_dz(const double* __restrict__ z
   }
 }
 
+// ------------------------------------------------------- K7: volume / mass sums of given fields
+// partials[row][block] = skipna sum over the block's share of a[row][i] * w[i] (w absent: of a[row][i]):
+// derived.calc_volo (derived.py:787-789: volcello.sum()) and derived.calc_masso on a density field that already
+// exists (derived.py:435-438: (rho * volcello).sum() per time step) without the rho * volcello temporary.
+template <typename TA, typename TW>
+__global__ void __launch_bounds__(kBlock) k_weighted_nansum(const TA* __restrict__ a, const TW* __restrict__ w, i64 n,
+                                                            double* __restrict__ partials /* [rows][gridDim.x] */) {
+  __shared__ double sm[kWarps];
+  const TA* row = a + (i64)blockIdx.y * n;
+  double acc = 0.0;
+  for (i64 i = (i64)blockIdx.x * kBlock + threadIdx.x; i < n; i += (i64)gridDim.x * kBlock) {
+    const double x = ldf(row + i);
+    const double p = w != nullptr ? x * ldf(w + i) : x;
+    if (!isnan(p)) acc += p;
+  }
+  acc = block_sum<kWarps>(acc, sm);
+  if (threadIdx.x == 0) partials[(i64)blockIdx.y * gridDim.x + blockIdx.x] = acc;
+}
+
 // ------------------------------------------------------- fixed-order second reduce stage
 // out[row] = sum_b partials[row][b]; one block per row, each thread a strided serial sum.
 __global__ void __launch_bounds__(kBlock) k_reduce_rows(const double* __restrict__ partials, i64 nblk,
@@ -1004,3 +1023,33 @@ int ml_steric_global(int eos, int dtype, const void* T, const void* S, int t_bca
 }
 
 }  // extern "C"
+
+int ml_calc_masso(int dtype, const void* rho, int w_dtype, const void* volcello, int64_t nrows, int64_t n, double* out,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  if (dtype != ML_F32 && dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown dtype id %d", dtype);
+  if (volcello != nullptr && w_dtype != ML_F32 && w_dtype != ML_F64) return fail(ML_ERR_DTYPE, "unknown weight dtype id %d", w_dtype);
+  ML_REQUIRE_PTR(rho);
+  ML_REQUIRE_PTR(out);
+  if (nrows < 0 || n < 0 || nrows > 65535) return fail(ML_ERR_SHAPE, "bad extents nrows=%lld n=%lld", (long long)nrows, (long long)n);
+  if (nrows == 0) return ML_OK;
+  ML_REQUIRE_ALIGNED(rho, elem_size(dtype));
+  const i64 want = cdiv(n > 0 ? n : 1, (i64)kBlock * 8);
+  const i64 nblk = want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want);  // ~8 blocks per SM, each thread a strided serial sum
+  if (workspace == nullptr || workspace_bytes < (size_t)(nrows * nblk) * sizeof(double))
+    return fail(ML_ERR_WORKSPACE, "workspace needs %zu bytes, got %zu", (size_t)(nrows * nblk) * sizeof(double), workspace_bytes);
+  ML_REQUIRE_ALIGNED(workspace, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* partials = (double*)workspace;
+  dim3 grid((unsigned)nblk, (unsigned)nrows);
+#define ML_WNS(TA, TW) k_weighted_nansum<TA, TW><<<grid, kBlock, 0, st>>>((const TA*)rho, (const TW*)volcello, n, partials)
+  if (dtype == ML_F32) {
+    if (volcello == nullptr || w_dtype == ML_F32) ML_WNS(float, float); else ML_WNS(float, double);
+  } else {
+    if (volcello == nullptr || w_dtype == ML_F64) ML_WNS(double, double); else ML_WNS(double, float);
+  }
+#undef ML_WNS
+  int rc = launched("k_weighted_nansum");
+  if (rc) return rc;
+  k_reduce_rows<<<(unsigned)nrows, kBlock, 0, st>>>(partials, nblk, out);
+  return launched("k_reduce_rows");
+}

@@ -118,28 +118,37 @@ def calc_dz(levels, interfaces, depth, top=0.0, bottom=None, fraction=False):
 
 
 def calc_volo(volcello):
-    """Total ocean volume (derived.py:769-795)."""
+    """Total ocean volume (derived.py:769-795): skipna sum, two fixed-order stages on the device (``ml_calc_masso``)."""
     volcello = _as_labeled(volcello)
     assert len(volcello.dims) == 3, "Expecting only 3 dimensions for volcello"
-    volo = volcello.sum()
+    volo = DataArray(core.weighted_nansum(volcello.data)[0], ())
     volo.attrs = {"standard_name": "sea_water_volume", "long_name": "Sea Water Volume", "units": "m3"}
     return volo
 
 
 def calc_masso(rho, volcello, tcoord="time"):
-    """Total ocean mass per time step (derived.py:414-444): skipna sum of ``rho * volcello``."""
+    """Total ocean mass per time step (derived.py:414-444): skipna sum of ``rho * volcello``, reduced on the device
+    without the ``rho * volcello`` temporary (``ml_calc_masso``)."""
     rho, volcello = _as_labeled(rho), _as_labeled(volcello)
     import torch
 
-    r, v = core.to_device(rho.data, torch.float64), core.to_device(volcello.data, torch.float64)
-    if tcoord in rho.dims and tcoord not in volcello.dims:
-        v = v.unsqueeze(rho.dims.index(tcoord))
-    prod = r * v
     if tcoord in rho.dims:
-        axes = tuple(i for i, d in enumerate(rho.dims) if d != tcoord)
-        masso = DataArray(torch.nansum(prod, dim=axes), (tcoord,))
+        if rho.dims[0] != tcoord:
+            rho = rho.transpose(tcoord, ...)
+        r = core.to_device(rho.data)
+        v = volcello
+        if tcoord in v.dims:  # a time-dependent volume: fall back to the element-wise product, row by row
+            v = v.transpose(tcoord, ...) if v.dims[0] != tcoord else v
+            vd = core.to_device(v.data)
+            rows = [core.weighted_nansum(r[t], vd[t])[0] for t in range(r.shape[0])]
+            masso = DataArray(torch.stack(rows), (tcoord,))
+        else:
+            if tuple(v.dims) != tuple(rho.dims[1:]):
+                v = v.transpose(*rho.dims[1:])
+            masso = DataArray(core.weighted_nansum(r, v.data, nrows=r.shape[0]), (tcoord,))
     else:
-        masso = DataArray(torch.nansum(prod), ())
+        v = volcello if tuple(volcello.dims) == tuple(rho.dims) else volcello.transpose(*rho.dims)
+        masso = DataArray(core.weighted_nansum(rho.data, v.data)[0], ())
     masso.attrs = {"standard_name": "sea_water_mass", "long_name": "Sea Water Mass", "units": "kg"}
     return masso
 

@@ -376,3 +376,26 @@ def test_stream_delta_rho(ml, eos, shape, bcast):
     assert np.array_equal(np.isnan(g), np.isnan(want))
     ok = ~np.isnan(want)
     assert np.max(np.abs(g[ok] - want[ok])) < 1e-9
+
+
+@pytest.mark.parametrize("a_dtype,w_dtype", [(np.float64, np.float32), (np.float64, np.float64), (np.float32, np.float32),
+                                             (np.float32, None)])
+@pytest.mark.parametrize("nrows,n", [(1, 7), (3, 4099), (12, 1 << 18), (1, 3_000_001)])
+def test_weighted_nansum(ml, a_dtype, w_dtype, nrows, n):
+    """ml_calc_masso: (rho * volcello).sum() per time step with NaNs skipped (derived.py:435-438) and, without
+    weights, volcello.sum() (derived.py:787-789); bitwise reproducible from call to call."""
+    from momlevel_b200 import core
+
+    rng = np.random.default_rng(n + nrows)
+    a = rng.uniform(990.0, 1060.0, (nrows, n)).astype(a_dtype)
+    a[0, n // 2] = np.nan
+    w = None
+    if w_dtype is not None:
+        w = rng.uniform(1e6, 1e9, n).astype(w_dtype)
+        w[: max(1, n // 10)] = np.nan
+    got = core.weighted_nansum(torch.from_numpy(a).cuda(), None if w is None else torch.from_numpy(w).cuda(), nrows=nrows)
+    again = core.weighted_nansum(torch.from_numpy(a).cuda(), None if w is None else torch.from_numpy(w).cuda(), nrows=nrows)
+    assert torch.equal(got, again)
+    a64 = a.astype(np.float64)
+    want = np.nansum(a64 * w.astype(np.float64)[None], axis=1) if w is not None else np.nansum(a64, axis=1)
+    assert np.allclose(got.cpu().numpy(), want, rtol=1e-13, atol=0)

@@ -263,18 +263,22 @@ def config4(rank, world, dev, window=12, parity=True, nt_override=None):
         if wi == 0:  # warm-up, untimed
             core.steric_global(T, S, V, pres)
             if t == 0:
-                core.reference_state(T[0], S[0], V, pres)
+                core.weighted_nansum(V)
         last = wi == len(starts) - 1
         if last:
             barrier(world)  # the gather must not be charged for ranks that are still generating their window
         torch.cuda.synchronize()
         a, b, g = ev(), ev(), ev()
         a.record()
-        if t == 0:  # the rank that owns step 0 owns the reference state (reference.py:71-80)
-            _, ref_sums = core.reference_state(T[0], S[0], V, pres)
-            alg_bytes += N * 20
         parts.append(core.steric_global(T, S, V, pres))
         alg_bytes += n * N * 8 + N * 4
+        if t == 0:
+            # The rank that owns step 0 owns the scalars of the reference state (reference.py:74-80): masso_ref IS
+            # the mass of step 0, which the series holds already (calc_masso(rho(t=0), volcello), the same sum), and
+            # volo is one skipna sum over volcello (derived.py:787-789) -- no pass over T and S for the reference
+            # density, which the global branch never reads (steric.py:134-142).
+            ref_sums = torch.cat([core.weighted_nansum(V), parts[0][:1]])
+            alg_bytes += N * 4
         if last:
             g.record()
             eta, href = mld.steric_global_sharded(None, None, None, None, None, None, area_sum, nt,
