@@ -18,7 +18,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+// The AVX-512 bodies exist on x86-64 hosts only; anything else (an aarch64 Grace host in front of the same GPU)
+// builds the scalar bodies alone.
+#if defined(__x86_64__) && !defined(ML_PACK_NO_X86)
+#define ML_PACK_X86 1
 #include <immintrin.h>
+#else
+#define ML_PACK_X86 0
+#endif
 
 #include "../../include/momlevel_b200.h"
 
@@ -26,10 +33,14 @@ namespace {
 
 // ML_PACK_FORCE_SCALAR=1 in the environment selects the scalar bodies on any CPU (tests/test_pack.py)
 bool has_avx512() {
+#if ML_PACK_X86
   static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw") &&
                          __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("popcnt") &&
                          !(getenv("ML_PACK_FORCE_SCALAR") && getenv("ML_PACK_FORCE_SCALAR")[0] == '1');
   return ok;
+#else
+  return false;
+#endif
 }
 
 inline bool present_f32(uint32_t bits) { return (bits & 0x7fffffffu) <= 0x7f800000u; }  // not NaN
@@ -55,6 +66,7 @@ uint64_t index_scalar(const float* v, int64_t ncol, uint32_t* words, uint32_t* b
   return run;
 }
 
+#if ML_PACK_X86
 __attribute__((target("avx512f,avx512bw,avx512vl,popcnt"))) uint64_t index_avx512(const float* v, int64_t ncol,
                                                                                    uint32_t* words,
                                                                                    uint32_t* before) {
@@ -79,6 +91,12 @@ __attribute__((target("avx512f,avx512bw,avx512vl,popcnt"))) uint64_t index_avx51
   return run;
 }
 
+#else
+uint64_t index_avx512(const float* v, int64_t ncol, uint32_t* words, uint32_t* before) {  // never selected
+  return index_scalar(v, ncol, words, before);
+}
+#endif
+
 // ---- pack --------------------------------------------------------------------------------
 
 void pack_scalar(const float* t, const float* s, const uint32_t* words, int64_t g0, int64_t g1, float* t_out,
@@ -96,7 +114,12 @@ void pack_scalar(const float* t, const float* s, const uint32_t* words, int64_t 
   }
 }
 
-#ifdef ML_PACK_PLAIN_STORES  // A/B: masked stores straight into the staging memory (tools/packbench.cpp)
+#if !ML_PACK_X86
+void pack_avx512(const float* t, const float* s, const uint32_t* words, int64_t g0, int64_t g1, int64_t, float* t_out,
+                 float* s_out, bool) {  // never selected
+  pack_scalar(t, s, words, g0, g1, t_out, s_out);
+}
+#elif defined(ML_PACK_PLAIN_STORES)  // A/B: masked stores straight into the staging memory (tools/packbench.cpp)
 __attribute__((target("avx512f,avx512bw,avx512vl,popcnt,bmi2"))) void pack_avx512(const float* t, const float* s,
                                                                                  const uint32_t* words, int64_t g0,
                                                                                  int64_t g1, int64_t ncol,
