@@ -596,6 +596,14 @@ def run_ours(args):
         extras["steric_local_selfref_fp64_storage_hbm_frac"] = (half * N * 16 + N * 8 + ncol * 8 * (half + 1)) / (ms * 1e-3) / 1e9 / peak
         extras["steric_local_selfref_fp64_storage_family"] = {1: "direct", 2: "tma"}.get(core.last_path(), "none")
         del T64, S64, V64
+        # a grid whose rows are not a multiple of 16 bytes (1441 x 1079 columns: odd): rank-1 tensor maps, one box per row
+        rgrid = synth.make_grid(nz, ny - 1, nx + 1, seed=123, device=dev)
+        rT, rS, rV = synth.make_fields(rgrid, nt, seed=123, dtype=torch.float32)
+        rz, rd = rgrid["z_i"].contiguous(), rgrid["deptho"].contiguous()
+        ms = timed(lambda: core.steric_local_selfref(rT, rS, rV, rz, rd, pres, want_rho_ref=False))
+        extras["steric_local_selfref_ragged_rows_gpts"] = nt * nz * (ny - 1) * (nx + 1) / ms / 1e6
+        extras["steric_local_selfref_ragged_rows_family"] = {1: "direct", 2: "tma"}.get(core.last_path(), "none")
+        del rT, rS, rV, rgrid
         extras["steric_local_selfref_call_gpts"] = points / k3_avg_ms / 1e6
         # the public call with everything around the kernel: validation, variant select, result Datasets,
         # the read-back of volo / masso (wall clock, synchronised on both sides)

@@ -64,6 +64,7 @@ struct Params {
   double coef;
   int nt, nz;
   int es;                 // bytes per stored value of T, S and v_ref: 4 or 8
+  int flat;               // rows are not a multiple of 16 bytes: rank-1 maps, one 1-D box per row (see refill_stage)
   int t_start;            // first time step covered by this launch
   int first_is_reference; // kLocal: step 0 of the field IS the reference state -> its height is exactly zero
   unsigned nchunks;       // time chunks covered by this launch; grid = tiles * nchunks, chunk fastest
@@ -89,7 +90,7 @@ enum Mode { kLocal = 0, kGlobal = 1, kSelfRef = 2 };
 #define ML_TMA_KERNEL_ATTR __launch_bounds__(kThreads, ctas_per_sm_of(MODE))
 #endif
 
-template <typename TIn, int EOS, int TC, int BC, int MODE>
+template <typename TIn, int EOS, int TC, int BC, int MODE, bool FLAT>
 __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
@@ -135,6 +136,18 @@ __global__ void ML_TMA_KERNEL_ATTR
     TIn* dT = stage_base + (size_t)s * kStageFloats;
     TIn* dS = dT + kRowsT * kTile;
     mbar_expect_tx(full + s, kStageBytes);
+    if (FLAT) {
+      // Rows that are not a multiple of 16 bytes (ncol % 4 != 0 for fp32): no strided tensor map can describe the
+      // field, but a rank-1 map over the flat array can, and a box may start at any element -- one 1-D box per row
+      // of the stage.  Columns past the end of a row hold the head of the next row (never stored), rows past the
+      // last step lie beyond the map and are zero-filled.
+      const i64 row0 = (i64)z * P.ncol + c0, step = (i64)nz * P.ncol;
+#pragma unroll
+      for (int k = 0; k < kRowsT; ++k) tma_load_1d(dT + k * kTile, &mapT, full + s, (int)(row0 + (BC == 1 ? 0 : (i64)(t0 + k) * step)));
+#pragma unroll
+      for (int k = 0; k < kRowsS; ++k) tma_load_1d(dS + k * kTile, &mapS, full + s, (int)(row0 + (BC == 2 ? 0 : (i64)(t0 + k) * step)));
+      return;
+    }
     if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
     if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
   };
@@ -354,12 +367,18 @@ __global__ void ML_TMA_KERNEL_ATTR
 
 // ----------------------------------------------------------------------- host side
 
+#ifndef ML_TMA_FLAT_TU
+static bool rows_aligned(int dtype, int64_t ncol) { return ncol % (dtype == ML_F32 ? 4 : 2) == 0; }
+
 static bool common_eligible(int dtype, int vref_dtype, const void* T, const void* S, int64_t nt, int64_t nz,
                             int64_t ncol) {
   if ((dtype != ML_F32 && dtype != ML_F64) || vref_dtype != dtype) return false;  // volcello stored like the fields
   if ((reinterpret_cast<uintptr_t>(T) | reinterpret_cast<uintptr_t>(S)) & 15u) return false;
-  const int per16 = dtype == ML_F32 ? 4 : 2;  // TMA global strides are multiples of 16 bytes
-  if (ncol % per16 != 0 || ncol < kTile || ncol > 0x7fffff00ll) return false;
+  if (ncol < kTile || ncol > 0x7fffff00ll) return false;
+  // rows that are not a multiple of 16 bytes go through rank-1 maps, whose 32-bit coordinate must reach the end of
+  // the last (zero-padded) chunk
+  const int64_t mtc = dtype == ML_F32 ? 12 : 6;
+  if (!rows_aligned(dtype, ncol) && (double)((nt + mtc - 1) / mtc * mtc) * (double)nz * (double)ncol >= 2147483647.0) return false;
   if (nt < 1 || nz < 1 || nz > 512) return false;
   // grid.x = tiles * time chunks (chunks of at least 4 steps)
   if ((double)((ncol + kTile - 1) / kTile) * (double)((nt + 3) / 4) > 2147483647.0) return false;
@@ -378,6 +397,10 @@ bool global_eligible(int dtype, const void* T, const void* S, int, int, const vo
   return common_eligible(dtype, vref_dtype, T, S, nt, nz, ncol);
 }
 
+#else
+static bool rows_aligned(int dtype, int64_t ncol);
+#endif
+
 template <int TC>
 inline size_t smem_bytes(int bc, int nz, int mode, int es) {
   const int kStages = stages_of(mode);
@@ -385,10 +408,10 @@ inline size_t smem_bytes(int bc, int nz, int mode, int es) {
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 
-template <typename TIn, int EOS, int TC, int BC, int MODE>
+template <typename TIn, int EOS, int TC, int BC, int MODE, bool FLAT>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
-  auto kern = k_steric_tma<TIn, EOS, TC, BC, MODE>;
+  auto kern = k_steric_tma<TIn, EOS, TC, BC, MODE, FLAT>;
   const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn));
   // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
   // is set on every launch (a host-side table lookup) rather than cached in a static
@@ -401,16 +424,16 @@ static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params
   return launched("k_steric_tma");
 }
 
-template <typename TIn, int EOS, int TC, int MODE>
+template <typename TIn, int EOS, int TC, int MODE, bool FLAT>
 static int launch_bc(int bc, const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles,
                      unsigned chunks, cudaStream_t st) {
 #ifdef ML_TMA_FAST_BUILD  // experiment builds: only the fp32 / Wright / 12-step / no-broadcast kernels
   if (sizeof(TIn) != 4 || EOS != 0 || TC != 12 || bc != 0) return fail(ML_ERR_MODE, "kernel not instantiated in a fast build");
-  return launch_one<float, 0, 12, 0, MODE>(mT, mS, P, tiles, chunks, st);
+  return launch_one<float, 0, 12, 0, MODE, FLAT>(mT, mS, P, tiles, chunks, st);
 #else
-  if (bc == 0) return launch_one<TIn, EOS, TC, 0, MODE>(mT, mS, P, tiles, chunks, st);
-  if (bc == 1) return launch_one<TIn, EOS, TC, 1, MODE>(mT, mS, P, tiles, chunks, st);
-  return launch_one<TIn, EOS, TC, 2, MODE>(mT, mS, P, tiles, chunks, st);
+  if (bc == 0) return launch_one<TIn, EOS, TC, 0, MODE, FLAT>(mT, mS, P, tiles, chunks, st);
+  if (bc == 1) return launch_one<TIn, EOS, TC, 1, MODE, FLAT>(mT, mS, P, tiles, chunks, st);
+  return launch_one<TIn, EOS, TC, 2, MODE, FLAT>(mT, mS, P, tiles, chunks, st);
 #endif
 }
 
@@ -444,8 +467,15 @@ static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int 
   g.tc = tc;
   g.t_start = t_start;
   g.chunks = chunks;
-  const bool okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
-  const bool okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
+  bool okT, okS;
+  if (P.flat) {
+    const i64 lvl = (i64)P.nz * P.ncol;
+    okT = make_flat_map(&g.mT, T, t_bcast ? lvl : lvl * P.nt, kTile, P.es);
+    okS = make_flat_map(&g.mS, S, s_bcast ? lvl : lvl * P.nt, kTile, P.es);
+  } else {
+    okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
+    okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
+  }
   return (okT && okS) ? ML_OK : fail(ML_ERR_ALIGN, "cuTensorMapEncodeTiled rejected the field layout");
 }
 
@@ -463,10 +493,10 @@ static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_
   return rc;
 }
 
-template <int MODE>
+template <int MODE, bool FLAT>
 static int launch_segment(int eos, const Plan& pl, const Segment& g, Params P, cudaStream_t st) {
   P.t_start = g.t_start;
-#define ML_TMA_GO(TIN, E, TCV) return launch_bc<TIN, E, TCV, MODE>(pl.bc, g.mT, g.mS, P, pl.tiles, g.chunks, st)
+#define ML_TMA_GO(TIN, E, TCV) return launch_bc<TIN, E, TCV, MODE, FLAT>(pl.bc, g.mT, g.mS, P, pl.tiles, g.chunks, st)
   if (P.es == 8) {  // fields stored as fp64
 #ifndef ML_TMA_FAST_BUILD
     if (eos == ML_EOS_WRIGHT) {
@@ -490,10 +520,24 @@ static int launch_segment(int eos, const Plan& pl, const Segment& g, Params P, c
 #undef ML_TMA_GO
 }
 
+// The kernels for rows that are not a multiple of 16 bytes (rank-1 maps, FLAT = true) are compiled in their own
+// translation unit (ml_tma_flat.cu includes this file with ML_TMA_FLAT_TU defined): a second set of instantiations
+// next to these would double the compile time of this file, and a run-time switch inside one kernel cost the
+// headline kernel a spill in its level loop.
+int launch_segment_flat(int mode, int eos, const Plan& pl, const Segment& g, const Params& P, cudaStream_t st);
+
+#ifdef ML_TMA_FLAT_TU
+int launch_segment_flat(int mode, int eos, const Plan& pl, const Segment& g, const Params& P, cudaStream_t st) {
+  if (mode == kLocal) return launch_segment<kLocal, true>(eos, pl, g, P, st);
+  if (mode == kGlobal) return launch_segment<kGlobal, true>(eos, pl, g, P, st);
+  return launch_segment<kSelfRef, true>(eos, pl, g, P, st);
+}
+#else
+
 template <int MODE>
 static int launch_plan(int eos, const Plan& pl, const Params& P, cudaStream_t st) {
   for (int i = 0; i < pl.nseg; ++i) {
-    int rc = launch_segment<MODE>(eos, pl, pl.seg[i], P, st);
+    int rc = P.flat ? launch_segment_flat(MODE, eos, pl, pl.seg[i], P, st) : launch_segment<MODE, false>(eos, pl, pl.seg[i], P, st);
     if (rc) return rc;
   }
   return ML_OK;
@@ -505,6 +549,7 @@ static Params base_params(const void* T, const void* S, const void* v_ref, int v
   P.T = T;
   P.S = S;
   P.es = vref_dtype == ML_F64 ? 8 : 4;  // eligibility guarantees fields and volcello share a dtype
+  P.flat = rows_aligned(vref_dtype, ncol) ? 0 : 1;
   P.rho_ref = nullptr;
   P.rho_ref_out = nullptr;
   P.v_ref = v_ref;
@@ -582,6 +627,8 @@ int launch_global(int eos, int, const void* T, const void* S, int t_bcast, int s
   if ((rc = launch_plan<kGlobal>(eos, pl, P, st))) return rc;
   return reduce_rows(partials, pl.tiles, masso, nt, st);
 }
+
+#endif  // ML_TMA_FLAT_TU
 
 }  // namespace tma
 }  // namespace ml

@@ -386,7 +386,7 @@ static int launch_all3(int eos, const void* T, const void* S, const void* Tr, co
 
 bool variants_eligible(int dtype, const void* T, const void* S, const void* Tr, const void* Sr, int vref_dtype,
                        int64_t nt, int64_t nz, int64_t ncol) {
-  if (dtype != ML_F32 || vref_dtype != ML_F32) return false;  // the one-pass kernel stages fp32 rows only
+  if (dtype != ML_F32 || vref_dtype != ML_F32 || ncol % 4 != 0) return false;  // fp32 rows of whole 16-byte units only
   if ((reinterpret_cast<uintptr_t>(Tr) | reinterpret_cast<uintptr_t>(Sr)) & 15u) return false;
   return local_eligible(dtype, T, S, 0, 0, nullptr, nullptr, vref_dtype, nt, nz, ncol, nullptr, nullptr);
 }

@@ -385,9 +385,10 @@ def test_time_axis_partition(ml, nt):
 
 @pytest.mark.parametrize("shape,dtype", [((13, 12, 16, 64), torch.float32),   # TMA family, 4-step chunks + a short one
                                          ((5, 75, 8, 96), torch.float32),     # full 75-level column
-                                         ((3, 10, 37, 53), torch.float32),    # ragged: single-variant fallback
+                                         ((3, 10, 37, 53), torch.float32),    # ragged rows: one rank-1-map launch per height
+                                         ((3, 10, 7, 31), torch.float32),     # fewer columns than a tile: the direct family
                                          ((6, 9, 16, 64), torch.float64),     # fp64 storage: one TMA launch per height
-                                         ((9, 9, 5, 59), torch.float64)])     # fp64, odd ncol: the direct family
+                                         ((9, 9, 5, 59), torch.float64)])     # fp64, odd ncol: rank-1 maps
 @pytest.mark.parametrize("eos", ["Wright", "linear"])
 def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     """steric_variants == steric + thermosteric + halosteric called one by one, and the oracle."""
@@ -398,7 +399,7 @@ def test_all_variants_in_one_pass(ml, shape, dtype, eos):
     res, ref = ml.steric_variants(ds, equation_of_state=eos)
     path = core.last_path()
     ncol = shape[2] * shape[3]
-    assert path == (2 if ncol % (4 if dtype == torch.float32 else 2) == 0 and ncol >= 256 else 1)
+    assert path == (2 if ncol >= 256 else 1)
     one, ref1 = ml.steric(ds, equation_of_state=eos)
     _close_nan(ref["rho"].values, ref1["rho"].values, rtol=1e-15)
     assert float(ref["volo"]) == pytest.approx(float(ref1["volo"]), rel=1e-13)
@@ -1076,6 +1077,8 @@ def test_random_shapes_tma_against_direct(ml, seed, dtype):
     ny = int(rng.integers(1, 9))
     per16 = 4 if dtype == torch.float32 else 2
     nx = per16 * int(rng.integers(256 // (per16 * ny) + 1, 800 // per16))  # rows of whole 16-byte units, ncol >= 256
+    if seed % 3 == 2:
+        nx += 1 + seed % 2  # rows that are NOT whole 16-byte units: rank-1 tensor maps, one 1-D box per row
     grid = synth.make_grid(nz, ny, nx, seed=seed, device="cuda")
     T, S, V = synth.make_fields(grid, nt, seed=seed, dtype=dtype)
     if nt > 1 and nz > 1:
@@ -1153,8 +1156,8 @@ def test_reference_density_is_produced_on_demand(ml):
     out = core.steric_local_selfref(ds13["thetao"].data, ds13["so"].data, ds13["volcello"].data[0], ds13["z_i"].data,
                                     ds13["deptho"].data, pres, want_rho_ref=False)
     assert out[1] is not None
-    # a ragged grid takes the direct family, which needs the field as well
-    dsr = synth.make_dataset(3, 10, 37, 53, seed=14, device="cuda", dtype=torch.float32)
+    # a grid with fewer columns than a tile takes the direct family, which needs the field as well
+    dsr = synth.make_dataset(3, 10, 7, 31, seed=14, device="cuda", dtype=torch.float32)
     out = core.steric_local_selfref(dsr["thetao"].data, dsr["so"].data, dsr["volcello"].data[0], dsr["z_i"].data,
                                     dsr["deptho"].data, pres, want_rho_ref=False)
     assert out[1] is not None and core.last_path() == 1
