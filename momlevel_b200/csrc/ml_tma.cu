@@ -33,7 +33,13 @@ namespace tma {
 // rho_ref / dz operands and fits 64 registers, so it runs four CTAs per SM with a 2-level ring (the
 // same bytes in flight per SM): +4.5 % (profiles/r01_experiments.md).  The self-reference mode reads
 // row 0 of the NEXT level while it works on this one and loses 15 % with a 2-level ring.
-__host__ __device__ constexpr int stages_of(int mode) { return mode == 1 /* kGlobal */ ? 2 : 4; }
+__host__ __device__ constexpr int stages_of(int mode, bool flat = false) { return mode == 1 /* kGlobal */ ? 2 : (flat ? 3 : 4); }
+// Row pitch of a stage in values.  FLAT (rows of the grid are not a multiple of 16 bytes): a box must START on 16
+// bytes in global memory, so it starts at the row's address rounded down and is one 16-byte unit wider; a row of the
+// stage then holds its 256 columns at an offset of 0 ... (16 / size - 1) values, and the pitch is the box width
+// rounded up to 128 bytes (the alignment a TMA destination needs).
+__host__ __device__ constexpr int row_box(int elem, bool flat) { return flat ? 256 + 16 / elem : 256; }
+__host__ __device__ constexpr int row_pitch(int elem, bool flat) { return flat ? (256 + 16 / elem + 128 / elem - 1) / (128 / elem) * (128 / elem) : 256; }
 __host__ __device__ constexpr int ctas_per_sm_of(int mode) { return mode == 1 /* kGlobal */ ? 4 : 2; }
 // Which column of the tile a thread integrates: 0 = thread i takes column i; otherwise the columns
 // are ranked by wet depth across the tile first (sorted_column below).  A warp skips a level when
@@ -95,11 +101,15 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
-  constexpr int kStages = stages_of(MODE);
+  constexpr int kStages = stages_of(MODE, FLAT);
   constexpr int SORT = ML_TMA_SORT;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
-  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kTile * sizeof(TIn);
+  constexpr int kPitch = row_pitch((int)sizeof(TIn), FLAT);   // values between the rows of a stage
+  constexpr int kBox = row_box((int)sizeof(TIn), FLAT);       // values one TMA box brings in
+  constexpr int kUnit = 16 / (int)sizeof(TIn);                // values per 16 bytes
+  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kPitch * sizeof(TIn);   // shared memory of a stage
+  constexpr uint32_t kStageTx = (uint32_t)(kRowsT + kRowsS) * kBox * sizeof(TIn);        // bytes its boxes deliver
   constexpr int kStageFloats = (int)(kStageBytes / sizeof(TIn));
   constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
@@ -134,22 +144,32 @@ __global__ void ML_TMA_KERNEL_ATTR
   auto refill_stage = [&](int z) {
     const int s = z % kStages;
     TIn* dT = stage_base + (size_t)s * kStageFloats;
-    TIn* dS = dT + kRowsT * kTile;
-    mbar_expect_tx(full + s, kStageBytes);
+    TIn* dS = dT + kRowsT * kPitch;
+    mbar_expect_tx(full + s, kStageTx);
     if (FLAT) {
       // Rows that are not a multiple of 16 bytes (ncol % 4 != 0 for fp32): no strided tensor map can describe the
-      // field, but a rank-1 map over the flat array can, and a box may start at any element -- one 1-D box per row
-      // of the stage.  Columns past the end of a row hold the head of the next row (never stored), rows past the
-      // last step lie beyond the map and are zero-filled.
+      // field, but a rank-1 map over the flat array can -- one 1-D box per row of the stage, started at the row's
+      // first value rounded down to 16 bytes (a box must start aligned; flat_off() is what the readers add).
+      // Columns past the end of a row hold the head of the next row (never stored), rows past the last step lie
+      // beyond the map and are zero-filled.
       const i64 row0 = (i64)z * P.ncol + c0, step = (i64)nz * P.ncol;
 #pragma unroll
-      for (int k = 0; k < kRowsT; ++k) tma_load_1d(dT + k * kTile, &mapT, full + s, (int)(row0 + (BC == 1 ? 0 : (i64)(t0 + k) * step)));
+      for (int k = 0; k < kRowsT; ++k)
+        tma_load_1d(dT + k * kPitch, &mapT, full + s, (int)((row0 + (BC == 1 ? 0 : (i64)(t0 + k) * step)) & ~(i64)(kUnit - 1)));
 #pragma unroll
-      for (int k = 0; k < kRowsS; ++k) tma_load_1d(dS + k * kTile, &mapS, full + s, (int)(row0 + (BC == 2 ? 0 : (i64)(t0 + k) * step)));
+      for (int k = 0; k < kRowsS; ++k)
+        tma_load_1d(dS + k * kPitch, &mapS, full + s, (int)((row0 + (BC == 2 ? 0 : (i64)(t0 + k) * step)) & ~(i64)(kUnit - 1)));
       return;
     }
     if (BC == 1) tma_load_2d(dT, &mapT, full + s, c0, z); else tma_load_3d(dT, &mapT, full + s, c0, z, t0);
     if (BC == 2) tma_load_2d(dS, &mapS, full + s, c0, z); else tma_load_3d(dS, &mapS, full + s, c0, z, t0);
+  };
+
+  // FLAT: where the tile's first column sits inside the stage row of (level z, step t) -- the same for every thread
+  // of the CTA, so this is uniform-datapath arithmetic; `fixed` marks a time-invariant operand ([z][col])
+  auto flat_off = [&](int z, int t, bool fixed) -> int {
+    if (!FLAT) return 0;
+    return (int)(((i64)z * P.ncol + c0 + (fixed ? 0 : (i64)t * nz * P.ncol)) & (i64)(kUnit - 1));
   };
 
   if (tid == 0) {
@@ -210,7 +230,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     if (SELFREF) {
       mbar_wait(full + 0, 0u);
       const TIn* row = stage_base + col;
-      sub_n = eos.rho_at((double)row[0], (double)row[kRowsT * kTile], s_p[0]);  // reference.py:60-71
+      sub_n = eos.rho_at((double)row[flat_off(0, t0, BC == 1)], (double)row[kRowsT * kPitch + flat_off(0, t0, BC == 2)], s_p[0]);  // reference.py:60-71
       if (in && P.rho_ref_out) P.rho_ref_out[c] = sub_n;
     }
     for (int z = 0; z < nz; ++z) {
@@ -261,25 +281,26 @@ __global__ void ML_TMA_KERNEL_ATTR
         // caught after the sweep and that column is redone with the skipna rule (repair pass below).
         const int first_wet = __shfl_sync(0xffffffffu, col, __ffs(live_lanes) - 1);  // every lane takes part
         const TIn* sT = stage_base + (size_t)s * kStageFloats + (live ? col : first_wet);
-        const TIn* sS = sT + kRowsT * kTile;
-        if (SELFREF) sub_n = eos.rho_at((double)rowN[0], (double)rowN[kRowsT * kTile], p_next);
+        const TIn* sS = sT + kRowsT * kPitch;
+        if (SELFREF)
+          sub_n = eos.rho_at((double)rowN[flat_off(zn, t0, BC == 1)], (double)rowN[kRowsT * kPitch + flat_off(zn, t0, BC == 2)], p_next);
         // a time-invariant operand is folded into the polynomial's coefficients once per level
         // (thermosteric +15 %, halosteric +16 %)
         typename Eos<EOS>::Pinned pin = {};
-        if (BC == 1) pin = eos.pin_t((double)sT[0]);
-        if (BC == 2) pin = eos.pin_s((double)sS[0]);
+        if (BC == 1) pin = eos.pin_t((double)sT[flat_off(z, 0, true)]);
+        if (BC == 2) pin = eos.pin_s((double)sS[flat_off(z, 0, true)]);
 #pragma unroll
         for (int kk = SELFREF ? 1 : 0; kk < TC; ++kk) {  // kSelfRef: step 0 is the reference itself
           if (MODE == kLocal && kk == 0 && zero_first) continue;  // ... and so it is here, by the caller's word
-          const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kTile];
-          const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kTile];
+          const double Tv = (double)sT[(BC == 1 ? 0 : kk) * kPitch + flat_off(z, t0 + kk, BC == 1)];
+          const double Sv = (double)sS[(BC == 2 ? 0 : kk) * kPitch + flat_off(z, t0 + kk, BC == 2)];
           const double rho = BC == 1 ? eos.rho_pinned_t(pin, Sv) : (BC == 2 ? eos.rho_pinned_s(pin, Tv) : eos.rho(Tv, Sv));
           acc[kk] = fma(w, GLOBAL ? rho : rho - sub, acc[kk]);
         }
       } else if (SELFREF) {
         // a warp without water still owes rho_ref of the next level (reference.py:71 evaluates the
         // EOS everywhere); over land T, S are missing and so is the result -- no arithmetic needed
-        const TIn tN = rowN[0], sN = rowN[kRowsT * kTile];
+        const TIn tN = rowN[flat_off(zn, t0, BC == 1)], sN = rowN[kRowsT * kPitch + flat_off(zn, t0, BC == 2)];
         sub_n = nan("");
         if (__any_sync(0xffffffffu, !(isnan(tN) || isnan(sN)))) sub_n = eos.rho_at((double)tN, (double)sN, p_next);
       }
@@ -402,9 +423,9 @@ static bool rows_aligned(int dtype, int64_t ncol);
 #endif
 
 template <int TC>
-inline size_t smem_bytes(int bc, int nz, int mode, int es) {
-  const int kStages = stages_of(mode);
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * es) + 3 * kStages * sizeof(uint64_t) +
+inline size_t smem_bytes(int bc, int nz, int mode, int es, bool flat) {
+  const int kStages = stages_of(mode, flat);
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * row_pitch(es, flat) * es) + 3 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 
@@ -412,7 +433,7 @@ template <typename TIn, int EOS, int TC, int BC, int MODE, bool FLAT>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
   auto kern = k_steric_tma<TIn, EOS, TC, BC, MODE, FLAT>;
-  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn));
+  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn), FLAT);
   // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
   // is set on every launch (a host-side table lookup) rather than cached in a static
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -470,8 +491,8 @@ static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int 
   bool okT, okS;
   if (P.flat) {
     const i64 lvl = (i64)P.nz * P.ncol;
-    okT = make_flat_map(&g.mT, T, t_bcast ? lvl : lvl * P.nt, kTile, P.es);
-    okS = make_flat_map(&g.mS, S, s_bcast ? lvl : lvl * P.nt, kTile, P.es);
+    okT = make_flat_map(&g.mT, T, t_bcast ? lvl : lvl * P.nt, row_box(P.es, true), P.es);
+    okS = make_flat_map(&g.mS, S, s_bcast ? lvl : lvl * P.nt, row_box(P.es, true), P.es);
   } else {
     okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
     okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
