@@ -33,13 +33,12 @@ namespace tma {
 // rho_ref / dz operands and fits 64 registers, so it runs four CTAs per SM with a 2-level ring (the
 // same bytes in flight per SM): +4.5 % (profiles/r01_experiments.md).  The self-reference mode reads
 // row 0 of the NEXT level while it works on this one and loses 15 % with a 2-level ring.
-__host__ __device__ constexpr int stages_of(int mode, bool flat = false) { return mode == 1 /* kGlobal */ ? 2 : (flat ? 3 : 4); }
-// Row pitch of a stage in values.  FLAT (rows of the grid are not a multiple of 16 bytes): a box must START on 16
-// bytes in global memory, so it starts at the row's address rounded down and is one 16-byte unit wider; a row of the
-// stage then holds its 256 columns at an offset of 0 ... (16 / size - 1) values, and the pitch is the box width
-// rounded up to 128 bytes (the alignment a TMA destination needs).
-__host__ __device__ constexpr int row_box(int elem, bool flat) { return flat ? 256 + 16 / elem : 256; }
-__host__ __device__ constexpr int row_pitch(int elem, bool flat) { return flat ? (256 + 16 / elem + 128 / elem - 1) / (128 / elem) * (128 / elem) : 256; }
+__host__ __device__ constexpr int stages_of(int mode) { return mode == 1 /* kGlobal */ ? 2 : 4; }
+// Columns a CTA owns.  FLAT (rows of the grid are not a multiple of 16 bytes): a TMA box must START on 16 bytes in
+// global memory and holds at most 256 values, so it starts at the row's address rounded down, and the CTA owns the
+// 256 - (16 / size) columns that are inside the box whatever the row's misalignment (252 for fp32, 254 for fp64);
+// the readers add the row's offset of 0 ... (16 / size - 1) values, the last few threads have no column.
+__host__ __device__ constexpr int cols_of(int elem, bool flat) { return flat ? 256 - 16 / elem : 256; }
 __host__ __device__ constexpr int ctas_per_sm_of(int mode) { return mode == 1 /* kGlobal */ ? 4 : 2; }
 // Which column of the tile a thread integrates: 0 = thread i takes column i; otherwise the columns
 // are ranked by wet depth across the tile first (sorted_column below).  A warp skips a level when
@@ -101,15 +100,15 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
-  constexpr int kStages = stages_of(MODE, FLAT);
+  constexpr int kStages = stages_of(MODE);
   constexpr int SORT = ML_TMA_SORT;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
-  constexpr int kPitch = row_pitch((int)sizeof(TIn), FLAT);   // values between the rows of a stage
-  constexpr int kBox = row_box((int)sizeof(TIn), FLAT);       // values one TMA box brings in
+  constexpr int kPitch = kTile;                               // values between the rows of a stage = one box
   constexpr int kUnit = 16 / (int)sizeof(TIn);                // values per 16 bytes
-  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kPitch * sizeof(TIn);   // shared memory of a stage
-  constexpr uint32_t kStageTx = (uint32_t)(kRowsT + kRowsS) * kBox * sizeof(TIn);        // bytes its boxes deliver
+  constexpr int kCols = cols_of((int)sizeof(TIn), FLAT);      // columns this CTA owns
+  constexpr uint32_t kStageBytes = (uint32_t)(kRowsT + kRowsS) * kPitch * sizeof(TIn);
+  constexpr uint32_t kStageTx = kStageBytes;
   constexpr int kStageFloats = (int)(kStageBytes / sizeof(TIn));
   constexpr int kRed = GLOBAL ? TC : 2;  // values reduced across the CTA at the end
 
@@ -133,7 +132,7 @@ __global__ void ML_TMA_KERNEL_ATTR
   // time-invariant rows they all read (rho_ref, v_ref, a broadcast operand) come from HBM once and
   // from L2 for the others; with the tiles fastest those rows were re-read from HBM for every chunk.
   const unsigned tile = blockIdx.x / P.nchunks;
-  const int c0 = (int)tile * kTile;
+  const int c0 = (int)tile * kCols;
   const int t0 = P.t_start + (int)(blockIdx.x - tile * P.nchunks) * TC;
   const int nz = P.nz;
 
@@ -193,19 +192,20 @@ __global__ void ML_TMA_KERNEL_ATTR
     // key = number of wet levels of the column: levels above the sea floor (local modes) or levels
     // whose reference volume is present (global mode, which has no deptho)
     const i64 cg = (i64)c0 + tid;
+    const bool owned = tid < kCols && cg < P.ncol;  // (FLAT: the last few threads of a CTA have no column)
     int key = 0;
     if (GLOBAL) {
-      if (cg < P.ncol)
+      if (owned)
         for (int z = 0; z < nz; ++z) key += vraw_isnan(ld_vraw(gV, (i64)z * P.ncol + cg)) ? 0 : 1;
     } else {
-      key = wet_levels(cg < P.ncol ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
+      key = wet_levels(owned ? __ldg(P.deptho + cg) : 0.0, s_zi, nz);
     }
     col = sorted_column(key, reinterpret_cast<unsigned*>(s_key), s_col);
   }
 
   {
     const i64 c = (i64)c0 + col;
-    const bool in = c < P.ncol;
+    const bool in = col < kCols && c < P.ncol;
     const i64 cc = in ? c : (P.ncol - 1);  // clamp: edge lanes read a valid column, never store
     Eos<EOS> eos;
     double acc[TC];
@@ -423,9 +423,9 @@ static bool rows_aligned(int dtype, int64_t ncol);
 #endif
 
 template <int TC>
-inline size_t smem_bytes(int bc, int nz, int mode, int es, bool flat) {
-  const int kStages = stages_of(mode, flat);
-  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * row_pitch(es, flat) * es) + 3 * kStages * sizeof(uint64_t) +
+inline size_t smem_bytes(int bc, int nz, int mode, int es) {
+  const int kStages = stages_of(mode);
+  return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * es) + 3 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
 
@@ -433,7 +433,7 @@ template <typename TIn, int EOS, int TC, int BC, int MODE, bool FLAT>
 static int launch_one(const CUtensorMap& mT, const CUtensorMap& mS, const Params& P, unsigned tiles, unsigned chunks,
                       cudaStream_t st) {
   auto kern = k_steric_tma<TIn, EOS, TC, BC, MODE, FLAT>;
-  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn), FLAT);
+  const size_t smem = smem_bytes<TC>(BC, P.nz, MODE, (int)sizeof(TIn));
   // opt in to > 48 KB of dynamic shared memory; the attribute is per device and per context, so it
   // is set on every launch (a host-side table lookup) rather than cached in a static
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -469,6 +469,10 @@ struct Segment {
   unsigned chunks;
 };
 
+static unsigned tiles_of(const Params& P) {
+  const int cols = cols_of(P.es, P.flat != 0);
+  return (unsigned)((P.ncol + cols - 1) / cols);
+}
 static int main_tc(int es) { return es == 4 ? 12 : 6; }
 static int remainder_tc(int steps, int es) {
   if (es == 4) return steps <= 4 ? 4 : (steps <= 8 ? 8 : 12);
@@ -491,8 +495,8 @@ static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int 
   bool okT, okS;
   if (P.flat) {
     const i64 lvl = (i64)P.nz * P.ncol;
-    okT = make_flat_map(&g.mT, T, t_bcast ? lvl : lvl * P.nt, row_box(P.es, true), P.es);
-    okS = make_flat_map(&g.mS, S, s_bcast ? lvl : lvl * P.nt, row_box(P.es, true), P.es);
+    okT = make_flat_map(&g.mT, T, t_bcast ? lvl : lvl * P.nt, kTile, P.es);
+    okS = make_flat_map(&g.mS, S, s_bcast ? lvl : lvl * P.nt, kTile, P.es);
   } else {
     okT = t_bcast ? make_map(&g.mT, T, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mT, T, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
     okS = s_bcast ? make_map(&g.mS, S, 2, P.ncol, P.nz, 1, 1, kTile, P.es) : make_map(&g.mS, S, 3, P.ncol, P.nz, P.nt, tc, kTile, P.es);
@@ -503,7 +507,7 @@ static int add_segment(Plan* pl, const void* T, const void* S, int t_bcast, int 
 // segments covering the time steps [t_begin, nt)
 static int make_plan(Plan* pl, const void* T, const void* S, int t_bcast, int s_bcast, const Params& P, int t_begin) {
   pl->bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
-  pl->tiles = (unsigned)((P.ncol + kTile - 1) / kTile);
+  pl->tiles = tiles_of(P);
   pl->nseg = 0;
   const int mtc = main_tc(P.es);
   const int steps = P.nt - t_begin, full = steps / mtc, rest = steps % mtc;
@@ -620,7 +624,7 @@ int launch_selfref(int eos, const void* T, const void* S, int t_bcast, int s_bca
   // the chunk that starts at the reference step: rho_ref, volo, masso and eta in one pass
   Plan first;
   first.bc = t_bcast ? 1 : (s_bcast ? 2 : 0);
-  first.tiles = (unsigned)((ncol + kTile - 1) / kTile);
+  first.tiles = tiles_of(P);
   first.nseg = 0;
   const int tc0 = nt >= main_tc(P.es) ? main_tc(P.es) : remainder_tc(nt, P.es);
   int rc = add_segment(&first, T, S, t_bcast, s_bcast, P, tc0, 0, 1u);
