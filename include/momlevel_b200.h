@@ -190,8 +190,8 @@ int ml_delta_rho_annual(int eos, int dtype, const void* T, const void* S, int t_
  *   v_ref       [nz][ncol] volcello at step 0
  *   rho_ref     [nz][ncol] fp64 out;  sums device fp64[2] out {volo, masso}
  *               rho_ref may be NULL when the caller does not need the field and one fused chunk serves the
- *               call (16-byte aligned fields with volcello stored alike, rows a multiple of 16 bytes,
- *               ncol >= 256, nt <= 12 for fp32 storage or <= 6 for fp64): the store is
+ *               call (16-byte aligned fields with volcello stored alike, ncol >= 256, nt <= 12 for fp32
+ *               storage or <= 6 for fp64): the store is
  *               7 % of the traffic of a 12-step call, and ml_reference_state produces the field on demand.
  *               Any other call with rho_ref == NULL returns ML_ERR_NULL.
  * ------------------------------------------------------------------------------------- */
