@@ -352,8 +352,12 @@ int ml_host_release(void);
  *                                       written with ordinary stores (meant to stay in the last-level cache,
  *                                       so that the packed bytes never touch DRAM), 4 = as 3 but a row goes
  *                                       as it is only while no packed row is waiting for the copy stream
- *                                       (checked on the simulated runtime only; not yet measured); threads <= 0 keeps
- *                                       the default (half the calling thread's CPU affinity count).
+ *                                       (modes 3 and 4 measured slower than 1: profiles/r02_experiments.md).
+ *                                       threads <= 0 leaves the number of packing threads to the library: it starts
+ *                                       from half the calling thread's CPU affinity count divided by the ranks on the
+ *                                       host (LOCAL_WORLD_SIZE) and, in mode 1, times every window on the copy stream
+ *                                       and settles on the fastest of {that, none, twice, half} for this machine and
+ *                                       load (kept per host thread between calls, tried afresh every 256 windows).
  *                                       Applies to the calling host thread.
  *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed
  *   ml_host_last_h2d_bytes()            bytes the last host call of this thread copied host -> device
@@ -370,6 +374,8 @@ int ml_host_release(void);
  * ------------------------------------------------------------------------------------- */
 int ml_host_set_packing(int mode, int threads);
 double ml_host_last_packed_fraction(void);
+/* packing threads of the calling thread's last window (what the tuner of ml_host_set_packing(1, 0) has settled on) */
+int ml_host_last_pack_threads(void);
 uint64_t ml_host_last_h2d_bytes(void);
 int ml_host_last_timings(double* ms4);
 uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t ncol, uint32_t* words,

@@ -53,6 +53,7 @@ EXPORTS = {
     "ml_host_release": (_i, []),
     "ml_host_set_packing": (_i, [_i, _i]),
     "ml_host_last_packed_fraction": (_d, []),
+    "ml_host_last_pack_threads": (_i, []),
     "ml_host_last_h2d_bytes": (ctypes.c_uint64, []),
     "ml_host_last_timings": (_i, [_vp]),
     "ml_pack_index_rows": (ctypes.c_uint64, [_vp, _i64, _i64, _vp, _vp, _vp]),

@@ -29,6 +29,7 @@ __all__ = [
     "host_last_transfer",
     "host_pack_simd",
     "host_last_timings",
+    "host_last_pack_threads",
     "last_path",
     "launch_count",
     "force_direct",
@@ -625,6 +626,11 @@ def host_last_transfer():
     """``(host->device bytes, share of level rows that crossed packed)`` of this thread's last ``*_host`` call."""
     L = _lib.lib()
     return int(L.ml_host_last_h2d_bytes()), float(L.ml_host_last_packed_fraction())
+
+
+def host_last_pack_threads():
+    """Packing threads of this thread's last window: with ``host_packing(1, 0)`` the library tunes the number itself."""
+    return int(_lib.lib().ml_host_last_pack_threads())
 
 
 def host_last_timings():

@@ -107,6 +107,45 @@ enum HostSlot {
   kHostSlots_
 };
 
+// How many threads pack, when the caller leaves it to the library (ml_host_set_packing(1, 0)).  Packing trades host
+// memory bandwidth for PCIe bytes, and which of the two runs out first depends on the machine and on who else is
+// using it (one rank of four packed SLOWER than plain copies on a box where four ranks still get the full PCIe rate
+// each; one or two ranks, or eight, did not).  So the library measures: every window's span on the copy stream is
+// timed with events, the first windows try {default, none, twice, half} the default thread count for two windows
+// each, and the rest run with whatever was fastest per step; the table lives with the thread's Resources, so later
+// calls start from it, and it is tried afresh every kRetry windows.
+struct PackTuner {
+  static constexpr int kChoices = 4;
+  static constexpr int kRetry = 256;
+  int64_t nz = 0, ncol = 0;        // the table belongs to this grid
+  int threads[kChoices] = {0, 0, 0, 0};
+  double ms_per_step[kChoices] = {-1.0, -1.0, -1.0, -1.0};
+  int64_t windows = 0;
+  void reset(int64_t nz_, int64_t ncol_, int dflt, int cap) {
+    nz = nz_;
+    ncol = ncol_;
+    threads[0] = dflt;
+    threads[1] = 0;
+    threads[2] = std::min(std::max(2 * dflt, 1), std::max(cap, 1));
+    threads[3] = std::max(dflt / 2, 1);
+    for (double& m : ms_per_step) m = -1.0;
+    windows = 0;
+  }
+  int choose() {  // which entry of threads[] the next window runs with
+    const int64_t w = windows++ % kRetry;
+    if (w < 2 * kChoices) return (int)(w / 2);
+    int best = 0;
+    for (int i = 1; i < kChoices; ++i)
+      if (ms_per_step[i] >= 0.0 && (ms_per_step[best] < 0.0 || ms_per_step[i] < ms_per_step[best])) best = i;
+    return best;
+  }
+  void report(int choice, double ms, int64_t steps) {
+    if (choice < 0 || steps <= 0 || ms <= 0.0) return;
+    const double v = ms / (double)steps;
+    ms_per_step[choice] = ms_per_step[choice] < 0.0 ? v : 0.5 * (ms_per_step[choice] + v);
+  }
+};
+
 struct Resources {
   static constexpr int kSlots = kDevSlots;
   static constexpr int kHostSlots = kHostSlots_;
@@ -120,6 +159,11 @@ struct Resources {
   cudaStream_t copy = nullptr, comp = nullptr, back = nullptr;  // host->device, kernels, device->host
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
   cudaEvent_t out_done[2] = {nullptr, nullptr};  // the outputs of a window of this parity have reached the host
+  cudaEvent_t win_start[2] = {nullptr, nullptr};  // the copy stream has reached this window (timed, with copied[])
+  PackTuner tuner;
+  int tuned_choice[2] = {-1, -1};  // what the window of this parity ran with, for the tuner's report
+  int64_t tuned_steps[2] = {0, 0};
+  int last_pack_threads = 0;
   cudaEvent_t ring[kRing] = {nullptr};
   cudaEvent_t slot_done[kStageRing] = {nullptr};  // the copies out of a slot of the staging ring have finished
   Pool pool;
@@ -144,7 +188,8 @@ struct Resources {
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (freed[i]) cudaEventDestroy(freed[i]);
       if (out_done[i]) cudaEventDestroy(out_done[i]);
-      copied[i] = freed[i] = out_done[i] = nullptr;
+      if (win_start[i]) cudaEventDestroy(win_start[i]);
+      copied[i] = freed[i] = out_done[i] = win_start[i] = nullptr;
     }
     for (int i = 0; i < kRing; ++i) {
       if (ring[i]) cudaEventDestroy(ring[i]);
@@ -173,7 +218,8 @@ struct Resources {
     if (!comp && (e = cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking)) != cudaSuccess) return e;
     if (!back && (e = cudaStreamCreateWithFlags(&back, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (int b = 0; b < 2; ++b) {
-      if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming)) != cudaSuccess) return e;
+      if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], 0)) != cudaSuccess) return e;  // timed: the tuner reads the span
+      if (!win_start[b] && (e = cudaEventCreateWithFlags(&win_start[b], 0)) != cudaSuccess) return e;
       if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if (!out_done[b] && (e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
@@ -298,6 +344,7 @@ struct PackPlan {
   uint8_t *flags[2] = {nullptr, nullptr}, *d_flags[2] = {nullptr, nullptr};  // [t][z]: 1 = row crossed packed
   int64_t rows_total = 0, rows_packed = 0;
   bool all_staged = false;  // pageable source: no row is copied straight from the caller's buffer
+  bool tuned = false;       // the number of packing threads is the library's to choose, window by window (PackTuner)
   // mode 3: packed rows wait for the copy engine in a ring of kStageRing row slots (T half, S half) that is
   // small enough to stay in the last-level cache, instead of in staging the size of the window
   bool ring = false;
@@ -375,6 +422,12 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   plan.ncol = ncol;
   plan.ngrp = (ncol + 31) / 32;
   plan.threads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
+  plan.tuned = r.pack_mode == 1 && r.pack_threads <= 0;
+  if (plan.tuned) {
+    const int cap = std::max(1, std::min(2 * default_threads(), 64));  // all the cores of this rank's share
+    if (r.tuner.nz != nz || r.tuner.ncol != ncol || r.tuner.threads[0] != default_threads()) r.tuner.reset(nz, ncol, default_threads(), cap);
+    plan.threads = std::max(plan.threads, r.tuner.threads[2]);  // the pool holds the largest choice
+  }
   plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / kSegmentGroups));
   const size_t nw = (size_t)nz * (size_t)plan.ngrp;
   void *hw, *hb, *hl;
@@ -488,6 +541,27 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   }
   // the staging of this parity was last read by the copies of window w - 2
   if (w >= 2) ML_CUDA(cudaEventSynchronize(r.copied[b]));
+  // how many threads pack this window: the caller's number, or -- left to the library -- what the tuner has found
+  // fastest on this machine, under this load (PackTuner); a pageable source is staged in full whatever it says
+  const bool tuned = plan.tuned && !plan.all_staged;
+  int active = plan.threads;
+  if (tuned) {
+    if (w >= 2 && r.tuned_choice[b] >= 0) {  // the span of window w - 2 on the copy stream is known now
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, r.win_start[b], r.copied[b]) == cudaSuccess)
+        r.tuner.report(r.tuned_choice[b], (double)ms, r.tuned_steps[b]);
+      else
+        cudaGetLastError();
+    }
+    const int choice = r.tuner.choose();
+    active = std::min(r.tuner.threads[choice], plan.threads);
+    r.tuned_choice[b] = choice;
+    r.tuned_steps[b] = nt_w;
+    ML_CUDA(cudaEventRecord(r.win_start[b], r.copy));
+  } else {
+    r.tuned_choice[b] = -1;
+  }
+  r.last_pack_threads = active;
 
   const float* Th = (const float*)T_w;
   const float* Sh = (const float*)S_w;
@@ -517,7 +591,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   float *stT = plan.stage[b][0], *stS = plan.stage[b][1];
   float *dpT = plan.d_packed[b][0], *dpS = plan.d_packed[b][1];
 
-  r.pool.start(plan.threads, [&, dev](int) {
+  r.pool.start(active, [&, dev](int) {
     cudaSetDevice(dev);
     for (;;) {
       int pos, seg, slot;
@@ -660,6 +734,8 @@ extern "C" int ml_host_set_packing(int mode, int threads) {
 }
 
 extern "C" double ml_host_last_packed_fraction(void) { return resources().last_packed_fraction; }
+
+extern "C" int ml_host_last_pack_threads(void) { return resources().last_pack_threads; }
 
 extern "C" uint64_t ml_host_last_h2d_bytes(void) { return resources().h2d_bytes.load(); }
 

@@ -14,7 +14,7 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_sizes", "assign_members", "assign_member_blocks", "gather_series",
-           "global_sea_level", "steric_global_sharded", "steric_local_members", "steric_local_pieces",
+           "global_sea_level", "steric_global_sharded", "finish_global_series", "steric_local_members", "steric_local_pieces",
            "bind_host_to_device", "local_world_size"]
 
 
@@ -145,6 +145,14 @@ def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_su
         return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
     mine = ref_sums if ref_sums is not None else torch.zeros(2, dtype=masso_local.dtype, device=masso_local.device)
     masso, extras = gather_series(masso_local, n_total, group=group, extra=mine.to(masso_local.device))
+    return finish_global_series(masso, extras, area_sum)
+
+
+def finish_global_series(masso, extras, area_sum):
+    """The host end of :func:`steric_global_sharded`: one read-back of the gathered series and the scalars that rode
+    with it, then the ``ln`` formula (steric.py:136-142).  ``extras`` is ``[world, 2]``: ``{volo, masso_ref}`` from the
+    rank that owns step 0, zeros from the others."""
+    n_total = masso.numel()
     host = torch.cat([masso, extras.reshape(-1)]).cpu().numpy()  # one read-back
     masso_h, extras_h = host[:n_total], host[n_total:].reshape(-1, 2)
     owner = int(np.argmax(extras_h[:, 0] != 0.0))  # the rank that holds step 0 (volo > 0)

@@ -89,6 +89,7 @@ struct Event {
   std::mutex m;
   std::condition_variable cv;
   uint64_t recorded = 0, completed = 0;
+  std::chrono::steady_clock::time_point when;  // of the last completion (cudaEventElapsedTime)
   void wait_for(uint64_t n) {
     std::unique_lock<std::mutex> l(m);
     cv.wait(l, [&] { return completed >= n; });
@@ -168,6 +169,7 @@ inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t s) {
     {
       std::lock_guard<std::mutex> l(e->m);
       if (e->completed < n) e->completed = n;
+      e->when = std::chrono::steady_clock::now();
     }
     e->cv.notify_all();
   });
@@ -180,6 +182,21 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t e) {
     n = e->recorded;
   }
   e->wait_for(n);
+  return cudaSuccess;
+}
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
+  std::chrono::steady_clock::time_point ta, tb;
+  {
+    std::lock_guard<std::mutex> l(a->m);
+    if (a->completed < a->recorded || a->recorded == 0) return cudaErrorNotReady;
+    ta = a->when;
+  }
+  {
+    std::lock_guard<std::mutex> l(b->m);
+    if (b->completed < b->recorded || b->recorded == 0) return cudaErrorNotReady;
+    tb = b->when;
+  }
+  *ms = std::chrono::duration<float, std::milli>(tb - ta).count();
   return cudaSuccess;
 }
 inline cudaError_t cudaEventQuery(cudaEvent_t e) {

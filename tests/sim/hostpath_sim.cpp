@@ -209,10 +209,10 @@ int main() {
       if (sh.pattern == 2) packable = 0;  // nothing present at all: the library does not bother (every row as it is)
       const int spws[] = {1, 2, (int)nt};
       for (int mode = 0; mode <= 4; ++mode)
-        for (int threads : {1, 3, 7})
+        for (int threads : {0, 1, 3, 7})  // 0: the library tunes the number of packing threads window by window
           for (int spw : spws)
             for (int slow = 0; slow < 2; ++slow) {
-              if (mode == 0 && threads != 1) continue;
+              if ((mode == 0 && threads != 1) || (mode != 1 && threads == 0)) continue;
               simcuda::copy_ns_per_kib() = slow ? 300 : 0;
               ml_host_set_packing(mode, threads);
               double sums[2] = {0, 0};
@@ -259,11 +259,11 @@ int main() {
         double* out_s[3];
         for (auto& o : out_s) o = alloc<double>((size_t)nt * ncol, pinned);
         for (int mode : {0, 1, 2, 4})
-          for (int threads : {1, 3})
+          for (int threads : {0, 1, 3})
             for (int domain = 0; domain < 2; ++domain)
               for (int supplied = 0; supplied < 2; ++supplied)
                 for (int slow = 0; slow < 2; ++slow) {
-                  if (mode == 0 && threads != 1) continue;
+                  if ((mode == 0 && threads != 1) || (mode != 1 && threads == 0)) continue;
                   simcuda::copy_ns_per_kib() = slow ? 300 : 0;
                   ml_host_set_packing(mode, threads);
                   for (auto& o : out_s) memset(o, 0, (size_t)nt * ncol * sizeof(double));

