@@ -29,6 +29,25 @@ def test_shard_sizes():
     assert mld.assign_members(30, 8, 6) == [24, 25, 26]
 
 
+def test_member_blocks_balance_and_cover():
+    """Config 3 cut by (member, 12-step block): contiguous shares that differ by at most one block, cover every block
+    once, and keep the blocks of one member on a rank together (whole members would leave 4,4,4,4,4,4,3,3)."""
+    for n_members, nt, world in [(30, 120, 8), (30, 120, 4), (30, 120, 1), (7, 25, 3), (2, 5, 5)]:
+        per = -(-nt // 12)
+        seen = []
+        loads = []
+        for r in range(world):
+            pieces = mld.assign_member_blocks(n_members, nt, world, r)
+            loads.append(sum(-(-(t1 - t0) // 12) for _, t0, t1 in pieces))
+            for m, t0, t1 in pieces:
+                assert 0 <= t0 < t1 <= nt and t0 % 12 == 0
+                seen += [(m, b) for b in range(t0 // 12, -(-t1 // 12))]
+        assert sorted(seen) == [(m, b) for m in range(n_members) for b in range(per)]
+        assert max(loads) - min(loads) <= 1
+    assert [sum(-(-(t1 - t0) // 12) for _, t0, t1 in mld.assign_member_blocks(30, 120, 8, r)) for r in range(8)] == \
+        [38, 38, 38, 38, 37, 37, 37, 37]
+
+
 def test_gather_series_without_process_group():
     x = torch.arange(5, dtype=torch.float64)
     assert torch.equal(mld.gather_series(x, 5), x)
@@ -52,6 +71,12 @@ def _worker(rank, world, port, nt, out_dir):
         _, _, masso_local = osteric.steric_global(d["thetao"][lo:hi], d["so"][lo:hi], d["z_l"], ref)
         masso = mld.gather_series(torch.from_numpy(np.ascontiguousarray(masso_local)), nt)
         eta, href = mld.global_sea_level(masso.numpy(), ref["volo"], ref["rhoga"], np.nansum(ref["areacello"]))
+        # the same with the scalars of the reference state riding in the gather: only the rank that owns step 0 has them
+        sums = torch.tensor([ref["volo"], ref["masso"]], dtype=torch.float64) if lo == 0 else None
+        eta2, href2 = mld.steric_global_sharded(None, None, None, None, None, None, np.nansum(ref["areacello"]), nt,
+                                                masso_local=torch.from_numpy(np.ascontiguousarray(masso_local)),
+                                                ref_sums=sums)
+        assert np.array_equal(eta2, eta) and href2 == href
         np.save(os.path.join(out_dir, f"eta_{rank}.npy"), eta)
         np.save(os.path.join(out_dir, f"href_{rank}.npy"), href)
     finally:
