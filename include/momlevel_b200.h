@@ -357,12 +357,16 @@ int ml_host_release(void);
  *                                       from half the calling thread's CPU affinity count divided by the ranks on the
  *                                       host (LOCAL_WORLD_SIZE) and, in mode 1, times every window on the copy stream
  *                                       and settles on the fastest of {that, none, twice, half} for this machine and
- *                                       load (kept per host thread between calls, tried afresh every 256 windows).
+ *                                       load (kept per host thread between calls, tried afresh every 256 windows);
+ *                                       a call that starts while "none" is in front moves every row as it is and does
+ *                                       not build the presence index either.
  *                                       Applies to the calling host thread.
  *   ml_host_last_packed_fraction()      share of the level rows of the last host call that crossed packed
  *   ml_host_last_h2d_bytes()            bytes the last host call of this thread copied host -> device
  *   ml_host_last_timings(ms4)           host wall time of the last ml_steric_local*_host call, milliseconds:
- *                                       presence index, windows, drain (kernels of the last window + read-back), whole call
+ *                                       presence index (made on the device behind the upload of volcello and read
+ *                                       back: k_presence_words / k_presence_before), windows, drain (kernels of the
+ *                                       last window + read-back), whole call
  * The two loops underneath are exported for testing (csrc/ml_pack.cpp, no CUDA inside):
  *   ml_pack_index_rows  v [nrows][ncol] fp32 -> words / before [nrows][ceil(ncol/32)]: bit i of a word
  *                       = column 32 g + i is not NaN; before = present cells of the row in front of the

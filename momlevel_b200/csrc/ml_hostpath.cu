@@ -134,10 +134,20 @@ struct PackTuner {
   int choose() {  // which entry of threads[] the next window runs with
     const int64_t w = windows++ % kRetry;
     if (w < 2 * kChoices) return (int)(w / 2);
-    int best = 0;
+    return best();
+  }
+  int best() const {
+    int b = 0;
     for (int i = 1; i < kChoices; ++i)
-      if (ms_per_step[i] >= 0.0 && (ms_per_step[best] < 0.0 || ms_per_step[i] < ms_per_step[best])) best = i;
-    return best;
+      if (ms_per_step[i] >= 0.0 && (ms_per_step[b] < 0.0 || ms_per_step[i] < ms_per_step[b])) b = i;
+    return b;
+  }
+  // Past the trial windows with plain copies in front: a call that starts now does not even build the presence
+  // index.  Its windows are counted by idle_window(), which stops at the next multiple of kRetry, so that the call
+  // after that one tries the choices again.
+  bool settled_on_none() const { return windows % kRetry >= 2 * kChoices && threads[best()] == 0 && ms_per_step[best()] >= 0.0; }
+  void idle_window() {
+    if (windows % kRetry != 0) ++windows;
   }
   void report(int choice, double ms, int64_t steps) {
     if (choice < 0 || steps <= 0 || ms <= 0.0) return;
@@ -345,6 +355,7 @@ struct PackPlan {
   int64_t rows_total = 0, rows_packed = 0;
   bool all_staged = false;  // pageable source: no row is copied straight from the caller's buffer
   bool tuned = false;       // the number of packing threads is the library's to choose, window by window (PackTuner)
+  bool tuned_off = false;   // ... and it has settled on none: this call moves every row as it is, without an index
   // mode 3: packed rows wait for the copy engine in a ring of kStageRing row slots (T half, S half) that is
   // small enough to stay in the last-level cache, instead of in staging the size of the window
   bool ring = false;
@@ -399,6 +410,68 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const float* __restrict__ p
   }
 }
 
+// The presence index of the reference volcello, made where the volume is going anyway: one 32-column word per
+// group (bit = the cell is not NaN, as ml_pack_index_rows has it), the count of present cells in front of each
+// group of its level, and the count of each level.  466 MB of an OM4p25 volume take ~0.1 ms here against 6 ms of
+// eight host threads -- 20 ms when four ranks scan at once -- and the host's memory system is what the packed
+// transfer is short of.
+__global__ void __launch_bounds__(256) k_presence_words(const float* __restrict__ v, uint32_t* __restrict__ words,
+                                                         int64_t ncol, int64_t ngrp) {
+  const int64_t g = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (g >= ngrp) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t z = blockIdx.y, col = g * 32 + lane;
+  bool here = false;
+  if (col < ncol) here = (__float_as_uint(v[(size_t)z * (size_t)ncol + (size_t)col]) & 0x7fffffffu) <= 0x7f800000u;
+  const uint32_t m = __ballot_sync(0xffffffffu, here);
+  if (lane == 0) words[(size_t)z * (size_t)ngrp + (size_t)g] = m;
+}
+
+__global__ void __launch_bounds__(1024) k_presence_before(const uint32_t* __restrict__ words, uint32_t* __restrict__ before,
+                                                           uint64_t* __restrict__ count, int64_t ngrp) {
+  __shared__ uint32_t warp_sum[32];
+  const uint32_t* w = words + (size_t)blockIdx.x * (size_t)ngrp;
+  uint32_t* b = before + (size_t)blockIdx.x * (size_t)ngrp;
+  const int64_t per = (ngrp + 1023) / 1024;
+  const int64_t g0 = min((int64_t)threadIdx.x * per, ngrp), g1 = min(g0 + per, ngrp);
+  uint32_t mine = 0;
+  for (int64_t g = g0; g < g1; ++g) mine += __popc(w[g]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t x = warp_sum[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += up;
+    }
+    warp_sum[lane] = x;
+  }
+  __syncthreads();
+  uint32_t run = incl - mine + (warp ? warp_sum[warp - 1] : 0u);
+  for (int64_t g = g0; g < g1; ++g) {
+    b[g] = run;
+    run += __popc(w[g]);
+  }
+  if (threadIdx.x == 1023) count[blockIdx.x] = run;
+}
+
+int launch_presence_index(cudaStream_t stream, const float* v, int64_t nz, int64_t ncol, int64_t ngrp, uint32_t* words,
+                          uint32_t* before, uint64_t* count) {
+  k_presence_words<<<dim3((unsigned)((ngrp + 7) / 8), (unsigned)nz), 256, 0, stream>>>(v, words, ncol, ngrp);
+  int rc = ml::launched("k_presence_words");
+  if (rc) return rc;
+  k_presence_before<<<(unsigned)nz, 1024, 0, stream>>>(words, before, count, ngrp);
+  return ml::launched("k_presence_before");
+}
+
 int launch_unpack(cudaStream_t stream, int nrows, int xblocks, const float* pT, const float* pS, float* T, float* S,
                   const uint32_t* words, const uint32_t* before, const uint64_t* lvloff, const uint8_t* flags, int nz,
                   int64_t ncol, int64_t ngrp, uint64_t nwet) {
@@ -411,13 +484,15 @@ int launch_unpack(cudaStream_t stream, int nrows, int xblocks, const float* pT, 
 // Presence words of the reference volcello, the device copies of them and the staging buffers.
 // Leaves plan.on false (every row crosses as it is) when packing is off, cannot help or cannot get
 // its pinned memory.
-int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_t nz, int64_t ncol, int64_t spw,
+int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* d_v0, int64_t nz, int64_t ncol, int64_t spw,
                  bool allowed, bool pageable) {
   using namespace ml;
   plan.on = false;
   plan.mode = r.pack_mode;
   plan.all_staged = false;
+  plan.tuned_off = false;
   if (!allowed || plan.mode == 0 || dtype != ML_F32) return ML_OK;
+  if (nz > 65535) return ML_OK;  // a level is a grid row of the index kernels
   plan.nz = nz;
   plan.ncol = ncol;
   plan.ngrp = (ncol + 31) / 32;
@@ -427,6 +502,11 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
     const int cap = std::max(1, std::min(2 * default_threads(), 64));  // all the cores of this rank's share
     if (r.tuner.nz != nz || r.tuner.ncol != ncol || r.tuner.threads[0] != default_threads()) r.tuner.reset(nz, ncol, default_threads(), cap);
     plan.threads = std::max(plan.threads, r.tuner.threads[2]);  // the pool holds the largest choice
+    if (!pageable && r.tuner.settled_on_none()) {
+      plan.tuned_off = true;
+      r.last_pack_threads = 0;
+      return ML_OK;
+    }
   }
   plan.nseg = (int)std::max<int64_t>(1, std::min<int64_t>(64, plan.ngrp / kSegmentGroups));
   const size_t nw = (size_t)nz * (size_t)plan.ngrp;
@@ -440,21 +520,29 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
   plan.before = (uint32_t*)hb;
   plan.lvloff = (uint64_t*)hl;
   r.pool.ensure(plan.threads);
-  std::vector<uint64_t> cnt((size_t)nz);
+  // the index is made on the device, behind the upload of the volume on the copy stream, and comes back for the
+  // packers; lvloff[1 ...] receives the level counts and is summed in place
+  void *dw, *db, *dl;
+  ML_CUDA(r.alloc(kDevWords, &dw, nw * 4));
+  ML_CUDA(r.alloc(kDevBefore, &db, nw * 4));
+  ML_CUDA(r.alloc(kDevLvlOff, &dl, (size_t)(nz + 1) * 8));
+  plan.d_words = (uint32_t*)dw;
+  plan.d_before = (uint32_t*)db;
+  plan.d_lvloff = (uint64_t*)dl;
   {
-    std::atomic<int64_t> next{0};
-    const float* v = (const float*)v0;
-    r.pool.start(plan.threads, [&](int) {
-      for (;;) {
-        const int64_t z = next.fetch_add(1);
-        if (z >= nz) break;
-        ml_pack_index_rows(v + z * ncol, 1, ncol, plan.words + z * plan.ngrp, plan.before + z * plan.ngrp, &cnt[z]);
-      }
-    });
-    r.pool.wait();
+    int rc = launch_presence_index(r.copy, (const float*)d_v0, nz, ncol, plan.ngrp, plan.d_words, plan.d_before, plan.d_lvloff + 1);
+    if (rc) return rc;
   }
+  ML_CUDA(cudaMemcpyAsync(plan.words, dw, nw * 4, cudaMemcpyDeviceToHost, r.copy));
+  ML_CUDA(cudaMemcpyAsync(plan.before, db, nw * 4, cudaMemcpyDeviceToHost, r.copy));
+  ML_CUDA(cudaMemcpyAsync(plan.lvloff + 1, plan.d_lvloff + 1, (size_t)nz * 8, cudaMemcpyDeviceToHost, r.copy));
+  ML_CUDA(cudaStreamSynchronize(r.copy));
+  std::vector<uint64_t> cnt((size_t)nz);
   plan.lvloff[0] = 0;
-  for (int64_t z = 0; z < nz; ++z) plan.lvloff[z + 1] = plan.lvloff[z] + cnt[z];
+  for (int64_t z = 0; z < nz; ++z) {
+    cnt[z] = plan.lvloff[z + 1];
+    plan.lvloff[z + 1] = plan.lvloff[z] + cnt[z];
+  }
   plan.nwet = plan.lvloff[nz];
   plan.order.resize((size_t)nz);
   for (int64_t z = 0; z < nz; ++z) plan.order[z] = (int)z;
@@ -508,17 +596,8 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* v0, int64_
     plan.flags[b] = (uint8_t*)hf + (size_t)b * flag_bytes;
     plan.d_flags[b] = (uint8_t*)df;
   }
-  void *dw, *db, *dl;
-  ML_CUDA(r.alloc(kDevWords, &dw, nw * 4));
-  ML_CUDA(r.alloc(kDevBefore, &db, nw * 4));
-  ML_CUDA(r.alloc(kDevLvlOff, &dl, (size_t)(nz + 1) * 8));
-  plan.d_words = (uint32_t*)dw;
-  plan.d_before = (uint32_t*)db;
-  plan.d_lvloff = (uint64_t*)dl;
-  ML_CUDA(cudaMemcpyAsync(dw, plan.words, nw * 4, cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(db, plan.before, nw * 4, cudaMemcpyHostToDevice, r.copy));
-  ML_CUDA(cudaMemcpyAsync(dl, plan.lvloff, (size_t)(nz + 1) * 8, cudaMemcpyHostToDevice, r.copy));
-  r.h2d_bytes += 2 * nw * 4 + (size_t)(nz + 1) * 8;
+  ML_CUDA(cudaMemcpyAsync(plan.d_lvloff, plan.lvloff, (size_t)(nz + 1) * 8, cudaMemcpyHostToDevice, r.copy));
+  r.h2d_bytes += (size_t)(nz + 1) * 8;
   plan.on = true;
   return ML_OK;
 }
@@ -537,6 +616,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
     r.h2d_bytes += 2 * bytes;
     ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
     ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
+    if (plan.tuned_off) r.tuner.idle_window();
     return ML_OK;
   }
   // the staging of this parity was last read by the copies of window w - 2
@@ -755,7 +835,6 @@ struct HostStream {
   Resources* r = nullptr;
   std::thread::id owner;
   int domain = ML_DOMAIN_LOCAL, eos = 0, dtype = 0, vref_dtype = 0;
-  const void* v_host = nullptr;  // the reference volume in host memory that stays valid until the first push
   size_t es = 4;
   int64_t nz = 0, ncol = 0, max_steps = 0;
   bool want[3] = {true, false, false};  // steric, thermosteric, halosteric
@@ -917,7 +996,6 @@ extern "C" int ml_host_stream_begin(int domain, int eos, int dtype, int variants
     }
   }
   ML_HS_CUDA(cudaMemcpyAsync(hs->dV, v_src, lvl * ves, cudaMemcpyHostToDevice, r.copy));
-  hs->v_host = v_src;
   r.h2d_bytes += (size_t)nz * sizeof(double) + lvl * ves;
   if (supplied) {
     if (local) ML_HS_CUDA(cudaMemcpyAsync(hs->dRho, rho_ref, lvl * sizeof(double), cudaMemcpyHostToDevice, r.copy));
@@ -970,9 +1048,8 @@ extern "C" int ml_host_stream_push(void* stream, const void* T_block, const void
     // rho_ref is defined where the volume is missing too (reference.py:71), so a stream that hands it back moves
     // every row as it is; so does one whose reference volume is not stored like the fields
     const bool pageable = is_pageable(T_block) || is_pageable(S_block);
-    ML_HS_RC(plan_packing(r, hs->plan, vdt == dtype ? dtype : ML_F64, hs->v_host, nz, ncol, hs->max_steps, !hs->want_rho_ref,
+    ML_HS_RC(plan_packing(r, hs->plan, vdt == dtype ? dtype : ML_F64, hs->dV, nz, ncol, hs->max_steps, !hs->want_rho_ref,
                           pageable));
-    hs->v_host = nullptr;
     hs->t_plan = now_ms();
   }
   if (w >= 2) {  // the outputs of block w - 2 have reached the host: its device output buffers and bounce buffers are free

@@ -134,6 +134,14 @@ static int launch_unpack(cudaStream_t stream, int nrows, int, const float* pT, c
   return 0;
 }
 
+// the index kernels, as the host body they must agree with (k_presence_* themselves are tested on the GPU)
+static int launch_presence_index(cudaStream_t stream, const float* v, int64_t nz, int64_t ncol, int64_t, uint32_t* words,
+                                 uint32_t* before, uint64_t* count) {
+  stream->enqueue([=] { ml_pack_index_rows(v, nz, ncol, words, before, count); });
+  ml::tls().launches += 2;
+  return 0;
+}
+
 #include "../../momlevel_b200/csrc/ml_hostpath.cu"
 #include "../../momlevel_b200/csrc/ml_pack.cpp"
 
@@ -244,6 +252,36 @@ int main() {
                        (long long)nt, (long long)nz, (long long)ncol, pinned, mode, threads, spw, slow, frac);
               }
             }
+      // ---- a tuner that has settled on plain copies: the call skips the index and the packers altogether, counts its
+      // windows up to the next retry point and no further, and the call after that one tries the choices again
+      if (pinned && sh.pattern != 2) {
+        simcuda::copy_ns_per_kib() = 0;
+        ml_host_set_packing(1, 0);
+        bool ok = ml_steric_global_host(0, ML_F32, T, S, V, p.data(), nt, nz, ncol, 1, masso.data()) == 0;  // the table is this grid's
+        PackTuner& tn = resources().tuner;
+        ok = ok && tn.nz == nz && tn.ncol == ncol;
+        const double table[4] = {5.0, 1.0, 5.0, 5.0};
+        for (int i = 0; i < 4; ++i) tn.ms_per_step[i] = table[i];
+        tn.windows = PackTuner::kRetry - 3;
+        ok = ok && tn.settled_on_none();
+        for (auto& e : eta) memset(e, 0, (size_t)nt * ncol * sizeof(double));
+        ok = ok && ml_steric_local_variants_host(0, ML_F32, T, S, V, z_i.data(), depth.data(), p.data(), -1.0, nt, nz, ncol, 1,
+                                                 eta[0], eta[1], eta[2], nullptr, nullptr) == 0;
+        ok = ok && ml_host_last_packed_fraction() == 0.0 && ml_host_last_pack_threads() == 0;
+        for (int v = 0; v < 3; ++v) ok = ok && same(eta[v], want[v].data(), (size_t)nt * ncol);
+        ok = ok && tn.windows == std::min<int64_t>(PackTuner::kRetry - 3 + nt, PackTuner::kRetry);
+        if (nt >= 3) {  // parked at the retry point: this call plans again and walks through the choices
+          ok = ok && !tn.settled_on_none();
+          ok = ok && ml_steric_global_host(0, ML_F32, T, S, V, p.data(), nt, nz, ncol, 1, masso.data()) == 0;
+          ok = ok && same(masso.data(), want_m.data(), (size_t)nt) && tn.windows == PackTuner::kRetry + nt;
+        }
+        ++runs;
+        if (!ok) {
+          ++bad;
+          printf("SETTLED TUNER MISMATCH nt=%lld nz=%lld ncol=%lld windows=%lld\n", (long long)nt, (long long)nz, (long long)ncol,
+                 (long long)tn.windows);
+        }
+      }
       // ---- the same fields pushed block by block (ml_host_stream_*): blocks of uneven length travel through two
       // scratch buffers, and a buffer is scribbled over as soon as the contract allows it (after the NEXT push returns)
       {

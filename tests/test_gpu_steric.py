@@ -1256,3 +1256,36 @@ def test_host_stream_global_series_longer_than_memory_budget(ml):
     assert sums == (float(sums_w[0]), float(sums_w[1]))
     with pytest.raises(RuntimeError):
         hs.push(T[:1].numpy(), S[:1].numpy())  # closed
+
+
+def test_public_call_on_a_checked_grid_does_not_synchronise(ml):
+    """The second ``steric(dset)`` on device-resident fields queues its work and returns: the value checks of the grid
+    arrays are remembered for the tensors they were made on, volo / masso are read back when they are looked at."""
+    from momlevel_b200 import synth
+
+    ds = synth.make_dataset(5, 10, 16, 64, seed=21, device="cuda", dtype=torch.float32)
+    res0, ref0 = ml.steric(ds)
+    want_eta = res0["steric"].data.clone()
+    want = [float(ref0[k]) for k in ("volo", "masso", "rhoga")]
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")  # any torch-side synchronisation raises
+    try:
+        res, ref = ml.steric(ds)
+        assert ref["volo"].is_lazy and ref["masso"].is_lazy and ref["rhoga"].is_lazy
+        assert ref["volo"].shape == () and ref["volo"].dims == ()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    assert torch.equal(torch.nan_to_num(res["steric"].data, nan=-1.0), torch.nan_to_num(want_eta, nan=-1.0))
+    assert [float(ref[k]) for k in ("volo", "masso", "rhoga")] == want
+    assert want[2] == want[1] / want[0]
+
+    # an in-place write to a grid array voids the entry: the check runs again and fires
+    ds["deptho"].data[0, 0] = -1.0
+    with pytest.raises(AssertionError, match="Depth values"):
+        ml.steric(ds)
+    ds["deptho"].data[0, 0] = 1.0
+    ml.steric(ds)
+    # so does another tensor in its place, equal or not
+    ds["areacello"] = type(ds["areacello"])(ds["areacello"].data * 10.0, ds["areacello"].dims)
+    with pytest.raises(ValueError, match="Errors found"):
+        ml.steric(ds)
