@@ -261,7 +261,7 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     Sh.copy_(S)
     Vh.copy_(V)
     z_h, d_h, p_h = z_i.cpu().numpy(), depth.cpu().numpy(), pres.cpu().numpy()
-    n_e2e = max(1, min(args.steps, 3))
+    n_e2e = max(1, min(args.steps, 5))
 
     # the ceiling the host-fed leg can be judged against: plain pinned cudaMemcpyAsync of 2 GB, all ranks at once
     n_probe = min(Th.numel(), 1 << 29)
@@ -323,6 +323,12 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
                        "once, slowest rank, measured in this run",
         "note": "frac counts the bytes that crossed PCIe per rank; dense_equivalent counts the caller's bytes (rows that "
                 "travel packed to their present cells make it exceed the link rate)"}
+    try:  # weak scaling of this leg against the committed one-GPU record (one batch per rank, one host for all ranks)
+        base = json.loads((ROOT / "profiles" / "r02_bench_1gpu.json").read_text())["e2e"]["value"]
+        line["e2e"]["efficiency_vs_n1"] = line["e2e"]["value"] / (world * float(base))
+        line["e2e"]["n1_source"] = "profiles/r02_bench_1gpu.json (committed one-GPU run of this leg)"
+    except (OSError, ValueError, KeyError, TypeError):
+        pass
     # the device-resident and the host-streamed paths must agree
     err = (eta_h.to(dev) - eta).abs()
     line["e2e"]["max_abs_diff_vs_resident_m"] = float(torch.nan_to_num(err).max())
