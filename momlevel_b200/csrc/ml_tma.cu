@@ -33,7 +33,16 @@ namespace tma {
 // rho_ref / dz operands and fits 64 registers, so it runs four CTAs per SM with a 2-level ring (the
 // same bytes in flight per SM): +4.5 % (profiles/r01_experiments.md).  The self-reference mode reads
 // row 0 of the NEXT level while it works on this one and loses 15 % with a 2-level ring.
-__host__ __device__ constexpr int stages_of(int mode) { return mode == 1 /* kGlobal */ ? 2 : 4; }
+// A launch with S held at its reference slab (thermosteric: BC == 2) stages TC + 1 rows per level instead of 2 TC, so the
+// same shared memory holds a ring twice as deep: 1.50 -> 1.44-1.47 ms on OM4p25 x 12.  Not so for the halosteric launch
+// (no change) nor for the global kernel (a deeper ring costs it its fourth CTA per SM: 1.37-1.50 -> 1.54 ms);
+// tools/pinned_probe.py, profiles/r02_experiments.md.
+#ifndef ML_TMA_BC_STAGES
+#define ML_TMA_BC_STAGES 8
+#endif
+__host__ __device__ constexpr int stages_of(int mode, int bc = 0, int es = 4) {
+  return mode == 1 /* kGlobal */ ? 2 : ((bc == 2 && es == 4) ? ML_TMA_BC_STAGES : 4);
+}
 // Columns a CTA owns.  FLAT (rows of the grid are not a multiple of 16 bytes): a TMA box must START on 16 bytes in
 // global memory and holds at most 256 values, so it starts at the row's address rounded down, and the CTA owns the
 // 256 - (16 / size) columns that are inside the box whatever the row's misalignment (252 for fp32, 254 for fp64);
@@ -100,7 +109,7 @@ __global__ void ML_TMA_KERNEL_ATTR
     k_steric_tma(const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapS, const Params P) {
   constexpr bool GLOBAL = MODE == kGlobal;
   constexpr bool SELFREF = MODE == kSelfRef;
-  constexpr int kStages = stages_of(MODE);
+  constexpr int kStages = stages_of(MODE, BC, (int)sizeof(TIn));
   constexpr int SORT = ML_TMA_SORT;
   constexpr int kRowsT = (BC == 1) ? 1 : TC;
   constexpr int kRowsS = (BC == 2) ? 1 : TC;
@@ -424,7 +433,7 @@ static bool rows_aligned(int dtype, int64_t ncol);
 
 template <int TC>
 inline size_t smem_bytes(int bc, int nz, int mode, int es) {
-  const int kStages = stages_of(mode);
+  const int kStages = stages_of(mode, bc, es);
   return (size_t)kStages * (size_t)((bc == 0 ? 2 * TC : TC + 1) * kTile * es) + 3 * kStages * sizeof(uint64_t) +
          (size_t)kConsumerWarps * TC * sizeof(double) + (size_t)(2 * nz + 1) * sizeof(double) + 2 * kTile * sizeof(int) + 128;
 }
