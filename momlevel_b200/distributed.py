@@ -46,15 +46,19 @@ def bind_host_to_device(device_index):
         return 0
 
 
-def shard_sizes(n, world):
-    """Sizes of ``world`` contiguous blocks covering ``n`` items; the first ``n % world`` get one more."""
+def shard_sizes(n, world, light_first=False):
+    """Sizes of ``world`` contiguous blocks covering ``n`` items; the first ``n % world`` get one more -- the LAST
+    ones with ``light_first``: the rank that owns step 0 of a global series also sums the reference volume
+    (reference.py:74-77), so it is the one to take a short block when the steps do not divide evenly."""
     base, extra = divmod(int(n), int(world))
-    return [base + (1 if r < extra else 0) for r in range(world)]
+    sizes = [base + (1 if r < extra else 0) for r in range(world)]
+    return sizes[::-1] if light_first else sizes
 
 
-def shard_range(n, world, rank):
-    """``(start, stop)`` of this rank's block, e.g. 365 steps on 8 ranks -> 46,46,46,46,46,45,45,45."""
-    sizes = shard_sizes(n, world)
+def shard_range(n, world, rank, light_first=False):
+    """``(start, stop)`` of this rank's block, e.g. 365 steps on 8 ranks -> 46,46,46,46,46,45,45,45
+    (45,45,45,46,46,46,46,46 with ``light_first``)."""
+    sizes = shard_sizes(n, world, light_first)
     start = sum(sizes[:rank])
     return start, start + sizes[rank]
 
@@ -87,7 +91,7 @@ def assign_member_blocks(n_members, nt, world, rank, block=12):
     return pieces
 
 
-def gather_series(local, n_total, group=None, extra=None):
+def gather_series(local, n_total, group=None, extra=None, light_first=False):
     """All-gather the ranks' contiguous shards of a 1-D series into the full series on every rank.
 
     ``local`` is this rank's block (length ``shard_sizes(n_total, world)[rank]``), a tensor on
@@ -95,12 +99,13 @@ def gather_series(local, n_total, group=None, extra=None):
     a single ``all_gather_into_tensor`` moves them.  ``extra`` (a small 1-D tensor of the same
     length on every rank, or ``None`` everywhere) rides in the same message: the scalars of the
     reference state, which only the rank that owns step 0 has; returns ``(series, extras[world, k])`` then.
+    ``light_first``: the blocks were cut with ``shard_range(..., light_first=True)``.
     """
     if not dist.is_available() or not dist.is_initialized():
         assert local.numel() == n_total
         return local.clone() if extra is None else (local.clone(), extra.clone().view(1, -1))
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    sizes = shard_sizes(n_total, world)
+    sizes = shard_sizes(n_total, world, light_first)
     assert local.numel() == sizes[rank], f"rank {rank} holds {local.numel()} values, expected {sizes[rank]}"
     width = max(sizes)
     k = 0 if extra is None else int(extra.numel())
@@ -123,7 +128,7 @@ def global_sea_level(masso, volo, rhoga, area_sum):
 
 
 def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_sum, n_total, eos="Wright", group=None,
-                          masso_local=None, ref_sums=None):
+                          masso_local=None, ref_sums=None, light_first=False):
     """Global steric series with the time axis sharded over ranks.
 
     Each rank passes its own contiguous block of time steps ``T_local, S_local`` (resident on
@@ -141,10 +146,11 @@ def steric_global_sharded(T_local, S_local, v_ref, p_level, volo, rhoga, area_su
     if masso_local is None:
         masso_local = core.steric_global(T_local, S_local, v_ref, p_level, eos=eos)
     if volo is not None and rhoga is not None:
-        masso = gather_series(masso_local, n_total, group=group)
+        masso = gather_series(masso_local, n_total, group=group, light_first=light_first)
         return global_sea_level(masso.cpu().numpy(), volo, rhoga, area_sum)
     mine = ref_sums if ref_sums is not None else torch.zeros(2, dtype=masso_local.dtype, device=masso_local.device)
-    masso, extras = gather_series(masso_local, n_total, group=group, extra=mine.to(masso_local.device))
+    masso, extras = gather_series(masso_local, n_total, group=group, extra=mine.to(masso_local.device),
+                                  light_first=light_first)
     return finish_global_series(masso, extras, area_sum)
 
 

@@ -22,6 +22,8 @@ def test_shard_sizes():
     assert mld.shard_sizes(365, 8) == [46, 46, 46, 46, 46, 45, 45, 45]
     assert mld.shard_sizes(30, 8) == [4, 4, 4, 4, 4, 4, 3, 3]  # config 3
     assert mld.shard_sizes(3, 8) == [1, 1, 1, 0, 0, 0, 0, 0]
+    assert mld.shard_sizes(365, 8, light_first=True) == [45, 45, 45, 46, 46, 46, 46, 46]  # rank 0 also sums the volume
+    assert mld.shard_range(365, 8, 0, light_first=True) == (0, 45) and mld.shard_range(365, 8, 7, light_first=True) == (319, 365)
     for n, w in [(365, 8), (12, 5), (7, 7), (1, 4), (0, 3)]:
         blocks = [mld.shard_range(n, w, r) for r in range(w)]
         assert blocks[0][0] == 0 and blocks[-1][1] == n
@@ -59,23 +61,23 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, nt, out_dir):
+def _worker(rank, world, port, nt, out_dir, light_first=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         d = testdata.generate_test_data(ntimes=nt)
         ref = osteric.reference_state(d["thetao"], d["so"], d["volcello"], d["areacello"], d["z_l"])
-        lo, hi = mld.shard_range(nt, world, rank)
+        lo, hi = mld.shard_range(nt, world, rank, light_first)
         # this rank's time block only (what its GPU would hold); the reference state is step 0,
         # which every rank regenerates itself instead of receiving it
         _, _, masso_local = osteric.steric_global(d["thetao"][lo:hi], d["so"][lo:hi], d["z_l"], ref)
-        masso = mld.gather_series(torch.from_numpy(np.ascontiguousarray(masso_local)), nt)
+        masso = mld.gather_series(torch.from_numpy(np.ascontiguousarray(masso_local)), nt, light_first=light_first)
         eta, href = mld.global_sea_level(masso.numpy(), ref["volo"], ref["rhoga"], np.nansum(ref["areacello"]))
         # the same with the scalars of the reference state riding in the gather: only the rank that owns step 0 has them
         sums = torch.tensor([ref["volo"], ref["masso"]], dtype=torch.float64) if lo == 0 else None
         eta2, href2 = mld.steric_global_sharded(None, None, None, None, None, None, np.nansum(ref["areacello"]), nt,
                                                 masso_local=torch.from_numpy(np.ascontiguousarray(masso_local)),
-                                                ref_sums=sums)
+                                                ref_sums=sums, light_first=light_first)
         assert np.array_equal(eta2, eta) and href2 == href
         np.save(os.path.join(out_dir, f"eta_{rank}.npy"), eta)
         np.save(os.path.join(out_dir, f"href_{rank}.npy"), href)
@@ -83,10 +85,10 @@ def _worker(rank, world, port, nt, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nt", [5, 12])
-def test_time_sharded_global_series_gloo(tmp_path, nt):
+@pytest.mark.parametrize("nt,light_first", [(5, False), (12, False), (5, True)])
+def test_time_sharded_global_series_gloo(tmp_path, nt, light_first):
     world = 2
-    mp.spawn(_worker, args=(world, _free_port(), nt, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), nt, str(tmp_path), light_first), nprocs=world, join=True)
     d = testdata.generate_test_data(ntimes=nt)
     ref = osteric.reference_state(d["thetao"], d["so"], d["volcello"], d["areacello"], d["z_l"])
     want, href, _ = osteric.steric_global(d["thetao"], d["so"], d["z_l"], ref)
