@@ -300,7 +300,15 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
     torch.cuda.synchronize()
     lib_threads = core.host_last_pack_threads()
     dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+    by_rank = None
     if world > 1:
+        # what each rank saw (the figure of merit is the slowest): mean ms per call, packing threads of its last window,
+        # share of rows it sent packed, host ms of its last call
+        mine = torch.tensor([float(dt[0]) * 1e3, float(lib_threads), core.host_last_transfer()[1],
+                             core.host_last_timings()["call_ms"]], dtype=torch.float64, device=dev)
+        every = torch.empty(world * 4, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        by_rank = [[round(x, 2) for x in row] for row in every.view(world, 4).cpu().tolist()]
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     dense = Th.numel() * 4 + Sh.numel() * 4 + Vh.numel() * 4 + (z_h.size + d_h.size + p_h.size) * 8
     # what the library copied: level rows cross PCIe either as they are or as the cells the reference reads
@@ -314,6 +322,8 @@ def run_e2e(args, line, core, dist, dev, world, barrier, T, S, V, grid, z_i, dep
                    "host_input_bytes_per_step": dense, "level_rows_sent_packed": packed_rows,
                    "host_pack_mode": pack_mode, "host_pack_threads": lib_threads, "host_pack_policy": "library-tuned (ml_host_set_packing(1, 0)): threads of the last window", "host_pack_simd": core.host_pack_simd(),
                    "last_call_host_ms": host_ms}
+    if by_rank is not None:
+        line["e2e"]["by_rank_ms_threads_packed_lastcall"] = by_rank
     line["e2e"]["roofline"] = {
         "bound": "pcie_h2d", "h2d_bytes": h2d, "achieved_gbs": h2d / float(dt[0]) / 1e9,
         "peak_concurrent_h2d_gbs": h2d_peak_gbs, "frac": h2d / float(dt[0]) / 1e9 / h2d_peak_gbs,

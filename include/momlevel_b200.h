@@ -357,7 +357,8 @@ int ml_host_release(void);
  *                                       from half the calling thread's CPU affinity count divided by the ranks on the
  *                                       host (LOCAL_WORLD_SIZE) and, in mode 1, times every window on the copy stream
  *                                       and settles on the fastest of {that, none, twice, half} for this machine and
- *                                       load (kept per host thread between calls, tried afresh every 256 windows);
+ *                                       load -- packing has to beat plain copies by 6 % to be chosen -- (kept per host
+ *                                       thread between calls, tried afresh every 256 windows);
  *                                       a call that starts while "none" is in front moves every row as it is and does
  *                                       not build the presence index either.
  *                                       Applies to the calling host thread.

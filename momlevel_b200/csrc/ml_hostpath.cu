@@ -136,10 +136,14 @@ struct PackTuner {
     if (w < 2 * kChoices) return (int)(w / 2);
     return best();
   }
+  // Packing has costs the span of a window on the copy stream does not show (the presence index at the start of every
+  // call, cores and memory bandwidth the caller could use), so it has to beat plain copies by kMargin to be chosen.
+  static constexpr double kMargin = 0.06;
+  double score(int i) const { return threads[i] == 0 ? ms_per_step[i] * (1.0 - kMargin) : ms_per_step[i]; }
   int best() const {
     int b = 0;
     for (int i = 1; i < kChoices; ++i)
-      if (ms_per_step[i] >= 0.0 && (ms_per_step[b] < 0.0 || ms_per_step[i] < ms_per_step[b])) b = i;
+      if (ms_per_step[i] >= 0.0 && (ms_per_step[b] < 0.0 || score(i) < score(b))) b = i;
     return b;
   }
   // Past the trial windows with plain copies in front: a call that starts now does not even build the presence
@@ -296,19 +300,28 @@ int local_ranks() {
   return (n >= 1 && n <= 1024) ? (int)n : 1;
 }
 
-int default_threads() {
+// Cores of this rank's share of the host: the calling thread's affinity mask divided by the ranks on the host.
+int cores_per_rank() {
   cpu_set_t set;
   int n = 0;
   if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
   if (n <= 0) n = (int)std::thread::hardware_concurrency();
+  return std::max(1, n / local_ranks());
+}
+
+int default_threads() {
   // half the cores: the packers and the DMA engine share the host's memory bandwidth, and past that point
   // every extra thread slows the copies by as much as it saves (tools/e2e_sweep.py: 4 / 6 / 8 / 10 / 12 / 15
   // threads on a 16-core host gave 156 / 148 / 145 / 148 / 152 / 157 ms for an OM4p25 year).  That half is
   // shared by the ranks of the host: with every rank taking half the affinity mask, four ranks oversubscribed
   // the cores and eight lost to plain copies (SCALE_r01: packed 366 ms against 409 ms dense at four ranks with
   // cores / (2 ranks) threads each, a tie at eight).
-  return std::max(1, std::min(n / (2 * local_ranks()), 64));
+  return std::max(1, std::min(cores_per_rank() / 2, 64));
 }
+
+// The most packers the tuner may try: the rank's share less one core for the calling thread, which queues the plain
+// rows and should not have to wait for a core behind its own packers.
+int max_threads() { return std::max(1, std::min(cores_per_rank() - 1, 64)); }
 
 // memcpy by the worker threads (one thread moves ~10 GB/s, the memory system many times that)
 void parallel_copy(Resources& r, void* dst, const void* src, size_t bytes, int threads) {
@@ -499,7 +512,7 @@ int plan_packing(Resources& r, PackPlan& plan, int dtype, const void* d_v0, int6
   plan.threads = r.pack_threads > 0 ? std::min(r.pack_threads, 64) : default_threads();
   plan.tuned = r.pack_mode == 1 && r.pack_threads <= 0;
   if (plan.tuned) {
-    const int cap = std::max(1, std::min(2 * default_threads(), 64));  // all the cores of this rank's share
+    const int cap = max_threads();
     if (r.tuner.nz != nz || r.tuner.ncol != ncol || r.tuner.threads[0] != default_threads()) r.tuner.reset(nz, ncol, default_threads(), cap);
     plan.threads = std::max(plan.threads, r.tuner.threads[2]);  // the pool holds the largest choice
     if (!pageable && r.tuner.settled_on_none()) {
