@@ -357,8 +357,10 @@ int ml_host_release(void);
  *                                       from half the calling thread's CPU affinity count divided by the ranks on the
  *                                       host (LOCAL_WORLD_SIZE) and, in mode 1, times every window on the copy stream
  *                                       and settles on the fastest of {that, none, twice, half} for this machine and
- *                                       load -- packing has to beat plain copies by 6 % to be chosen -- (kept per host
- *                                       thread between calls, tried afresh every 256 windows);
+ *                                       load -- packing has to beat plain copies by 6 % to be chosen, and the ranks of
+ *                                       a host (LOCAL_WORLD_SIZE > 1 under torchrun) choose from the element-wise
+ *                                       maximum of their tables, i.e. together and for the slowest of them -- (kept
+ *                                       per host thread between calls, tried afresh every 256 windows);
  *                                       a call that starts while "none" is in front moves every row as it is and does
  *                                       not build the presence index either.
  *                                       Applies to the calling host thread.
@@ -383,6 +385,13 @@ double ml_host_last_packed_fraction(void);
 int ml_host_last_pack_threads(void);
 uint64_t ml_host_last_h2d_bytes(void);
 int ml_host_last_timings(double* ms4);
+/* Test entry of the table the ranks of a host share for that decision (POSIX shared memory named after the job's
+ * MASTER_ADDR / MASTER_PORT / TORCHELASTIC_RUN_ID and the user id): attaches to a made-up job `port` as `rank` of
+ * `ranks`, publishes ms4 (ms per step of {default, none, twice, half}; negative = unknown), waits up to wait_ms for the
+ * others, writes the element-wise maximum over the ranks to combined4 (unknown anywhere = unknown) and returns the
+ * number of ranks it saw.  No CUDA inside. */
+int ml_host_tuner_share_selftest(const char* port, int rank, int ranks, int64_t nz, int64_t ncol, const double* ms4,
+                                 double* combined4, int wait_ms);
 uint64_t ml_pack_index_rows(const float* v, int64_t nrows, int64_t ncol, uint32_t* words,
                             uint32_t* before, uint64_t* row_count);
 void ml_pack_rows(const float* t_row, const float* s_row, const uint32_t* words, const uint32_t* before,

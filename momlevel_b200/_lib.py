@@ -56,6 +56,7 @@ EXPORTS = {
     "ml_host_last_pack_threads": (_i, []),
     "ml_host_last_h2d_bytes": (ctypes.c_uint64, []),
     "ml_host_last_timings": (_i, [_vp]),
+    "ml_host_tuner_share_selftest": (_i, [ctypes.c_char_p, _i, _i, _i64, _i64, _vp, _vp, _i]),
     "ml_pack_index_rows": (ctypes.c_uint64, [_vp, _i64, _i64, _vp, _vp, _vp]),
     "ml_pack_rows": (None, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ml_pack_rows_cached": (None, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp]),

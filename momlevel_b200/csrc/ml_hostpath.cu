@@ -6,9 +6,13 @@
 // windows, the host->device copy of window k+1 running on a copy stream while the kernels of
 // window k run on the compute stream.  Pinned (page-locked) host buffers make the copies
 // truly asynchronous; pageable buffers work but serialise inside the driver.
+#include <fcntl.h>
 #include <sched.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
@@ -107,13 +111,127 @@ enum HostSlot {
   kHostSlots_
 };
 
+// Ranks that share this host's cores and memory system: one process per GPU under torchrun exports
+// LOCAL_WORLD_SIZE; a lone process counts as one.
+int local_ranks() {
+  const char* v = getenv("LOCAL_WORLD_SIZE");
+  if (v == nullptr || *v == 0) return 1;
+  const long n = strtol(v, nullptr, 10);
+  return (n >= 1 && n <= 1024) ? (int)n : 1;
+}
+
+// The ranks of one host decide TOGETHER how to move their rows.  They share the host's memory system, so a rank that
+// packs slows the plain copies of its neighbours: four ranks that each took what was fastest for themselves ended at
+// 227 / 273 / 304 / 253 ms -- two packing, two not -- where all four copying plainly took 230 ms each, and the job
+// runs at the pace of its slowest rank.  Every rank therefore publishes its table of timings in a small POSIX
+// shared-memory segment named after the job (MASTER_ADDR / MASTER_PORT / TORCHELASTIC_RUN_ID and the user id), and
+// every rank picks from the element-wise MAXIMUM over the ranks' tables: the same numbers, hence the same choice.
+// Without those variables, or if the segment cannot be had, a rank decides from its own table.
+struct SharedTuning {
+  static constexpr int kMaxRanks = 64;
+  struct Slot {
+    int64_t nz, ncol;
+    int32_t threads[4];
+    double ms[4];
+    int32_t seen, pad_;  // ml_host_tuner_share_selftest only
+  };
+  Slot* slots = nullptr;  // [kMaxRanks], zero-filled by ftruncate
+  int me = -1, ranks = 1;
+  char name[64] = {0};
+  explicit SharedTuning(bool from_env = true) {
+#ifndef ML_HOSTPATH_TEST_HOOKS
+    if (!from_env) return;
+    ranks = local_ranks();
+    const char* lr = getenv("LOCAL_RANK");
+    const char *addr = getenv("MASTER_ADDR"), *port = getenv("MASTER_PORT"), *run = getenv("TORCHELASTIC_RUN_ID");
+    if (ranks <= 1 || ranks > kMaxRanks || lr == nullptr || (port == nullptr && run == nullptr)) return;
+    const long r = strtol(lr, nullptr, 10);
+    if (r < 0 || r >= ranks) return;
+    attach(addr, port, run, (int)r);
+#endif
+  }
+  void attach(const char* addr, const char* port, const char* run, int rank) {
+    uint64_t h = 1469598103934665603ull;  // FNV-1a over the job's coordinates
+    for (const char* part : {addr, port, run})
+      for (const char* c = part ? part : ""; ; ++c) {
+        h = (h ^ (uint64_t)(unsigned char)*c) * 1099511628211ull;
+        if (*c == 0) break;
+      }
+    snprintf(name, sizeof(name), "/momlevel_b200_tuner_%u_%016llx", (unsigned)getuid(), (unsigned long long)h);
+    const int fd = shm_open(name, O_CREAT | O_RDWR, 0600);
+    if (fd < 0) return;
+    const size_t bytes = sizeof(Slot) * kMaxRanks;
+    void* m = ftruncate(fd, (off_t)bytes) == 0 ? mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0) : MAP_FAILED;
+    close(fd);
+    if (m == MAP_FAILED) return;
+    slots = static_cast<Slot*>(m);
+    me = rank;
+    clear();
+  }
+  ~SharedTuning() {
+    if (slots == nullptr) return;
+    clear();
+    munmap(slots, sizeof(Slot) * kMaxRanks);
+    if (me == 0) shm_unlink(name);  // the name goes; ranks that still have it mapped keep the memory
+  }
+  void clear() {
+    if (slots == nullptr) return;
+    for (int i = 0; i < 4; ++i) __atomic_store_n(reinterpret_cast<int64_t*>(&slots[me].ms[i]), (int64_t)0xbff0000000000000ll, __ATOMIC_RELAXED);  // -1.0
+    __atomic_store_n(&slots[me].nz, (int64_t)0, __ATOMIC_RELAXED);
+  }
+  // this rank's table, for the others to see
+  void publish(int64_t nz, int64_t ncol, const int* threads, const double* ms) {
+    if (slots == nullptr) return;
+    Slot& s = slots[me];
+    for (int i = 0; i < 4; ++i) {
+      __atomic_store_n(&s.threads[i], (int32_t)threads[i], __ATOMIC_RELAXED);
+      int64_t bits;
+      memcpy(&bits, &ms[i], 8);
+      __atomic_store_n(reinterpret_cast<int64_t*>(&s.ms[i]), bits, __ATOMIC_RELAXED);
+    }
+    __atomic_store_n(&s.ncol, ncol, __ATOMIC_RELAXED);
+    __atomic_store_n(&s.nz, nz, __ATOMIC_RELEASE);
+  }
+  // element-wise maximum over the ranks that work on the same grid with the same choices (own table included);
+  // a choice some rank has no timing for yet stays unknown (-1)
+  void combine(int64_t nz, int64_t ncol, const int* threads, const double* mine, double* out) const {
+    for (int i = 0; i < 4; ++i) out[i] = mine[i];
+    if (slots == nullptr) return;
+    for (int r = 0; r < ranks; ++r) {
+      if (r == me) continue;
+      const Slot& s = slots[r];
+      if (__atomic_load_n(&s.nz, __ATOMIC_ACQUIRE) != nz || __atomic_load_n(&s.ncol, __ATOMIC_RELAXED) != ncol) continue;
+      bool same = true;
+      for (int i = 0; i < 4; ++i) same = same && __atomic_load_n(&s.threads[i], __ATOMIC_RELAXED) == threads[i];
+      double theirs[4];
+      bool any = false;
+      for (int i = 0; i < 4; ++i) {
+        const int64_t bits = __atomic_load_n(reinterpret_cast<const int64_t*>(&s.ms[i]), __ATOMIC_RELAXED);
+        memcpy(&theirs[i], &bits, 8);
+        any = any || theirs[i] >= 0.0;
+      }
+      if (!same || !any) continue;  // a rank that is not timing its windows (pageable source, fixed thread count) has no say
+      for (int i = 0; i < 4; ++i) {
+        if (theirs[i] < 0.0 || out[i] < 0.0) out[i] = -1.0;
+        else out[i] = std::max(out[i], theirs[i]);
+      }
+    }
+  }
+};
+
+SharedTuning& shared_tuning() {
+  static SharedTuning t;  // one per process, attached on first use
+  return t;
+}
+
 // How many threads pack, when the caller leaves it to the library (ml_host_set_packing(1, 0)).  Packing trades host
 // memory bandwidth for PCIe bytes, and which of the two runs out first depends on the machine and on who else is
 // using it (one rank of four packed SLOWER than plain copies on a box where four ranks still get the full PCIe rate
-// each; one or two ranks, or eight, did not).  So the library measures: every window's span on the copy stream is
-// timed with events, the first windows try {default, none, twice, half} the default thread count for two windows
-// each, and the rest run with whatever was fastest per step; the table lives with the thread's Resources, so later
-// calls start from it, and it is tried afresh every kRetry windows.
+// each; one or two ranks, or eight, did not).  So the library measures: every window's interval on the copy stream
+// (idle gap in front of it included) is timed with events, the first windows try {default, none, twice, half} the
+// default thread count for two windows each, and the rest run with whatever was fastest per step -- for the slowest
+// rank of the host (SharedTuning above); the table lives with the thread's Resources, so later calls start from it,
+// and it is tried afresh every kRetry windows.
 struct PackTuner {
   static constexpr int kChoices = 4;
   static constexpr int kRetry = 256;
@@ -130,26 +248,32 @@ struct PackTuner {
     threads[3] = std::max(dflt / 2, 1);
     for (double& m : ms_per_step) m = -1.0;
     windows = 0;
+    shared_tuning().publish(nz, ncol, threads, ms_per_step);
   }
   int choose() {  // which entry of threads[] the next window runs with
     const int64_t w = windows++ % kRetry;
     if (w < 2 * kChoices) return (int)(w / 2);
     return best();
   }
-  // Packing has costs the span of a window on the copy stream does not show (the presence index at the start of every
-  // call, cores and memory bandwidth the caller could use), so it has to beat plain copies by kMargin to be chosen.
+  // Packing has costs the interval of a window on the copy stream does not show (the presence index at the start of
+  // every call, cores and memory bandwidth the caller could use), so it has to beat plain copies by kMargin to be chosen.
   static constexpr double kMargin = 0.06;
-  double score(int i) const { return threads[i] == 0 ? ms_per_step[i] * (1.0 - kMargin) : ms_per_step[i]; }
   int best() const {
-    int b = 0;
-    for (int i = 1; i < kChoices; ++i)
-      if (ms_per_step[i] >= 0.0 && (ms_per_step[b] < 0.0 || score(i) < score(b))) b = i;
-    return b;
+    double ms[kChoices];
+    shared_tuning().combine(nz, ncol, threads, ms_per_step, ms);
+    auto score = [&](int i) { return threads[i] == 0 ? ms[i] * (1.0 - kMargin) : ms[i]; };
+    int b = -1;
+    for (int i = 0; i < kChoices; ++i)
+      if (ms[i] >= 0.0 && (b < 0 || score(i) < score(b))) b = i;
+    return b < 0 ? 0 : b;
   }
   // Past the trial windows with plain copies in front: a call that starts now does not even build the presence
   // index.  Its windows are counted by idle_window(), which stops at the next multiple of kRetry, so that the call
   // after that one tries the choices again.
-  bool settled_on_none() const { return windows % kRetry >= 2 * kChoices && threads[best()] == 0 && ms_per_step[best()] >= 0.0; }
+  bool settled_on_none() const {
+    const int b = best();
+    return windows % kRetry >= 2 * kChoices && threads[b] == 0 && ms_per_step[b] >= 0.0;
+  }
   void idle_window() {
     if (windows % kRetry != 0) ++windows;
   }
@@ -157,6 +281,7 @@ struct PackTuner {
     if (choice < 0 || steps <= 0 || ms <= 0.0) return;
     const double v = ms / (double)steps;
     ms_per_step[choice] = ms_per_step[choice] < 0.0 ? v : 0.5 * (ms_per_step[choice] + v);
+    shared_tuning().publish(nz, ncol, threads, ms_per_step);
   }
 };
 
@@ -173,7 +298,10 @@ struct Resources {
   cudaStream_t copy = nullptr, comp = nullptr, back = nullptr;  // host->device, kernels, device->host
   cudaEvent_t copied[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
   cudaEvent_t out_done[2] = {nullptr, nullptr};  // the outputs of a window of this parity have reached the host
-  cudaEvent_t win_start[2] = {nullptr, nullptr};  // the copy stream has reached this window (timed, with copied[])
+  // win_start[w & 3]: the copy stream is done with window w - 1 (recorded right behind copied[] of that window; at the
+  // first window: when its first copy is queued).  Timed against copied[] of window w it spans the window AND the idle
+  // gap in front of it -- what a step costs -- and four of them keep a window's mark until its span has been read.
+  cudaEvent_t win_start[4] = {nullptr, nullptr, nullptr, nullptr};
   PackTuner tuner;
   int tuned_choice[2] = {-1, -1};  // what the window of this parity ran with, for the tuner's report
   int64_t tuned_steps[2] = {0, 0};
@@ -202,8 +330,11 @@ struct Resources {
       if (copied[i]) cudaEventDestroy(copied[i]);
       if (freed[i]) cudaEventDestroy(freed[i]);
       if (out_done[i]) cudaEventDestroy(out_done[i]);
+      copied[i] = freed[i] = out_done[i] = nullptr;
+    }
+    for (int i = 0; i < 4; ++i) {
       if (win_start[i]) cudaEventDestroy(win_start[i]);
-      copied[i] = freed[i] = out_done[i] = win_start[i] = nullptr;
+      win_start[i] = nullptr;
     }
     for (int i = 0; i < kRing; ++i) {
       if (ring[i]) cudaEventDestroy(ring[i]);
@@ -233,10 +364,11 @@ struct Resources {
     if (!back && (e = cudaStreamCreateWithFlags(&back, cudaStreamNonBlocking)) != cudaSuccess) return e;
     for (int b = 0; b < 2; ++b) {
       if (!copied[b] && (e = cudaEventCreateWithFlags(&copied[b], 0)) != cudaSuccess) return e;  // timed: the tuner reads the span
-      if (!win_start[b] && (e = cudaEventCreateWithFlags(&win_start[b], 0)) != cudaSuccess) return e;
       if (!freed[b] && (e = cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming)) != cudaSuccess) return e;
       if (!out_done[b] && (e = cudaEventCreateWithFlags(&out_done[b], cudaEventDisableTiming)) != cudaSuccess) return e;
     }
+    for (int i = 0; i < 4; ++i)
+      if (!win_start[i] && (e = cudaEventCreateWithFlags(&win_start[i], 0)) != cudaSuccess) return e;
     for (int i = 0; i < kRing; ++i)
       if (!ring[i] && (e = cudaEventCreateWithFlags(&ring[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     for (int i = 0; i < kStageRing; ++i)
@@ -289,15 +421,6 @@ Resources& resources() {
 
 double now_ms() {
   return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-// Ranks that share this host's cores and memory system: one process per GPU under torchrun exports
-// LOCAL_WORLD_SIZE; a lone process counts as one.
-int local_ranks() {
-  const char* v = getenv("LOCAL_WORLD_SIZE");
-  if (v == nullptr || *v == 0) return 1;
-  const long n = strtol(v, nullptr, 10);
-  return (n >= 1 && n <= 1024) ? (int)n : 1;
 }
 
 // Cores of this rank's share of the host: the calling thread's affinity mask divided by the ranks on the host.
@@ -641,7 +764,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
   if (tuned) {
     if (w >= 2 && r.tuned_choice[b] >= 0) {  // the span of window w - 2 on the copy stream is known now
       float ms = 0.0f;
-      if (cudaEventElapsedTime(&ms, r.win_start[b], r.copied[b]) == cudaSuccess)
+      if (cudaEventElapsedTime(&ms, r.win_start[(w - 2) & 3], r.copied[b]) == cudaSuccess)
         r.tuner.report(r.tuned_choice[b], (double)ms, r.tuned_steps[b]);
       else
         cudaGetLastError();
@@ -650,7 +773,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
     active = std::min(r.tuner.threads[choice], plan.threads);
     r.tuned_choice[b] = choice;
     r.tuned_steps[b] = nt_w;
-    ML_CUDA(cudaEventRecord(r.win_start[b], r.copy));
+    if (w == 0 || r.tuned_choice[b ^ 1] < 0) ML_CUDA(cudaEventRecord(r.win_start[w & 3], r.copy));  // else: behind window w - 1
   } else {
     r.tuned_choice[b] = -1;
   }
@@ -801,6 +924,7 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
     r.h2d_bytes += (size_t)nrows;
   }
   ML_CUDA(cudaEventRecord(r.copied[b], r.copy));
+  if (tuned) ML_CUDA(cudaEventRecord(r.win_start[(w + 1) & 3], r.copy));  // the next window's interval starts here
   ML_CUDA(cudaStreamWaitEvent(r.comp, r.copied[b], 0));
   if (sh.packed) {
     const int xblocks = (int)((plan.ngrp + 31) / 32);
@@ -812,6 +936,35 @@ int stage_window(Resources& r, PackPlan& plan, int b, int64_t w, const void* T_w
 }
 
 }  // namespace
+
+// Test entry (tests/test_host_logic.py, two processes on the CPU box): attach to the segment of a made-up job as
+// `rank` of `ranks`, publish `ms4`, wait (at most wait_ms) until every rank has published, return the combined table,
+// and leave only when every rank has read it.  Returns the number of ranks seen, or a negative status.
+extern "C" int ml_host_tuner_share_selftest(const char* port, int rank, int ranks, int64_t nz, int64_t ncol, const double* ms4,
+                                            double* combined4, int wait_ms) {
+  if (port == nullptr || ms4 == nullptr || combined4 == nullptr || rank < 0 || rank >= ranks || ranks > SharedTuning::kMaxRanks)
+    return ML_ERR_SHAPE;
+  SharedTuning t(false);  // never the segment of the job this process may belong to
+  t.ranks = ranks;
+  t.attach("selftest", port, "selftest", rank);
+  if (t.slots == nullptr) return ML_ERR_MODE;
+  const int threads[4] = {4, 0, 8, 2};
+  __atomic_store_n(&t.slots[rank].seen, 0, __ATOMIC_RELAXED);
+  t.publish(nz, ncol, threads, ms4);
+  auto count = [&](bool read) {
+    int n = 0;
+    for (int r = 0; r < ranks; ++r)
+      n += __atomic_load_n(&t.slots[r].nz, __ATOMIC_ACQUIRE) == nz && (!read || __atomic_load_n(&t.slots[r].seen, __ATOMIC_ACQUIRE) == 1);
+    return n;
+  };
+  const double t0 = now_ms();
+  while (count(false) < ranks && now_ms() - t0 < (double)wait_ms) usleep(1000);
+  const int seen = count(false);
+  t.combine(nz, ncol, threads, ms4, combined4);
+  __atomic_store_n(&t.slots[rank].seen, 1, __ATOMIC_RELEASE);
+  while (count(true) < ranks && now_ms() - t0 < 2.0 * (double)wait_ms) usleep(1000);
+  return seen;
+}
 
 extern "C" int ml_host_release(void) {
   resources().release();

@@ -341,3 +341,42 @@ def test_annual_average_reads_a_calendar_time_axis():
     b = Datetime(1900, 2, 28, calendar="julian") + datetime.timedelta(days=1)
     assert (b.month, b.day) == (2, 29)
     assert Datetime(2001, 1, 1, calendar="360_day") - Datetime(2000, 1, 1, calendar="360_day") == datetime.timedelta(days=360)
+
+
+# ---------------------------------------------------------------- the table the ranks of a host share (csrc/ml_hostpath.cu)
+
+def _share_worker(rank, ranks, port, tables, out):
+    import ctypes
+
+    from momlevel_b200 import _lib
+
+    L = _lib.lib()
+    ms = (ctypes.c_double * 4)(*tables[rank])
+    got = (ctypes.c_double * 4)()
+    seen = L.ml_host_tuner_share_selftest(port.encode(), rank, ranks, 75, 1555200, ctypes.cast(ms, ctypes.c_void_p),
+                                          ctypes.cast(got, ctypes.c_void_p), 20000)
+    out.put((rank, seen, list(got)))
+
+
+def test_ranks_of_a_host_see_the_same_combined_table():
+    """Every rank picks its packing threads from the element-wise maximum of all ranks' timings, so they pick the same:
+    three processes publish different tables through the POSIX shared-memory segment and must read identical maxima;
+    a choice one of them has not timed yet stays unknown for all."""
+    import multiprocessing as mp
+    import os
+
+    ctx = mp.get_context("spawn")
+    ranks = 3
+    tables = [[20.0, 25.0, 19.0, 22.0], [21.0, 24.0, 30.0, 22.5], [18.0, 26.0, 17.0, -1.0]]
+    out = ctx.Queue()
+    port = f"selftest-{os.getpid()}"
+    procs = [ctx.Process(target=_share_worker, args=(r, ranks, port, tables, out)) for r in range(ranks)]
+    for p in procs:
+        p.start()
+    results = sorted(out.get(timeout=120) for _ in range(ranks))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, seen, got in results:
+        assert seen == ranks, (rank, seen)
+        assert got == [21.0, 26.0, 30.0, -1.0], (rank, got)
