@@ -380,3 +380,35 @@ def test_ranks_of_a_host_see_the_same_combined_table():
     for rank, seen, got in results:
         assert seen == ranks, (rank, seen)
         assert got == [21.0, 26.0, 30.0, -1.0], (rank, got)
+
+
+def test_checked_grid_entries_stand_for_the_tensors_they_were_made_on():
+    """steric._checked_before: an entry is void after an in-place write to one of its tensors, for another tensor
+    object in its place (equal values or not), and once a tensor is gone (its id may be handed out again)."""
+    import gc
+    import importlib
+
+    import torch
+
+    st = importlib.import_module("momlevel_b200.steric")  # the package exports the function under the same name
+
+    st._CHECKED_GRIDS.clear()
+    arrs = tuple(torch.arange(4, dtype=torch.float64) + i for i in range(4))
+    assert st._checked_before(arrs) is None
+    st._remember_checked(arrs, 3.6e14)
+    assert st._checked_before(arrs) == 3.6e14
+    assert st._checked_before(arrs[:3] + (arrs[3].clone(),)) is None  # another object, same values
+    arrs[1][0] = -1.0                                                 # in-place write: _version moves
+    assert st._checked_before(arrs) is None
+    st._remember_checked(arrs, 1.0)
+    assert st._checked_before(arrs) == 1.0
+    key = tuple(id(a) for a in arrs)
+    kept = arrs[1:]
+    del arrs
+    gc.collect()
+    refs, _, _ = st._CHECKED_GRIDS[key]
+    assert refs[0]() is None  # the entry cannot be mistaken for a new tensor that lands on the same id
+    for _ in range(40):  # the table does not grow without bound
+        st._remember_checked(tuple(torch.zeros(1) for _ in range(4)), 0.0)
+    assert len(st._CHECKED_GRIDS) <= 16
+    del kept
