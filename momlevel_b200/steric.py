@@ -337,6 +337,27 @@ def _host_resident(dset, tcoord, zcoord, zbounds, need_depth=True):
         return False
 
 
+def _device_grid_checks(dset, zcoord, zbounds, strict, additional_vars):
+    """The value checks of a device-resident Dataset's grid arrays, queued BEHIND the launch they guard: one read-back
+    of {areacello total, three sign flags} the first time these tensors are seen, nothing after that
+    (``_checked_before``).  Raises what the eager checks raise (util.py:783-792, derived.py:284-292); returns
+    ``areacello.sum()``."""
+    arrs = (dset["areacello"].data, dset["deptho"].data, dset[zcoord].data, dset[zbounds].data)
+    area_total = _checked_before(arrs)
+    if area_total is not None:
+        validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=area_total)
+        return area_total
+    host = torch.stack([torch.nansum(arrs[0].to(torch.float64))]
+                       + [(a < 0).any().to(torch.float64) for a in arrs[1:]]).cpu()  # the one synchronisation
+    area_total = float(host[0])
+    validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=area_total)  # util.py:783-792
+    assert not bool(host[1]), "Depth values must all be positive-definite"  # derived.py:284-292
+    assert not bool(host[2]), "Vertical coordinate levels must all be positive-definite"
+    assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
+    _remember_checked(arrs, area_total)
+    return area_total
+
+
 def _selfref_host(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds):
     """``setup_reference_state(dset)`` + the local column integral for fields that live in HOST memory.
 
@@ -394,19 +415,7 @@ def _selfref(dset, pres, eos, variant, rhozero, tcoord, zcoord, zbounds, deferre
         t_bcast=variant == "halosteric", s_bcast=variant == "thermosteric", want_rho_ref=False)
     area_total = None
     if deferred:  # the value checks ride behind the kernel; volo / masso stay on the device until they are looked at
-        arrs = (dset["areacello"].data, dset["deptho"].data, dset[zcoord].data, dset[zbounds].data)
-        area_total = _checked_before(arrs)
-        if area_total is None:
-            host = torch.stack([torch.nansum(arrs[0].to(torch.float64))]
-                               + [(a < 0).any().to(torch.float64) for a in arrs[1:]]).cpu()  # the one synchronisation
-            area_total = float(host[0])
-            validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=area_total)  # util.py:783-792
-            assert not bool(host[1]), "Depth values must all be positive-definite"  # derived.py:284-292
-            assert not bool(host[2]), "Vertical coordinate levels must all be positive-definite"
-            assert not bool(host[3]), "Vertical coordinate interfaces must all be positive-definite"
-            _remember_checked(arrs, area_total)
-        else:
-            validate_dataset(dset, strict=strict, additional_vars=additional_vars, area_total=area_total)
+        area_total = _device_grid_checks(dset, zcoord, zbounds, strict, additional_vars)
     return _reference_from_pass(dset, tcoord, eos, rho, sums, pres), eta, area_total
 
 
@@ -591,10 +600,15 @@ def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rh
 
     dset = dset.rename(varname_map)
     tcoord, zcoord, zbounds = default_coords(coord_names)
-    validate_dataset(dset, strict=strict, additional_vars=[zbounds, "deptho"])
+    # device-resident fields without a supplied reference: the value checks ride behind the launch, as in steric()
+    deferred = reference is None and _on_one_cuda_device(
+        dset, ("thetao", "so", "volcello", "areacello", "deptho", zcoord, zbounds))
+    validate_dataset(dset, strict=strict, additional_vars=[zbounds, "deptho"], area_total=False if deferred else None)
     pres = _pressure(dset, zcoord, patm)
     eos_func_from_str(equation_of_state)
-    _check_depths(dset, zcoord, zbounds)
+    if not deferred:
+        _check_depths(dset, zcoord, zbounds)
+    area_total = None
     full = dset["thetao"]
     if full.dims[0] != tcoord or full.dims[1] != zcoord or dset["so"].dims != full.dims:
         raise ValueError(f"expecting fields laid out ({tcoord}, {zcoord}, y, x), got {full.dims}")
@@ -623,8 +637,10 @@ def steric_variants(dset, reference=None, coord_names=None, varname_map=None, rh
                                              torch.tensor([volo, masso], dtype=torch.float64), pres)
         else:
             etas, rho, sums = core.steric_local_variants(*args, V0, *tail, **kw)
+            if deferred:
+                area_total = _device_grid_checks(dset, zcoord, zbounds, strict, [zbounds, "deptho"])
             reference = _reference_from_pass(dset, tcoord, equation_of_state, rho, sums)
-        validate_dataset(reference, reference=True, strict=strict)
+        validate_dataset(reference, reference=True, strict=strict, area_total=area_total)
     result = Dataset()
     for variant in VARIANTS:
         result[variant] = DataArray(etas[variant], (tcoord,) + full.dims[2:], attrs={

@@ -1279,10 +1279,21 @@ def test_public_call_on_a_checked_grid_does_not_synchronise(ml):
     assert [float(ref[k]) for k in ("volo", "masso", "rhoga")] == want
     assert want[2] == want[1] / want[0]
 
+    # the three-height call shares the remembered checks and hands back the same lazy scalars
+    first, _ = ml.steric_variants(ds)
+    again, vref = ml.steric_variants(ds)
+    assert vref["volo"].is_lazy  # the sums of the one-pass kernel are added in another order: equal to rounding
+    assert float(vref["volo"]) == pytest.approx(want[0], rel=1e-12) and float(vref["masso"]) == pytest.approx(want[1], rel=1e-12)
+    for v in ("steric", "thermosteric", "halosteric"):
+        assert torch.equal(torch.nan_to_num(again[v].data, nan=-1.0), torch.nan_to_num(first[v].data, nan=-1.0))
+    assert torch.equal(torch.nan_to_num(again["steric"].data, nan=-1.0), torch.nan_to_num(want_eta, nan=-1.0))
+
     # an in-place write to a grid array voids the entry: the check runs again and fires
     ds["deptho"].data[0, 0] = -1.0
     with pytest.raises(AssertionError, match="Depth values"):
         ml.steric(ds)
+    with pytest.raises(AssertionError, match="Depth values"):
+        ml.steric_variants(ds)
     ds["deptho"].data[0, 0] = 1.0
     ml.steric(ds)
     # so does another tensor in its place, equal or not
