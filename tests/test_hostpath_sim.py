@@ -34,3 +34,18 @@ def test_host_path_under_a_simulated_runtime(tmp_path):
     out = run.stdout + run.stderr
     assert "ThreadSanitizer" not in out, out[-4000:]
     assert run.returncode == 0 and ", 0 mismatches" in out, out[-4000:]
+
+
+def test_packing_tuner_unit(tmp_path):
+    """csrc/ml_hosttune.h on its own: trial order, the margin plain copies enjoy, the settled-on-none shortcut and its
+    retry point, a rank's share of the cores (tests/sim/tuner_unit.cpp)."""
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("no g++")
+    exe = tmp_path / "tuner_unit"
+    src = ROOT / "tests" / "sim" / "tuner_unit.cpp"
+    res = subprocess.run([gxx, "-std=c++17", "-DML_HOSTPATH_TEST_HOOKS", "-I", str(ROOT / "tests" / "sim"), "-x", "c++", str(src),
+                          "-o", str(exe)], capture_output=True, text=True, cwd=ROOT)
+    assert res.returncode == 0, res.stderr[-3000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0 and "0 failed" in run.stdout, run.stdout[-2000:]
